@@ -1,0 +1,199 @@
+"""Analytic invariants for the oracle's rigid-body + contact dynamics (the RaiSim boundary is "parity unpinned":
+there is no RaiSim output to diff against, so M(q), h(q,u) and the contact solver are checked against physics)."""
+import numpy as np
+import pytest
+
+from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg
+from oracle_lib import Oracle, S, STATE_DIM
+
+
+def _cfg(**kw):
+    d = trot_cfg(num_envs=1, num_threads=1, StochasticDynamics=False, ObsNoise=0.0)
+    d.update(kw)
+    return d
+
+
+def _rand_state(rng, z=0.5, vel=1.0):
+    s = np.zeros(STATE_DIM)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    s[S["gc"]] = np.concatenate([[rng.uniform(-5, 5), rng.uniform(-5, 5), z], q,
+                                 np.tile([0.0, -0.78, 1.57], 4) + rng.uniform(-0.5, 0.5, 12)])
+    s[S["gv"]] = np.concatenate([rng.normal(size=3) * vel, rng.normal(size=3) * 2 * vel, rng.normal(size=12) * 5 * vel])
+    return s
+
+
+def _energy_momentum(o, with_rotors=True):
+    k = o.body_kin(0)
+    Iw = np.einsum("bij,bjk,blk->bil", k["R"], k["I"], k["R"])
+    ke = 0.5 * np.sum(k["mass"] * np.sum(k["vc"] ** 2, 1)) + 0.5 * np.einsum("bi,bij,bj->", k["w"], Iw, k["w"])
+    if with_rotors:   # reflected rotor inertias (URDF rotor_inertia) carry 1/2 J qd^2 each
+        qd = o.get_state(0)[S["gv"]][6:]
+        ke += 0.5 * np.sum(np.tile([0.003708, 0.003708, 0.008966], 4) * qd ** 2)
+    pe = 9.81 * np.sum(k["mass"] * k["pc"][:, 2])
+    P = np.sum(k["mass"][:, None] * k["vc"], 0)
+    com = np.sum(k["mass"][:, None] * k["pc"], 0) / k["mass"].sum()
+    L = np.sum(np.einsum("bij,bj->bi", Iw, k["w"]) + k["mass"][:, None] * np.cross(k["pc"] - com, k["vc"]), 0)
+    return ke, pe, P, L
+
+
+def test_total_mass_symmetry_positive_definite():
+    o = Oracle(_cfg())
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        o.set_state(0, _rand_state(rng))
+        M, h = o.mass_and_h(0)
+        assert abs(M[0, 0] - 8.88) < 1e-12 and abs(M[1, 1] - 8.88) < 1e-12      # URDF masses: 3.72 + 4*(0.54+0.636+0.064+0.05)
+        assert np.abs(M - M.T).max() < 1e-15
+        assert np.linalg.eigvalsh(M).min() > 1e-3
+        assert np.abs(M[0:3, 0:3] - 8.88 * np.eye(3)).max() < 1e-12
+
+
+def test_velocity_kinematics_match_finite_differences_of_positions():
+    """body COM velocities / toe velocities == d/dt of FK positions along the flow of gv."""
+    o = Oracle(_cfg())
+    rng = np.random.default_rng(1)
+    s = _rand_state(rng)
+    o.set_state(0, s)
+    k0 = o.body_kin(0); toe0, vtoe0 = o.toe_kin(0)
+    eps = 1e-7
+    s2 = s.copy()
+    gc, gv = s[S["gc"]].copy(), s[S["gv"]]
+    gc[0:3] += eps * gv[0:3]
+    w = gv[3:6]; th = np.linalg.norm(w) * eps
+    dq = np.concatenate([[np.cos(th / 2)], np.sin(th / 2) * w / np.linalg.norm(w)])
+    q = gc[3:7]
+    gc[3:7] = np.array([dq[0] * q[0] - dq[1:] @ q[1:], *(dq[0] * q[1:] + q[0] * dq[1:] + np.cross(dq[1:], q[1:]))])
+    gc[7:] += eps * gv[6:]
+    s2[S["gc"]] = gc
+    o.set_state(0, s2)
+    k1 = o.body_kin(0); toe1, _ = o.toe_kin(0)
+    assert np.abs((k1["pc"] - k0["pc"]) / eps - k0["vc"]).max() < 1e-5
+    assert np.abs((toe1 - toe0) / eps - vtoe0).max() < 1e-5
+
+
+def test_mass_matrix_equals_kinetic_energy_hessian():
+    o = Oracle(_cfg())
+    rng = np.random.default_rng(2)
+    s = _rand_state(rng)
+    o.set_state(0, s)
+    M, _ = o.mass_and_h(0)
+    # rotor inertias enter M but not the link kinetic energy: remove them before comparing
+    rotor = np.tile([0.003708, 0.003708, 0.008966], 4)
+    Mlink = M - np.diag(np.concatenate([np.zeros(6), rotor]))
+    for _ in range(6):
+        u = rng.normal(size=18)
+        s2 = s.copy(); s2[S["gv"]] = u
+        o.set_state(0, s2)
+        ke, _, _, _ = _energy_momentum(o, with_rotors=False)
+        assert abs(0.5 * u @ Mlink @ u - ke) < 1e-10 * max(1.0, ke)
+
+
+def test_gravity_term_is_potential_gradient():
+    o = Oracle(_cfg())
+    rng = np.random.default_rng(3)
+    s = _rand_state(rng); s[S["gv"]] = 0
+    o.set_state(0, s)
+    _, h = o.mass_and_h(0)
+    assert abs(h[2] - 8.88 * 9.81) < 1e-10 and np.abs(h[0:2]).max() < 1e-12
+    eps = 1e-6
+    for j in range(12):
+        sp = s.copy(); sp[7 + j] += eps
+        sm = s.copy(); sm[7 + j] -= eps
+        o.set_state(0, sp); _, pe_p, _, _ = _energy_momentum(o)
+        o.set_state(0, sm); _, pe_m, _, _ = _energy_momentum(o)
+        assert abs((pe_p - pe_m) / (2 * eps) - h[6 + j]) < 1e-6
+
+
+@pytest.mark.parametrize("dt,tol", [(2.5e-4, 2e-2), (2.5e-5, 2e-3)])
+def test_free_flight_conserves_energy_and_momentum(dt, tol):
+    """No contact, zero torque, no joint damping: E, L and P - m g t drift O(dt) (semi-implicit Euler)."""
+    o = Oracle(_cfg(simulation_dt=dt, joint_damping=0.0))
+    rng = np.random.default_rng(4)
+    s = _rand_state(rng, z=3.0, vel=0.6)
+    o.set_state(0, s)
+    ke0, pe0, P0, L0 = _energy_momentum(o)
+    n = int(round(0.05 / dt))
+    for _ in range(n):
+        o.integrate(0, np.zeros(12))
+    ke1, pe1, P1, L1 = _energy_momentum(o)
+    assert abs((ke1 + pe1) - (ke0 + pe0)) < tol * (ke0 + abs(pe0) * 0 + 1.0)
+    assert np.abs(L1 - L0).max() < tol * (np.abs(L0).max() + 0.1)
+    assert np.abs(P1 - (P0 + np.array([0, 0, -8.88 * 9.81 * n * dt]))).max() < tol * 5e-3   # O(dt) integrator error
+
+
+def test_energy_error_is_first_order_in_dt():
+    errs = []
+    for dt in (4e-4, 1e-4):
+        o = Oracle(_cfg(simulation_dt=dt, joint_damping=0.0))
+        rng = np.random.default_rng(5)
+        o.set_state(0, _rand_state(rng, z=3.0, vel=0.8))
+        ke0, pe0, _, L0 = _energy_momentum(o)
+        for _ in range(int(round(0.04 / dt))):
+            o.integrate(0, np.zeros(12))
+        ke1, pe1, _, L1 = _energy_momentum(o)
+        errs.append(abs(ke1 + pe1 - ke0 - pe0))
+    assert errs[1] < errs[0] * 0.4       # ~4x smaller for 4x smaller dt
+
+
+def test_static_stance_supports_weight_and_does_not_slide():
+    """PD holding the nominal pose on four feet: after settling, sum of normal forces = m g, no horizontal drift."""
+    o = Oracle(_cfg())
+    s = np.zeros(STATE_DIM)
+    q = np.tile([0.0, -0.78, 1.57], 4)
+    s[S["gc"]] = np.concatenate([[0, 0, 0.30], [1, 0, 0, 0], q])
+    o.set_state(0, s)
+    for i in range(8000):
+        st = o.get_state(0)
+        tau = 40.0 * (q - st[7:19]) - 4.0 * st[25:37]      # extra joint damping so the fore-aft sway dies out quickly
+        o.integrate(0, tau)
+    ci = o.contact_info(0)
+    st = o.get_state(0)
+    assert ci["foot_in_contact"].tolist() == [1, 1, 1, 1]
+    fz = ci["foot_impulse"][:, 2].sum() / 2.5e-4
+    assert abs(fz - 8.88 * 9.81) < 0.02 * 8.88 * 9.81
+    assert np.abs(st[S["gv"]]).max() < 2e-3
+    assert np.abs(st[0:2]).max() < 3e-2
+    assert np.all(ci["foot_impulse"][:, 2] > 0)
+    # friction cone respected
+    ft = np.linalg.norm(ci["foot_impulse"][:, :2], axis=1)
+    assert np.all(ft <= 0.6 * ci["foot_impulse"][:, 2] * (1 + 1e-9))
+
+
+def test_contact_never_pulls_and_respects_cone_during_sliding():
+    o = Oracle(_cfg())
+    s = np.zeros(STATE_DIM)
+    q = np.tile([0.0, -0.78, 1.57], 4)
+    s[S["gc"]] = np.concatenate([[0, 0, 0.29], [1, 0, 0, 0], q])
+    s[S["gv"]][0] = 3.0          # sliding forward at 3 m/s with feet on the ground
+    o.set_state(0, s)
+    slid = False
+    for i in range(400):
+        st = o.get_state(0)
+        o.integrate(0, 40.0 * (q - st[7:19]) - 1.0 * st[25:37])
+        ci = o.contact_info(0)
+        for l in range(4):
+            if ci["foot_in_contact"][l]:
+                lam = ci["foot_impulse"][l]
+                assert lam[2] >= 0
+                ft = np.hypot(lam[0], lam[1])
+                assert ft <= 0.6 * lam[2] * (1 + 1e-6) + 1e-12
+                if lam[2] > 0 and ft > 0.59 * lam[2]:
+                    slid = True
+    assert slid
+    assert o.get_state(0)[19] < 3.0      # friction decelerates the trunk
+
+
+def test_drop_with_restitution_bounces_below_drop_height():
+    o = Oracle(_cfg())
+    s = np.zeros(STATE_DIM)
+    q = np.tile([0.0, -0.78, 1.57], 4)
+    s[S["gc"]] = np.concatenate([[0, 0, 0.45], [1, 0, 0, 0], q])
+    o.set_state(0, s)
+    zmin, zs = 1.0, []
+    for i in range(3000):
+        st = o.get_state(0)
+        o.integrate(0, 40.0 * (q - st[7:19]) - 1.0 * st[25:37])
+        zs.append(o.get_state(0)[2])
+    zs = np.array(zs)
+    assert zs.min() > 0.15 and zs.max() <= 0.45 + 1e-9
+    assert abs(zs[-1] - zs[-200]) < 2e-3      # came to rest

@@ -1,0 +1,69 @@
+"""ctypes binding of the C ABI (include/irrl_b200.h).  There is no CPU fallback: if the shared library is missing
+or no CUDA device is present every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libirrl_b200.so")
+_lib = None
+
+c_f32p = C.c_void_p   # raw addresses: host numpy buffers or device pointers
+
+
+class RolloutBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "actions", "values", "neglogps", "rewards", "dones", "cur_obs", "cur_done",
+                                           "state", "ep_return", "ep_length")]
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m high_speed_quadrupedal_locomotion_by_irrl_b200.build` "
+                           "(the CUDA extension is mandatory, there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.irrl_last_error.restype = C.c_char_p
+    L.irrl_version.restype = C.c_char_p
+    L.irrl_get_extra_info_name.restype = C.c_char_p
+    L.irrl_get_extra_info_name.argtypes = [C.c_void_p, C.c_int]
+    L.irrl_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.irrl_destroy.argtypes = [C.c_void_p]
+    L.irrl_destroy.restype = None
+    L.irrl_get_tick.restype = C.c_uint32
+    L.irrl_get_tick.argtypes = [C.c_void_p]
+    L.irrl_set_tick.argtypes = [C.c_void_p, C.c_uint32]
+    for name in ("init", "close", "curriculum_update", "stop_recording_video", "show_window", "hide_window",
+                 "get_ob_dim", "get_action_dim", "get_extra_info_dim", "get_num_envs", "get_origin_state_dim"):
+        getattr(L, "irrl_" + name).argtypes = [C.c_void_p]
+    for name in ("reset", "observe", "is_terminal_state", "origin_state", "reference_state", "get_joint_effort", "get_generalized_force",
+                 "get_inverse_mass_matrix", "get_nonlinear", "get_mass_matrix", "set_contact_coefficient", "get_sphere_info",
+                 "get_model_params", "get_state", "set_state", "get_solver_sweeps", "set_stream"):
+        getattr(L, "irrl_" + name).argtypes = [C.c_void_p, C.c_void_p]
+    L.irrl_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.irrl_test_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.irrl_last_episode_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.irrl_running_episode_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.irrl_set_seed.argtypes = [C.c_void_p, C.c_int]
+    L.irrl_set_simulation_time_step.argtypes = [C.c_void_p, C.c_double]
+    L.irrl_set_control_time_step.argtypes = [C.c_void_p, C.c_double]
+    L.irrl_start_recording_video.argtypes = [C.c_void_p, C.c_char_p]
+    L.irrl_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.irrl_set_ref_traj.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.irrl_policy_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.irrl_policy_set_params.argtypes = [C.c_void_p, C.c_void_p]
+    L.irrl_policy_destroy.argtypes = [C.c_void_p]
+    L.irrl_policy_destroy.restype = None
+    L.irrl_policy_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.irrl_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RolloutBuffers), C.c_int]
+    L.irrl_gae.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().irrl_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what or 'irrl'} failed ({rc}): {msg}")

@@ -1,0 +1,627 @@
+// Host shim: the C ABI of include/irrl_b200.h over the sm_100a kernels.
+// This is the thin replacement of VectorizedEnvironment<ENVIRONMENT> (VEC:127-382) + the pybind module
+// (raisim_gym.cpp:14-47): it owns the device state, parses the YAML `environment:` map (ENV:1594-1659,
+// VEC:136-171), launches kernels on one stream and stages host buffers through pinned memory.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/irrl_b200.h"
+#include "env_kernels.h"
+
+using namespace irrl;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+
+// ------------------------------------------------------------------ minimal YAML flat-map reader
+// Accepts what run_bp_v5.py:205-207 produces (a block-style mapping of scalars), optionally nested under an
+// `environment:` key when a whole config file is passed.
+struct YamlMap {
+    std::map<std::string, std::string> kv;
+    static std::string trim(const std::string& s) {
+        size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+        return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+    }
+    bool parse(const std::string& text, std::string& err) {
+        std::istringstream in(text); std::string line; bool has_env = false; std::map<std::string, std::string> top, env;
+        bool in_env = false;
+        while (std::getline(in, line)) {
+            size_t hash = std::string::npos; bool q = false;
+            for (size_t i = 0; i < line.size(); ++i) { if (line[i] == '\'' || line[i] == '"') q = !q; if (line[i] == '#' && !q && (i == 0 || line[i - 1] == ' ' || line[i - 1] == '\t')) { hash = i; break; } }
+            if (hash != std::string::npos) line = line.substr(0, hash);
+            if (trim(line).empty() || trim(line) == "---") continue;
+            size_t indent = line.find_first_not_of(" \t");
+            size_t colon = line.find(':');
+            if (colon == std::string::npos) { err = "YAML: cannot parse line '" + line + "'"; return false; }
+            std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+            if (key.size() >= 2 && (key.front() == '"' || key.front() == '\'')) key = key.substr(1, key.size() - 2);
+            if (val.size() >= 2 && (val.front() == '"' || val.front() == '\'') && val.back() == val.front()) val = val.substr(1, val.size() - 2);
+            if (indent == 0) { in_env = false; if (key == "environment" && val.empty()) { in_env = true; has_env = true; continue; } top[key] = val; }
+            else { if (in_env) env[key] = val; else top[key] = val; }
+        }
+        kv = has_env ? env : top;
+        return true;
+    }
+    bool has(const std::string& k) const { return kv.count(k) != 0; }
+    static bool to_bool(const std::string& v, bool& out) {
+        std::string s; for (char c : v) s += (char)tolower(c);
+        if (s == "true" || s == "yes" || s == "on" || s == "1") { out = true; return true; }
+        if (s == "false" || s == "no" || s == "off" || s == "0") { out = false; return true; }
+        return false;
+    }
+};
+
+struct irrl_env_impl {
+    EnvParams P{};
+    DevState S{};
+    int device = 0;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    uint32_t tick = 0;
+    bool initialised = false;
+    std::string resource_dir, ref_path;
+    std::vector<std::string> extra_names;
+    // staging (device + pinned host)
+    float *d_action = nullptr, *d_ob = nullptr, *d_reward = nullptr, *d_extra = nullptr, *d_ep_ret = nullptr, *d_scratch = nullptr;
+    uint8_t* d_done = nullptr; int* d_ep_len = nullptr;
+    float* d_ref = nullptr;
+    unsigned char* h_pin = nullptr; size_t h_pin_bytes = 0; size_t scratch_floats = 0;
+    std::vector<void*> allocs;
+};
+struct irrl_policy_impl {
+    int device = 0;
+    float* d_params = nullptr;
+    PolicyWeights W{};
+    // staging for host callers
+    int cap = 0; float *d_obs = nullptr, *d_state = nullptr, *d_action = nullptr, *d_clipped = nullptr, *d_value = nullptr, *d_nlp = nullptr; uint8_t* d_done = nullptr;
+    unsigned char* h_pin = nullptr;
+};
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T> int dev_alloc(irrl_env_impl* E, T** p, size_t n) {
+    void* q = nullptr; CUDA_OK(cudaMalloc(&q, n * sizeof(T))); CUDA_OK(cudaMemset(q, 0, n * sizeof(T)));
+    E->allocs.push_back(q); *p = reinterpret_cast<T*>(q); return 0;
+}
+
+int read_cfg(irrl_env_impl* E, const YamlMap& y) {
+    EnvParams& P = E->P;
+    std::string missing;
+    auto num = [&](const char* k, double& out) { auto it = y.kv.find(k); if (it == y.kv.end()) { missing = k; return false; }
+        char* end = nullptr; out = strtod(it->second.c_str(), &end); if (end == it->second.c_str()) { bool b; if (YamlMap::to_bool(it->second, b)) { out = b; return true; } missing = std::string(k) + " (not a number: '" + it->second + "')"; return false; } return true; };
+    auto flg = [&](const char* k, int& out) { auto it = y.kv.find(k); if (it == y.kv.end()) { missing = k; return false; }
+        bool b; if (!YamlMap::to_bool(it->second, b)) { missing = std::string(k) + " (not a bool: '" + it->second + "')"; return false; } out = b ? 1 : 0; return true; };
+    double d; int f;
+#define NUM(key, field) if (!num(key, d)) goto bad; field = (float)d;
+#define FLG(key, field) if (!flg(key, f)) goto bad; field = f;
+#define IGN(key) if (!y.has(key)) { missing = key; goto bad; }
+    {
+        // VEC:146-171
+        if (!num("num_envs", d)) goto bad; P.N = (int)d;
+        IGN("num_threads");
+        double sim_dt, ctl_dt; if (!num("simulation_dt", sim_dt)) goto bad; if (!num("control_dt", ctl_dt)) goto bad;
+        P.sim_dt = (float)sim_dt; P.control_dt = (float)ctl_dt; P.loop_count = int(ctl_dt / sim_dt + 1e-10);   // ENV:711
+        if (!num("seedd", d)) goto bad; P.seed = (uint32_t)(int)d;                                               // VEC:171
+        // ENV:1598-1613
+        NUM("abad", P.abad) NUM("period", P.period) NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
+        IGN("down_height") IGN("gait_step")
+        NUM("Vx", P.Vx_max) P.Vx_min = 0.f;                                                                      // ENV:1606-1607, 2054
+        NUM("Vy", P.Vy_max) P.Vy_min = -P.Vy_max; NUM("Omega", P.omega_max) P.omega_min = -P.omega_max;
+        NUM("LeanFront", P.lean_front) NUM("LeanHind", P.lean_hind)
+        // ENV:1616-1629
+        FLG("Terrain", P.flag_terrain) FLG("Manual", P.flag_manual) { int crucial; FLG("Crutial", crucial) if (crucial) return fail(-3, "Crutial: True (meteor spheres, ENV:815-861) is not implemented in this build"); }
+        FLG("Filter", P.flag_filter) IGN("Camera") FLG("StochasticDynamics", P.flag_stochastic) FLG("HeightVariable", P.flag_height_variable)
+        FLG("TimeBasedContact", P.flag_time_contact) FLG("ManualTraj", P.flag_manual_traj) IGN("MotorDynamics") FLG("ObsFilter", P.flag_obs_filter)
+        FLG("WILDCAT", P.flag_wildcat) FLG("ForceDisturbance", P.flag_force_dist) IGN("Convert2Torque")
+        // ENV:1632-1639
+        NUM("terminalRewardCoeff", P.terminal_coeff) NUM("EndEffectorRewardCoeff", P.ee_coeff) NUM("BodyPosRewardCoeff", P.pos_coeff)
+        NUM("BodyAttitudeRewardCoeff", P.atti_coeff) NUM("JointRewardCoeff", P.joint_coeff) NUM("VelRewardCoeff", P.vel_coeff)
+        NUM("TorqueCoeff", P.torque_coeff) NUM("ContactCoeff", P.contact_coeff)
+        // ENV:1643-1658
+        NUM("Stiffness", P.stiffness) IGN("Stiffness_Low") NUM("AbadRatio", P.abad_ratio) NUM("Damping", P.damping)
+        double freq; if (!num("Freq", freq)) goto bad;
+        NUM("max_time", P.max_time) IGN("CubeNum") IGN("FPS") NUM("ActionNoise", P.action_noise) NUM("ObsNoise", P.noise_flag)
+        if (!num("GaitType", d)) goto bad; P.gait_type = (int)d;
+        NUM("MotorMaxTorque", P.motor_max_torque) NUM("MotorCriticalSpeed", P.motor_crit_speed) NUM("MotorMaxSpeed", P.motor_max_speed)
+        P.filter_para = P.flag_filter ? (float)(1.0 - freq * ctl_dt) : 0.f;                                      // ENV:396
+        P.obs_filter_alpha = P.flag_obs_filter ? (float)(2.0 * 3.14 * ctl_dt * 20.0 / (2.0 * 3.14 * ctl_dt * 20.0 + 1.0)) : 1.f;   // ENV:425-426, 2026
+        if (y.has("RefTraj")) E->ref_path = y.kv.at("RefTraj");
+        // optional solver / model switches of this implementation
+        auto opt = [&](const char* k, double dflt) { double v; return y.has(k) && num(k, v) ? v : dflt; };
+        P.joint_damping = (float)opt("joint_damping", 0.01);                                                     // URDF:56
+        P.solver_iters = (int)opt("solver_iters", 20); P.slide_iters = (int)opt("slide_iters", 3); P.solver_tol = (float)opt("solver_tol", 1e-6);
+        P.mu = (float)opt("friction", 0.6); P.restitution = (float)opt("restitution", 0.2); P.rest_threshold = (float)opt("restitution_threshold", 0.01);   // ENV:433
+    }
+    if (P.N <= 0) return fail(-3, "num_envs must be positive");
+    if (P.flag_terrain) return fail(-3, "Terrain: True (RaiSim Perlin HeightMap, ENV:252-265) is not implemented in this build");
+    if (P.flag_force_dist && P.flag_manual) return fail(-3, "ForceDisturbance with Manual (state_disturbance, ENV:912-940) is not implemented in this build");
+    // ForceDisturbance without Manual: force_attack(random() < 0.0027) never fires -> zero external force.
+    switch (P.gait_type) {                                                                                       // ENV:398-409
+        case 0: P.phase[0] = 0.5f; P.phase[1] = 0.f; P.phase[2] = 0.f; P.phase[3] = 0.5f; break;
+        case 1: P.phase[0] = 0.5f; P.phase[1] = 0.5f; P.phase[2] = 0.f; P.phase[3] = 0.f; break;
+        case 2: P.phase[0] = 0.f; P.phase[1] = 0.25f; P.phase[2] = 0.5f; P.phase[3] = 0.75f; break;
+        default: P.phase[0] = P.phase[1] = P.phase[2] = P.phase[3] = 0.f;
+    }
+    return 0;
+bad:
+    return fail(-3, "Node cfg[\"" + missing + "\"] doesn't exist");   // GYM:41-42 READ_YAML
+#undef NUM
+#undef FLG
+#undef IGN
+}
+
+void model_defaults(EnvParams& P) {
+    // hard-coded members ENV:1949-1952, 1988-1999, 2043
+    P.l_thigh = 0.209f; P.l_calf = 0.2175f; P.l_hip = 0.085f;
+    P.max_len = (float)std::sqrt(0.085 * 0.085 + (0.2175 + 0.209) * (0.2175 + 0.209));                           // ENV:395
+    P.joint_noise = 0.002f; P.joint_vel_noise = 0.8f; P.posture_sigma = 0.02f; P.omega_sigma = 0.5f; P.cmd_update = 0.995f;
+    // URDF
+    P.I0[0] = 0.016269f; P.I0[1] = 0.050813f; P.I0[2] = 0.060989f;                                              // URDF:21
+    P.I1[0] = 0.000391f; P.I1[1] = 0.000739f; P.I1[2] = 0.000488f;                                              // URDF:64
+    P.I2[0] = 0.001724f; P.I2[1] = 0.001907f; P.I2[2] = 0.000468f; P.I2[3] = 0.000228f;                         // URDF:92
+    const double ms = 0.064, mt = 0.05, zs = -0.0865, zt = -0.19;                                               // URDF:115-119, 152-162
+    const double zc = (ms * zs + mt * zt) / (ms + mt), ds = zs - zc, dt = zt - zc;
+    P.I3[0] = (float)(0.000716 + ms * ds * ds + 0.000025 + mt * dt * dt);
+    P.I3[1] = (float)(0.000721 + ms * ds * ds + 0.000025 + mt * dt * dt);
+    P.I3[2] = (float)(0.000012 + 0.000025);
+    P.rotor[0] = 0.003708f; P.rotor[1] = 0.003708f; P.rotor[2] = 0.008966f;                                     // URDF:56,84,110
+    P.off1x = 0.212f; P.off1y = 0.051f; P.off2y = 0.085f;                                                       // URDF:52,80
+    P.toe_z = -0.19f; P.toe_r = 0.0275f;                                                                        // URDF:162,148
+    P.box_half[0] = 0.15f; P.box_half[1] = 0.1f; P.box_half[2] = 0.05f;                                         // URDF:26
+    P.gravity = 9.81f;
+    P.m0 = 3.72f; P.com0[0] = 0.f; P.com0[1] = 0.f; P.com0[2] = -0.003f;                                        // URDF:18-20
+    P.m1 = 0.54f; P.com1[0] = 0.058f; P.com1[1] = 0.00485f; P.com1[2] = 0.f;                                    // URDF:62-63 (x sx, y sy)
+    P.m2 = 0.636f; P.com2[0] = 0.f; P.com2[1] = -0.019f; P.com2[2] = -0.01865f;                                 // URDF:90-91 (y sy)
+    P.m3 = (float)(ms + mt); P.com3z = (float)zc; P.knee_z = -0.201f;                                           // URDF:106
+}
+
+int load_csv(const std::string& path, std::vector<float>& out, int& rows, int& cols) {
+    // readCSV_m  VEC:33-76
+    std::ifstream in(path); rows = 0; cols = 0;
+    if (!in.is_open()) { fprintf(stdout, "Can Not Load Parameter File of %s\n", path.c_str()); return -1; }   // VEC:71-73
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        int c = 0; const char* start = line.c_str();
+        for (size_t i = 0; i <= line.size(); ++i) if (i == line.size() || line[i] == ',') { out.push_back((float)atof(start)); start = line.c_str() + i + 1; ++c; }
+        if (rows == 0) cols = c; else if (c != cols) return -1;
+        ++rows;
+    }
+    return 0;
+}
+
+int ensure_pin(irrl_env_impl* E, size_t bytes) {
+    if (bytes <= E->h_pin_bytes) return 0;
+    if (E->h_pin) cudaFreeHost(E->h_pin);
+    CUDA_OK(cudaMallocHost((void**)&E->h_pin, bytes)); E->h_pin_bytes = bytes; return 0;
+}
+int ensure_scratch(irrl_env_impl* E, size_t floats) {
+    if (floats <= E->scratch_floats) return 0;
+    void* q; CUDA_OK(cudaMalloc(&q, floats * sizeof(float))); E->allocs.push_back(q); E->d_scratch = (float*)q; E->scratch_floats = floats; return 0;
+}
+// copy a device result [count] to the caller (host or device pointer)
+int deliver(irrl_env_impl* E, void* user, const void* dev, size_t bytes) {
+    if (!user) return 0;
+    if (is_device_ptr(user)) { CUDA_OK(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToDevice, E->stream)); return 0; }
+    if (int rc = ensure_pin(E, bytes)) return rc;
+    CUDA_OK(cudaMemcpyAsync(E->h_pin, dev, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    memcpy(user, E->h_pin, bytes); return 0;
+}
+#define ENV(e) irrl_env_impl* E = reinterpret_cast<irrl_env_impl*>(e); if (!E) return fail(-1, "null env"); cudaSetDevice(E->device)
+#define NEED_INIT() if (!E->initialised) return fail(-1, "irrl_init() has not been called")
+
+StepArgs make_args(irrl_env_impl* E, const float* action, float* ob, float* reward, uint8_t* done, float* extra) {
+    StepArgs a; a.P = E->P; a.S = E->S; a.action = action; a.ob = ob; a.reward = reward; a.done = done; a.extra = extra;
+    a.ep_ret_out = E->d_ep_ret; a.ep_len_out = E->d_ep_len; a.tick = E->tick; return a;
+}
+
+// generic probe helper: run `fn` into a device buffer of `per_env` floats and deliver
+template <typename F> int probe(irrl_env_impl* E, float* out, int per_env, F fn) {
+    size_t n = (size_t)E->P.N * per_env;
+    if (is_device_ptr(out)) { fn(out); CUDA_OK(cudaGetLastError()); return 0; }
+    if (int rc = ensure_scratch(E, n)) return rc;
+    fn(E->d_scratch); CUDA_OK(cudaGetLastError());
+    return deliver(E, out, E->d_scratch, n * sizeof(float));
+}
+}  // namespace
+
+extern "C" {
+
+const char* irrl_last_error(void) { return g_err.c_str(); }
+const char* irrl_version(void) { return "irrl_b200 0.1.0 (sm_100a)"; }
+
+int irrl_create(const char* resource_dir, const char* cfg_yaml, int device, int env_offset, irrl_env** out) {
+    if (!out || !cfg_yaml) return fail(-1, "null argument");
+    *out = nullptr;
+    int ndev = 0; cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(-2, "no CUDA device: this library has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(-2, "invalid CUDA device ordinal");
+    irrl_env_impl* E = new irrl_env_impl(); E->device = device; E->resource_dir = resource_dir ? resource_dir : "";
+    YamlMap y; std::string err;
+    if (!y.parse(cfg_yaml, err)) { delete E; return fail(-3, err); }
+    model_defaults(E->P);
+    if (int rc = read_cfg(E, y)) { delete E; return rc; }
+    E->P.env_offset = (uint32_t)env_offset;
+    E->extra_names = {"EndEffectorReward(0.15)", "Height_Keep_Reward(0.1)", "base height", "Balance_Keep_Reward(0.1)", "JointReward(0.65)", "VelocityReward(0.2)"};   // ENV:944-949
+    *out = reinterpret_cast<irrl_env*>(E);
+    return 0;
+}
+
+void irrl_destroy(irrl_env* env) {
+    irrl_env_impl* E = reinterpret_cast<irrl_env_impl*>(env); if (!E) return;
+    cudaSetDevice(E->device);
+    if (E->stream) cudaStreamSynchronize(E->stream);
+    for (void* p : E->allocs) cudaFree(p);
+    if (E->h_pin) cudaFreeHost(E->h_pin);
+    if (E->own_stream && E->stream) cudaStreamDestroy(E->stream);
+    delete E;
+}
+
+int irrl_set_stream(irrl_env* env, void* s) {
+    ENV(env);
+    if (E->own_stream && E->stream) { cudaStreamSynchronize(E->stream); cudaStreamDestroy(E->stream); }
+    E->stream = reinterpret_cast<cudaStream_t>(s); E->own_stream = false; return 0;
+}
+
+int irrl_init(irrl_env* env) {
+    ENV(env);
+    if (E->initialised) return 0;
+    const size_t N = (size_t)E->P.N;
+    if (!E->stream) { CUDA_OK(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking)); E->own_stream = true; }
+    int rc = 0;
+    rc |= dev_alloc(E, &E->S.base, N * 16); rc |= dev_alloc(E, &E->S.cmd, N * 8); rc |= dev_alloc(E, &E->S.legs, N * 64);
+    rc |= dev_alloc(E, &E->S.legs2, N * 48); rc |= dev_alloc(E, &E->S.obd, N * 36); rc |= dev_alloc(E, &E->S.obd_last, N * 36);
+    rc |= dev_alloc(E, &E->S.legmodel, N * 64); rc |= dev_alloc(E, &E->S.basemodel, N * 8);
+    rc |= dev_alloc(E, &E->S.frame_idx, N); rc |= dev_alloc(E, &E->S.itera, N); rc |= dev_alloc(E, &E->S.ep_len, N);
+    rc |= dev_alloc(E, &E->S.ep_ret, N); rc |= dev_alloc(E, &E->S.solver_sweeps, N);
+    rc |= dev_alloc(E, &E->d_action, N * 12); rc |= dev_alloc(E, &E->d_ob, N * 35); rc |= dev_alloc(E, &E->d_reward, N);
+    rc |= dev_alloc(E, &E->d_extra, N * 6); rc |= dev_alloc(E, &E->d_done, N); rc |= dev_alloc(E, &E->d_ep_ret, N); rc |= dev_alloc(E, &E->d_ep_len, N);
+    if (rc) return rc;
+    if (int r2 = ensure_pin(E, N * (35 + 12 + 1 + 6 + 2) * sizeof(float) + N)) return r2;
+    // optional reference table (VEC:158-169); a missing file is only a warning there (VEC:71-73)
+    if (!E->P.flag_manual_traj && !E->P.flag_manual && !E->ref_path.empty() && !E->d_ref) {
+        std::vector<float> tab; int rows, cols;
+        if (load_csv(E->ref_path, tab, rows, cols) == 0 && cols == 30) { if (int r3 = irrl_set_ref_traj(env, tab.data(), rows)) return r3; }
+    }
+    if (!E->P.flag_manual_traj && !E->P.flag_manual && !E->d_ref)
+        return fail(-3, "ManualTraj: False needs a reference table: RefTraj file with 30 columns (ENV:17-21) or irrl_set_ref_traj()");
+    launch_env_init(E->P, E->S, E->stream); CUDA_OK(cudaGetLastError());
+    E->initialised = true;
+    // VEC:172-182: every env is reset once during init
+    StepArgs a = make_args(E, nullptr, nullptr, nullptr, nullptr, nullptr);
+    launch_env_reset(a, E->stream); CUDA_OK(cudaGetLastError());
+    E->tick++;
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+int irrl_get_ob_dim(irrl_env*) { return OB_DIM; }
+int irrl_get_action_dim(irrl_env*) { return ACT_DIM; }
+int irrl_get_extra_info_dim(irrl_env*) { return EXTRA_DIM; }
+int irrl_get_origin_state_dim(irrl_env*) { return IRRL_ORIGIN_STATE_DIM; }
+int irrl_get_num_envs(irrl_env* env) { irrl_env_impl* E = reinterpret_cast<irrl_env_impl*>(env); return E ? E->P.N : 0; }
+const char* irrl_get_extra_info_name(irrl_env* env, int i) {
+    irrl_env_impl* E = reinterpret_cast<irrl_env_impl*>(env); if (!E || i < 0 || i >= (int)E->extra_names.size()) return nullptr; return E->extra_names[i].c_str();
+}
+
+int irrl_reset(irrl_env* env, float* ob) {
+    ENV(env); NEED_INIT();
+    bool dev = is_device_ptr(ob);
+    StepArgs a = make_args(E, nullptr, E->P.flag_obs_filter ? nullptr : (dev ? ob : E->d_ob), nullptr, nullptr, nullptr);
+    launch_env_reset(a, E->stream); CUDA_OK(cudaGetLastError());
+    E->tick++;
+    if (E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, dev ? ob : E->d_ob, E->stream); CUDA_OK(cudaGetLastError()); }
+    if (!dev) return deliver(E, ob, E->d_ob, (size_t)E->P.N * OB_DIM * sizeof(float));
+    return 0;
+}
+
+int irrl_observe(irrl_env* env, float* ob) {
+    ENV(env); NEED_INIT();
+    return probe(E, ob, OB_DIM, [&](float* d) { launch_env_observe(E->P, E->S, d, E->stream); });
+}
+
+static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* reward, uint8_t* done, float* extra) {
+    const size_t N = (size_t)E->P.N;
+    const bool dev = is_device_ptr(action);
+    if (dev) {
+        if ((ob && !is_device_ptr(ob)) || (reward && !is_device_ptr(reward)) || (done && !is_device_ptr(done)) || (extra && !is_device_ptr(extra)))
+            return fail(-1, "irrl_step: action is device memory, so every output must be device memory too");
+        if (!reward || !done) return fail(-1, "irrl_step: reward and done are required");
+        StepArgs a = make_args(E, action, E->P.flag_obs_filter ? nullptr : ob, reward, done, extra);
+        launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
+        E->tick++;
+        if (E->P.flag_obs_filter && ob) { launch_env_observe(E->P, E->S, ob, E->stream); CUDA_OK(cudaGetLastError()); }
+        return 0;
+    }
+    if (!action || !reward || !done) return fail(-1, "irrl_step: action, reward and done are required");
+    // host path: pinned staging, one H2D, one kernel, D2H of the results, then a blocking copy-out
+    unsigned char* pin = E->h_pin;
+    float* p_act = reinterpret_cast<float*>(pin);
+    memcpy(p_act, action, N * 12 * sizeof(float));
+    CUDA_OK(cudaMemcpyAsync(E->d_action, p_act, N * 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
+    StepArgs a = make_args(E, E->d_action, E->P.flag_obs_filter ? nullptr : E->d_ob, E->d_reward, E->d_done, E->d_extra);
+    launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
+    E->tick++;
+    if (E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, E->d_ob, E->stream); CUDA_OK(cudaGetLastError()); }
+    float* p_ob = p_act + N * 12; float* p_rew = p_ob + N * 35; float* p_ext = p_rew + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_ext + N * 6);
+    if (ob) CUDA_OK(cudaMemcpyAsync(p_ob, E->d_ob, N * 35 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaMemcpyAsync(p_rew, E->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (extra) CUDA_OK(cudaMemcpyAsync(p_ext, E->d_extra, N * 6 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaMemcpyAsync(p_done, E->d_done, N, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    if (ob) memcpy(ob, p_ob, N * 35 * sizeof(float));
+    memcpy(reward, p_rew, N * sizeof(float));
+    if (extra) memcpy(extra, p_ext, N * 6 * sizeof(float));
+    memcpy(done, p_done, N);
+    return 0;
+}
+
+int irrl_step(irrl_env* env, const float* action, float* ob, float* reward, uint8_t* done, float* extra) {
+    ENV(env); NEED_INIT();
+    return step_impl(E, action, ob, reward, done, extra);
+}
+
+int irrl_test_step(irrl_env* env, const float* action, float* ob, float* reward, uint8_t* done, float* extra) {
+    // VEC:280-290: only environment 0 advances; rows 1.. of the outputs are left untouched
+    ENV(env); NEED_INIT();
+    if (is_device_ptr(action)) return fail(-1, "irrl_test_step takes host buffers");
+    if (!action || !reward || !done) return fail(-1, "irrl_test_step: action, reward and done are required");
+    EnvParams saved = E->P; E->P.N = 1;
+    float ob1[35], rew1, ext1[6]; uint8_t done1;
+    // stage only row 0
+    CUDA_OK(cudaMemcpyAsync(E->d_action, action, 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
+    StepArgs a = make_args(E, E->d_action, E->P.flag_obs_filter ? nullptr : E->d_ob, E->d_reward, E->d_done, E->d_extra);
+    launch_env_step(a, E->stream); cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess && E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, E->d_ob, E->stream); ce = cudaGetLastError(); }
+    E->P = saved; E->tick++;
+    CUDA_OK(ce);
+    CUDA_OK(cudaMemcpyAsync(ob1, E->d_ob, sizeof(ob1), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaMemcpyAsync(&rew1, E->d_reward, sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaMemcpyAsync(ext1, E->d_extra, sizeof(ext1), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaMemcpyAsync(&done1, E->d_done, 1, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    if (ob) memcpy(ob, ob1, sizeof(ob1));
+    reward[0] = rew1; done[0] = done1; if (extra) memcpy(extra, ext1, sizeof(ext1));
+    return 0;
+}
+
+int irrl_last_episode_stats(irrl_env* env, float* ep_return, int32_t* ep_length) {
+    ENV(env); NEED_INIT();
+    if (int rc = deliver(E, ep_return, E->d_ep_ret, (size_t)E->P.N * sizeof(float))) return rc;
+    return deliver(E, ep_length, E->d_ep_len, (size_t)E->P.N * sizeof(int));
+}
+int irrl_running_episode_stats(irrl_env* env, float* ep_return, int32_t* ep_length, int clear) {
+    ENV(env); NEED_INIT();
+    if (int rc = deliver(E, ep_return, E->S.ep_ret, (size_t)E->P.N * sizeof(float))) return rc;
+    if (int rc = deliver(E, ep_length, E->S.ep_len, (size_t)E->P.N * sizeof(int))) return rc;
+    if (clear) { CUDA_OK(cudaMemsetAsync(E->S.ep_ret, 0, (size_t)E->P.N * sizeof(float), E->stream)); CUDA_OK(cudaMemsetAsync(E->S.ep_len, 0, (size_t)E->P.N * sizeof(int), E->stream)); }
+    return 0;
+}
+
+int irrl_set_seed(irrl_env* env, int seed) { ENV(env); E->P.seed = (uint32_t)seed; return 0; }
+int irrl_close(irrl_env* env) { ENV(env); if (E->stream) CUDA_OK(cudaStreamSynchronize(E->stream)); return 0; }
+int irrl_set_simulation_time_step(irrl_env* env, double dt) { ENV(env); E->P.sim_dt = (float)dt; E->P.loop_count = int((double)E->P.control_dt / dt + 1e-10); return 0; }
+int irrl_set_control_time_step(irrl_env* env, double dt) { ENV(env); E->P.control_dt = (float)dt; E->P.loop_count = int(dt / (double)E->P.sim_dt + 1e-10); return 0; }
+int irrl_curriculum_update(irrl_env* env) { ENV(env); return 0; }
+int irrl_start_recording_video(irrl_env* env, const char*) { ENV(env); return 0; }
+int irrl_stop_recording_video(irrl_env* env) { ENV(env); return 0; }
+int irrl_show_window(irrl_env* env) { ENV(env); return 0; }
+int irrl_hide_window(irrl_env* env) { ENV(env); return 0; }
+
+int irrl_get_state(irrl_env* env, float* out) { ENV(env); NEED_INIT(); return probe(E, out, STATE_DIM, [&](float* d) { launch_env_get_state(E->P, E->S, d, E->stream); }); }
+int irrl_set_state(irrl_env* env, const float* in) {
+    ENV(env); NEED_INIT();
+    size_t n = (size_t)E->P.N * STATE_DIM;
+    const float* src = in;
+    if (!is_device_ptr(in)) { if (int rc = ensure_scratch(E, n)) return rc; CUDA_OK(cudaMemcpyAsync(E->d_scratch, in, n * sizeof(float), cudaMemcpyHostToDevice, E->stream)); src = E->d_scratch; }
+    launch_env_set_state(E->P, E->S, src, E->stream); CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+int irrl_set_tick(irrl_env* env, uint32_t tick) { ENV(env); E->tick = tick; return 0; }
+uint32_t irrl_get_tick(irrl_env* env) { irrl_env_impl* E = reinterpret_cast<irrl_env_impl*>(env); return E ? E->tick : 0; }
+
+int irrl_is_terminal_state(irrl_env* env, uint8_t* terminal) {
+    ENV(env); NEED_INIT();
+    std::vector<float> s((size_t)E->P.N * STATE_DIM);
+    if (int rc = irrl_get_state(env, s.data())) return rc;
+    std::vector<uint8_t> t(E->P.N);
+    for (int i = 0; i < E->P.N; ++i) { const float* x = &s[(size_t)i * STATE_DIM]; t[i] = (x[2] < 0.15f || x[2] > 0.65f || x[109 + 31] < 0.5f) ? 1 : 0; }   // ENV:1560
+    if (is_device_ptr(terminal)) { CUDA_OK(cudaMemcpy(terminal, t.data(), t.size(), cudaMemcpyHostToDevice)); } else memcpy(terminal, t.data(), t.size());
+    return 0;
+}
+
+static int state_slice(irrl_env* env, float* out, int width, const std::vector<std::pair<int, int>>& spans) {
+    irrl_env_impl* E = reinterpret_cast<irrl_env_impl*>(env);
+    std::vector<float> s((size_t)E->P.N * STATE_DIM), o((size_t)E->P.N * width);
+    if (int rc = irrl_get_state(env, s.data())) return rc;
+    for (int i = 0; i < E->P.N; ++i) { int c = 0; for (auto& sp : spans) for (int k = 0; k < sp.second; ++k) o[(size_t)i * width + c++] = s[(size_t)i * STATE_DIM + sp.first + k]; }
+    if (is_device_ptr(out)) { CUDA_OK(cudaMemcpy(out, o.data(), o.size() * sizeof(float), cudaMemcpyHostToDevice)); } else memcpy(out, o.data(), o.size() * sizeof(float));
+    return 0;
+}
+int irrl_origin_state(irrl_env* env, float* out) { ENV(env); NEED_INIT(); return state_slice(env, out, 41, {{0, 19}, {19, 18}, {105, 4}}); }          // ENV:1323
+int irrl_reference_state(irrl_env* env, float* out) { ENV(env); NEED_INIT(); return state_slice(env, out, 24, {{67, 12}, {79, 12}}); }                  // ENV:1343
+int irrl_get_joint_effort(irrl_env* env, float* out) { ENV(env); NEED_INIT(); return state_slice(env, out, 12, {{179, 12}}); }                          // ENV:1354
+int irrl_get_generalized_force(irrl_env* env, float* out) {
+    ENV(env); NEED_INIT();
+    std::vector<float> je((size_t)E->P.N * 12), o((size_t)E->P.N * 18, 0.f);
+    if (int rc = state_slice(env, je.data(), 12, {{179, 12}})) return rc;
+    for (int i = 0; i < E->P.N; ++i) for (int k = 0; k < 12; ++k) o[(size_t)i * 18 + 6 + k] = je[(size_t)i * 12 + k];                                   // ggff.head(6) = 0
+    if (is_device_ptr(out)) { CUDA_OK(cudaMemcpy(out, o.data(), o.size() * sizeof(float), cudaMemcpyHostToDevice)); } else memcpy(out, o.data(), o.size() * sizeof(float));
+    return 0;
+}
+int irrl_get_inverse_mass_matrix(irrl_env* env, float* out) { ENV(env); NEED_INIT(); return probe(E, out, 324, [&](float* d) { launch_env_probe(E->P, E->S, nullptr, d, nullptr, E->stream); }); }
+int irrl_get_nonlinear(irrl_env* env, float* out) { ENV(env); NEED_INIT(); return probe(E, out, 18, [&](float* d) { launch_env_probe(E->P, E->S, nullptr, nullptr, d, E->stream); }); }
+int irrl_get_mass_matrix(irrl_env* env, float* out) { ENV(env); NEED_INIT(); return probe(E, out, 324, [&](float* d) { launch_env_probe(E->P, E->S, d, nullptr, nullptr, E->stream); }); }
+
+int irrl_set_contact_coefficient(irrl_env* env, const float* coeff) {
+    ENV(env); NEED_INIT();
+    std::vector<float> c((size_t)E->P.N * 3), bm((size_t)E->P.N * 8);
+    if (is_device_ptr(coeff)) { CUDA_OK(cudaMemcpy(c.data(), coeff, c.size() * sizeof(float), cudaMemcpyDeviceToHost)); } else memcpy(c.data(), coeff, c.size() * sizeof(float));
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    CUDA_OK(cudaMemcpy(bm.data(), E->S.basemodel, bm.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < E->P.N; ++i) { bm[(size_t)i * 8 + 4] = c[(size_t)i * 3]; bm[(size_t)i * 8 + 5] = c[(size_t)i * 3 + 1]; bm[(size_t)i * 8 + 6] = c[(size_t)i * 3 + 2]; }
+    CUDA_OK(cudaMemcpy(E->S.basemodel, bm.data(), bm.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+int irrl_get_sphere_info(irrl_env* env, float*) { ENV(env); return fail(-3, "Please make sure the [Flag_Crucial] is True (not implemented in this build)"); }   // ENV:1434
+int irrl_get_model_params(irrl_env* env, float* out) {
+    ENV(env); NEED_INIT();
+    const int N = E->P.N; std::vector<float> bm((size_t)N * 8), lm((size_t)N * 64), o((size_t)N * 94);
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    CUDA_OK(cudaMemcpy(bm.data(), E->S.basemodel, bm.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(lm.data(), E->S.legmodel, lm.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; ++i) {
+        float* r = &o[(size_t)i * 94]; const float* b = &bm[(size_t)i * 8];
+        r[0] = b[4]; r[1] = b[5]; r[2] = b[6];
+        r[3] = b[0]; r[4] = b[1]; r[5] = b[2]; r[6] = b[3]; r[7] = r[8] = r[9] = 0.f;
+        for (int l = 0; l < 4; ++l) {
+            const float* m = &lm[((size_t)i * 4 + l) * 16]; float sx = (l < 2) ? 1.f : -1.f, sy = (l & 1) ? 1.f : -1.f;
+            const float offs[3][3] = {{E->P.off1x * sx, E->P.off1y * sy, 0.f}, {0.f, E->P.off2y * sy, 0.f}, {0.f, 0.f, m[3]}};
+            for (int b3 = 0; b3 < 3; ++b3) { float* q = r + 3 + 7 * (1 + 3 * l + b3); q[0] = m[b3]; for (int a = 0; a < 3; ++a) { q[1 + a] = m[4 + 4 * b3 + a]; q[4 + a] = offs[b3][a]; } }
+        }
+    }
+    if (is_device_ptr(out)) { CUDA_OK(cudaMemcpy(out, o.data(), o.size() * sizeof(float), cudaMemcpyHostToDevice)); } else memcpy(out, o.data(), o.size() * sizeof(float));
+    return 0;
+}
+
+int irrl_integrate(irrl_env* env, const float* tau, float* contact_out) {
+    ENV(env); NEED_INIT();
+    const size_t N = (size_t)E->P.N;
+    const float* dtau = tau;
+    if (!is_device_ptr(tau)) { CUDA_OK(cudaMemcpyAsync(E->d_action, tau, N * 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream)); dtau = E->d_action; }
+    bool cdev = is_device_ptr(contact_out);
+    if (int rc = ensure_scratch(E, N * 16)) return rc;
+    launch_env_integrate(E->P, E->S, dtau, contact_out ? (cdev ? contact_out : E->d_scratch) : nullptr, E->stream); CUDA_OK(cudaGetLastError());
+    if (contact_out && !cdev) return deliver(E, contact_out, E->d_scratch, N * 16 * sizeof(float));
+    CUDA_OK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+int irrl_get_solver_sweeps(irrl_env* env, int32_t* out) { ENV(env); NEED_INIT(); return deliver(E, out, E->S.solver_sweeps, (size_t)E->P.N * sizeof(int)); }
+
+int irrl_set_ref_traj(irrl_env* env, const float* table, int rows) {
+    ENV(env);
+    if (!table || rows <= 0) return fail(-1, "empty reference table");
+    float* d = nullptr; CUDA_OK(cudaMalloc((void**)&d, (size_t)rows * 30 * sizeof(float))); E->allocs.push_back(d);
+    CUDA_OK(cudaMemcpy(d, table, (size_t)rows * 30 * sizeof(float), is_device_ptr(table) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    E->d_ref = d; E->P.ref = d; E->P.ref_rows = rows; E->P.frame_max = rows / 2; E->P.frame_len = int(E->P.max_time / E->P.control_dt);   // ENV:538-539
+    return 0;
+}
+
+// ------------------------------------------------------------------ policy
+static void bind_weights(irrl_policy_impl* Pn) {
+    const float* p = Pn->d_params; PolicyWeights& W = Pn->W;
+    const int in[4] = {35, 48, 35, 48};
+    for (int i = 0; i < 4; ++i) { W.wx[i] = p; p += in[i] * 192; W.wh[i] = p; p += 48 * 192; W.b[i] = p; p += 192; }
+    W.vf_w = p; p += 48; W.vf_b = p; p += 1; W.pi_w = p; p += 48 * 12; W.pi_b = p; p += 12; W.logstd = p; p += 12; /* q head (unused by act) follows */
+}
+int irrl_policy_create(int device, const float* params, irrl_policy** out) {
+    if (!out || !params) return fail(-1, "null argument");
+    int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(-2, "no CUDA device: this library has no CPU fallback"); }
+    CUDA_OK(cudaSetDevice(device));
+    irrl_policy_impl* Pn = new irrl_policy_impl(); Pn->device = device;
+    CUDA_OK(cudaMalloc((void**)&Pn->d_params, IRRL_POLICY_NUM_PARAMS * sizeof(float)));
+    bind_weights(Pn);
+    *out = reinterpret_cast<irrl_policy*>(Pn);
+    return irrl_policy_set_params(*out, params);
+}
+int irrl_policy_set_params(irrl_policy* pol, const float* params) {
+    irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return fail(-1, "null policy");
+    CUDA_OK(cudaSetDevice(Pn->device));
+    CUDA_OK(cudaMemcpy(Pn->d_params, params, IRRL_POLICY_NUM_PARAMS * sizeof(float), is_device_ptr(params) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return 0;
+}
+void irrl_policy_destroy(irrl_policy* pol) {
+    irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return;
+    cudaSetDevice(Pn->device); cudaDeviceSynchronize();
+    cudaFree(Pn->d_params); cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
+    if (Pn->h_pin) cudaFreeHost(Pn->h_pin);
+    delete Pn;
+}
+int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs, const uint8_t* done, float* state, float* action, float* clipped,
+                    float* value, float* neglogp, int deterministic, uint32_t seed, uint32_t env_offset, uint32_t tick) {
+    irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return fail(-1, "null policy");
+    if (!obs || !state || !action || !value || !neglogp || n <= 0) return fail(-1, "irrl_policy_act: null argument");
+    CUDA_OK(cudaSetDevice(Pn->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ActArgs a; a.W = Pn->W; a.N = n; a.deterministic = deterministic; a.seed = seed; a.env_offset = env_offset; a.tick = tick; a.mean = nullptr;
+    const bool dev = is_device_ptr(obs);
+    if (dev) {
+        a.obs = obs; a.done = done; a.state = state; a.action = action; a.clipped = clipped; a.value = value; a.neglogp = neglogp;
+        launch_lstm_act(a, st); CUDA_OK(cudaGetLastError()); return 0;
+    }
+    const size_t N = (size_t)n;
+    if (n > Pn->cap) {
+        cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
+        if (Pn->h_pin) cudaFreeHost(Pn->h_pin);
+        CUDA_OK(cudaMalloc((void**)&Pn->d_obs, N * 35 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_state, N * 384 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_action, N * 12 * 4));
+        CUDA_OK(cudaMalloc((void**)&Pn->d_clipped, N * 12 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_value, N * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_nlp, N * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_done, N));
+        CUDA_OK(cudaMallocHost((void**)&Pn->h_pin, N * (35 + 384 + 12 + 12 + 1 + 1) * 4 + N));
+        Pn->cap = n;
+    }
+    float* p_obs = reinterpret_cast<float*>(Pn->h_pin); float* p_state = p_obs + N * 35; float* p_act = p_state + N * 384; float* p_clip = p_act + N * 12;
+    float* p_val = p_clip + N * 12; float* p_nlp = p_val + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_nlp + N);
+    memcpy(p_obs, obs, N * 35 * 4); memcpy(p_state, state, N * 384 * 4); if (done) memcpy(p_done, done, N);
+    CUDA_OK(cudaMemcpyAsync(Pn->d_obs, p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(Pn->d_state, p_state, N * 384 * 4, cudaMemcpyHostToDevice, st));
+    if (done) CUDA_OK(cudaMemcpyAsync(Pn->d_done, p_done, N, cudaMemcpyHostToDevice, st));
+    a.obs = Pn->d_obs; a.done = done ? Pn->d_done : nullptr; a.state = Pn->d_state; a.action = Pn->d_action; a.clipped = Pn->d_clipped; a.value = Pn->d_value; a.neglogp = Pn->d_nlp;
+    launch_lstm_act(a, st); CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(p_state, Pn->d_state, N * 384 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    memcpy(state, p_state, N * 384 * 4); memcpy(action, p_act, N * 12 * 4); if (clipped) memcpy(clipped, p_clip, N * 12 * 4);
+    memcpy(value, p_val, N * 4); memcpy(neglogp, p_nlp, N * 4);
+    return 0;
+}
+
+int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* b, int deterministic) {
+    ENV(env); NEED_INIT();
+    irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn || !b) return fail(-1, "null argument");
+    if (E->P.flag_obs_filter) return fail(-3, "irrl_rollout does not support ObsFilter: True");
+    const size_t N = (size_t)E->P.N;
+    for (const void* p : {(const void*)b->obs, (const void*)b->actions, (const void*)b->values, (const void*)b->neglogps, (const void*)b->rewards,
+                          (const void*)b->dones, (const void*)b->cur_obs, (const void*)b->cur_done, (const void*)b->state})
+        if (!is_device_ptr(p)) return fail(-1, "irrl_rollout: all buffers must be device memory");
+    for (int t = 0; t < T; ++t) {
+        // mb_obs / mb_dones hold the inputs of model.step (ppo2.py:520-526)
+        CUDA_OK(cudaMemcpyAsync(b->obs + (size_t)t * N * 35, b->cur_obs, N * 35 * sizeof(float), cudaMemcpyDeviceToDevice, E->stream));
+        CUDA_OK(cudaMemcpyAsync(b->dones + (size_t)t * N, b->cur_done, N, cudaMemcpyDeviceToDevice, E->stream));
+        ActArgs a; a.W = Pn->W; a.N = (int)N; a.deterministic = deterministic; a.seed = E->P.seed; a.env_offset = E->P.env_offset; a.tick = E->tick; a.mean = nullptr;
+        a.obs = b->cur_obs; a.done = b->cur_done; a.state = b->state; a.action = b->actions + (size_t)t * N * 12; a.clipped = E->d_action;
+        a.value = b->values + (size_t)t * N; a.neglogp = b->neglogps + (size_t)t * N;
+        launch_lstm_act(a, E->stream);
+        StepArgs s = make_args(E, E->d_action, b->cur_obs, b->rewards + (size_t)t * N, b->cur_done, nullptr);
+        if (b->ep_return && b->ep_length) { s.ep_ret_out = b->ep_return + (size_t)t * N; s.ep_len_out = b->ep_length + (size_t)t * N; }
+        launch_env_step(s, E->stream);
+        E->tick++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int irrl_gae(void* cuda_stream, int T, int n, const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+             const uint8_t* last_dones, float gamma, float lam, float* adv, float* returns) {
+    launch_gae(rewards, values, dones, last_values, last_dones, adv, returns, T, n, gamma, lam, reinterpret_cast<cudaStream_t>(cuda_stream));
+    CUDA_OK(cudaGetLastError()); return 0;
+}
+
+}  // extern "C"

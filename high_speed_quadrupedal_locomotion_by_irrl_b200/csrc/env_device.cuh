@@ -1,0 +1,634 @@
+// Device-side building blocks of the bp5 environment step for sm_100a.
+//
+// Mapping: ONE ROBOT = ONE QUAD OF LANES (lane l of the quad owns leg l: FR, FL, HR, HL); a warp carries
+// 8 robots.  The kinematic tree is a 6-DoF trunk with four identical 3-link chains, so the branch
+// parallelism of every tree algorithm (FK, RNEA, CRBA, the block-arrow factorisation of M) is exactly 4;
+// wider cooperative mappings leave lanes idle.  Trunk quantities are replicated in the 4 lanes and the
+// per-leg contributions are combined with two __shfl_xor steps (bit-identical in every lane).
+//
+// Frame convention: world-aligned axes, positions relative to the trunk origin ("base frame B0": an inertial
+// frame whose origin coincides with the trunk origin at this instant).  Generalised velocity as in RaiSim:
+// gv = [v_trunk_origin (world), omega (world), joint rates]  (ENV:999-1000).
+//
+// The CPU oracle (oracle/bp5_oracle.hpp) computes the same physics with dense textbook algorithms; this file
+// uses composite inertias (CRBA), a recursive Newton-Euler pass for h, and a Schur complement onto the trunk.
+#pragma once
+#include <cuda_runtime.h>
+#include "irrl_params.h"
+
+namespace irrl {
+
+#define IRRL_PI_REF 3.1415926f /* ENV:45 (sic) */
+#define FULLMASK 0xffffffffu
+
+// ------------------------------------------------------------------ tiny vector algebra
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator-(f3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ f3 axpy(float s, f3 a, f3 b) { return mk(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+__device__ __forceinline__ float comp(f3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// symmetric 3x3
+struct S3 { float xx, xy, xz, yy, yz, zz; };
+__device__ __forceinline__ f3 mul(const S3& s, f3 v) {
+    return mk(fmaf(s.xx, v.x, fmaf(s.xy, v.y, s.xz * v.z)), fmaf(s.xy, v.x, fmaf(s.yy, v.y, s.yz * v.z)),
+              fmaf(s.xz, v.x, fmaf(s.yz, v.y, s.zz * v.z)));
+}
+__device__ __forceinline__ S3 operator+(const S3& a, const S3& b) {
+    S3 r; r.xx = a.xx + b.xx; r.xy = a.xy + b.xy; r.xz = a.xz + b.xz; r.yy = a.yy + b.yy; r.yz = a.yz + b.yz; r.zz = a.zz + b.zz; return r;
+}
+// s += k * e e^T
+__device__ __forceinline__ void add_outer(S3& s, float k, f3 e) {
+    float kx = k * e.x, ky = k * e.y, kz = k * e.z;
+    s.xx = fmaf(kx, e.x, s.xx); s.xy = fmaf(kx, e.y, s.xy); s.xz = fmaf(kx, e.z, s.xz);
+    s.yy = fmaf(ky, e.y, s.yy); s.yz = fmaf(ky, e.z, s.yz); s.zz = fmaf(kz, e.z, s.zz);
+}
+// s += k * (a b^T + b a^T)
+__device__ __forceinline__ void add_sym_outer(S3& s, float k, f3 a, f3 b) {
+    s.xx = fmaf(2.f * k * a.x, b.x, s.xx); s.yy = fmaf(2.f * k * a.y, b.y, s.yy); s.zz = fmaf(2.f * k * a.z, b.z, s.zz);
+    s.xy += k * (a.x * b.y + a.y * b.x); s.xz += k * (a.x * b.z + a.z * b.x); s.yz += k * (a.y * b.z + a.z * b.y);
+}
+// parallel-axis term m (|c|^2 1 - c c^T)
+__device__ __forceinline__ void add_point_mass(S3& s, float m, f3 c) {
+    float c2 = dot(c, c);
+    s.xx += m * (c2 - c.x * c.x); s.yy += m * (c2 - c.y * c.y); s.zz += m * (c2 - c.z * c.z);
+    s.xy -= m * c.x * c.y; s.xz -= m * c.x * c.z; s.yz -= m * c.y * c.z;
+}
+// inverse of a symmetric PD 3x3
+__device__ __forceinline__ S3 inv_sym3(const S3& a) {
+    float c00 = a.yy * a.zz - a.yz * a.yz, c01 = a.xz * a.yz - a.xy * a.zz, c02 = a.xy * a.yz - a.xz * a.yy;
+    float det = a.xx * c00 + a.xy * c01 + a.xz * c02;
+    float id = 1.0f / det;
+    S3 r; r.xx = c00 * id; r.xy = c01 * id; r.xz = c02 * id;
+    r.yy = (a.xx * a.zz - a.xz * a.xz) * id; r.yz = (a.xy * a.xz - a.xx * a.yz) * id; r.zz = (a.xx * a.yy - a.xy * a.xy) * id;
+    return r;
+}
+
+// ------------------------------------------------------------------ quad (4-lane group) collectives
+__device__ __forceinline__ float qsum(float v) {
+    v += __shfl_xor_sync(FULLMASK, v, 1); v += __shfl_xor_sync(FULLMASK, v, 2); return v;
+}
+__device__ __forceinline__ float qmax(float v) {
+    v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, 1)); v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, 2)); return v;
+}
+__device__ __forceinline__ float qbcast(float v, int src_leg) { return __shfl_sync(FULLMASK, v, src_leg, 4); }
+__device__ __forceinline__ int qbcasti(int v, int src_leg) { return __shfl_sync(FULLMASK, v, src_leg, 4); }
+__device__ __forceinline__ f3 qsum3(f3 v) { return mk(qsum(v.x), qsum(v.y), qsum(v.z)); }
+
+// ------------------------------------------------------------------ Philox4x32-10 (same specification as the oracle)
+__device__ __forceinline__ uint4 philox(uint32_t seed, uint32_t env, uint32_t tick, uint32_t purpose) {
+    uint32_t c0 = env, c1 = tick, c2 = purpose, c3 = 0u, k0 = seed, k1 = 0x1BD11BDAu;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float usym(uint32_t x) { return (float)(x >> 8) * (1.0f / 8388608.0f) - 1.0f; }
+__device__ __forceinline__ uint32_t pick(uint4 r, int i) { return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w)); }
+// four standard normals (Box-Muller) from one block
+__device__ __forceinline__ void gauss4(uint32_t seed, uint32_t env, uint32_t tick, uint32_t purpose, float g[4]) {
+    uint4 r = philox(seed, env, tick, purpose);
+    float u1 = (float)((r.x >> 8) + 1u) * (1.0f / 16777216.0f), u2 = u01(r.y);
+    float rad = sqrtf(-2.0f * logf(u1)), s, c; sincosf(6.283185307179586f * u2, &s, &c);
+    g[0] = rad * c; g[1] = rad * s;
+    u1 = (float)((r.z >> 8) + 1u) * (1.0f / 16777216.0f); u2 = u01(r.w);
+    rad = sqrtf(-2.0f * logf(u1)); sincosf(6.283185307179586f * u2, &s, &c);
+    g[2] = rad * c; g[3] = rad * s;
+}
+
+// ------------------------------------------------------------------ per-robot / per-leg register state
+struct Base {
+    f3 p; float qw, qx, qy, qz; f3 v, w;
+};
+struct LegModel {   // per-env (domain-randomised) leg parameters, ENV:435-477
+    float m1, m2, m3, knee_z; f3 com1, com2, com3;
+    float sx, sy;   // +-1 : front/hind, left/right
+};
+struct BaseModel { float m0; f3 com0; float mu, rest, thr; };
+
+// rotation matrix columns from quaternion (w,x,y,z)   ENV:986-992
+__device__ __forceinline__ void quat_cols(float w, float x, float y, float z, f3& ex, f3& ey, f3& ez) {
+    ex = mk(1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y));
+    ey = mk(2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x));
+    ez = mk(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
+}
+
+// Forward kinematics of one leg (positions relative to the trunk origin, world axes)
+struct LegKin {
+    f3 a1, a2;            // joint axes (a3 == a2: hip and knee axes are parallel)
+    f3 j1, j2, j3, toe;   // joint origins, toe frame origin
+    f3 r1, r2, r3;        // COM offsets from the own joint origin
+    f3 e1y, e1z, e2x, e2z, e3x, e3z;   // link frame axes needed for the inertia tensors
+};
+__device__ __forceinline__ void leg_fk(const EnvParams& P, const LegModel& lm, f3 bx, f3 by, f3 bz, f3 q, LegKin& k) {
+    float s1, c1, s2, c2, s3, c3;
+    sincosf(q.x, &s1, &c1); sincosf(q.y, &s2, &c2); sincosf(q.z, &s3, &c3);
+    // R1 = Rb Rx(q1)
+    f3 e1x = bx; k.e1y = axpy(c1, by, s1 * bz); k.e1z = axpy(c1, bz, -s1 * by);
+    // R2 = R1 Ry(-q2)   (axis 0 -1 0, URDF:79,105)
+    k.e2x = axpy(c2, e1x, s2 * k.e1z); k.e2z = axpy(c2, k.e1z, -s2 * e1x);
+    // R3 = R2 Ry(-q3)
+    k.e3x = axpy(c3, k.e2x, s3 * k.e2z); k.e3z = axpy(c3, k.e2z, -s3 * k.e2x);
+    k.a1 = bx; k.a2 = -k.e1y;
+    k.j1 = axpy(P.off1x * lm.sx, bx, (P.off1y * lm.sy) * by);
+    k.j2 = axpy(P.off2y * lm.sy, k.e1y, k.j1);
+    k.j3 = axpy(lm.knee_z, k.e2z, k.j2);
+    k.toe = axpy(P.toe_z, k.e3z, k.j3);
+    k.r1 = axpy(lm.com1.x, e1x, axpy(lm.com1.y, k.e1y, lm.com1.z * k.e1z));
+    k.r2 = axpy(lm.com2.x, k.e2x, axpy(lm.com2.y, k.e1y, lm.com2.z * k.e2z));
+    k.r3 = axpy(lm.com3.x, k.e3x, axpy(lm.com3.y, k.e1y, lm.com3.z * k.e3z));
+}
+// world-frame link inertia tensors about the link COM
+__device__ __forceinline__ void leg_inertias(const EnvParams& P, const LegModel& lm, f3 bx, const LegKin& k, S3& I1, S3& I2, S3& I3) {
+    I1 = S3{0, 0, 0, 0, 0, 0}; add_outer(I1, P.I1[0], bx); add_outer(I1, P.I1[1], k.e1y); add_outer(I1, P.I1[2], k.e1z);
+    I2 = S3{0, 0, 0, 0, 0, 0}; add_outer(I2, P.I2[0], k.e2x); add_outer(I2, P.I2[1], k.e1y); add_outer(I2, P.I2[2], k.e2z);
+    add_sym_outer(I2, -P.I2[3] * lm.sy, k.e1y, k.e2z);            // iyz = -0.000228 * sy  (URDF:92,210)
+    I3 = S3{0, 0, 0, 0, 0, 0}; add_outer(I3, P.I3[0], k.e3x); add_outer(I3, P.I3[1], k.e1y); add_outer(I3, P.I3[2], k.e3z);
+}
+
+// Factorised dynamics of one robot, distributed over the quad.
+struct Dyn {
+    // leg-local (this lane)
+    S3 Dinv;              // inverse of the 3x3 leg block of M
+    float B[6][3];        // coupling block trunk(6) x leg joints(3): columns (P_k ; L_k)
+    float Y[6][3];        // B Dinv
+    // trunk, replicated
+    float L[21];          // Cholesky factor of the Schur complement S (lower, row-major packed), diagonal stored INVERTED
+    float hb[6];          // bias force on the trunk rows
+    f3 hl;                // bias force on this leg's joints
+};
+
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// Mass matrix blocks + bias forces for the current state.  Mfull (optional) receives this lane's view of the
+// un-factorised blocks for the probe kernels: A (21 packed, replicated), B (18), D (6).
+__device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm, const BaseModel& bm, const Base& b,
+                                         f3 bx, f3 by, f3 bz, const LegKin& k, f3 qd, Dyn& d,
+                                         float* Aout = nullptr, S3* Dout = nullptr) {
+    S3 I1, I2, I3; leg_inertias(P, lm, bx, k, I1, I2, I3);
+    const f3 w0 = b.w;
+    // ---- velocities
+    f3 w1 = axpy(qd.x, k.a1, w0), w2 = axpy(qd.y, k.a2, w1), w3 = axpy(qd.z, k.a2, w2);
+    // ---- bias accelerations (joint accelerations and trunk acceleration zero)
+    f3 al1 = qd.x * cross(w0, k.a1);
+    f3 al2 = axpy(qd.y, cross(w1, k.a2), al1);
+    f3 al3 = axpy(qd.z, cross(w2, k.a2), al2);
+    f3 d12 = k.j2 - k.j1, d23 = k.j3 - k.j2;
+    f3 aj1 = cross(w0, cross(w0, k.j1));
+    f3 aj2 = aj1 + cross(al1, d12) + cross(w1, cross(w1, d12));
+    f3 aj3 = aj2 + cross(al2, d23) + cross(w2, cross(w2, d23));
+    f3 g = mk(0.f, 0.f, P.gravity);
+    f3 F1 = lm.m1 * (aj1 + cross(al1, k.r1) + cross(w1, cross(w1, k.r1)) + g);
+    f3 F2 = lm.m2 * (aj2 + cross(al2, k.r2) + cross(w2, cross(w2, k.r2)) + g);
+    f3 F3 = lm.m3 * (aj3 + cross(al3, k.r3) + cross(w3, cross(w3, k.r3)) + g);
+    f3 N1 = mul(I1, al1) + cross(w1, mul(I1, w1));
+    f3 N2 = mul(I2, al2) + cross(w2, mul(I2, w2));
+    f3 N3 = mul(I3, al3) + cross(w3, mul(I3, w3));
+    // ---- backward pass: moments about the joint origins
+    f3 n3 = N3 + cross(k.r3, F3), f3_ = F3;
+    f3 n2 = N2 + cross(k.r2, F2) + n3 + cross(d23, f3_), f2_ = F2 + f3_;
+    f3 n1 = N1 + cross(k.r1, F1) + n2 + cross(d12, f2_), f1_ = F1 + f2_;
+    d.hl = mk(dot(k.a1, n1), dot(k.a2, n2), dot(k.a2, n3));
+    f3 fb = f1_, nb = n1 + cross(k.j1, f1_);
+    // trunk body itself (identical in the 4 lanes; added after the quad reduction)
+    S3 I0 = S3{0, 0, 0, 0, 0, 0}; add_outer(I0, P.I0[0], bx); add_outer(I0, P.I0[1], by); add_outer(I0, P.I0[2], bz);
+    f3 r0 = axpy(bm.com0.x, bx, axpy(bm.com0.y, by, bm.com0.z * bz));
+    f3 F0 = bm.m0 * (cross(w0, cross(w0, r0)) + g);
+    f3 N0 = cross(w0, mul(I0, w0)) + cross(r0, F0);
+    fb = qsum3(fb) + F0; nb = qsum3(nb) + N0;
+    d.hb[0] = fb.x; d.hb[1] = fb.y; d.hb[2] = fb.z; d.hb[3] = nb.x; d.hb[4] = nb.y; d.hb[5] = nb.z;
+
+    // ---- composite inertias about the trunk origin: (mass, first moment, second moment)
+    f3 c3 = k.j3 + k.r3, c2 = k.j2 + k.r2, c1 = k.j1 + k.r1;
+    float mC = lm.m3; f3 hC = lm.m3 * c3; S3 IC = I3; add_point_mass(IC, lm.m3, c3);
+    // joint 3 (knee): motion subspace (lin = j3 x a, ang = a)
+    f3 s3l = cross(k.j3, k.a2);
+    f3 P3 = axpy(mC, s3l, cross(k.a2, hC)), L3 = cross(hC, s3l) + mul(IC, k.a2);
+    mC += lm.m2; hC = axpy(lm.m2, c2, hC); IC = IC + I2; add_point_mass(IC, lm.m2, c2);
+    f3 s2l = cross(k.j2, k.a2);
+    f3 P2 = axpy(mC, s2l, cross(k.a2, hC)), L2 = cross(hC, s2l) + mul(IC, k.a2);
+    mC += lm.m1; hC = axpy(lm.m1, c1, hC); IC = IC + I1; add_point_mass(IC, lm.m1, c1);
+    f3 s1l = cross(k.j1, k.a1);
+    f3 P1 = axpy(mC, s1l, cross(k.a1, hC)), L1 = cross(hC, s1l) + mul(IC, k.a1);
+    d.B[0][0] = P1.x; d.B[1][0] = P1.y; d.B[2][0] = P1.z; d.B[3][0] = L1.x; d.B[4][0] = L1.y; d.B[5][0] = L1.z;
+    d.B[0][1] = P2.x; d.B[1][1] = P2.y; d.B[2][1] = P2.z; d.B[3][1] = L2.x; d.B[4][1] = L2.y; d.B[5][1] = L2.z;
+    d.B[0][2] = P3.x; d.B[1][2] = P3.y; d.B[2][2] = P3.z; d.B[3][2] = L3.x; d.B[4][2] = L3.y; d.B[5][2] = L3.z;
+    S3 D;   // leg block of M (+ rotor inertias on the diagonal, URDF rotor_inertia)
+    D.xx = dot(s1l, P1) + dot(k.a1, L1) + P.rotor[0];
+    D.xy = dot(s1l, P2) + dot(k.a1, L2);
+    D.xz = dot(s1l, P3) + dot(k.a1, L3);
+    D.yy = dot(s2l, P2) + dot(k.a2, L2) + P.rotor[1];
+    D.yz = dot(s2l, P3) + dot(k.a2, L3);
+    D.zz = dot(s3l, P3) + dot(k.a2, L3) + P.rotor[2];
+    if (Dout) *Dout = D;
+    d.Dinv = inv_sym3(D);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        d.Y[a][0] = d.B[a][0] * d.Dinv.xx + d.B[a][1] * d.Dinv.xy + d.B[a][2] * d.Dinv.xz;
+        d.Y[a][1] = d.B[a][0] * d.Dinv.xy + d.B[a][1] * d.Dinv.yy + d.B[a][2] * d.Dinv.yz;
+        d.Y[a][2] = d.B[a][0] * d.Dinv.xz + d.B[a][1] * d.Dinv.yz + d.B[a][2] * d.Dinv.zz;
+    }
+    // ---- trunk block A (whole-robot composite) and Schur complement S = A - sum_l Y_l B_l^T, reduced over the quad
+    float S[21];
+    {
+        // this leg's composite contribution to A, in (lin, ang) ordering: [[m 1, -[h]x],[[h]x, Io]]
+        S[tri(0, 0)] = mC; S[tri(1, 0)] = 0.f; S[tri(1, 1)] = mC; S[tri(2, 0)] = 0.f; S[tri(2, 1)] = 0.f; S[tri(2, 2)] = mC;
+        S[tri(3, 0)] = 0.f;   S[tri(3, 1)] = -hC.z; S[tri(3, 2)] = hC.y;
+        S[tri(4, 0)] = hC.z;  S[tri(4, 1)] = 0.f;   S[tri(4, 2)] = -hC.x;
+        S[tri(5, 0)] = -hC.y; S[tri(5, 1)] = hC.x;  S[tri(5, 2)] = 0.f;
+        S[tri(3, 3)] = IC.xx; S[tri(4, 3)] = IC.xy; S[tri(4, 4)] = IC.yy; S[tri(5, 3)] = IC.xz; S[tri(5, 4)] = IC.yz; S[tri(5, 5)] = IC.zz;
+    }
+    if (Aout) {   // un-reduced A for the probes
+#pragma unroll
+        for (int i = 0; i < 21; ++i) Aout[i] = S[i];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = 0; c <= a; ++c)
+            S[tri(a, c)] -= d.Y[a][0] * d.B[c][0] + d.Y[a][1] * d.B[c][1] + d.Y[a][2] * d.B[c][2];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) S[i] = qsum(S[i]);
+    {   // trunk body
+        f3 h0 = bm.m0 * r0; S3 Io = I0; add_point_mass(Io, bm.m0, r0);
+        float A0[21];
+        A0[tri(0, 0)] = bm.m0; A0[tri(1, 0)] = 0.f; A0[tri(1, 1)] = bm.m0; A0[tri(2, 0)] = 0.f; A0[tri(2, 1)] = 0.f; A0[tri(2, 2)] = bm.m0;
+        A0[tri(3, 0)] = 0.f;   A0[tri(3, 1)] = -h0.z; A0[tri(3, 2)] = h0.y;
+        A0[tri(4, 0)] = h0.z;  A0[tri(4, 1)] = 0.f;   A0[tri(4, 2)] = -h0.x;
+        A0[tri(5, 0)] = -h0.y; A0[tri(5, 1)] = h0.x;  A0[tri(5, 2)] = 0.f;
+        A0[tri(3, 3)] = Io.xx; A0[tri(4, 3)] = Io.xy; A0[tri(4, 4)] = Io.yy; A0[tri(5, 3)] = Io.xz; A0[tri(5, 4)] = Io.yz; A0[tri(5, 5)] = Io.zz;
+#pragma unroll
+        for (int i = 0; i < 21; ++i) S[i] += A0[i];
+        if (Aout) {
+#pragma unroll
+            for (int i = 0; i < 21; ++i) Aout[i] = qsum(Aout[i]) + A0[i];
+        }
+    }
+    // ---- Cholesky of S (6x6), diagonal stored as its reciprocal
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        float dj = S[tri(j, j)];
+#pragma unroll
+        for (int c = 0; c < j; ++c) dj = fmaf(-d.L[tri(j, c)], d.L[tri(j, c)], dj);
+        float inv = rsqrtf(dj);
+        inv = inv * (1.5f - 0.5f * dj * inv * inv);     // one Newton step: full fp32 accuracy
+        d.L[tri(j, j)] = inv;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            float s = S[tri(i, j)];
+#pragma unroll
+            for (int c = 0; c < j; ++c) s = fmaf(-d.L[tri(i, c)], d.L[tri(j, c)], s);
+            d.L[tri(i, j)] = s * inv;
+        }
+    }
+}
+
+// y = L^-1 z  (forward substitution, in place)
+__device__ __forceinline__ void fwd6(const float* L, float* z) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        float s = z[i];
+#pragma unroll
+        for (int c = 0; c < i; ++c) s = fmaf(-L[tri(i, c)], z[c], s);
+        z[i] = s * L[tri(i, i)];
+    }
+}
+// x = L^-T y  (back substitution, in place)
+__device__ __forceinline__ void bwd6(const float* L, float* y) {
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        float s = y[i];
+#pragma unroll
+        for (int c = i + 1; c < 6; ++c) s = fmaf(-L[tri(c, i)], y[c], s);
+        y[i] = s * L[tri(i, i)];
+    }
+}
+
+// Solve M x = r for a general right-hand side (rb replicated, rl per lane).  Outputs xb (replicated), xl.
+__device__ __forceinline__ void solve_full(const Dyn& d, const float* rb, f3 rl, float* xb, f3& xl) {
+    f3 t = mul(d.Dinv, rl);
+    float z[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) z[a] = qsum(d.B[a][0] * t.x + d.B[a][1] * t.y + d.B[a][2] * t.z);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) xb[a] = rb[a] - z[a];
+    fwd6(d.L, xb); bwd6(d.L, xb);
+    xl = mk(t.x - (d.Y[0][0] * xb[0] + d.Y[1][0] * xb[1] + d.Y[2][0] * xb[2] + d.Y[3][0] * xb[3] + d.Y[4][0] * xb[4] + d.Y[5][0] * xb[5]),
+            t.y - (d.Y[0][1] * xb[0] + d.Y[1][1] * xb[1] + d.Y[2][1] * xb[2] + d.Y[3][1] * xb[3] + d.Y[4][1] * xb[4] + d.Y[5][1] * xb[5]),
+            t.z - (d.Y[0][2] * xb[0] + d.Y[1][2] * xb[1] + d.Y[2][2] * xb[2] + d.Y[3][2] * xb[3] + d.Y[4][2] * xb[4] + d.Y[5][2] * xb[5]));
+}
+
+// ------------------------------------------------------------------ hard-contact single-contact solve
+// v: contact velocity with the current impulse lo applied, G: 3x3 Delassus block (symmetric), n = +z.
+// Same rule as the oracle's solve_one_contact (separation / stick / slide with a fixed point on the
+// sliding direction).
+__device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Ginv, f3 lo, float vtn, float mu, int slide_iters) {
+    f3 e = mk(v.x, v.y, v.z - vtn);
+    f3 ls = lo - mul(Ginv, e);
+    if (!(ls.z > 0.f)) return mk(0.f, 0.f, 0.f);
+    float lt = sqrtf(ls.x * ls.x + ls.y * ls.y);
+    if (lt <= mu * ls.z) return ls;
+    f3 b = v - mul(G, lo);
+    float dx = ls.x / lt, dy = ls.y / lt, lnz = 0.f;
+    for (int it = 0; it < slide_iters; ++it) {
+        float den = G.zz + mu * (G.xz * dx + G.yz * dy);
+        if (!(den > 1e-12f)) break;
+        lnz = fmaxf((vtn - b.z) / den, 0.f);
+        float l0 = mu * lnz * dx, l1 = mu * lnz * dy;
+        float vx = b.x + G.xx * l0 + G.xy * l1 + G.xz * lnz;
+        float vy = b.y + G.xy * l0 + G.yy * l1 + G.yz * lnz;
+        float vn = sqrtf(vx * vx + vy * vy);
+        if (vn > 1e-9f) { dx = -vx / vn; dy = -vy / vn; }
+    }
+    {
+        float den = G.zz + mu * (G.xz * dx + G.yz * dy);
+        if (den > 1e-12f) lnz = fmaxf((vtn - b.z) / den, 0.f);
+    }
+    return mk(mu * lnz * dx, mu * lnz * dy, lnz);
+}
+
+// Per-contact data in the reduced trunk space: v_i = c_i + Q_i^T y + T_i lambda_i,  y = sum_j Q_j lambda_j
+struct Contact {
+    float Q[6][3];   // L^-1 E_i^T
+    S3 T, G, Ginv;   // leg-local Delassus term, full diagonal block and its inverse
+    f3 c, lam;
+    float vtn;
+    int active;
+};
+// Build Q, G for a contact at point x (relative to the trunk origin).  Jl (3 columns) is the leg part of the
+// contact Jacobian (zero for a trunk contact).
+__device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1, f3 Jl2, bool on_leg, Contact& ct) {
+    // E = J_b - J_l Y^T : 3x6.  J_b = [1, -[x]x]
+    float E[3][6];
+    E[0][0] = 1.f; E[0][1] = 0.f; E[0][2] = 0.f; E[0][3] = 0.f;  E[0][4] = x.z;  E[0][5] = -x.y;
+    E[1][0] = 0.f; E[1][1] = 1.f; E[1][2] = 0.f; E[1][3] = -x.z; E[1][4] = 0.f;  E[1][5] = x.x;
+    E[2][0] = 0.f; E[2][1] = 0.f; E[2][2] = 1.f; E[2][3] = x.y;  E[2][4] = -x.x; E[2][5] = 0.f;
+    if (on_leg) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            E[0][a] -= Jl0.x * d.Y[a][0] + Jl1.x * d.Y[a][1] + Jl2.x * d.Y[a][2];
+            E[1][a] -= Jl0.y * d.Y[a][0] + Jl1.y * d.Y[a][1] + Jl2.y * d.Y[a][2];
+            E[2][a] -= Jl0.z * d.Y[a][0] + Jl1.z * d.Y[a][1] + Jl2.z * d.Y[a][2];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float z[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) z[a] = E[r][a];
+        fwd6(d.L, z);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ct.Q[a][r] = z[a];
+    }
+    // T = J_l Dinv J_l^T
+    ct.T = S3{0, 0, 0, 0, 0, 0};
+    if (on_leg) {
+        // rows of J_l: (Jl0.r, Jl1.r, Jl2.r)
+        f3 rx = mk(Jl0.x, Jl1.x, Jl2.x), ry = mk(Jl0.y, Jl1.y, Jl2.y), rz = mk(Jl0.z, Jl1.z, Jl2.z);
+        f3 dx = mul(d.Dinv, rx), dy = mul(d.Dinv, ry), dz = mul(d.Dinv, rz);
+        ct.T.xx = dot(rx, dx); ct.T.xy = dot(rx, dy); ct.T.xz = dot(rx, dz); ct.T.yy = dot(ry, dy); ct.T.yz = dot(ry, dz); ct.T.zz = dot(rz, dz);
+    }
+    S3 G = ct.T;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        G.xx = fmaf(ct.Q[a][0], ct.Q[a][0], G.xx); G.xy = fmaf(ct.Q[a][0], ct.Q[a][1], G.xy); G.xz = fmaf(ct.Q[a][0], ct.Q[a][2], G.xz);
+        G.yy = fmaf(ct.Q[a][1], ct.Q[a][1], G.yy); G.yz = fmaf(ct.Q[a][1], ct.Q[a][2], G.yz); G.zz = fmaf(ct.Q[a][2], ct.Q[a][2], G.zz);
+    }
+    ct.G = G; ct.Ginv = inv_sym3(G);
+}
+
+// One Gauss-Seidel visit of the contact slot owned by lane `owner`: every lane evaluates its own slot, only the
+// owner's result is committed and its trunk-space increment is broadcast to the quad.
+__device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int owner, bool frozen, float mu, int slide_iters,
+                                         float& maxd, float& maxl) {
+    f3 v = ct.c + mul(ct.T, ct.lam);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { v.x = fmaf(ct.Q[a][0], y[a], v.x); v.y = fmaf(ct.Q[a][1], y[a], v.y); v.z = fmaf(ct.Q[a][2], y[a], v.z); }
+    f3 ln = solve_one_contact(v, ct.G, ct.Ginv, ct.lam, ct.vtn, mu, slide_iters);
+    bool commit = (leg == owner) && ct.active && !frozen;
+    f3 dl = commit ? (ln - ct.lam) : mk(0.f, 0.f, 0.f);
+    if (commit) {
+        ct.lam = ln;
+        maxd = fmaxf(maxd, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
+        maxl = fmaxf(maxl, fmaxf(fabsf(ln.x), fmaxf(fabsf(ln.y), fabsf(ln.z))));
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        float dy = ct.Q[a][0] * dl.x + ct.Q[a][1] * dl.y + ct.Q[a][2] * dl.z;
+        y[a] += qbcast(dy, owner);
+    }
+}
+
+struct ContactOut { int foot_active; f3 foot_impulse; int sweeps; };
+
+// ------------------------------------------------------------------ one world.integrate() (ENV:768)
+// tau: this leg's joint torques.  fext: optional external generalised force on the trunk (6).
+__device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegModel& lm, const BaseModel& bm, int leg,
+                                                  Base& b, f3& q, f3& qd, f3 tau, ContactOut& out) {
+    const float dt = P.sim_dt;
+    f3 bx, by, bz; quat_cols(b.qw, b.qx, b.qy, b.qz, bx, by, bz);
+    LegKin k; leg_fk(P, lm, bx, by, bz, q, k);
+    Dyn d; dynamics(P, lm, bm, b, bx, by, bz, k, qd, d);
+
+    // ---- free acceleration in the factorised form:  t = Dinv r_l,  w = L^-1 (r_b - sum B t)
+    f3 rl = mk(tau.x - P.joint_damping * qd.x - d.hl.x, tau.y - P.joint_damping * qd.y - d.hl.y, tau.z - P.joint_damping * qd.z - d.hl.z);
+    f3 t = mul(d.Dinv, rl);
+    float wv[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) wv[a] = -d.hb[a] - qsum(d.B[a][0] * t.x + d.B[a][1] * t.y + d.B[a][2] * t.z);
+    fwd6(d.L, wv);
+
+    // ---- collision detection against the plane z = 0 (ENV:268)
+    Contact cf;   // foot contact of this leg (slot 0 of this lane)
+    f3 xf = mk(k.toe.x, k.toe.y, k.toe.z - P.toe_r);                     // contact point on the sphere
+    cf.active = (b.p.z + k.toe.z - P.toe_r <= 0.f) ? 1 : 0;
+    f3 Jl0 = cross(k.a1, xf - k.j1), Jl1 = cross(k.a2, xf - k.j2), Jl2 = cross(k.a2, xf - k.j3);
+    // trunk box corners: lane l tests corners 2l and 2l+1, the quad then ranks the hits in corner order
+    int hit0, hit1; f3 xc0, xc1;
+    {
+        int c0 = 2 * leg, c1 = 2 * leg + 1;
+        f3 l0 = mk((c0 & 1) ? P.box_half[0] : -P.box_half[0], (c0 & 2) ? P.box_half[1] : -P.box_half[1], (c0 & 4) ? P.box_half[2] : -P.box_half[2]);
+        f3 l1 = mk((c1 & 1) ? P.box_half[0] : -P.box_half[0], (c1 & 2) ? P.box_half[1] : -P.box_half[1], (c1 & 4) ? P.box_half[2] : -P.box_half[2]);
+        xc0 = axpy(l0.x, bx, axpy(l0.y, by, l0.z * bz)); xc1 = axpy(l1.x, bx, axpy(l1.y, by, l1.z * bz));
+        hit0 = (b.p.z + xc0.z <= 0.f) ? 1 : 0; hit1 = (b.p.z + xc1.z <= 0.f) ? 1 : 0;
+    }
+    int hits = hit0 | (hit1 << 1);
+    int allhits = 0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) allhits |= qbcasti(hits, l) << (2 * l);
+    const bool any_box = __any_sync(FULLMASK, allhits != 0);
+    const bool any_foot_or_box = __any_sync(FULLMASK, cf.active || allhits != 0);
+
+    float ytot[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) ytot[a] = dt * wv[a];
+    f3 lam_leg = mk(0.f, 0.f, 0.f);
+    out.sweeps = 0;
+    cf.lam = mk(0.f, 0.f, 0.f);
+    if (any_foot_or_box) {
+        // ---- foot contact setup (every lane builds its own slot)
+        contact_setup(d, xf, Jl0, Jl1, Jl2, true, cf);
+        {
+            f3 vpre = b.v + cross(b.w, xf) + qd.x * Jl0 + qd.y * Jl1 + qd.z * Jl2;        // J u (pre-step)
+            f3 jt = t.x * Jl0 + t.y * Jl1 + t.z * Jl2;                                    // J_l Dinv r_l
+            f3 qw_ = mk(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { qw_.x = fmaf(cf.Q[a][0], wv[a], qw_.x); qw_.y = fmaf(cf.Q[a][1], wv[a], qw_.y); qw_.z = fmaf(cf.Q[a][2], wv[a], qw_.z); }
+            cf.c = vpre + dt * (qw_ + jt);
+            cf.vtn = (vpre.z < -bm.thr) ? -bm.rest * vpre.z : 0.f;
+        }
+        // ---- trunk box contact slot (k-th penetrating corner in corner order belongs to lane k, at most 4)
+        Contact cb; cb.active = 0; cb.lam = mk(0.f, 0.f, 0.f);
+        if (any_box) {
+            int rank = -1, cnt = 0; f3 xb = mk(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                // corner c lives on lane c>>1 as xc0 (even) or xc1 (odd)
+                f3 src = (c & 1) ? xc1 : xc0;
+                float px = qbcast(src.x, c >> 1), py = qbcast(src.y, c >> 1), pz = qbcast(src.z, c >> 1);
+                if ((allhits >> c) & 1) { if (cnt == leg) { rank = c; xb = mk(px, py, pz); } cnt++; }
+            }
+            cb.active = (rank >= 0) ? 1 : 0;
+            contact_setup(d, xb, mk(0, 0, 0), mk(0, 0, 0), mk(0, 0, 0), false, cb);
+            f3 vpre = b.v + cross(b.w, xb);
+            f3 qw_ = mk(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { qw_.x = fmaf(cb.Q[a][0], wv[a], qw_.x); qw_.y = fmaf(cb.Q[a][1], wv[a], qw_.y); qw_.z = fmaf(cb.Q[a][2], wv[a], qw_.z); }
+            cb.c = vpre + dt * qw_;
+            cb.vtn = (vpre.z < -bm.thr) ? -bm.rest * vpre.z : 0.f;
+        }
+        // ---- per-contact Gauss-Seidel in the 6-dimensional trunk space
+        float y[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool frozen = !(qsum((float)(cf.active + cb.active)) > 0.f);    // robots without contacts never iterate
+        int sweeps = 0;
+        for (int sweep = 0; sweep < P.solver_iters; ++sweep) {
+            if (__all_sync(FULLMASK, frozen)) break;
+            float maxd = 0.f, maxl = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) gs_visit(cf, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
+            if (any_box) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) gs_visit(cb, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
+            }
+            maxd = qmax(maxd); maxl = qmax(maxl);
+            if (!frozen) { sweeps = sweep + 1; if (maxd <= P.solver_tol * maxl) frozen = true; }
+        }
+        out.sweeps = sweeps;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) ytot[a] += y[a];
+        lam_leg = cf.lam;
+    }
+    out.foot_active = cf.active; out.foot_impulse = cf.lam;
+
+    // ---- new velocity: u+ = u + M^-1 (dt r + J^T lambda)
+    bwd6(d.L, ytot);                                                    // trunk increment
+    f3 jl = mk(dot(Jl0, lam_leg), dot(Jl1, lam_leg), dot(Jl2, lam_leg));   // J_l^T lambda
+    f3 tl = axpy(dt, t, mul(d.Dinv, jl));
+    f3 dq = mk(tl.x - (d.Y[0][0] * ytot[0] + d.Y[1][0] * ytot[1] + d.Y[2][0] * ytot[2] + d.Y[3][0] * ytot[3] + d.Y[4][0] * ytot[4] + d.Y[5][0] * ytot[5]),
+               tl.y - (d.Y[0][1] * ytot[0] + d.Y[1][1] * ytot[1] + d.Y[2][1] * ytot[2] + d.Y[3][1] * ytot[3] + d.Y[4][1] * ytot[4] + d.Y[5][1] * ytot[5]),
+               tl.z - (d.Y[0][2] * ytot[0] + d.Y[1][2] * ytot[1] + d.Y[2][2] * ytot[2] + d.Y[3][2] * ytot[3] + d.Y[4][2] * ytot[4] + d.Y[5][2] * ytot[5]));
+    b.v = b.v + mk(ytot[0], ytot[1], ytot[2]);
+    b.w = b.w + mk(ytot[3], ytot[4], ytot[5]);
+    qd = qd + dq;
+    // ---- semi-implicit Euler on the configuration
+    b.p = axpy(dt, b.v, b.p);
+    {
+        float wn = sqrtf(dot(b.w, b.w)), th = wn * dt, kk, cw;
+        if (th > 1e-8f) { float sh; sincosf(0.5f * th, &sh, &cw); kk = sh / wn; } else { kk = 0.5f * dt; cw = 1.f; }
+        float dx = kk * b.w.x, dy = kk * b.w.y, dz = kk * b.w.z;
+        float ow = cw * b.qw - dx * b.qx - dy * b.qy - dz * b.qz;
+        float ox = cw * b.qx + dx * b.qw + dy * b.qz - dz * b.qy;
+        float oy = cw * b.qy - dx * b.qz + dy * b.qw + dz * b.qx;
+        float oz = cw * b.qz + dx * b.qy - dy * b.qx + dz * b.qw;
+        float nn = rsqrtf(ow * ow + ox * ox + oy * oy + oz * oz);
+        nn = nn * (1.5f - 0.5f * (ow * ow + ox * ox + oy * oy + oz * oz) * nn * nn);
+        b.qw = ow * nn; b.qx = ox * nn; b.qy = oy * nn; b.qz = oz * nn;
+    }
+    q = axpy(dt, qd, q);
+}
+
+// ------------------------------------------------------------------ gait generator + IK (ENV:1687-1890), one leg per lane
+__device__ __forceinline__ float bezier_b(float ph) { return ph * ph * ph + 3.0f * (ph * ph * (1.0f - ph)); }   // ENV:89
+
+// ENV:1687-1751.  theta starts at 0 (the reference keeps a stale value and prints "error" on infeasible targets).
+__device__ __forceinline__ f3 leg_ik(const EnvParams& P, float x, float y, float z, bool is_right) {
+    float th0 = 0.f, th1 = 0.f, th2 = 0.f;
+    float ll = sqrtf(x * x + y * y + z * z);
+    if (ll > P.max_len) { float s = (P.max_len - 1e-5f) / ll; x *= s; y *= s; z *= s; }
+    float l_hip = P.l_hip, l_thigh = P.l_thigh, l_calf = P.l_calf;
+    float den = z * z + y * y;
+    float root = sqrtf(y * y * (den - l_hip * l_hip));
+    float temp = is_right ? (-z * l_hip - root) / den : (z * l_hip + root) / den;
+    if (fabsf(temp) <= 1.f) th0 = asinf(temp);
+    float lr = sqrtf(x * x + y * y + z * z - l_hip * l_hip);
+    lr = (lr > (l_thigh + l_calf)) ? (l_thigh + l_calf - 1e-4f) : lr;
+    temp = (l_thigh * l_thigh + l_calf * l_calf - lr * lr) / 2.f / l_thigh / l_calf + 1e-5f;
+    if (fabsf(temp) <= 1.f) th2 = -(IRRL_PI_REF - acosf(temp));
+    float temp1 = x / lr;
+    float temp2 = (lr * lr + l_thigh * l_thigh - l_calf * l_calf) / 2.f / lr / l_thigh - 1e-5f;
+    if (fabsf(temp1) <= 1.f && fabsf(temp2) <= 1.f) th1 = acosf(temp2) - asinf(temp1);
+    return mk(th0, -th1, -th2);   // ENV:1879-1881
+}
+
+struct GaitCmd { float gait_step, side_step, rot_step, up_height; };
+__device__ __forceinline__ GaitCmd gait_cmd(const EnvParams& P, const float* cf) {
+    GaitCmd g;
+    g.gait_step = cf[0] * P.lam * P.period; if (P.flag_wildcat) g.gait_step = -g.gait_step;    // ENV:1772-1773
+    g.side_step = cf[1] * P.lam * P.period;                                                    // ENV:1775
+    g.rot_step = cf[2] * P.period * 0.4f;                                                      // ENV:1777
+    g.up_height = P.up_height_max;
+    if (P.flag_height_variable) {                                                              // ENV:1779-1792
+        float ratio = fabsf(cf[0]) / P.Vx_max;
+        if (P.Vy_max > 0.f) ratio = fmaxf(ratio, fabsf(cf[1]) / P.Vy_max);
+        if (P.omega_max > 0.f) ratio = fmaxf(ratio, fabsf(cf[2] / P.omega_max));
+        g.up_height = (ratio > 0.1f) ? P.up_height_max : ratio * P.up_height_max;
+    }
+    return g;
+}
+// reference joint angles + toe target of leg `leg` at time tt (body of the loops ENV:1802-1842 / 1844-1885)
+__device__ __forceinline__ f3 leg_reference(const EnvParams& P, const GaitCmd& g, int leg, float tt, f3& toe) {
+    float real_phase = fmodf(tt + P.phase[leg] * P.period, P.period) / P.period;
+    float anti = (leg < 2) ? 1.0f : -1.0f;
+    float ax = g.gait_step / 2.0f, ay = g.side_step / 2.0f + anti * g.rot_step / 2.0f;        // p0 of stance = (ax, ay)
+    float bxx = -g.gait_step / 2.0f, byy = -g.side_step / 2.0f + -anti * g.rot_step / 2.0f;   // pf of stance
+    if (real_phase < P.lam) {
+        float bz = bezier_b(real_phase / P.lam);
+        toe = mk(ax + bz * (bxx - ax), ay + bz * (byy - ay), -P.stand_height + bz * 0.f);
+    } else {
+        float r = (real_phase - P.lam) / (1.0f - P.lam);
+        float bz = bezier_b(r);
+        float width = 1.0f;
+        float gz = g.up_height * expf(-(r - width / 2.f) * (r - width / 2.f) / (2.f * (width / 6.f) * (width / 6.f)));   // ENV:96-99
+        toe = mk(bxx + bz * (ax - bxx), byy + bz * (ay - byy), -P.stand_height + gz);
+    }
+    float off = (leg == 0) ? (-P.l_hip + P.lean_front) : (leg == 1) ? (P.l_hip - P.lean_front) : (leg == 2) ? (-P.l_hip + P.lean_hind) : (P.l_hip - P.lean_hind);   // ENV:1795-1798
+    return leg_ik(P, toe.x, toe.y + off, toe.z, (leg == 0) || (leg == 2));
+}
+
+// shaping functions for the contact reward (ENV:118-156)
+__device__ __forceinline__ float smooth_raw(float phase, float slope, float lam) {
+    float f = fmodf(phase, 1.0f);
+    if (f < lam) return (sinf(f / lam * 2.f * IRRL_PI_REF) * slope) + 0.5f;
+    return (-sinf((f - lam) / (1.0f - lam) * 2.f * IRRL_PI_REF) * slope) + 0.5f;
+}
+__device__ __forceinline__ float smooth_function(float phase, float slope, float lam) {
+    float t = smooth_raw(phase, slope, lam); return t > 1.f ? 1.f : (t < 0.f ? 0.f : t);
+}
+__device__ __forceinline__ float smooth_function2(float phase, float slope, float lam) {
+    float t = smooth_raw(phase, slope, lam); return t > 1.f ? 0.f : (t < 0.f ? 1.f : 1.f - t);
+}
+
+}  // namespace irrl

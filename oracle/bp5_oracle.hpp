@@ -297,7 +297,7 @@ template <typename T> struct Env {
     // contact material: default (0.6, 0.2, 0.01) ENV:433
     T mu = T(0.6), restitution = T(0.2), rest_threshold = T(0.01);
     int solver_iters = 20;        // per-contact Gauss-Seidel sweeps cap (new spec)
-    T solver_tol = T(1e-7);       // relative impulse change for early exit
+    T solver_tol = T(1e-5);       // relative impulse change for early exit
     int slide_iters = 3;          // fixed-point iterations for the sliding direction
 
     // ---- state
@@ -351,7 +351,7 @@ template <typename T> struct Env {
         simulation_dt_ = T(c.get("simulation_dt")); control_dt_ = T(c.get("control_dt"));   // VEC:151-152
         // solver / model switches (new-spec, optional)
         model.joint_damping = T(c.get_or("joint_damping", 0.01));
-        solver_iters = (int)c.get_or("solver_iters", 20); solver_tol = T(c.get_or("solver_tol", 1e-7)); slide_iters = (int)c.get_or("slide_iters", 3);
+        solver_iters = (int)c.get_or("solver_iters", 20); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 3);
         mu = T(c.get_or("friction", 0.6)); restitution = T(c.get_or("restitution", 0.2)); rest_threshold = T(c.get_or("restitution_threshold", 0.01));
 
         // gc_init_ ENV:317-322
@@ -928,10 +928,12 @@ template <typename T> struct VecEnv {
         uint32_t seed = (uint32_t)(int)c.get("seedd");   // VEC:171 (double truncated to int)
         envs.resize(n);
         for (int i = 0; i < n; ++i) envs[i].configure(c, (uint32_t)(env_offset + i), seed);
+        if (envs[0].flag_ManualTraj || envs[0].flag_manual) reset_all();   // VEC:172-182: init() resets every env once (tick 0)
     }
     void set_ref(const float* data, int rows) {   // VEC:158-182
         ref.assign(data, data + (size_t)rows * 30); ref_rows = rows;
         for (auto& e : envs) { e.ref = ref.data(); e.ref_rows = rows; e.frame_max = rows / 2; e.frame_len = int(e.max_time / e.control_dt_); }   // ENV:538-539
+        if (tick == 0 && !(envs[0].flag_ManualTraj || envs[0].flag_manual)) reset_all();   // table mode: the init reset needs the table
     }
     void reset_all() {   // VEC:201-207 (serial in the reference)
         #pragma omp parallel for schedule(dynamic) num_threads(num_threads)

@@ -59,6 +59,9 @@ def load() -> C.CDLL:
     L.irrl_policy_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     L.irrl_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RolloutBuffers), C.c_int]
     L.irrl_gae.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.irrl_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.irrl_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.irrl_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -3,6 +3,7 @@
 // (raisim_gym.cpp:14-47): it owns the device state, parses the YAML `environment:` map (ENV:1594-1659,
 // VEC:136-171), launches kernels on one stream and stages host buffers through pinned memory.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +77,8 @@ struct irrl_env_impl {
     float* d_ref = nullptr;
     unsigned char* h_pin = nullptr; size_t h_pin_bytes = 0; size_t scratch_floats = 0;
     std::vector<void*> allocs;
+    // optional per-kernel timing of irrl_rollout (CUDA events on the env's stream)
+    bool profiling = false; std::vector<cudaEvent_t> prof_events; double prof_act_ms = 0, prof_step_ms = 0; long prof_count = 0;
 };
 struct irrl_policy_impl {
     int device = 0;
@@ -523,6 +526,37 @@ int irrl_set_ref_traj(irrl_env* env, const float* table, int rows) {
     return 0;
 }
 
+// ------------------------------------------------------------------ measured FP32 (non-tensor) peak: register-resident FMA chains
+__global__ void fp32_peak_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 123.456f) out[0] = a0;
+}
+int irrl_measure_fp32_peak(int device, double* tflops) {
+    CUDA_OK(cudaSetDevice(device));
+    float* d; CUDA_OK(cudaMalloc((void**)&d, 4));
+    cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    const int iters = 4096, threads = 256, blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0); fp32_peak_kernel<<<blocks, threads>>>(d, iters); cudaEventRecord(e1); CUDA_OK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double fl = 2.0 * 64.0 * iters * (double)threads * blocks;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (tflops) *tflops = best;
+    return 0;
+}
+
 // ------------------------------------------------------------------ policy
 static void bind_weights(irrl_policy_impl* Pn) {
     const float* p = Pn->d_params; PolicyWeights& W = Pn->W;
@@ -560,13 +594,13 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
     CUDA_OK(cudaSetDevice(Pn->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     ActArgs a; a.W = Pn->W; a.N = n; a.deterministic = deterministic; a.seed = seed; a.env_offset = env_offset; a.tick = tick; a.mean = nullptr;
-    const bool dev = is_device_ptr(obs);
-    if (dev) {
-        a.obs = obs; a.done = done; a.state = state; a.action = action; a.clipped = clipped; a.value = value; a.neglogp = neglogp;
-        launch_lstm_act(a, st); CUDA_OK(cudaGetLastError()); return 0;
-    }
     const size_t N = (size_t)n;
-    if (n > Pn->cap) {
+    // every pointer is classified on its own: e.g. the LSTM state may stay resident on the device while
+    // observations / actions travel through host memory (the reference's Runner keeps `states` opaque, ppo2.py:520)
+    const bool h_obs = !is_device_ptr(obs), h_done = done && !is_device_ptr(done), h_state = !is_device_ptr(state), h_act = !is_device_ptr(action),
+               h_clip = clipped && !is_device_ptr(clipped), h_val = !is_device_ptr(value), h_nlp = !is_device_ptr(neglogp);
+    const bool any_host = h_obs || h_done || h_state || h_act || h_clip || h_val || h_nlp;
+    if (any_host && n > Pn->cap) {
         cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
         if (Pn->h_pin) cudaFreeHost(Pn->h_pin);
         CUDA_OK(cudaMalloc((void**)&Pn->d_obs, N * 35 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_state, N * 384 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_action, N * 12 * 4));
@@ -576,20 +610,25 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
     }
     float* p_obs = reinterpret_cast<float*>(Pn->h_pin); float* p_state = p_obs + N * 35; float* p_act = p_state + N * 384; float* p_clip = p_act + N * 12;
     float* p_val = p_clip + N * 12; float* p_nlp = p_val + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_nlp + N);
-    memcpy(p_obs, obs, N * 35 * 4); memcpy(p_state, state, N * 384 * 4); if (done) memcpy(p_done, done, N);
-    CUDA_OK(cudaMemcpyAsync(Pn->d_obs, p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(Pn->d_state, p_state, N * 384 * 4, cudaMemcpyHostToDevice, st));
-    if (done) CUDA_OK(cudaMemcpyAsync(Pn->d_done, p_done, N, cudaMemcpyHostToDevice, st));
-    a.obs = Pn->d_obs; a.done = done ? Pn->d_done : nullptr; a.state = Pn->d_state; a.action = Pn->d_action; a.clipped = Pn->d_clipped; a.value = Pn->d_value; a.neglogp = Pn->d_nlp;
+    if (h_obs) { memcpy(p_obs, obs, N * 35 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_obs, p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st)); }
+    if (h_state) { memcpy(p_state, state, N * 384 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_state, p_state, N * 384 * 4, cudaMemcpyHostToDevice, st)); }
+    if (h_done) { memcpy(p_done, done, N); CUDA_OK(cudaMemcpyAsync(Pn->d_done, p_done, N, cudaMemcpyHostToDevice, st)); }
+    a.obs = h_obs ? Pn->d_obs : obs; a.done = done ? (h_done ? Pn->d_done : done) : nullptr; a.state = h_state ? Pn->d_state : state;
+    a.action = h_act ? Pn->d_action : action; a.clipped = clipped ? (h_clip ? Pn->d_clipped : clipped) : nullptr;
+    a.value = h_val ? Pn->d_value : value; a.neglogp = h_nlp ? Pn->d_nlp : neglogp;
     launch_lstm_act(a, st); CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpyAsync(p_state, Pn->d_state, N * 384 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
+    if (!any_host) return 0;
+    if (h_state) CUDA_OK(cudaMemcpyAsync(p_state, Pn->d_state, N * 384 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_act) CUDA_OK(cudaMemcpyAsync(p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_clip) CUDA_OK(cudaMemcpyAsync(p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_val) CUDA_OK(cudaMemcpyAsync(p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
+    if (h_nlp) CUDA_OK(cudaMemcpyAsync(p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    memcpy(state, p_state, N * 384 * 4); memcpy(action, p_act, N * 12 * 4); if (clipped) memcpy(clipped, p_clip, N * 12 * 4);
-    memcpy(value, p_val, N * 4); memcpy(neglogp, p_nlp, N * 4);
+    if (h_state) memcpy(state, p_state, N * 384 * 4);
+    if (h_act) memcpy(action, p_act, N * 12 * 4);
+    if (h_clip) memcpy(clipped, p_clip, N * 12 * 4);
+    if (h_val) memcpy(value, p_val, N * 4);
+    if (h_nlp) memcpy(neglogp, p_nlp, N * 4);
     return 0;
 }
 
@@ -601,6 +640,7 @@ int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buff
     for (const void* p : {(const void*)b->obs, (const void*)b->actions, (const void*)b->values, (const void*)b->neglogps, (const void*)b->rewards,
                           (const void*)b->dones, (const void*)b->cur_obs, (const void*)b->cur_done, (const void*)b->state})
         if (!is_device_ptr(p)) return fail(-1, "irrl_rollout: all buffers must be device memory");
+    if (E->profiling) while ((int)E->prof_events.size() < 3 * T) { cudaEvent_t ev; CUDA_OK(cudaEventCreate(&ev)); E->prof_events.push_back(ev); }
     for (int t = 0; t < T; ++t) {
         // mb_obs / mb_dones hold the inputs of model.step (ppo2.py:520-526)
         CUDA_OK(cudaMemcpyAsync(b->obs + (size_t)t * N * 35, b->cur_obs, N * 35 * sizeof(float), cudaMemcpyDeviceToDevice, E->stream));
@@ -608,14 +648,33 @@ int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buff
         ActArgs a; a.W = Pn->W; a.N = (int)N; a.deterministic = deterministic; a.seed = E->P.seed; a.env_offset = E->P.env_offset; a.tick = E->tick; a.mean = nullptr;
         a.obs = b->cur_obs; a.done = b->cur_done; a.state = b->state; a.action = b->actions + (size_t)t * N * 12; a.clipped = E->d_action;
         a.value = b->values + (size_t)t * N; a.neglogp = b->neglogps + (size_t)t * N;
+        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[3 * t + 0], E->stream));
         launch_lstm_act(a, E->stream);
+        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[3 * t + 1], E->stream));
         StepArgs s = make_args(E, E->d_action, b->cur_obs, b->rewards + (size_t)t * N, b->cur_done, nullptr);
         if (b->ep_return && b->ep_length) { s.ep_ret_out = b->ep_return + (size_t)t * N; s.ep_len_out = b->ep_length + (size_t)t * N; }
         launch_env_step(s, E->stream);
+        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[3 * t + 2], E->stream));
         E->tick++;
     }
     CUDA_OK(cudaGetLastError());
+    if (E->profiling) {
+        CUDA_OK(cudaStreamSynchronize(E->stream));
+        for (int t = 0; t < T; ++t) {
+            float m1 = 0, m2 = 0;
+            CUDA_OK(cudaEventElapsedTime(&m1, E->prof_events[3 * t], E->prof_events[3 * t + 1]));
+            CUDA_OK(cudaEventElapsedTime(&m2, E->prof_events[3 * t + 1], E->prof_events[3 * t + 2]));
+            E->prof_act_ms += m1; E->prof_step_ms += m2; E->prof_count++;
+        }
+    }
     return 0;
+}
+
+int irrl_set_profiling(irrl_env* env, int on) {
+    ENV(env); E->profiling = on != 0; E->prof_act_ms = E->prof_step_ms = 0; E->prof_count = 0; return 0;
+}
+int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total, int64_t* launches_each) {
+    ENV(env); if (act_ms_total) *act_ms_total = E->prof_act_ms; if (step_ms_total) *step_ms_total = E->prof_step_ms; if (launches_each) *launches_each = E->prof_count; return 0;
 }
 
 int irrl_gae(void* cuda_stream, int T, int n, const float* rewards, const float* values, const uint8_t* dones, const float* last_values,

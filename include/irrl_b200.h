@@ -141,6 +141,11 @@ typedef struct irrl_rollout_buffers {
     int32_t* ep_length;/* [T,N] (may be NULL) */
 } irrl_rollout_buffers;
 int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* buf, int deterministic);
+/* optional per-kernel timing of irrl_rollout with CUDA events on the env's stream (bench.py's roofline leg) */
+int irrl_set_profiling(irrl_env* env, int on);
+int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total, int64_t* launches_each);
+/* register-resident FMA micro-benchmark: the non-tensor FP32 peak of this device in TFLOP/s (roofline denominator) */
+int irrl_measure_fp32_peak(int device, double* tflops);
 /* GAE(gamma, lambda) reverse scan  ppo2.py:554-568; all device pointers, [T,N] */
 int irrl_gae(void* cuda_stream, int T, int n, const float* rewards, const float* values, const uint8_t* dones,
              const float* last_values, const uint8_t* last_dones, float gamma, float lam, float* adv, float* returns);

@@ -517,10 +517,10 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
         for (int sweep = 0; sweep < P.solver_iters; ++sweep) {
             if (__all_sync(FULLMASK, frozen)) break;
             float maxd = 0.f, maxl = 0.f;
-#pragma unroll
+#pragma unroll 1
             for (int o = 0; o < 4; ++o) gs_visit(cf, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
             if (any_box) {
-#pragma unroll
+#pragma unroll 1
                 for (int o = 0; o < 4; ++o) gs_visit(cb, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
             }
             maxd = qmax(maxd); maxl = qmax(maxl);
@@ -599,7 +599,9 @@ __device__ __forceinline__ GaitCmd gait_cmd(const EnvParams& P, const float* cf)
     return g;
 }
 // reference joint angles + toe target of leg `leg` at time tt (body of the loops ENV:1802-1842 / 1844-1885)
-__device__ __forceinline__ f3 leg_reference(const EnvParams& P, const GaitCmd& g, int leg, float tt, f3& toe) {
+// __noinline__: a single copy of this code serves every call site, so equal inputs give bit-equal joint references
+// (the reference relies on that: the second command_obs_update of reset() yields jointDotRef_ == 0 exactly, ENV:628, 1886)
+static __device__ __noinline__ f3 leg_reference(const EnvParams& P, const GaitCmd& g, int leg, float tt, f3& toe) {
     float real_phase = fmodf(tt + P.phase[leg] * P.period, P.period) / P.period;
     float anti = (leg < 2) ? 1.0f : -1.0f;
     float ax = g.gait_step / 2.0f, ay = g.side_step / 2.0f + anti * g.rot_step / 2.0f;        // p0 of stance = (ax, ay)

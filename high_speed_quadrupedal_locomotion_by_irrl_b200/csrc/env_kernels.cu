@@ -164,7 +164,7 @@ __device__ __forceinline__ float contact_flag(const EnvParams& P, const EnvRegs&
 }
 
 // ------------------------------------------------------------------ reset (ENV:547-635)
-__device__ __forceinline__ void reset_env(const EnvParams& P, const DevState& S, int r, int gid, int leg, uint32_t tick, EnvRegs& e) {
+static __device__ __noinline__ void reset_env(const EnvParams& P, const DevState& S, int r, int gid, int leg, uint32_t tick, EnvRegs& e) {
     e.itera += 1;                                                                  // ENV:554
     uint4 rr = philox(P.seed, gid, tick, P_RST_TIME_CMD);
     e.t0 = P.flag_manual ? 0.f : u01(rr.w);                                        // ENV:557
@@ -336,7 +336,9 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
     if (done) {
         rew += P.terminal_coeff;                                          // VEC:370
         e.ep_ret += rew; ep_ret_out = e.ep_ret; ep_len_out = e.ep_len;
-        reset_env(P, S, r, gid, leg, A.tick, e);                          // VEC:369
+        EnvRegs tmp = e;                                                  // only the copy has its address taken (rare path)
+        reset_env(P, S, r, gid, leg, A.tick, tmp);                        // VEC:369
+        e = tmp;
     } else {
         e.ep_ret += rew;
     }

@@ -296,7 +296,7 @@ template <typename T> struct Env {
     T mass_distrubance_ratio = T(0.15), com_distrubance = T(0.02), calf_distrubance = T(0.01);  // ENV:2069-2071
     // contact material: default (0.6, 0.2, 0.01) ENV:433
     T mu = T(0.6), restitution = T(0.2), rest_threshold = T(0.01);
-    int solver_iters = 20;        // per-contact Gauss-Seidel sweeps cap (new spec)
+    int solver_iters = 8;         // per-contact Gauss-Seidel sweeps cap (new spec)
     T solver_tol = T(1e-5);       // relative impulse change for early exit
     int slide_iters = 3;          // fixed-point iterations for the sliding direction
 
@@ -351,7 +351,7 @@ template <typename T> struct Env {
         simulation_dt_ = T(c.get("simulation_dt")); control_dt_ = T(c.get("control_dt"));   // VEC:151-152
         // solver / model switches (new-spec, optional)
         model.joint_damping = T(c.get_or("joint_damping", 0.01));
-        solver_iters = (int)c.get_or("solver_iters", 20); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 3);
+        solver_iters = (int)c.get_or("solver_iters", 8); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 3);
         mu = T(c.get_or("friction", 0.6)); restitution = T(c.get_or("restitution", 0.2)); rest_threshold = T(c.get_or("restitution_threshold", 0.01));
 
         // gc_init_ ENV:317-322

@@ -244,6 +244,7 @@ def run_b200(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms_max = float(t_ms.item())
     value = world * N * K / (total_ms_max * 1e-3)
+    sw = np.zeros(N, np.int32); env.getSolverSweeps(sw)
     episodes_done = int(buf_done.sum().item())
     mean_rew = float(buf_rew.mean().item())
 
@@ -326,7 +327,7 @@ def run_b200(args):
                     "path": "irrl_policy_act + irrl_step with host numpy buffers (pinned staging inside the C ABI); LSTM state device-resident"},
             "gpu_launches": 2 * K, "kernels": ["lstm_act_kernel", "env_step_kernel"], "memcpy_d2d_per_step": 2,
             "roofline": roof, "clocks": clocks, "wall_s": wall,
-            "sanity": {"mean_reward": mean_rew, "episodes_finished": episodes_done}}
+            "sanity": {"mean_reward": mean_rew, "episodes_finished": episodes_done, "gs_sweeps_last_substep": {"mean": float(sw.mean()), "max": int(sw.max()), "hist": np.bincount(sw, minlength=9).tolist()}}}
     if not args.no_cpu_baseline:
         v, cores, sample = cpu_arm(args.cpu_envs, budget_s=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

@@ -146,7 +146,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         // optional solver / model switches of this implementation
         auto opt = [&](const char* k, double dflt) { double v; return y.has(k) && num(k, v) ? v : dflt; };
         P.joint_damping = (float)opt("joint_damping", 0.01);                                                     // URDF:56
-        P.solver_iters = (int)opt("solver_iters", 8); P.slide_iters = (int)opt("slide_iters", 3); P.solver_tol = (float)opt("solver_tol", 1e-5);
+        P.solver_iters = (int)opt("solver_iters", 10); P.slide_iters = (int)opt("slide_iters", 1); P.solver_tol = (float)opt("solver_tol", 1e-5);
         P.mu = (float)opt("friction", 0.6); P.restitution = (float)opt("restitution", 0.2); P.rest_threshold = (float)opt("restitution_threshold", 0.01);   // ENV:433
     }
     if (P.N <= 0) return fail(-3, "num_envs must be positive");

@@ -335,14 +335,17 @@ __device__ __forceinline__ void solve_full(const Dyn& d, const float* rb, f3 rl,
 // v: contact velocity with the current impulse lo applied, G: 3x3 Delassus block (symmetric), n = +z.
 // Same rule as the oracle's solve_one_contact (separation / stick / slide with a fixed point on the
 // sliding direction).
+__device__ __forceinline__ float rsqrt_nr(float x) { float r = rsqrtf(x); return r * (1.5f - 0.5f * x * r * r); }   // ~1 ulp
 __device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Ginv, f3 lo, float vtn, float mu, int slide_iters) {
     f3 e = mk(v.x, v.y, v.z - vtn);
     f3 ls = lo - mul(Ginv, e);
     if (!(ls.z > 0.f)) return mk(0.f, 0.f, 0.f);
-    float lt = sqrtf(ls.x * ls.x + ls.y * ls.y);
-    if (lt <= mu * ls.z) return ls;
+    float lt2 = ls.x * ls.x + ls.y * ls.y;
+    float mz = mu * ls.z;
+    if (lt2 <= mz * mz) return ls;
     f3 b = v - mul(G, lo);
-    float dx = ls.x / lt, dy = ls.y / lt, lnz = 0.f;
+    float il = rsqrt_nr(lt2);
+    float dx = ls.x * il, dy = ls.y * il, lnz = 0.f;
     for (int it = 0; it < slide_iters; ++it) {
         float den = G.zz + mu * (G.xz * dx + G.yz * dy);
         if (!(den > 1e-12f)) break;
@@ -350,8 +353,8 @@ __device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Gin
         float l0 = mu * lnz * dx, l1 = mu * lnz * dy;
         float vx = b.x + G.xx * l0 + G.xy * l1 + G.xz * lnz;
         float vy = b.y + G.xy * l0 + G.yy * l1 + G.yz * lnz;
-        float vn = sqrtf(vx * vx + vy * vy);
-        if (vn > 1e-9f) { dx = -vx / vn; dy = -vy / vn; }
+        float vn2 = vx * vx + vy * vy;
+        if (vn2 > 1e-18f) { float iv = rsqrt_nr(vn2); dx = -vx * iv; dy = -vy * iv; }
     }
     {
         float den = G.zz + mu * (G.xz * dx + G.yz * dy);
@@ -414,13 +417,16 @@ __device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1
 // owner's result is committed and its trunk-space increment is broadcast to the quad.
 __device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int owner, bool frozen, float mu, int slide_iters,
                                          float& maxd, float& maxl) {
-    f3 v = ct.c + mul(ct.T, ct.lam);
-#pragma unroll
-    for (int a = 0; a < 6; ++a) { v.x = fmaf(ct.Q[a][0], y[a], v.x); v.y = fmaf(ct.Q[a][1], y[a], v.y); v.z = fmaf(ct.Q[a][2], y[a], v.z); }
-    f3 ln = solve_one_contact(v, ct.G, ct.Ginv, ct.lam, ct.vtn, mu, slide_iters);
-    bool commit = (leg == owner) && ct.active && !frozen;
-    f3 dl = commit ? (ln - ct.lam) : mk(0.f, 0.f, 0.f);
+    // only the owner of an active, unconverged contact evaluates the solve: idle lanes (swinging feet) would otherwise
+    // drag the whole warp through the sliding branch with meaningless velocities
+    const bool commit = (leg == owner) && ct.active && !frozen;
+    f3 dl = mk(0.f, 0.f, 0.f);
     if (commit) {
+        f3 v = ct.c + mul(ct.T, ct.lam);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { v.x = fmaf(ct.Q[a][0], y[a], v.x); v.y = fmaf(ct.Q[a][1], y[a], v.y); v.z = fmaf(ct.Q[a][2], y[a], v.z); }
+        f3 ln = solve_one_contact(v, ct.G, ct.Ginv, ct.lam, ct.vtn, mu, slide_iters);
+        dl = ln - ct.lam;
         ct.lam = ln;
         maxd = fmaxf(maxd, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
         maxl = fmaxf(maxl, fmaxf(fabsf(ln.x), fmaxf(fabsf(ln.y), fabsf(ln.z))));
@@ -510,18 +516,34 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
             cb.c = vpre + dt * qw_;
             cb.vtn = (vpre.z < -bm.thr) ? -bm.rest * vpre.z : 0.f;
         }
-        // ---- per-contact Gauss-Seidel in the 6-dimensional trunk space
+        // ---- per-contact iteration in the 6-dimensional trunk space: feet simultaneously (block Jacobi, they couple only
+        //      weakly through the trunk), trunk-box corners one after the other (Gauss-Seidel), same schedule as the oracle
         float y[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         bool frozen = !(qsum((float)(cf.active + cb.active)) > 0.f);    // robots without contacts never iterate
         int sweeps = 0;
         for (int sweep = 0; sweep < P.solver_iters; ++sweep) {
             if (__all_sync(FULLMASK, frozen)) break;
             float maxd = 0.f, maxl = 0.f;
-#pragma unroll 1
-            for (int o = 0; o < 4; ++o) gs_visit(cf, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
+            {   // feet: block Jacobi -- every lane updates its own foot contact from the same trunk-space vector y
+                f3 dl = mk(0.f, 0.f, 0.f);
+                if (cf.active && !frozen) {
+                    f3 v = cf.c + mul(cf.T, cf.lam);
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) { v.x = fmaf(cf.Q[a][0], y[a], v.x); v.y = fmaf(cf.Q[a][1], y[a], v.y); v.z = fmaf(cf.Q[a][2], y[a], v.z); }
+                    f3 ln = solve_one_contact(v, cf.G, cf.Ginv, cf.lam, cf.vtn, bm.mu, P.slide_iters);
+                    dl = ln - cf.lam; cf.lam = ln;
+                    maxd = fmaxf(maxd, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
+                    maxl = fmaxf(maxl, fmaxf(fabsf(ln.x), fmaxf(fabsf(ln.y), fabsf(ln.z))));
+                }
+#pragma unroll
+                for (int a = 0; a < 6; ++a) y[a] += qsum(cf.Q[a][0] * dl.x + cf.Q[a][1] * dl.y + cf.Q[a][2] * dl.z);
+            }
             if (any_box) {
 #pragma unroll 1
-                for (int o = 0; o < 4; ++o) gs_visit(cb, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
+                for (int o = 0; o < 4; ++o) {
+                    if (!__any_sync(FULLMASK, leg == o && cb.active && !frozen)) continue;
+                    gs_visit(cb, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
+                }
             }
             maxd = qmax(maxd); maxl = qmax(maxl);
             if (!frozen) { sweeps = sweep + 1; if (maxd <= P.solver_tol * maxl) frozen = true; }

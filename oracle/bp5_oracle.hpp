@@ -296,9 +296,10 @@ template <typename T> struct Env {
     T mass_distrubance_ratio = T(0.15), com_distrubance = T(0.02), calf_distrubance = T(0.01);  // ENV:2069-2071
     // contact material: default (0.6, 0.2, 0.01) ENV:433
     T mu = T(0.6), restitution = T(0.2), rest_threshold = T(0.01);
-    int solver_iters = 8;         // per-contact Gauss-Seidel sweeps cap (new spec)
+    int solver_iters = 10;        // per-contact Gauss-Seidel sweeps cap (new spec)
     T solver_tol = T(1e-5);       // relative impulse change for early exit
-    int slide_iters = 3;          // fixed-point iterations for the sliding direction
+    int slide_iters = 1;          // fixed-point iterations for the sliding direction
+    int solver_jacobi = 1;        // 1: feet updated simultaneously per sweep (see integrate())
 
     // ---- state
     Model<T> model;
@@ -351,7 +352,7 @@ template <typename T> struct Env {
         simulation_dt_ = T(c.get("simulation_dt")); control_dt_ = T(c.get("control_dt"));   // VEC:151-152
         // solver / model switches (new-spec, optional)
         model.joint_damping = T(c.get_or("joint_damping", 0.01));
-        solver_iters = (int)c.get_or("solver_iters", 8); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 3);
+        solver_iters = (int)c.get_or("solver_iters", 10); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 1); solver_jacobi = (int)c.get_or("solver_jacobi", 1);
         mu = T(c.get_or("friction", 0.6)); restitution = T(c.get_or("restitution", 0.2)); rest_threshold = T(c.get_or("restitution_threshold", 0.01));
 
         // gc_init_ ENV:317-322
@@ -550,8 +551,14 @@ template <typename T> struct Env {
             // per-contact Gauss-Seidel (normal = +z on the plane, so contact frame == world frame)
             for (int sweep = 0; sweep < solver_iters; ++sweep) {
                 T maxd = 0, maxl = 0;
+                // schedule: the (<= 4) foot contacts are updated simultaneously from the impulses of the previous sweep
+                // (block Jacobi: feet couple only weakly, through the trunk), the trunk-box corners one after the other
+                // with the freshest impulses (Gauss-Seidel: they sit on the same rigid body).  solver_jacobi = 0 gives
+                // plain Gauss-Seidel over all contacts.
+                T lam_prev[3 * MAXC]; for (int q = 0; q < 3 * nc; ++q) lam_prev[q] = lam[q];
                 for (int i = 0; i < nc; ++i) {
-                    T v[3]; for (int r = 0; r < 3; ++r) { T acc = c[3 * i + r]; for (int q = 0; q < 3 * nc; ++q) acc += G[3 * i + r][q] * lam[q]; v[r] = acc; }
+                    const T* lsrc = (solver_jacobi && cs[i].kind < 4) ? lam_prev : lam;
+                    T v[3]; for (int r = 0; r < 3; ++r) { T acc = c[3 * i + r]; for (int q = 0; q < 3 * nc; ++q) acc += G[3 * i + r][q] * lsrc[q]; v[r] = acc; }
                     T Gii[3][3], Ginv[3][3]; for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) Gii[r][s] = G[3 * i + r][3 * i + s];
                     inv3(Gii, Ginv);
                     T lo[3] = {lam[3 * i], lam[3 * i + 1], lam[3 * i + 2]}, ln[3];

@@ -8,7 +8,7 @@ import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); r=d['roofline']
-        print('N=%d value=%.3e e2e=%.3e ms/step=%.4f step_kernel_ms=%.4f act_kernel_ms=%.4f frac=%s clocks=%s rew=%.3f eps=%d' % (d['config']['envs_per_gpu'], d['value'], d['e2e']['value'], d['ms_per_step'], r['kernel_ms'], r['lstm_act']['kernel_ms'], r['frac'], d['clocks']['sm_mhz'], d['sanity']['mean_reward'], d['sanity']['episodes_finished']))
+        print('N=%d value=%.3e e2e=%.3e ms/step=%.4f step_kernel_ms=%.4f act_kernel_ms=%.4f frac=%s clocks=%s rew=%.3f eps=%d' % (d['config']['envs_per_gpu'], d['value'], d['e2e']['value'], d['ms_per_step'], r['kernel_ms'], r['lstm_act']['kernel_ms'], r['frac'], d['clocks']['sm_mhz'], d['sanity']['mean_reward'], d['sanity']['episodes_finished']), d['sanity']['gs_sweeps_last_substep'])
     else: print(l.rstrip()[:300])
 "
 done

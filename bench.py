@@ -193,7 +193,10 @@ def run_b200(args):
     N = args.envs_per_gpu; K = args.steps; Wm = max(args.warmup, 3)
     cfg = workload_cfg(N)
     env = FlexibleGymEnv("", dump_yaml(cfg), device=local, env_offset=rank * N)
-    stream = torch.cuda.current_stream(dev)
+    # one explicit (non-default) stream carries everything: env/policy kernels, the L2 flush and the timing events
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     env.setStream(stream.cuda_stream)
     env.init()
     W, wname = policy_weights()
@@ -325,7 +328,7 @@ def run_b200(args):
                        "parallelism": f"env-shard x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "path": "irrl_policy_act + irrl_step with host numpy buffers (pinned staging inside the C ABI); LSTM state device-resident"},
-            "gpu_launches": 2 * K, "kernels": ["lstm_act_kernel", "env_step_kernel"], "memcpy_d2d_per_step": 2,
+            "gpu_launches": 2 * K, "kernels": ["lstm_act_kernel", "env_step_kernel"], "memcpy_d2d_per_step": 0,
             "roofline": roof, "clocks": clocks, "wall_s": wall,
             "sanity": {"mean_reward": mean_rew, "episodes_finished": episodes_done, "gs_sweeps_last_substep": {"mean": float(sw.mean()), "max": int(sw.max()), "hist": np.bincount(sw, minlength=9).tolist()}}}
     if not args.no_cpu_baseline:

@@ -37,6 +37,8 @@ struct PolicyWeights {      // device pointers, fp32, layouts as in the referenc
     const float* vf_w;      // [48]
     const float* vf_b;      // [1]
     const float* logstd;    // [12]
+    const float* wcat[4];   // derived: [96][192] = [wx ; wh ; 0-pad] with gate-interleaved columns (unit pair, unit, gate)
+    const float* bperm[4];  // derived: [192] biases in the same column order
 };
 struct ActArgs {
     PolicyWeights W;
@@ -48,6 +50,8 @@ struct ActArgs {
     float* value;           // [N]
     float* neglogp;         // [N]
     float* mean;            // [N,12] may be null
+    float* obs_store;       // [N,35] copy of obs (Runner's mb_obs), may be null
+    uint8_t* done_store;    // [N] copy of the mask (Runner's mb_dones), may be null
     int N; int deterministic;
     uint32_t seed, env_offset, tick;
 };

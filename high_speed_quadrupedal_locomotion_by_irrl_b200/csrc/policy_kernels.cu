@@ -4,115 +4,151 @@
 // `lstm`, `linear`, DiagGaussian sample + neglogp) and Runner's GAE loop (ppo2.py:554-568).
 // One launch = both towers x both layers + pi/V heads + Gaussian sample + neglogp + done-mask state reset.
 //
-// v1 mapping (fp32 CUDA cores, exact against the numpy oracle): a CTA owns a tile of TM environments; the first
-// 192 threads run the pi tower (one gate column each), the next 192 the V tower.  Inputs/hidden states of the
-// tile sit transposed in shared memory ([k][env]) so a gate column reads 4 envs per LDS.128 broadcast and
-// streams its weight column from L2 (the 283 KB of weights stay L2-resident across CTAs).
+// Mapping (fp32 FMA pipe, agrees with the numpy oracle to ~1e-6): a CTA owns 32 environments and both towers
+// (192 threads each).  Every layer is one register-tiled GEMM gates[32 x 192] = [x ; h]^T[32 x 96] W[96 x 192]:
+// a thread owns 4 envs x 8 columns, the 8 columns being the i,f,o,g gates of two hidden units (weights are stored
+// gate-interleaved once at load time), so the cell update happens in registers with no gate round trip.  Weight
+// rows stream L2 -> shared memory in 16-row cp.async stages (double buffered); activations sit transposed and
+// XOR-swizzled in shared memory.  The rollout stores of Runner.run (mb_obs, mb_dones) ride along.
 #include "env_device.cuh"
 #include "env_kernels.h"
 
 namespace irrl {
 
-constexpr int TM = 16;          // environments per CTA
 constexpr int H = LSTM_H;       // 48
 constexpr int G4 = 4 * H;       // 192 gate columns per layer
+constexpr int TM = 32;          // environments per CTA
+constexpr int KP = 96;          // padded reduction length of every layer ([x ; h] rows: 35+48 -> 96, 48+48 = 96)
+constexpr int KC = 16;          // rows of W per cp.async stage
+constexpr int NTHR = 2 * G4;    // 384 threads: tower = t / 192, then (col-group 0..23) x (env-group 0..7)
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// gates[col] for TM envs: acc[e] = b[col] + sum_k xT[k][e] * Wx[k][col] + sum_k hT[k][e] * Wh[k][col]
-template <int KIN>
-__device__ __forceinline__ void gate_column(const float* __restrict__ Wx, const float* __restrict__ Wh, const float* __restrict__ bias,
-                                            const float (*xT)[TM], const float (*hT)[TM], int col, float acc[TM]) {
-    float b = bias[col];
-#pragma unroll
-    for (int e = 0; e < TM; ++e) acc[e] = b;
-#pragma unroll 4
-    for (int k = 0; k < KIN; ++k) {
-        float w = __ldg(Wx + (size_t)k * G4 + col);
-        const float4* xr = reinterpret_cast<const float4*>(xT[k]);
-#pragma unroll
-        for (int e4 = 0; e4 < TM / 4; ++e4) {
-            float4 x = xr[e4];
-            acc[4 * e4 + 0] = fmaf(x.x, w, acc[4 * e4 + 0]); acc[4 * e4 + 1] = fmaf(x.y, w, acc[4 * e4 + 1]);
-            acc[4 * e4 + 2] = fmaf(x.z, w, acc[4 * e4 + 2]); acc[4 * e4 + 3] = fmaf(x.w, w, acc[4 * e4 + 3]);
-        }
-    }
-#pragma unroll 4
-    for (int k = 0; k < H; ++k) {
-        float w = __ldg(Wh + (size_t)k * G4 + col);
-        const float4* hr = reinterpret_cast<const float4*>(hT[k]);
-#pragma unroll
-        for (int e4 = 0; e4 < TM / 4; ++e4) {
-            float4 x = hr[e4];
-            acc[4 * e4 + 0] = fmaf(x.x, w, acc[4 * e4 + 0]); acc[4 * e4 + 1] = fmaf(x.y, w, acc[4 * e4 + 1]);
-            acc[4 * e4 + 2] = fmaf(x.z, w, acc[4 * e4 + 2]); acc[4 * e4 + 3] = fmaf(x.w, w, acc[4 * e4 + 3]);
-        }
-    }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// env column of the transposed activation tiles is XOR-swizzled by the row so that the transposing stores
+// (lanes along k, one env) hit 8 banks instead of 1 while the GEMM's float4 reads stay 16-byte aligned
+__device__ __forceinline__ int swz(int k, int env) { return (((env >> 2) ^ (k & 7)) << 2) | (env & 3); }
 
 struct __align__(16) ActSmem {
-    float obsT[OB_DIM + 1][TM];        // input, transposed
-    float hT[2][2][H][TM];             // [tower][layer] hidden state h(t-1) (masked), transposed
-    float cS[2][2][H][TM];             // [tower][layer] cell state
-    float gates[2][G4][TM];            // [tower] gate pre-activations of the current layer
-    float hnew[2][H][TM];              // [tower] output of the current layer (input of the next)
-    float mean[TM][ACT_DIM];
+    float X[2][2][KP][TM];        // [tower][layer] GEMM input, transposed: rows = [x ; h(t-1) masked ; 0-pad]
+    float W[2][2][KC][G4];        // [stage][tower] weight rows of the current K chunk (gate-interleaved columns)
+    float Hout[2][H][TM];         // [tower] output of the top layer
     float nlp[TM][ACT_DIM];
 };
 
-__global__ void __launch_bounds__(2 * G4) lstm_act_kernel(const __grid_constant__ ActArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ActSmem& s = *reinterpret_cast<ActSmem*>(smem_raw);
-    const int t = threadIdx.x, tower = t / G4, col = t % G4;
-    const int e0 = blockIdx.x * TM;
-    const PolicyWeights& W = A.W;
-    // ---- stage obs and (masked) state, transposed
-    for (int i = t; i < TM * OB_DIM; i += 2 * G4) {
-        int e = i / OB_DIM, k = i % OB_DIM; int env = min(e0 + e, A.N - 1);
-        s.obsT[k][e] = A.obs[(size_t)env * OB_DIM + k];
-    }
-    for (int i = t; i < TM * LSTM_STATE; i += 2 * G4) {
-        int e = i / LSTM_STATE, k = i % LSTM_STATE; int env = min(e0 + e, A.N - 1);
-        float keep = (A.done && A.done[env]) ? 0.f : 1.f;                 // SB lstm(): c *= 1-m, h *= 1-m
-        float v = A.state[(size_t)env * LSTM_STATE + k] * keep;
-        int tw = k / (4 * H), rem = k % (4 * H), layer = rem / (2 * H), ch = (rem % (2 * H)) / H, u = rem % H;   // [c0,h0,c1,h1] per tower
-        if (ch == 0) s.cS[tw][layer][u][e] = v; else s.hT[tw][layer][u][e] = v;
-    }
-    __syncthreads();
-    // ---- two layers per tower
-    for (int layer = 0; layer < 2; ++layer) {
-        float acc[TM];
-        int wi = tower * 2 + layer;
-        if (layer == 0) gate_column<OB_DIM>(W.wx[wi], W.wh[wi], W.b[wi], s.obsT, s.hT[tower][0], col, acc);
-        else gate_column<H>(W.wx[wi], W.wh[wi], W.b[wi], s.hnew[tower], s.hT[tower][1], col, acc);
+// one LSTM layer for both towers: gates = X^T W (+b) by register tiling (4 envs x 8 columns per thread, the 8 columns
+// being the i,f,o,g gates of two hidden units), then the cell update in registers.
+__device__ __forceinline__ void lstm_layer(const ActArgs& A, ActSmem& s, int layer, int t, int e0) {
+    const int tower = t / G4, tt = t % G4, eg = tt & 7, cg = tt >> 3;
+    const float* Wg = A.W.wcat[tower * 2 + layer];       // [KP][192], columns permuted to (unit pair, unit, gate)
+    float acc[4][8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(A.W.bperm[tower * 2 + layer] + 8 * cg));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(A.W.bperm[tower * 2 + layer] + 8 * cg + 4));
 #pragma unroll
-        for (int e = 0; e < TM; ++e) s.gates[tower][col][e] = acc[e];
+        for (int e = 0; e < 4; ++e) { acc[e][0] = b0.x; acc[e][1] = b0.y; acc[e][2] = b0.z; acc[e][3] = b0.w; acc[e][4] = b1.x; acc[e][5] = b1.y; acc[e][6] = b1.z; acc[e][7] = b1.w; }
+    }
+    // stage loader: KC x 192 floats per tower = 768 float4 -> 2 per thread of the tower
+    auto load_chunk = [&](int c, int stage) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int idx = tt + i * G4;                       // 0..383 float4 slots of this tower's chunk... (KC*192/4 = 768)
+            for (int j = idx; j < KC * G4 / 4; j += 2 * G4) {
+                int row = j / (G4 / 4), c4 = j % (G4 / 4);
+                cp_async16(&s.W[stage][tower][row][4 * c4], Wg + (size_t)(c * KC + row) * G4 + 4 * c4);
+            }
+        }
+    };
+    constexpr int NCH = KP / KC;
+    load_chunk(0, 0); cp_async_commit();
+    for (int c = 0; c < NCH; ++c) {
+        if (c + 1 < NCH) { load_chunk(c + 1, (c + 1) & 1); cp_async_commit(); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
-        // cell update: (env, unit) pairs, gate order i,f,o,g (CustomerLstmNN.py:119-126)
-        for (int i = col; i < TM * H; i += G4) {
-            int u = i / TM, e = i % TM;
-            float ig = sigmoidf_(s.gates[tower][u][e]), fg = sigmoidf_(s.gates[tower][H + u][e]);
-            float og = sigmoidf_(s.gates[tower][2 * H + u][e]), gg = tanhf(s.gates[tower][3 * H + u][e]);
-            float c = fg * s.cS[tower][layer][u][e] + ig * gg;
-            float h = og * tanhf(c);
-            s.hnew[tower][u][e] = h;
-            int env = e0 + e;
-            if (env < A.N) {
-                float* st = A.state + (size_t)env * LSTM_STATE + tower * 4 * H + layer * 2 * H;
-                st[u] = c; st[H + u] = h;
+        const float (*Wc)[G4] = s.W[c & 1][tower];
+        const float (*Xc)[TM] = s.X[tower][layer];
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const int k = c * KC + kk;
+            const float4 x = *reinterpret_cast<const float4*>(&Xc[k][((eg ^ (k & 7)) << 2)]);
+            const float4 w0 = *reinterpret_cast<const float4*>(&Wc[kk][8 * cg]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&Wc[kk][8 * cg + 4]);
+            const float xe[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[e][0] = fmaf(xe[e], w0.x, acc[e][0]); acc[e][1] = fmaf(xe[e], w0.y, acc[e][1]);
+                acc[e][2] = fmaf(xe[e], w0.z, acc[e][2]); acc[e][3] = fmaf(xe[e], w0.w, acc[e][3]);
+                acc[e][4] = fmaf(xe[e], w1.x, acc[e][4]); acc[e][5] = fmaf(xe[e], w1.y, acc[e][5]);
+                acc[e][6] = fmaf(xe[e], w1.z, acc[e][6]); acc[e][7] = fmaf(xe[e], w1.w, acc[e][7]);
             }
         }
         __syncthreads();
     }
-    // ---- heads
-    if (tower == 0) {
-        // pi: 48 -> 12, one (env, action) per thread; Gaussian sample + neglogp terms
-        int e = col / ACT_DIM, a = col % ACT_DIM; int env = e0 + e;
+    // cell update (gate order i,f,o,g  CustomerLstmNN.py:119-126); c(t-1) straight from HBM with the done mask
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int el = 4 * eg + e, env = e0 + el, envc = min(env, A.N - 1);
+        const float keep = (A.done && A.done[envc]) ? 0.f : 1.f;
+        float* st = A.state + (size_t)envc * LSTM_STATE + tower * 4 * H + layer * 2 * H;
+        const float2 cold = *reinterpret_cast<const float2*>(st + 2 * cg);
+        float cn[2], hn[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float ig = sigmoidf_(acc[e][4 * u + 0]), fg = sigmoidf_(acc[e][4 * u + 1]), og = sigmoidf_(acc[e][4 * u + 2]), gg = tanhf(acc[e][4 * u + 3]);
+            cn[u] = fg * ((u ? cold.y : cold.x) * keep) + ig * gg;
+            hn[u] = og * tanhf(cn[u]);
+            const int unit = 2 * cg + u;
+            if (layer == 0) s.X[tower][1][unit][swz(unit, el)] = hn[u]; else s.Hout[tower][unit][swz(unit, el)] = hn[u];
+        }
+        if (env < A.N) {
+            *reinterpret_cast<float2*>(st + 2 * cg) = make_float2(cn[0], cn[1]);
+            *reinterpret_cast<float2*>(st + H + 2 * cg) = make_float2(hn[0], hn[1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHR, 2) lstm_act_kernel(const __grid_constant__ ActArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ActSmem& s = *reinterpret_cast<ActSmem*>(smem_raw);
+    const int t = threadIdx.x;
+    const int e0 = blockIdx.x * TM;
+    const PolicyWeights& W = A.W;
+    // ---- stage the inputs transposed: layer-0 rows = [obs(35) ; h0 ; 0], layer-1 rows 48.. = h1 (rows 0..47 come from layer 0)
+    for (int i = t; i < TM * OB_DIM; i += NTHR) {          // the tile's observations are one contiguous block
+        int e = i / OB_DIM, k = i % OB_DIM; int env = min(e0 + e, A.N - 1);
+        float v = A.obs[(size_t)env * OB_DIM + k];
+        s.X[0][0][k][swz(k, e)] = v; s.X[1][0][k][swz(k, e)] = v;
+        if (A.obs_store && e0 + e < A.N) A.obs_store[(size_t)env * OB_DIM + k] = v;     // mb_obs (ppo2.py:522)
+    }
+    for (int i = t; i < TM * 4 * H; i += NTHR) {           // h(t-1) of the 4 (tower, layer) cells, masked (SB lstm(): h *= 1-m)
+        int e = i / (4 * H), r = i % (4 * H), cell = r / H, u = r % H, tower = cell >> 1, layer = cell & 1;
+        int env = min(e0 + e, A.N - 1);
+        float keep = (A.done && A.done[env]) ? 0.f : 1.f;
+        float v = A.state[(size_t)env * LSTM_STATE + tower * 4 * H + layer * 2 * H + H + u] * keep;
+        int row = (layer == 0 ? OB_DIM : H) + u;
+        s.X[tower][layer][row][swz(row, e)] = v;
+    }
+    for (int i = t; i < 2 * (KP - OB_DIM - H) * TM; i += NTHR) {   // zero padding rows 83..95 of layer 0
+        int tower = i / ((KP - OB_DIM - H) * TM), r = i % ((KP - OB_DIM - H) * TM);
+        s.X[tower][0][OB_DIM + H + r / TM][r % TM] = 0.f;
+    }
+    if (A.done_store && t < TM && e0 + t < A.N) A.done_store[e0 + t] = A.done ? A.done[e0 + t] : 0;     // mb_dones (ppo2.py:526)
+    __syncthreads();
+    lstm_layer(A, s, 0, t, e0);
+    __syncthreads();
+    lstm_layer(A, s, 1, t, e0);
+    __syncthreads();
+    // ---- heads: pi 48 -> 12 (one (env, action) per thread), V 48 -> 1; Gaussian sample + neglogp
+    {
+        const int e = t % TM, a = t / TM, env = e0 + e;     // 32 x 12 = 384 threads
         float m = W.pi_b[a];
 #pragma unroll 8
-        for (int k = 0; k < H; ++k) m = fmaf(s.hnew[0][k][e], __ldg(W.pi_w + k * ACT_DIM + a), m);
-        float ls = W.logstd[a], sd = expf(ls);
-        float eps = 0.f;
+        for (int k = 0; k < H; ++k) m = fmaf(s.Hout[0][k][swz(k, e)], __ldg(W.pi_w + k * ACT_DIM + a), m);
+        float ls = W.logstd[a], sd = expf(ls), eps = 0.f;
         if (!A.deterministic) {
             float g[4]; gauss4(A.seed, (uint32_t)min(env, A.N - 1) + A.env_offset, A.tick, P_POLICY_EPS + (a >> 2), g);
             eps = g[a & 3];
@@ -125,11 +161,12 @@ __global__ void __launch_bounds__(2 * G4) lstm_act_kernel(const __grid_constant_
             if (A.clipped) A.clipped[(size_t)env * ACT_DIM + a] = fminf(fmaxf(act, -1.f), 1.f);   // ppo2.py:529-531
             if (A.mean) A.mean[(size_t)env * ACT_DIM + a] = m;
         }
-    } else if (col < TM) {
-        int e = col, env = e0 + e;
+    }
+    if (t < TM) {
+        const int e = t, env = e0 + e;
         float v = W.vf_b[0];
 #pragma unroll 8
-        for (int k = 0; k < H; ++k) v = fmaf(s.hnew[1][k][e], __ldg(W.vf_w + k), v);
+        for (int k = 0; k < H; ++k) v = fmaf(s.Hout[1][k][swz(k, e)], __ldg(W.vf_w + k), v);
         if (env < A.N) A.value[env] = v;
     }
     __syncthreads();
@@ -145,7 +182,7 @@ void launch_lstm_act(const ActArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(lstm_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ActSmem)); configured = true; }
     int grid = (a.N + TM - 1) / TM;
-    lstm_act_kernel<<<grid, 2 * G4, sizeof(ActSmem), st>>>(a);
+    lstm_act_kernel<<<grid, NTHR, sizeof(ActSmem), st>>>(a);
 }
 
 // ------------------------------------------------------------------ GAE (ppo2.py:554-568): one thread per env, reverse scan

@@ -78,11 +78,12 @@ struct irrl_env_impl {
     unsigned char* h_pin = nullptr; size_t h_pin_bytes = 0; size_t scratch_floats = 0;
     std::vector<void*> allocs;
     // optional per-kernel timing of irrl_rollout (CUDA events on the env's stream)
-    bool profiling = false; std::vector<cudaEvent_t> prof_events; double prof_act_ms = 0, prof_step_ms = 0; long prof_count = 0;
+    bool profiling = false; std::vector<cudaEvent_t> prof_events; size_t prof_cursor = 0; double prof_act_ms = 0, prof_step_ms = 0; long prof_count = 0;
 };
 struct irrl_policy_impl {
     int device = 0;
     float* d_params = nullptr;
+    float* d_derived = nullptr;   // 4 x ([96][192] + [192]) gate-interleaved copies for the act kernel
     PolicyWeights W{};
     // staging for host callers
     int cap = 0; float *d_obs = nullptr, *d_state = nullptr, *d_action = nullptr, *d_clipped = nullptr, *d_value = nullptr, *d_nlp = nullptr; uint8_t* d_done = nullptr;
@@ -563,6 +564,24 @@ static void bind_weights(irrl_policy_impl* Pn) {
     const int in[4] = {35, 48, 35, 48};
     for (int i = 0; i < 4; ++i) { W.wx[i] = p; p += in[i] * 192; W.wh[i] = p; p += 48 * 192; W.b[i] = p; p += 192; }
     W.vf_w = p; p += 48; W.vf_b = p; p += 1; W.pi_w = p; p += 48 * 12; W.pi_b = p; p += 12; W.logstd = p; p += 12; /* q head (unused by act) follows */
+    for (int i = 0; i < 4; ++i) { W.wcat[i] = Pn->d_derived + (size_t)i * (96 * 192 + 192); W.bperm[i] = W.wcat[i] + 96 * 192; }
+}
+// gate-interleaved, zero-padded [x ; h] weight blocks: new column (u/2)*8 + (u%2)*4 + g  <-  original column g*48 + u
+static int upload_derived(irrl_policy_impl* Pn, const float* host_params) {
+    std::vector<float> d((size_t)4 * (96 * 192 + 192), 0.f);
+    const float* p = host_params; const int in[4] = {35, 48, 35, 48};
+    for (int i = 0; i < 4; ++i) {
+        const float* wx = p; p += in[i] * 192; const float* wh = p; p += 48 * 192; const float* b = p; p += 192;
+        float* o = d.data() + (size_t)i * (96 * 192 + 192);
+        for (int g = 0; g < 4; ++g) for (int uu = 0; uu < 48; ++uu) {
+            int src = g * 48 + uu, dst = (uu / 2) * 8 + (uu % 2) * 4 + g;
+            for (int k = 0; k < in[i]; ++k) o[(size_t)k * 192 + dst] = wx[(size_t)k * 192 + src];
+            for (int k = 0; k < 48; ++k) o[(size_t)(in[i] + k) * 192 + dst] = wh[(size_t)k * 192 + src];
+            o[96 * 192 + dst] = b[src];
+        }
+    }
+    CUDA_OK(cudaMemcpy(Pn->d_derived, d.data(), d.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
 }
 int irrl_policy_create(int device, const float* params, irrl_policy** out) {
     if (!out || !params) return fail(-1, "null argument");
@@ -570,6 +589,7 @@ int irrl_policy_create(int device, const float* params, irrl_policy** out) {
     CUDA_OK(cudaSetDevice(device));
     irrl_policy_impl* Pn = new irrl_policy_impl(); Pn->device = device;
     CUDA_OK(cudaMalloc((void**)&Pn->d_params, IRRL_POLICY_NUM_PARAMS * sizeof(float)));
+    CUDA_OK(cudaMalloc((void**)&Pn->d_derived, (size_t)4 * (96 * 192 + 192) * sizeof(float)));
     bind_weights(Pn);
     *out = reinterpret_cast<irrl_policy*>(Pn);
     return irrl_policy_set_params(*out, params);
@@ -578,12 +598,14 @@ int irrl_policy_set_params(irrl_policy* pol, const float* params) {
     irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return fail(-1, "null policy");
     CUDA_OK(cudaSetDevice(Pn->device));
     CUDA_OK(cudaMemcpy(Pn->d_params, params, IRRL_POLICY_NUM_PARAMS * sizeof(float), is_device_ptr(params) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-    return 0;
+    std::vector<float> hp(IRRL_POLICY_NUM_PARAMS);
+    CUDA_OK(cudaMemcpy(hp.data(), Pn->d_params, hp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    return upload_derived(Pn, hp.data());
 }
 void irrl_policy_destroy(irrl_policy* pol) {
     irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return;
     cudaSetDevice(Pn->device); cudaDeviceSynchronize();
-    cudaFree(Pn->d_params); cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
+    cudaFree(Pn->d_params); cudaFree(Pn->d_derived); cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
     if (Pn->h_pin) cudaFreeHost(Pn->h_pin);
     delete Pn;
 }
@@ -593,7 +615,7 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
     if (!obs || !state || !action || !value || !neglogp || n <= 0) return fail(-1, "irrl_policy_act: null argument");
     CUDA_OK(cudaSetDevice(Pn->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-    ActArgs a; a.W = Pn->W; a.N = n; a.deterministic = deterministic; a.seed = seed; a.env_offset = env_offset; a.tick = tick; a.mean = nullptr;
+    ActArgs a; a.W = Pn->W; a.N = n; a.deterministic = deterministic; a.seed = seed; a.env_offset = env_offset; a.tick = tick; a.mean = nullptr; a.obs_store = nullptr; a.done_store = nullptr;
     const size_t N = (size_t)n;
     // every pointer is classified on its own: e.g. the LSTM state may stay resident on the device while
     // observations / actions travel through host memory (the reference's Runner keeps `states` opaque, ppo2.py:520)
@@ -640,41 +662,46 @@ int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buff
     for (const void* p : {(const void*)b->obs, (const void*)b->actions, (const void*)b->values, (const void*)b->neglogps, (const void*)b->rewards,
                           (const void*)b->dones, (const void*)b->cur_obs, (const void*)b->cur_done, (const void*)b->state})
         if (!is_device_ptr(p)) return fail(-1, "irrl_rollout: all buffers must be device memory");
-    if (E->profiling) while ((int)E->prof_events.size() < 3 * T) { cudaEvent_t ev; CUDA_OK(cudaEventCreate(&ev)); E->prof_events.push_back(ev); }
+    // profiling never blocks: events are appended per step and only read back by irrl_get_profile
+    if (E->profiling) while (E->prof_events.size() < E->prof_cursor + 3 * (size_t)T) { cudaEvent_t ev; CUDA_OK(cudaEventCreate(&ev)); E->prof_events.push_back(ev); }
     for (int t = 0; t < T; ++t) {
         // mb_obs / mb_dones hold the inputs of model.step (ppo2.py:520-526)
-        CUDA_OK(cudaMemcpyAsync(b->obs + (size_t)t * N * 35, b->cur_obs, N * 35 * sizeof(float), cudaMemcpyDeviceToDevice, E->stream));
-        CUDA_OK(cudaMemcpyAsync(b->dones + (size_t)t * N, b->cur_done, N, cudaMemcpyDeviceToDevice, E->stream));
         ActArgs a; a.W = Pn->W; a.N = (int)N; a.deterministic = deterministic; a.seed = E->P.seed; a.env_offset = E->P.env_offset; a.tick = E->tick; a.mean = nullptr;
+        a.obs_store = b->obs + (size_t)t * N * 35; a.done_store = b->dones + (size_t)t * N;     // stored by the act kernel itself
         a.obs = b->cur_obs; a.done = b->cur_done; a.state = b->state; a.action = b->actions + (size_t)t * N * 12; a.clipped = E->d_action;
         a.value = b->values + (size_t)t * N; a.neglogp = b->neglogps + (size_t)t * N;
-        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[3 * t + 0], E->stream));
+        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 0], E->stream));
         launch_lstm_act(a, E->stream);
-        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[3 * t + 1], E->stream));
+        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 1], E->stream));
         StepArgs s = make_args(E, E->d_action, b->cur_obs, b->rewards + (size_t)t * N, b->cur_done, nullptr);
         if (b->ep_return && b->ep_length) { s.ep_ret_out = b->ep_return + (size_t)t * N; s.ep_len_out = b->ep_length + (size_t)t * N; }
         launch_env_step(s, E->stream);
-        if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[3 * t + 2], E->stream));
+        if (E->profiling) { CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 2], E->stream)); E->prof_cursor += 3; }
         E->tick++;
     }
     CUDA_OK(cudaGetLastError());
-    if (E->profiling) {
-        CUDA_OK(cudaStreamSynchronize(E->stream));
-        for (int t = 0; t < T; ++t) {
-            float m1 = 0, m2 = 0;
-            CUDA_OK(cudaEventElapsedTime(&m1, E->prof_events[3 * t], E->prof_events[3 * t + 1]));
-            CUDA_OK(cudaEventElapsedTime(&m2, E->prof_events[3 * t + 1], E->prof_events[3 * t + 2]));
-            E->prof_act_ms += m1; E->prof_step_ms += m2; E->prof_count++;
-        }
-    }
     return 0;
 }
 
 int irrl_set_profiling(irrl_env* env, int on) {
-    ENV(env); E->profiling = on != 0; E->prof_act_ms = E->prof_step_ms = 0; E->prof_count = 0; return 0;
+    ENV(env);
+    if (E->stream) CUDA_OK(cudaStreamSynchronize(E->stream));
+    E->profiling = on != 0; E->prof_cursor = 0; E->prof_act_ms = E->prof_step_ms = 0; E->prof_count = 0; return 0;
 }
 int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total, int64_t* launches_each) {
-    ENV(env); if (act_ms_total) *act_ms_total = E->prof_act_ms; if (step_ms_total) *step_ms_total = E->prof_step_ms; if (launches_each) *launches_each = E->prof_count; return 0;
+    ENV(env);
+    if (E->stream) CUDA_OK(cudaStreamSynchronize(E->stream));
+    E->prof_act_ms = E->prof_step_ms = 0; E->prof_count = 0;
+    for (size_t i = 0; i + 2 < E->prof_cursor; i += 3) {
+        float m1 = 0, m2 = 0;
+        CUDA_OK(cudaEventElapsedTime(&m1, E->prof_events[i], E->prof_events[i + 1]));
+        CUDA_OK(cudaEventElapsedTime(&m2, E->prof_events[i + 1], E->prof_events[i + 2]));
+        E->prof_act_ms += m1; E->prof_step_ms += m2; E->prof_count++;
+    }
+    if (act_ms_total) *act_ms_total = E->prof_act_ms;
+    if (step_ms_total) *step_ms_total = E->prof_step_ms;
+    if (launches_each) *launches_each = E->prof_count;
+    return 0;
 }
 
 int irrl_gae(void* cuda_stream, int T, int n, const float* rewards, const float* values, const uint8_t* dones, const float* last_values,

@@ -62,6 +62,8 @@ def load() -> C.CDLL:
     L.irrl_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.irrl_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.irrl_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.irrl_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.irrl_host_unregister.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -70,3 +72,12 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().irrl_last_error().decode(errors="replace")
         raise RuntimeError(f"{what or 'irrl'} failed ({rc}): {msg}")
+
+
+def pin(array) -> bool:
+    """Page-lock a numpy array in place (cudaHostRegister) so the C ABI can DMA straight into it.  Returns False
+    (and leaves the array pageable) when registration is not possible."""
+    try:
+        return load().irrl_host_register(C.c_void_p(array.ctypes.data), C.c_size_t(array.nbytes)) == 0
+    except Exception:
+        return False

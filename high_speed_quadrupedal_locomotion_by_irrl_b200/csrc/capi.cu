@@ -97,6 +97,14 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister): DMA can target it directly, no staging copy needed
+bool is_pinned_host_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 template <typename T> int dev_alloc(irrl_env_impl* E, T** p, size_t n) {
     void* q = nullptr; CUDA_OK(cudaMalloc(&q, n * sizeof(T))); CUDA_OK(cudaMemset(q, 0, n * sizeof(T)));
     E->allocs.push_back(q); *p = reinterpret_cast<T*>(q); return 0;
@@ -221,6 +229,10 @@ int ensure_scratch(irrl_env_impl* E, size_t floats) {
 int deliver(irrl_env_impl* E, void* user, const void* dev, size_t bytes) {
     if (!user) return 0;
     if (is_device_ptr(user)) { CUDA_OK(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToDevice, E->stream)); return 0; }
+    if (is_pinned_host_ptr(user)) {
+        CUDA_OK(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, E->stream));
+        CUDA_OK(cudaStreamSynchronize(E->stream)); return 0;
+    }
     if (int rc = ensure_pin(E, bytes)) return rc;
     CUDA_OK(cudaMemcpyAsync(E->h_pin, dev, bytes, cudaMemcpyDeviceToHost, E->stream));
     CUDA_OK(cudaStreamSynchronize(E->stream));
@@ -353,25 +365,27 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
         return 0;
     }
     if (!action || !reward || !done) return fail(-1, "irrl_step: action, reward and done are required");
-    // host path: pinned staging, one H2D, one kernel, D2H of the results, then a blocking copy-out
+    // host path: one H2D, one kernel, D2H of the results, one synchronisation.  Page-locked caller buffers
+    // (cudaHostRegister / irrl_host_register) are DMA targets themselves; pageable ones go through pinned staging.
     unsigned char* pin = E->h_pin;
     float* p_act = reinterpret_cast<float*>(pin);
-    memcpy(p_act, action, N * 12 * sizeof(float));
-    CUDA_OK(cudaMemcpyAsync(E->d_action, p_act, N * 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
+    float* p_ob = p_act + N * 12; float* p_rew = p_ob + N * 35; float* p_ext = p_rew + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_ext + N * 6);
+    const bool pa = is_pinned_host_ptr(action), po = ob && is_pinned_host_ptr(ob), pr = is_pinned_host_ptr(reward), pd = is_pinned_host_ptr(done), pe = extra && is_pinned_host_ptr(extra);
+    if (!pa) memcpy(p_act, action, N * 12 * sizeof(float));
+    CUDA_OK(cudaMemcpyAsync(E->d_action, pa ? action : p_act, N * 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
     StepArgs a = make_args(E, E->d_action, E->P.flag_obs_filter ? nullptr : E->d_ob, E->d_reward, E->d_done, E->d_extra);
     launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
     E->tick++;
     if (E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, E->d_ob, E->stream); CUDA_OK(cudaGetLastError()); }
-    float* p_ob = p_act + N * 12; float* p_rew = p_ob + N * 35; float* p_ext = p_rew + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_ext + N * 6);
-    if (ob) CUDA_OK(cudaMemcpyAsync(p_ob, E->d_ob, N * 35 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    CUDA_OK(cudaMemcpyAsync(p_rew, E->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    if (extra) CUDA_OK(cudaMemcpyAsync(p_ext, E->d_extra, N * 6 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    CUDA_OK(cudaMemcpyAsync(p_done, E->d_done, N, cudaMemcpyDeviceToHost, E->stream));
+    if (ob) CUDA_OK(cudaMemcpyAsync(po ? ob : p_ob, E->d_ob, N * 35 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaMemcpyAsync(pr ? reward : p_rew, E->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (extra) CUDA_OK(cudaMemcpyAsync(pe ? extra : p_ext, E->d_extra, N * 6 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(cudaMemcpyAsync(pd ? done : p_done, E->d_done, N, cudaMemcpyDeviceToHost, E->stream));
     CUDA_OK(cudaStreamSynchronize(E->stream));
-    if (ob) memcpy(ob, p_ob, N * 35 * sizeof(float));
-    memcpy(reward, p_rew, N * sizeof(float));
-    if (extra) memcpy(extra, p_ext, N * 6 * sizeof(float));
-    memcpy(done, p_done, N);
+    if (ob && !po) memcpy(ob, p_ob, N * 35 * sizeof(float));
+    if (!pr) memcpy(reward, p_rew, N * sizeof(float));
+    if (extra && !pe) memcpy(extra, p_ext, N * 6 * sizeof(float));
+    if (!pd) memcpy(done, p_done, N);
     return 0;
 }
 
@@ -632,25 +646,27 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
     }
     float* p_obs = reinterpret_cast<float*>(Pn->h_pin); float* p_state = p_obs + N * 35; float* p_act = p_state + N * 384; float* p_clip = p_act + N * 12;
     float* p_val = p_clip + N * 12; float* p_nlp = p_val + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_nlp + N);
-    if (h_obs) { memcpy(p_obs, obs, N * 35 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_obs, p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st)); }
-    if (h_state) { memcpy(p_state, state, N * 384 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_state, p_state, N * 384 * 4, cudaMemcpyHostToDevice, st)); }
-    if (h_done) { memcpy(p_done, done, N); CUDA_OK(cudaMemcpyAsync(Pn->d_done, p_done, N, cudaMemcpyHostToDevice, st)); }
+    const bool q_obs = h_obs && is_pinned_host_ptr(obs), q_done = h_done && is_pinned_host_ptr(done), q_state = h_state && is_pinned_host_ptr(state),
+               q_act = h_act && is_pinned_host_ptr(action), q_clip = h_clip && is_pinned_host_ptr(clipped), q_val = h_val && is_pinned_host_ptr(value), q_nlp = h_nlp && is_pinned_host_ptr(neglogp);
+    if (h_obs) { if (!q_obs) memcpy(p_obs, obs, N * 35 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_obs, q_obs ? obs : p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st)); }
+    if (h_state) { if (!q_state) memcpy(p_state, state, N * 384 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_state, q_state ? state : p_state, N * 384 * 4, cudaMemcpyHostToDevice, st)); }
+    if (h_done) { if (!q_done) memcpy(p_done, done, N); CUDA_OK(cudaMemcpyAsync(Pn->d_done, q_done ? done : p_done, N, cudaMemcpyHostToDevice, st)); }
     a.obs = h_obs ? Pn->d_obs : obs; a.done = done ? (h_done ? Pn->d_done : done) : nullptr; a.state = h_state ? Pn->d_state : state;
     a.action = h_act ? Pn->d_action : action; a.clipped = clipped ? (h_clip ? Pn->d_clipped : clipped) : nullptr;
     a.value = h_val ? Pn->d_value : value; a.neglogp = h_nlp ? Pn->d_nlp : neglogp;
     launch_lstm_act(a, st); CUDA_OK(cudaGetLastError());
     if (!any_host) return 0;
-    if (h_state) CUDA_OK(cudaMemcpyAsync(p_state, Pn->d_state, N * 384 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_act) CUDA_OK(cudaMemcpyAsync(p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_clip) CUDA_OK(cudaMemcpyAsync(p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_val) CUDA_OK(cudaMemcpyAsync(p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
-    if (h_nlp) CUDA_OK(cudaMemcpyAsync(p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
+    if (h_state) CUDA_OK(cudaMemcpyAsync(q_state ? state : p_state, Pn->d_state, N * 384 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_act) CUDA_OK(cudaMemcpyAsync(q_act ? action : p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_clip) CUDA_OK(cudaMemcpyAsync(q_clip ? clipped : p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_val) CUDA_OK(cudaMemcpyAsync(q_val ? value : p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
+    if (h_nlp) CUDA_OK(cudaMemcpyAsync(q_nlp ? neglogp : p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    if (h_state) memcpy(state, p_state, N * 384 * 4);
-    if (h_act) memcpy(action, p_act, N * 12 * 4);
-    if (h_clip) memcpy(clipped, p_clip, N * 12 * 4);
-    if (h_val) memcpy(value, p_val, N * 4);
-    if (h_nlp) memcpy(neglogp, p_nlp, N * 4);
+    if (h_state && !q_state) memcpy(state, p_state, N * 384 * 4);
+    if (h_act && !q_act) memcpy(action, p_act, N * 12 * 4);
+    if (h_clip && !q_clip) memcpy(clipped, p_clip, N * 12 * 4);
+    if (h_val && !q_val) memcpy(value, p_val, N * 4);
+    if (h_nlp && !q_nlp) memcpy(neglogp, p_nlp, N * 4);
     return 0;
 }
 
@@ -703,6 +719,13 @@ int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total,
     if (launches_each) *launches_each = E->prof_count;
     return 0;
 }
+
+int irrl_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(-1, "irrl_host_register: null argument");
+    if (is_pinned_host_ptr(ptr)) return 0;
+    CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0;
+}
+int irrl_host_unregister(void* ptr) { if (!ptr) return 0; cudaError_t e = cudaHostUnregister(ptr); if (e != cudaSuccess) cudaGetLastError(); return 0; }
 
 int irrl_gae(void* cuda_stream, int T, int n, const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
              const uint8_t* last_dones, float gamma, float lam, float* adv, float* returns) {

@@ -22,7 +22,9 @@ constexpr int KP = 96;          // padded reduction length of every layer ([x ; 
 constexpr int KC = 16;          // rows of W per cp.async stage
 constexpr int NTHR = 2 * G4;    // 384 threads: tower = t / 192, then (col-group 0..23) x (env-group 0..7)
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// ex2.approx-based forms: relative error ~1e-6, far inside the 2e-5 parity bar (tests/test_gpu_policy_parity.py)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { float e = __expf(-2.0f * fabsf(x)); float r = __fdividef(1.0f - e, 1.0f + e); return copysignf(r, x); }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -53,15 +55,12 @@ __device__ __forceinline__ void lstm_layer(const ActArgs& A, ActSmem& s, int lay
 #pragma unroll
         for (int e = 0; e < 4; ++e) { acc[e][0] = b0.x; acc[e][1] = b0.y; acc[e][2] = b0.z; acc[e][3] = b0.w; acc[e][4] = b1.x; acc[e][5] = b1.y; acc[e][6] = b1.z; acc[e][7] = b1.w; }
     }
-    // stage loader: KC x 192 floats per tower = 768 float4 -> 2 per thread of the tower
+    // stage loader: KC x 192 floats per tower = 768 float4 -> 4 per thread of the tower (slot j = tt + 192 i)
     auto load_chunk = [&](int c, int stage) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            int idx = tt + i * G4;                       // 0..383 float4 slots of this tower's chunk... (KC*192/4 = 768)
-            for (int j = idx; j < KC * G4 / 4; j += 2 * G4) {
-                int row = j / (G4 / 4), c4 = j % (G4 / 4);
-                cp_async16(&s.W[stage][tower][row][4 * c4], Wg + (size_t)(c * KC + row) * G4 + 4 * c4);
-            }
+        for (int i = 0; i < 4; ++i) {
+            const int j = tt + i * G4, row = j / (G4 / 4), c4 = j % (G4 / 4);
+            cp_async16(&s.W[stage][tower][row][4 * c4], Wg + (size_t)(c * KC + row) * G4 + 4 * c4);
         }
     };
     constexpr int NCH = KP / KC;
@@ -98,9 +97,9 @@ __device__ __forceinline__ void lstm_layer(const ActArgs& A, ActSmem& s, int lay
         float cn[2], hn[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            float ig = sigmoidf_(acc[e][4 * u + 0]), fg = sigmoidf_(acc[e][4 * u + 1]), og = sigmoidf_(acc[e][4 * u + 2]), gg = tanhf(acc[e][4 * u + 3]);
+            float ig = sigmoidf_(acc[e][4 * u + 0]), fg = sigmoidf_(acc[e][4 * u + 1]), og = sigmoidf_(acc[e][4 * u + 2]), gg = tanhf_(acc[e][4 * u + 3]);
             cn[u] = fg * ((u ? cold.y : cold.x) * keep) + ig * gg;
-            hn[u] = og * tanhf(cn[u]);
+            hn[u] = og * tanhf_(cn[u]);
             const int unit = 2 * cg + u;
             if (layer == 0) s.X[tower][1][unit][swz(unit, el)] = hn[u]; else s.Hout[tower][unit][swz(unit, el)] = hn[u];
         }
@@ -124,13 +123,22 @@ __global__ void __launch_bounds__(NTHR, 2) lstm_act_kernel(const __grid_constant
         s.X[0][0][k][swz(k, e)] = v; s.X[1][0][k][swz(k, e)] = v;
         if (A.obs_store && e0 + e < A.N) A.obs_store[(size_t)env * OB_DIM + k] = v;     // mb_obs (ppo2.py:522)
     }
-    for (int i = t; i < TM * 4 * H; i += NTHR) {           // h(t-1) of the 4 (tower, layer) cells, masked (SB lstm(): h *= 1-m)
-        int e = i / (4 * H), r = i % (4 * H), cell = r / H, u = r % H, tower = cell >> 1, layer = cell & 1;
-        int env = min(e0 + e, A.N - 1);
-        float keep = (A.done && A.done[env]) ? 0.f : 1.f;
-        float v = A.state[(size_t)env * LSTM_STATE + tower * 4 * H + layer * 2 * H + H + u] * keep;
-        int row = (layer == 0 ? OB_DIM : H) + u;
-        s.X[tower][layer][row][swz(row, e)] = v;
+    {   // h(t-1) of the 4 (tower, layer) cells, masked (SB lstm(): h *= 1-m); 16 elements per thread, loads batched
+        float hv[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            int i = t + it * NTHR, e = i / (4 * H), r = i % (4 * H), cell = r / H, u = r % H;
+            int env = min(e0 + e, A.N - 1);
+            hv[it] = A.state[(size_t)env * LSTM_STATE + (cell >> 1) * 4 * H + (cell & 1) * 2 * H + H + u];
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            int i = t + it * NTHR, e = i / (4 * H), r = i % (4 * H), cell = r / H, u = r % H, tower = cell >> 1, layer = cell & 1;
+            int env = min(e0 + e, A.N - 1);
+            float keep = (A.done && A.done[env]) ? 0.f : 1.f;
+            int row = (layer == 0 ? OB_DIM : H) + u;
+            s.X[tower][layer][row][swz(row, e)] = hv[it] * keep;
+        }
     }
     for (int i = t; i < 2 * (KP - OB_DIM - H) * TM; i += NTHR) {   // zero padding rows 83..95 of layer 0
         int tower = i / ((KP - OB_DIM - H) * TM), r = i % ((KP - OB_DIM - H) * TM);

@@ -77,6 +77,13 @@ class RaisimGymVecEnv:
         self._extraInfo = np.zeros([self.num_envs, len(self._extraInfoNames)], dtype=np.float32)
         self._ep_ret = np.zeros(self.num_envs, dtype=np.float32)
         self._ep_len = np.zeros(self.num_envs, dtype=np.int32)
+        # the wrapper owns these buffers (as in the reference): page-lock them once so step() DMAs straight into them
+        try:
+            from . import _lib
+            for buf in (self._observation, self._reward, self._done, self._extraInfo):
+                _lib.pin(buf)
+        except Exception:
+            pass
         self._track = track_rewards
         self.rewards = [[] for _ in range(self.num_envs)] if track_rewards else None
 

@@ -19,6 +19,7 @@
 #ifndef IRRL_B200_H
 #define IRRL_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -141,6 +142,11 @@ typedef struct irrl_rollout_buffers {
     int32_t* ep_length;/* [T,N] (may be NULL) */
 } irrl_rollout_buffers;
 int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* buf, int deterministic);
+/* page-lock a caller-owned host buffer (cudaHostRegister) so that irrl_step / irrl_policy_act DMA straight into it
+ * instead of staging through the library's pinned buffer; RaisimGymVecEnv does this once for the buffers it owns
+ * (RaisimGymVecEnv.py:14-19). */
+int irrl_host_register(void* ptr, size_t bytes);
+int irrl_host_unregister(void* ptr);
 /* optional per-kernel timing of irrl_rollout with CUDA events on the env's stream (bench.py's roofline leg) */
 int irrl_set_profiling(irrl_env* env, int on);
 int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total, int64_t* launches_each);

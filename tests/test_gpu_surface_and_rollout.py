@@ -1,0 +1,172 @@
+"""-m gpu: the reference-facing Python surface (RaisimGymVecEnv / FlexibleGymEnv), the device rollout against the
+step-by-step host API, the RefTraj table mode against the oracle, CUDA-side shard determinism and one PPO iteration."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from high_speed_quadrupedal_locomotion_by_irrl_b200 import _lib
+from high_speed_quadrupedal_locomotion_by_irrl_b200._flexible_robot import FlexibleGymEnv
+from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg, dump_yaml
+from high_speed_quadrupedal_locomotion_by_irrl_b200.policy import FusedLstmPolicy, PARAM_NAMES
+from high_speed_quadrupedal_locomotion_by_irrl_b200.vec_env import RaisimGymVecEnv
+from oracle_lib import Oracle, S
+from gpu_lib import Cuda, rel
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _weights():
+    z = np.load(os.path.join(G, "bp5_155_params.npz"))
+    return [z[k] for k in PARAM_NAMES]
+
+
+def test_vecenv_surface_matches_reference_adapter():
+    n = 33
+    env = RaisimGymVecEnv(FlexibleGymEnv("", dump_yaml(trot_cfg(num_envs=n, StochasticDynamics=False))))
+    assert env.num_envs == n and env.num_obs == 35 and env.num_acts == 12
+    assert env.observation_space.shape == (35,) and env.action_space.shape == (12,) and (env.action_space.high == 1).all()
+    assert len(env.extra_info_names) == 6 and "base height" in env.extra_info_names
+    ob = env.reset()
+    assert ob.shape == (n, 35) and ob.dtype == np.float32 and ob is not env._observation           # returns a copy (PYV:98)
+    ob2, rew, done, info = env.step(np.zeros((n, 12), np.float32))
+    assert ob2.shape == (n, 35) and rew.shape == (n,) and done.dtype == bool and len(info) == 6 * n   # PYV:36-38: 6N entries
+    j = env.extra_info_names.index("base height")
+    assert info[j * n + 5]["extra_info"]["base height"] == pytest.approx(float(env._extraInfo[5, j]))
+    assert info.copy() is not None
+    # probes (PYV:54-93)
+    assert env.OriginState().shape == (n, 41) and env.ReferenceState().shape == (n, 24) and env.GetJointEffort().shape == (n, 12)
+    assert env.GetGeneralizedForce().shape == (n, 18) and env.GetInverseMassMatrix().shape == (n, 324) and env.GetNonlinear().shape == (n, 18)
+    Mi = env.GetInverseMassMatrix().reshape(n, 18, 18)
+    assert np.abs(Mi - Mi.transpose(0, 2, 1)).max() < 1e-3 * np.abs(Mi).max()
+    assert np.abs(env.OriginState()[:, 3:7] ** 2).sum(1) == pytest.approx(np.ones(n), abs=1e-5)      # unit quaternions
+    env.SetContactCoefficient(np.tile(np.array([[0.8, 0.2, 0.01]], np.float32), (n, 1)))             # RUN:317-318
+    with pytest.raises(RuntimeError):
+        env.GetSphereInfo()                                                                           # needs Crutial (ENV:1434)
+    env.show_window(); env.hide_window(); env.start_recording_video("x.mp4"); env.stop_recording_video(); env.curriculum_callback()
+    # forcing episodes to end: info[i]['episode'] carries r and l (PYV:42-50)
+    st = np.zeros((n, 192), np.float32); env.wrapper.getState(st); st[:, 2] = 0.05; env.wrapper.setState(st)
+    _, rew, done, info = env.step(np.zeros((n, 12), np.float32))
+    assert done.all()
+    assert all("episode" in info[i] and info[i]["episode"]["l"] == 2 for i in range(n))
+    assert info[0]["episode"]["r"] == pytest.approx(float(info.episodes()[0]["r"]))
+    obs, infos = env.reset_and_update_info()
+    assert len(infos) == n and "episode" in infos[0]
+
+
+def test_numpy_argument_checks_like_pybind_eigen_ref():
+    n = 4
+    w = FlexibleGymEnv("", dump_yaml(trot_cfg(num_envs=n, StochasticDynamics=False))); w.init()
+    good = [np.zeros((n, 12), np.float32), np.zeros((n, 35), np.float32), np.zeros(n, np.float32), np.zeros(n, bool), np.zeros((n, 6), np.float32)]
+    w.step(*good)
+    for i, bad in ((0, np.zeros((n, 12), np.float64)), (1, np.zeros((n, 36), np.float32)), (2, np.zeros((n, 1), np.float32)),
+                   (1, np.zeros((35, n), np.float32).T), (3, np.zeros(n, np.int32))):
+        args = list(good); args[i] = bad
+        with pytest.raises(TypeError):
+            w.step(*args)
+
+
+def test_test_step_advances_only_env0():
+    n = 5
+    c = Cuda(trot_cfg(num_envs=n, StochasticDynamics=False, ObsNoise=0.0))
+    before = c.get_state()
+    ob = np.full((n, 35), 7.0, np.float32); rew = np.full(n, 7.0, np.float32); done = np.zeros(n, bool); ex = np.full((n, 6), 7.0, np.float32)
+    c.env.testStep(np.zeros((n, 12), np.float32), ob, rew, done, ex)
+    after = c.get_state()
+    assert np.abs(after[0, S["gc"]] - before[0, S["gc"]]).max() > 0
+    assert np.array_equal(after[1:, S["gc"]], before[1:, S["gc"]])
+    assert (ob[1:] == 7.0).all() and (rew[1:] == 7.0).all() and rew[0] != 7.0      # VEC:280-290 touches row 0 only
+
+
+def test_device_rollout_equals_step_by_step_host_calls():
+    import torch
+    n, T = 96, 12
+    cfg = trot_cfg(num_envs=n, StochasticDynamics=True, ObsNoise=2.0)
+    W = _weights()
+    L = _lib.load()
+    # (a) device rollout
+    a = Cuda(cfg); pol_a = FusedLstmPolicy(W, n_env=n, seed=a.env._L.irrl_get_num_envs(a.env.handle) * 0 + 1)
+    dev = torch.device("cuda:0")
+    f = dict(device=dev, dtype=torch.float32)
+    buf = dict(obs=torch.empty((T, n, 35), **f), actions=torch.empty((T, n, 12), **f), values=torch.empty((T, n), **f), neglogps=torch.empty((T, n), **f),
+               rewards=torch.empty((T, n), **f), dones=torch.empty((T, n), device=dev, dtype=torch.uint8))
+    cur_obs = torch.zeros((n, 35), **f); cur_done = torch.zeros((n,), device=dev, dtype=torch.uint8); state = torch.zeros((n, 384), **f)
+    a.env.setTick(9); a.env.reset(cur_obs)
+    rb = _lib.RolloutBuffers(obs=buf["obs"].data_ptr(), actions=buf["actions"].data_ptr(), values=buf["values"].data_ptr(), neglogps=buf["neglogps"].data_ptr(),
+                             rewards=buf["rewards"].data_ptr(), dones=buf["dones"].data_ptr(), cur_obs=cur_obs.data_ptr(), cur_done=cur_done.data_ptr(),
+                             state=state.data_ptr(), ep_return=None, ep_length=None)
+    _lib.check(L.irrl_rollout(a.env.handle, pol_a.handle, T, C.byref(rb), 0))
+    torch.cuda.synchronize()
+    # (b) the same through host numpy calls (model.step + env.step), same seeds and ticks
+    b = Cuda(cfg); pol_b = FusedLstmPolicy(W, n_env=n, seed=1)
+    b.env.setTick(9); ob = b.reset()
+    st = np.zeros((n, 384), np.float32); done = np.zeros(n, bool)
+    for t in range(T):
+        tick = b.env.getTick()
+        act, val, st, nlp, clip = pol_b.step(ob, st, done, tick=tick, return_clipped=True)
+        assert np.array_equal(buf["obs"][t].cpu().numpy(), ob)
+        assert np.array_equal(buf["actions"][t].cpu().numpy(), act) and np.array_equal(buf["values"][t].cpu().numpy(), val)
+        assert np.array_equal(buf["dones"][t].cpu().numpy().astype(bool), done)
+        ob, rew, done, _ = b.step(clip)
+        assert np.array_equal(buf["rewards"][t].cpu().numpy(), rew)
+    assert np.array_equal(cur_obs.cpu().numpy(), ob) and np.array_equal(state.cpu().numpy(), st)
+
+
+def test_cuda_shards_equal_one_job():
+    cfg = trot_cfg(num_envs=64, StochasticDynamics=True, ObsNoise=2.0)
+    whole = Cuda(cfg); a = Cuda(dict(cfg, num_envs=32), env_offset=0); b = Cuda(dict(cfg, num_envs=32), env_offset=32)
+    for c in (whole, a, b):
+        c.env.setTick(4)
+    ow, oa, ob = whole.reset(), a.reset(), b.reset()
+    assert np.array_equal(ow[:32], oa) and np.array_equal(ow[32:], ob)
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        act = np.clip(rng.normal(0, 0.2, size=(64, 12)), -1, 1).astype(np.float32)
+        w = whole.step(act); x = a.step(act[:32]); y = b.step(act[32:])
+        for i in range(4):
+            assert np.array_equal(w[i][:32], x[i]) and np.array_equal(w[i][32:], y[i])
+
+
+def test_ref_traj_table_mode_matches_oracle(tmp_path):
+    """ManualTraj False: references, phase and command come from the [rows,30] table (ENV:17-21, 972, 1102-1106, 1664-1682),
+    loaded from the CSV named by RefTraj (VEC:33-76, 158-182)."""
+    rows = 4000
+    rng = np.random.default_rng(11)
+    tab = np.zeros((rows, 30), np.float32)
+    tt = np.arange(rows) * 0.002
+    tab[:, 0:12] = np.tile([0.0, -0.78, 1.57], 4) + 0.2 * np.sin(2 * np.pi * 5 * tt)[:, None] * rng.uniform(0.5, 1, 12)
+    tab[:, 12:24] = np.gradient(tab[:, 0:12], 0.002, axis=0)
+    tab[:, 24] = 0.28; tab[:, 25] = np.sin(2 * np.pi * 5 * tt); tab[:, 26] = np.cos(2 * np.pi * 5 * tt); tab[:, 27] = 1.0
+    path = tmp_path / "ref_traj.csv"
+    np.savetxt(path, tab, delimiter=",", fmt="%.7g")
+    n = 48
+    cfg = trot_cfg(num_envs=n, num_threads=4, StochasticDynamics=False, ObsNoise=0.0, ManualTraj=False, RefTraj=str(path))
+    c = Cuda(cfg)
+    o = Oracle(cfg); o.L.bp5o_set_ref(o.h, np.loadtxt(path, delimiter=",", dtype=np.float32).ctypes.data_as(C.c_void_p), rows)
+    o.set_tick(1); c.env.setTick(1)
+    obo, obg = o.reset(), c.reset()
+    assert rel(obg, obo) < 1e-5
+    so, sg = o.get_state(), c.get_state()
+    assert np.array_equal(sg[:, S["frame_idx"]], so[:, S["frame_idx"]]) and so[:, S["frame_idx"]].max() > 100   # random start frames
+    for t in range(8):
+        c.set_state(o.get_state().astype(np.float32))
+        act = np.clip(rng.normal(0, 0.2, size=(n, 12)), -1, 1).astype(np.float32)
+        obo, ro, do, _ = o.step(act); obg, rg, dg, _ = c.step(act)
+        assert (do == dg).all() and rel(obg, obo) < 2e-5 and rel(rg, ro) < 2e-5
+
+
+def test_one_ppo_iteration_runs_and_updates_parameters():
+    import torch
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.ppo2 import PPO2
+    n = 64
+    env = RaisimGymVecEnv(FlexibleGymEnv("", dump_yaml(trot_cfg(num_envs=n, StochasticDynamics=True, ObsNoise=2.0))))
+    model = PPO2(env, policy_params=_weights(), n_steps=24, noptepochs=2, learning_rate=1e-4, verbose=0)
+    before = [p.clone() for p in model.model.param_list()]
+    hist = model.learn(total_timesteps=n * 24)
+    assert len(hist) == 1 and np.isfinite(hist[0]["policy_loss"]) and np.isfinite(hist[0]["value_loss"]) and hist[0]["fps"] > 0
+    changed = [float((a - b).abs().max()) for a, b in zip(model.model.param_list(), before)]
+    names_changed = [nm for nm, c in zip(PARAM_NAMES, changed) if c > 0]
+    assert "lstm_pi0_wx" in names_changed and "vf_w" in names_changed and "q_w" not in names_changed
+    assert len(hist[0]) >= 10 and np.isfinite(hist[0]["ep_reward_mean"])

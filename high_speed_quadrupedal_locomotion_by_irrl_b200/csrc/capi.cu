@@ -70,6 +70,7 @@ struct irrl_env_impl {
     uint32_t tick = 0;
     bool initialised = false;
     std::string resource_dir, ref_path;
+    double max_time_d = 0, control_dt_d = 0, sim_dt_d = 0;   // YAML values in double: integer counts are derived like the reference does
     std::vector<std::string> extra_names;
     // staging (device + pinned host)
     float *d_action = nullptr, *d_ob = nullptr, *d_reward = nullptr, *d_extra = nullptr, *d_ep_ret = nullptr, *d_scratch = nullptr;
@@ -127,6 +128,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         IGN("num_threads");
         double sim_dt, ctl_dt; if (!num("simulation_dt", sim_dt)) goto bad; if (!num("control_dt", ctl_dt)) goto bad;
         P.sim_dt = (float)sim_dt; P.control_dt = (float)ctl_dt; P.loop_count = int(ctl_dt / sim_dt + 1e-10);   // ENV:711
+        E->control_dt_d = ctl_dt; E->sim_dt_d = sim_dt;
         if (!num("seedd", d)) goto bad; P.seed = (uint32_t)(int)d;                                               // VEC:171
         // ENV:1598-1613
         NUM("abad", P.abad) NUM("period", P.period) NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
@@ -146,7 +148,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         // ENV:1643-1658
         NUM("Stiffness", P.stiffness) IGN("Stiffness_Low") NUM("AbadRatio", P.abad_ratio) NUM("Damping", P.damping)
         double freq; if (!num("Freq", freq)) goto bad;
-        NUM("max_time", P.max_time) IGN("CubeNum") IGN("FPS") NUM("ActionNoise", P.action_noise) NUM("ObsNoise", P.noise_flag)
+        NUM("max_time", P.max_time) E->max_time_d = d; IGN("CubeNum") IGN("FPS") NUM("ActionNoise", P.action_noise) NUM("ObsNoise", P.noise_flag)
         if (!num("GaitType", d)) goto bad; P.gait_type = (int)d;
         NUM("MotorMaxTorque", P.motor_max_torque) NUM("MotorCriticalSpeed", P.motor_crit_speed) NUM("MotorMaxSpeed", P.motor_max_speed)
         P.filter_para = P.flag_filter ? (float)(1.0 - freq * ctl_dt) : 0.f;                                      // ENV:396
@@ -433,8 +435,8 @@ int irrl_running_episode_stats(irrl_env* env, float* ep_return, int32_t* ep_leng
 
 int irrl_set_seed(irrl_env* env, int seed) { ENV(env); E->P.seed = (uint32_t)seed; return 0; }
 int irrl_close(irrl_env* env) { ENV(env); if (E->stream) CUDA_OK(cudaStreamSynchronize(E->stream)); return 0; }
-int irrl_set_simulation_time_step(irrl_env* env, double dt) { ENV(env); E->P.sim_dt = (float)dt; E->P.loop_count = int((double)E->P.control_dt / dt + 1e-10); return 0; }
-int irrl_set_control_time_step(irrl_env* env, double dt) { ENV(env); E->P.control_dt = (float)dt; E->P.loop_count = int(dt / (double)E->P.sim_dt + 1e-10); return 0; }
+int irrl_set_simulation_time_step(irrl_env* env, double dt) { ENV(env); E->P.sim_dt = (float)dt; E->sim_dt_d = dt; E->P.loop_count = int(E->control_dt_d / dt + 1e-10); return 0; }
+int irrl_set_control_time_step(irrl_env* env, double dt) { ENV(env); E->P.control_dt = (float)dt; E->control_dt_d = dt; E->P.loop_count = int(dt / E->sim_dt_d + 1e-10); return 0; }
 int irrl_curriculum_update(irrl_env* env) { ENV(env); return 0; }
 int irrl_start_recording_video(irrl_env* env, const char*) { ENV(env); return 0; }
 int irrl_stop_recording_video(irrl_env* env) { ENV(env); return 0; }
@@ -537,7 +539,7 @@ int irrl_set_ref_traj(irrl_env* env, const float* table, int rows) {
     if (!table || rows <= 0) return fail(-1, "empty reference table");
     float* d = nullptr; CUDA_OK(cudaMalloc((void**)&d, (size_t)rows * 30 * sizeof(float))); E->allocs.push_back(d);
     CUDA_OK(cudaMemcpy(d, table, (size_t)rows * 30 * sizeof(float), is_device_ptr(table) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-    E->d_ref = d; E->P.ref = d; E->P.ref_rows = rows; E->P.frame_max = rows / 2; E->P.frame_len = int(E->P.max_time / E->P.control_dt);   // ENV:538-539
+    E->d_ref = d; E->P.ref = d; E->P.ref_rows = rows; E->P.frame_max = rows / 2; E->P.frame_len = int(E->max_time_d / E->control_dt_d);   // ENV:538-539 (double, like the reference)
     return 0;
 }
 

@@ -62,6 +62,8 @@ def load() -> C.CDLL:
     L.irrl_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.irrl_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.irrl_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.irrl_lstm_pw_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
+    L.irrl_lstm_pw_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9
     L.irrl_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.irrl_host_unregister.argtypes = [C.c_void_p]
     _lib = L
@@ -75,9 +77,15 @@ def check(rc: int, what: str = "") -> None:
 
 
 def pin(array) -> bool:
-    """Page-lock a numpy array in place (cudaHostRegister) so the C ABI can DMA straight into it.  Returns False
-    (and leaves the array pageable) when registration is not possible."""
+    """Page-lock a numpy array in place (cudaHostRegister) so the C ABI can DMA straight into it; the registration is
+    dropped again when the array is garbage-collected.  Returns False (array stays pageable) when not possible."""
+    import weakref
     try:
-        return load().irrl_host_register(C.c_void_p(array.ctypes.data), C.c_size_t(array.nbytes)) == 0
+        L = load()
+        addr = array.ctypes.data
+        if L.irrl_host_register(C.c_void_p(addr), C.c_size_t(array.nbytes)) != 0:
+            return False
+        weakref.finalize(array, L.irrl_host_unregister, C.c_void_p(addr))
+        return True
     except Exception:
         return False

@@ -99,11 +99,16 @@ bool is_device_ptr(const void* p) {
 }
 
 // page-locked host memory (cudaHostAlloc / cudaHostRegister): DMA can target it directly, no staging copy needed
-bool is_pinned_host_ptr(const void* p) {
+bool is_pinned_host_ptr(const void* p, size_t bytes = 1) {
     if (!p) return false;
-    cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    // both ends of the range must be page-locked (a stale registration may cover only part of a recycled allocation)
+    const void* ends[2] = {p, static_cast<const char*>(p) + (bytes ? bytes - 1 : 0)};
+    for (const void* q : ends) {
+        cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, q);
+        if (e != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
 }
 
 template <typename T> int dev_alloc(irrl_env_impl* E, T** p, size_t n) {
@@ -231,7 +236,7 @@ int ensure_scratch(irrl_env_impl* E, size_t floats) {
 int deliver(irrl_env_impl* E, void* user, const void* dev, size_t bytes) {
     if (!user) return 0;
     if (is_device_ptr(user)) { CUDA_OK(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToDevice, E->stream)); return 0; }
-    if (is_pinned_host_ptr(user)) {
+    if (is_pinned_host_ptr(user, bytes)) {
         CUDA_OK(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, E->stream));
         CUDA_OK(cudaStreamSynchronize(E->stream)); return 0;
     }
@@ -372,7 +377,7 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
     unsigned char* pin = E->h_pin;
     float* p_act = reinterpret_cast<float*>(pin);
     float* p_ob = p_act + N * 12; float* p_rew = p_ob + N * 35; float* p_ext = p_rew + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_ext + N * 6);
-    const bool pa = is_pinned_host_ptr(action), po = ob && is_pinned_host_ptr(ob), pr = is_pinned_host_ptr(reward), pd = is_pinned_host_ptr(done), pe = extra && is_pinned_host_ptr(extra);
+    const bool pa = is_pinned_host_ptr(action, N * 48), po = ob && is_pinned_host_ptr(ob, N * 140), pr = is_pinned_host_ptr(reward, N * 4), pd = is_pinned_host_ptr(done, N), pe = extra && is_pinned_host_ptr(extra, N * 24);
     if (!pa) memcpy(p_act, action, N * 12 * sizeof(float));
     CUDA_OK(cudaMemcpyAsync(E->d_action, pa ? action : p_act, N * 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
     StepArgs a = make_args(E, E->d_action, E->P.flag_obs_filter ? nullptr : E->d_ob, E->d_reward, E->d_done, E->d_extra);
@@ -648,8 +653,8 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
     }
     float* p_obs = reinterpret_cast<float*>(Pn->h_pin); float* p_state = p_obs + N * 35; float* p_act = p_state + N * 384; float* p_clip = p_act + N * 12;
     float* p_val = p_clip + N * 12; float* p_nlp = p_val + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_nlp + N);
-    const bool q_obs = h_obs && is_pinned_host_ptr(obs), q_done = h_done && is_pinned_host_ptr(done), q_state = h_state && is_pinned_host_ptr(state),
-               q_act = h_act && is_pinned_host_ptr(action), q_clip = h_clip && is_pinned_host_ptr(clipped), q_val = h_val && is_pinned_host_ptr(value), q_nlp = h_nlp && is_pinned_host_ptr(neglogp);
+    const bool q_obs = h_obs && is_pinned_host_ptr(obs, N * 140), q_done = h_done && is_pinned_host_ptr(done, N), q_state = h_state && is_pinned_host_ptr(state, N * 1536),
+               q_act = h_act && is_pinned_host_ptr(action, N * 48), q_clip = h_clip && is_pinned_host_ptr(clipped, N * 48), q_val = h_val && is_pinned_host_ptr(value, N * 4), q_nlp = h_nlp && is_pinned_host_ptr(neglogp, N * 4);
     if (h_obs) { if (!q_obs) memcpy(p_obs, obs, N * 35 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_obs, q_obs ? obs : p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st)); }
     if (h_state) { if (!q_state) memcpy(p_state, state, N * 384 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_state, q_state ? state : p_state, N * 384 * 4, cudaMemcpyHostToDevice, st)); }
     if (h_done) { if (!q_done) memcpy(p_done, done, N); CUDA_OK(cudaMemcpyAsync(Pn->d_done, q_done ? done : p_done, N, cudaMemcpyHostToDevice, st)); }
@@ -722,9 +727,19 @@ int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total,
     return 0;
 }
 
+int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,
+                     float* c_out, float* h_out, float* hm_next, float* cm_next) {
+    launch_lstm_pw_fwd(rows, n_env, z, c_prev_masked, keep_next, gates, c_out, h_out, hm_next, cm_next, reinterpret_cast<cudaStream_t>(cuda_stream));
+    CUDA_OK(cudaGetLastError()); return 0;
+}
+int irrl_lstm_pw_bwd(void* cuda_stream, int rows, int n_env, const float* dh_out, const float* carry_h, const float* carry_c, const float* keep_up,
+                     const float* gates, const float* c, const float* c_prev_masked, float* dz, float* dcm_prev) {
+    launch_lstm_pw_bwd(rows, n_env, dh_out, carry_h, carry_c, keep_up, gates, c, c_prev_masked, dz, dcm_prev, reinterpret_cast<cudaStream_t>(cuda_stream));
+    CUDA_OK(cudaGetLastError()); return 0;
+}
 int irrl_host_register(void* ptr, size_t bytes) {
     if (!ptr || !bytes) return fail(-1, "irrl_host_register: null argument");
-    if (is_pinned_host_ptr(ptr)) return 0;
+    if (is_pinned_host_ptr(ptr, bytes)) return 0;
     CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0;
 }
 int irrl_host_unregister(void* ptr) { if (!ptr) return 0; cudaError_t e = cudaHostUnregister(ptr); if (e != cudaSuccess) cudaGetLastError(); return 0; }

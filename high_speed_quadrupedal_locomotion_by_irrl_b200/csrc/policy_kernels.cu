@@ -213,4 +213,50 @@ void launch_gae(const float* rewards, const float* values, const uint8_t* dones,
     gae_kernel<<<(N + 127) / 128, 128, 0, st>>>(rewards, values, dones, last_values, last_dones, adv, ret, T, N, gamma, lam);
 }
 
+// ------------------------------------------------------------------ BPTT building blocks for the PPO learner (ppo2.py:136-197)
+// The recurrent part of training is a time loop of [h W_h GEMM (cuBLAS) -> fused cell kernel]; these two kernels are the fused
+// element-wise halves (forward and backward) so that one LSTM step costs two launches instead of ~30 element-wise ones.
+// rows = towers * envs; z / gates are [rows,192] in the checkpoint's gate order i,f,o,g; everything else [rows,48].
+__global__ void lstm_pw_fwd_kernel(int rows, int n_env, const float* __restrict__ z, const float* __restrict__ c_prev_masked,
+                                   const float* __restrict__ keep_next, float* __restrict__ gates, float* __restrict__ c_out,
+                                   float* __restrict__ h_out, float* __restrict__ hm_next, float* __restrict__ cm_next) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= rows * H) return;
+    int r = idx / H, u = idx % H;
+    const float* zr = z + (size_t)r * G4;
+    float i = 1.f / (1.f + expf(-zr[u])), f = 1.f / (1.f + expf(-zr[H + u])), o = 1.f / (1.f + expf(-zr[2 * H + u])), g = tanhf(zr[3 * H + u]);
+    float c = f * c_prev_masked[idx] + i * g, h = o * tanhf(c);
+    float* gr = gates + (size_t)r * G4; gr[u] = i; gr[H + u] = f; gr[2 * H + u] = o; gr[3 * H + u] = g;
+    c_out[idx] = c; h_out[idx] = h;
+    float k = keep_next ? keep_next[r % n_env] : 1.f;          // SB lstm(): c *= 1-m ; h *= 1-m before the next cell
+    hm_next[idx] = h * k; cm_next[idx] = c * k;
+}
+// dh_out [rows,48] = dL/dh_t from above; carry_h = dz_{t+1} W_h^T (gradient w.r.t. the masked h fed to step t+1), carry_c likewise;
+// keep_up = keep_{t+1}.  Outputs dz_t [rows,192] and carry_c for step t-1 (gradient w.r.t. the masked c fed to this step).
+__global__ void lstm_pw_bwd_kernel(int rows, int n_env, const float* __restrict__ dh_out, const float* __restrict__ carry_h,
+                                   const float* __restrict__ carry_c, const float* __restrict__ keep_up, const float* __restrict__ gates,
+                                   const float* __restrict__ c, const float* __restrict__ c_prev_masked, float* __restrict__ dz,
+                                   float* __restrict__ dcm_prev) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= rows * H) return;
+    int r = idx / H, u = idx % H;
+    float k = keep_up ? keep_up[r % n_env] : 0.f;
+    float dh = dh_out[idx] + (carry_h ? carry_h[idx] * k : 0.f);
+    float dc = carry_c ? carry_c[idx] * k : 0.f;
+    const float* gr = gates + (size_t)r * G4;
+    float i = gr[u], f = gr[H + u], o = gr[2 * H + u], g = gr[3 * H + u];
+    float tc = tanhf(c[idx]);
+    dc += dh * o * (1.f - tc * tc);
+    float* dr = dz + (size_t)r * G4;
+    dr[u] = dc * g * i * (1.f - i); dr[H + u] = dc * c_prev_masked[idx] * f * (1.f - f);
+    dr[2 * H + u] = dh * tc * o * (1.f - o); dr[3 * H + u] = dc * i * (1.f - g * g);
+    dcm_prev[idx] = dc * f;
+}
+void launch_lstm_pw_fwd(int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates, float* c_out,
+                        float* h_out, float* hm_next, float* cm_next, cudaStream_t st) {
+    lstm_pw_fwd_kernel<<<(rows * H + 255) / 256, 256, 0, st>>>(rows, n_env, z, c_prev_masked, keep_next, gates, c_out, h_out, hm_next, cm_next);
+}
+void launch_lstm_pw_bwd(int rows, int n_env, const float* dh_out, const float* carry_h, const float* carry_c, const float* keep_up,
+                        const float* gates, const float* c, const float* c_prev_masked, float* dz, float* dcm_prev, cudaStream_t st) {
+    lstm_pw_bwd_kernel<<<(rows * H + 255) / 256, 256, 0, st>>>(rows, n_env, dh_out, carry_h, carry_c, keep_up, gates, c, c_prev_masked, dz, dcm_prev);
+}
+
 }  // namespace irrl

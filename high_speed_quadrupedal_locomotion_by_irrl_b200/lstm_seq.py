@@ -1,0 +1,80 @@
+"""Manual BPTT through one LSTM layer of BOTH towers over a whole rollout, for the PPO learner (ppo2.py:136-197).
+
+Time loop = [batched h W_h GEMM (cuBLAS) -> fused cell kernel (irrl_lstm_pw_fwd / _bwd)]: two launches per step in each direction.
+The input projections x W_x + b of all T steps and the weight gradient dW_h = sum_t h_{t-1}^T dz_t are single large GEMMs outside
+the loop.  Layout is time-major ([T, tower, env, ...]) -- exactly how the device rollout stores mb_* -- so every step is a contiguous slice.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class LstmLayerSeq(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xw, wh, c0, h0, keep):
+        """xw [T,K,N,192] (x W_x + b), wh [K,48,192], c0/h0 [K,N,48] state before step 0 (unmasked), keep [T,N] = 1 - mask.
+        Returns H [T,K,N,48] (unmasked outputs), c_T, h_T [K,N,48]."""
+        L = _lib.load()
+        T, K, N, _ = xw.shape
+        rows = K * N
+        st = C.c_void_p(torch.cuda.current_stream(xw.device).cuda_stream)
+        xw = xw.contiguous(); keep = keep.contiguous()
+        gates = torch.empty_like(xw); Cs = xw.new_empty((T, K, N, 48)); Hs = xw.new_empty((T, K, N, 48))
+        HM = xw.new_empty((T, K, N, 48)); CM = xw.new_empty((T, K, N, 48))          # masked h/c fed INTO step t
+        HM[0] = h0 * keep[0].view(1, N, 1); CM[0] = c0 * keep[0].view(1, N, 1)
+        hm_n = xw.new_empty((K, N, 48)); cm_n = xw.new_empty((K, N, 48))
+        z = xw.new_empty((K, N, 192))
+        for t in range(T):
+            torch.baddbmm(xw[t], HM[t], wh, out=z)
+            last = t + 1 == T
+            _lib.check(L.irrl_lstm_pw_fwd(st, rows, N, _p(z), _p(CM[t]), _p(keep[t + 1]) if not last else None, _p(gates[t]), _p(Cs[t]), _p(Hs[t]),
+                                          _p(HM[t + 1]) if not last else _p(hm_n), _p(CM[t + 1]) if not last else _p(cm_n)))
+        ctx.save_for_backward(wh, keep, gates, Cs, HM, CM)
+        return Hs, Cs[T - 1].clone(), Hs[T - 1].clone()
+
+    @staticmethod
+    def backward(ctx, dH, dcT, dhT):
+        L = _lib.load()
+        wh, keep, gates, Cs, HM, CM = ctx.saved_tensors
+        T, K, N, _ = gates.shape
+        rows = K * N
+        st = C.c_void_p(torch.cuda.current_stream(gates.device).cuda_stream)
+        dH = dH.contiguous()
+        DZ = torch.empty_like(gates)
+        whT = wh.transpose(1, 2).contiguous()
+        carry_h = gates.new_empty((K, N, 48)); carry_c = gates.new_empty((K, N, 48)); carry_c2 = gates.new_empty((K, N, 48))
+        dh_last = dH[T - 1] + (dhT if dhT is not None else 0)
+        for t in range(T - 1, -1, -1):
+            last = t + 1 == T
+            dh_in = dh_last if last else dH[t]
+            _lib.check(L.irrl_lstm_pw_bwd(st, rows, N, _p(dh_in.contiguous()), None if last else _p(carry_h), None if last else _p(carry_c),
+                                          None if last else _p(keep[t + 1]), _p(gates[t]), _p(Cs[t]), _p(CM[t]), _p(DZ[t]), _p(carry_c2)))
+            carry_c, carry_c2 = carry_c2, carry_c
+            torch.bmm(DZ[t], whT, out=carry_h)            # gradient w.r.t. the masked h fed to step t
+        # weight gradient: one batched GEMM over all (t, env) rows
+        dwh = torch.bmm(HM.permute(1, 3, 0, 2).reshape(K, 48, T * N), DZ.permute(1, 0, 2, 3).reshape(K, T * N, 192))
+        return DZ, dwh, None, None, None
+
+
+def lstm_layer_reference(xw, wh, c0, h0, keep):
+    """The same computation with plain autograd ops (CPU tests / cross-check of the manual backward)."""
+    T, K, N, _ = xw.shape
+    c, h = c0, h0
+    out = []
+    for t in range(T):
+        k = keep[t].view(1, N, 1)
+        c = c * k; h = h * k
+        z = xw[t] + torch.bmm(h, wh)
+        i, f, o, g = z.chunk(4, dim=2)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out.append(h)
+    return torch.stack(out, 0), c, h

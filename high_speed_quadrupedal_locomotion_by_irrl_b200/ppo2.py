@@ -74,6 +74,27 @@ class LstmActorCritic(torch.nn.Module):
         new_state = torch.cat([cs[0], hs[0], cs[1], hs[1], cs[2], hs[2], cs[3], hs[3]], 1)
         return mean, value, new_state
 
+    def forward_time_major(self, obs, keep, state, fused: Optional[bool] = None):
+        """obs [T,N,35] (time-major, as the device rollout stores it), keep [T,N] = 1 - mask, state [N,384] at t = 0.
+        Returns mean [T,N,12], value [T,N].  On CUDA the recurrence runs through the fused BPTT path (lstm_seq.LstmLayerSeq)."""
+        from .lstm_seq import LstmLayerSeq, lstm_layer_reference
+        T, N, _ = obs.shape
+        H = 48
+        fused = obs.is_cuda if fused is None else fused
+        layer = LstmLayerSeq.apply if fused else lstm_layer_reference
+        st = state.view(N, 2, 2, 2, H)                                  # [env, tower, layer, (c,h), unit]
+        c0 = st[:, :, 0, 0].transpose(0, 1).contiguous(); h0 = st[:, :, 0, 1].transpose(0, 1).contiguous()
+        c1 = st[:, :, 1, 0].transpose(0, 1).contiguous(); h1 = st[:, :, 1, 1].transpose(0, 1).contiguous()
+        wx0 = torch.stack([self.lstm_pi0_wx, self.lstm_v0_wx]); wh0 = torch.stack([self.lstm_pi0_wh, self.lstm_v0_wh]); b0 = torch.stack([self.lstm_pi0_b, self.lstm_v0_b])
+        wx1 = torch.stack([self.lstm_pi1_wx, self.lstm_v1_wx]); wh1 = torch.stack([self.lstm_pi1_wh, self.lstm_v1_wh]); b1 = torch.stack([self.lstm_pi1_b, self.lstm_v1_b])
+        xw0 = torch.matmul(obs.unsqueeze(1), wx0) + b0.view(1, 2, 1, -1)             # [T,2,N,192]: all input projections in one GEMM
+        H0, _, _ = layer(xw0, wh0, c0, h0, keep)
+        xw1 = torch.matmul(H0, wx1) + b1.view(1, 2, 1, -1)
+        H1, _, _ = layer(xw1, wh1, c1, h1, keep)
+        mean = H1[:, 0] @ self.pi_w + self.pi_b
+        value = (H1[:, 1] @ self.vf_w + self.vf_b).squeeze(-1)
+        return mean, value
+
     def neglogp(self, mean, actions):
         logstd = self.pi_logstd.reshape(1, 1, -1)                                        # SURVEY.md 9.8
         return 0.5 * (((actions - mean) / logstd.exp()) ** 2).sum(-1) + 0.5 * LOG2PI * actions.shape[-1] + logstd.sum()
@@ -82,9 +103,13 @@ class LstmActorCritic(torch.nn.Module):
         return (self.pi_logstd + 0.5 * (LOG2PI + 1.0)).sum()
 
 
-def ppo_loss(model: LstmActorCritic, obs, masks, state, actions, advs, returns, old_values, old_neglogp, cliprange, ent_coef, vf_coef):
-    """ppo2.py:152-175 on [N,T,...] tensors (env-major like swap_and_flatten); advs already normalised."""
-    mean, vpred, _ = model.forward_sequence(obs, masks, state)
+def ppo_loss(model: LstmActorCritic, obs, masks, state, actions, advs, returns, old_values, old_neglogp, cliprange, ent_coef, vf_coef, time_major=False):
+    """ppo2.py:152-175.  Env-major [N,T,...] tensors (swap_and_flatten order) or, with time_major=True, [T,N,...] ones
+    (the device rollout's native layout, served by the fused BPTT path); advs already normalised."""
+    if time_major:
+        mean, vpred = model.forward_time_major(obs, 1.0 - masks, state)
+    else:
+        mean, vpred, _ = model.forward_sequence(obs, masks, state)
     neglogpac = model.neglogp(mean, actions)
     entropy = model.entropy()
     vpredclipped = old_values + torch.clamp(vpred - old_values, -cliprange, cliprange)
@@ -222,21 +247,24 @@ class PPO2:
     def _update(self, mb_states, lr, cliprange):
         b = self._buf
         N, T = self.n_envs, self.n_steps
-        # env-major views (swap_and_flatten, ppo2.py:572-574)
-        obs = b["obs"].transpose(0, 1); actions = b["actions"].transpose(0, 1); returns = b["ret"].transpose(0, 1)
-        values = b["values"].transpose(0, 1); neglogps = b["neglogps"].transpose(0, 1); masks = b["dones"].transpose(0, 1).float()
+        # the rollout buffers are time-major [T,N,...]; an env minibatch is a gather along dim 1 (the reference flattens env-major,
+        # ppo2.py:572-574 / 385-386 -- same samples, the loss is a mean over them)
+        obs, actions, returns, values, neglogps = b["obs"], b["actions"], b["ret"], b["values"], b["neglogps"]
+        masks = b["dones"].float()
         envs_per_batch = N // self.nminibatches
         gen = torch.Generator(device="cpu"); gen.manual_seed(self.num_timesteps + 17 * self.rank)
         stats: List[Dict[str, torch.Tensor]] = []
+        full = self.nminibatches == 1
         for epoch in range(self.noptepochs):
             perm = torch.randperm(N, generator=gen).to(self.dev)                          # ppo2.py:388 shuffle env indices
             for start in range(0, N, envs_per_batch):
                 idx = perm[start:start + envs_per_batch]
-                advs = returns[idx] - values[idx]                                         # ppo2.py:262
+                sel = (lambda x: x) if full else (lambda x: x.index_select(1, idx))        # with one minibatch the order is irrelevant
+                advs = sel(returns) - sel(values)                                         # ppo2.py:262
                 mean, std = global_mean_std(advs)
                 advs = (advs - mean) / (std + 1e-8)                                       # ppo2.py:263
-                loss, st = ppo_loss(self.model, obs[idx], masks[idx], mb_states[idx], actions[idx], advs, returns[idx], values[idx], neglogps[idx],
-                                    cliprange, self.ent_coef, self.vf_coef)
+                loss, st = ppo_loss(self.model, sel(obs), sel(masks), mb_states if full else mb_states[idx], sel(actions), advs, sel(returns), sel(values),
+                                    sel(neglogps), cliprange, self.ent_coef, self.vf_coef, time_major=True)
                 grads = torch.autograd.grad(loss, self.model.param_list(), allow_unused=True)
                 grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, self.model.param_list())]   # the q head is unused by the loss
                 grads = allreduce_grads(grads)

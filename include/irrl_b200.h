@@ -142,6 +142,12 @@ typedef struct irrl_rollout_buffers {
     int32_t* ep_length;/* [T,N] (may be NULL) */
 } irrl_rollout_buffers;
 int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* buf, int deterministic);
+/* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,
+ * z / gates [rows,192] in gate order i,f,o,g, the rest [rows,48]; keep = 1 - done mask per env (run_bp_v5.py:151-153 lstm(..., masks, ...)) */
+int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,
+                     float* c_out, float* h_out, float* hm_next, float* cm_next);
+int irrl_lstm_pw_bwd(void* cuda_stream, int rows, int n_env, const float* dh_out, const float* carry_h, const float* carry_c, const float* keep_up,
+                     const float* gates, const float* c, const float* c_prev_masked, float* dz, float* dcm_prev);
 /* page-lock a caller-owned host buffer (cudaHostRegister) so that irrl_step / irrl_policy_act DMA straight into it
  * instead of staging through the library's pinned buffer; RaisimGymVecEnv does this once for the buffers it owns
  * (RaisimGymVecEnv.py:14-19). */

@@ -134,3 +134,12 @@ def test_world_size_2_gloo_advantage_stats_and_gradient_allreduce():
     for rank, ok_stats, err in res:
         assert ok_stats, rank
         assert err < 2e-6, (rank, err)      # mean over equal shards == mean over the concatenated batch
+
+
+def test_time_major_forward_equals_env_major_forward_cpu():
+    W = _weights(); m = LstmActorCritic(W)
+    rng = np.random.default_rng(6)
+    obs, masks, st, *_ = _batch(rng, 5, 8)
+    mean_a, val_a, _ = m.forward_sequence(torch.tensor(obs), torch.tensor(masks), torch.tensor(st))
+    mean_b, val_b = m.forward_time_major(torch.tensor(obs).transpose(0, 1).contiguous(), 1.0 - torch.tensor(masks).t().contiguous(), torch.tensor(st), fused=False)
+    assert torch.allclose(mean_a.transpose(0, 1), mean_b, atol=1e-5) and torch.allclose(val_a.t(), val_b, atol=1e-5)

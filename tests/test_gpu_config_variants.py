@@ -1,0 +1,98 @@
+"""-m gpu: every YAML switch of the hot path (ENV:1616-1629, 1643-1658) against the oracle: action low-pass filter, observation
+filter, time-based contact flags, variable foot height, WILDCAT mirroring, gallop phases, action noise, the manual (tele-op test)
+configuration of bp5_test.yaml and non-default time steps."""
+import numpy as np
+import pytest
+
+from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg, test_cfg as manual_test_cfg
+from oracle_lib import Oracle, S
+from gpu_lib import Cuda, rel
+
+pytestmark = pytest.mark.gpu
+N = 128
+
+
+def _run(cfg, steps=12, sigma=0.25, tol=2e-5, seed=0):
+    """Teacher-forced single-step comparisons.  fp32 (CUDA) and fp64 (oracle) cannot agree on a contact threshold that a toe
+    crosses within ~1e-7 m (about one touchdown in a thousand): such knife-edge envs are allowed as rare outliers (<= 1 % per
+    step, and only when their contact masks differ); every other env must meet the tolerance and all flags bit-exactly."""
+    o, c = Oracle(cfg), Cuda(cfg)
+    rng = np.random.default_rng(seed)
+    o.set_tick(1); c.env.setTick(1)
+    obo, obg = o.reset(), c.reset()
+    assert rel(obg, obo) < max(tol, 5e-5)
+    n_out = 0
+    for t in range(steps):
+        c.set_state(o.get_state().astype(np.float32))
+        a = np.clip(rng.normal(0, sigma, size=(o.n, 12)), -1, 1).astype(np.float32)
+        obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
+        so, sg = o.get_state(), c.get_state()
+        knife = (sg[:, S["contact"]] != so[:, S["contact"]]).any(axis=1) | (do != dg)
+        ok = ~knife
+        assert knife.sum() <= max(1, o.n // 100), (t, int(knife.sum()))
+        n_out += int(knife.sum())
+        assert (do[ok] == dg[ok]).all(), t
+        assert rel(obg[ok], obo[ok]) < tol and rel(rg[ok], ro[ok]) < tol and rel(eg[ok], eo[ok]) < tol, (t, rel(obg[ok], obo[ok]), rel(rg[ok], ro[ok]))
+        assert rel(sg[ok][:, S["ptarget_last"]], so[ok][:, S["ptarget_last"]]) < tol
+        assert rel(sg[ok][:, S["torque_last"]], so[ok][:, S["torque_last"]]) < 1e-4
+    assert n_out <= max(2, steps * o.n // 500)
+    return o, c
+
+
+def _cfg(**kw):
+    d = trot_cfg(num_envs=N, num_threads=8, StochasticDynamics=False, ObsNoise=0.0)
+    d.update(kw)
+    return d
+
+
+def test_action_lowpass_filter():            # ENV:396, 703
+    _run(_cfg(Filter=True, Freq=30))
+
+
+def test_observation_filter_is_stateful():   # ENV:1251-1256, 425-426
+    cfg = _cfg(ObsFilter=True, ObsNoise=2.0)
+    o, c = _run(cfg)
+    # observe() applies the filter again on every call (stateful in the reference)
+    c.set_state(o.get_state().astype(np.float32))
+    a1, b1 = o.observe(), c.observe()
+    a2, b2 = o.observe(), c.observe()
+    assert rel(b1, a1) < 2e-5 and rel(b2, a2) < 2e-5
+
+
+def test_time_based_contact_flags():         # ENV:1169-1188
+    o, c = _run(_cfg(TimeBasedContact=True))
+    assert set(np.unique(c.get_state()[:, S["contact"]])) <= {0.0, 1.0}
+
+
+def test_height_variable_and_lean():         # ENV:1779-1798
+    _run(_cfg(HeightVariable=True, LeanFront=0.01, LeanHind=-0.01, Vy=0.3))
+
+
+def test_wildcat_bounding_and_gallop():      # ENV:403-409, 589, 1501, 1773
+    _run(_cfg(WILDCAT=True, GaitType=1))
+    _run(_cfg(GaitType=2, lam=0.4, period=0.25))
+
+
+def test_action_noise_shared_scalar():       # ENV:704-705
+    _run(_cfg(ActionNoise=0.1))
+
+
+def test_abad_offset_and_gains():            # ENV:317-322, 340-350, 375-380
+    _run(_cfg(abad=0.1, AbadRatio=0.7, Stiffness=60.0, Damping=2.0, MotorCriticalSpeed=14.2, MotorMaxSpeed=40))
+
+
+def test_manual_teleop_configuration():      # bp5_test.yaml: Manual True -> fixed initial state, no command / gait updates
+    cfg = manual_test_cfg(num_envs=3, render=False)
+    o, c = _run(cfg, steps=10, sigma=0.1)
+    sg = c.get_state()
+    assert np.abs(sg[:, S["command"]]).max() == 0 and np.abs(sg[:, S["joint_dot_ref"]]).max() == 0
+
+
+def test_other_time_steps_loop_count():      # ENV:711
+    o, c = _run(_cfg(simulation_dt=0.0005, control_dt=0.004), steps=6)
+
+
+def test_ragged_counts_with_noise_and_dr():
+    for n in (1, 5, 31, 33, 65):
+        cfg = trot_cfg(num_envs=n, num_threads=2, StochasticDynamics=True, ObsNoise=2.0)
+        _run(cfg, steps=3)

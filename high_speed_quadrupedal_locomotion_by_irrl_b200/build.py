@@ -13,6 +13,8 @@ SOURCES = ["env_kernels.cu", "policy_kernels.cu", "capi.cu"]
 HEADERS = ["env_device.cuh", "env_kernels.h", "irrl_params.h", os.path.join("..", "..", "include", "irrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+if os.environ.get("IRRL_STEP_MINBLOCKS"):      # tuning knob: register cap of the step kernel = 65536 / (64 * minblocks)
+    NVCC_FLAGS += ["-DSTEP_MINBLOCKS=" + os.environ["IRRL_STEP_MINBLOCKS"]]
 
 
 def _nvcc():

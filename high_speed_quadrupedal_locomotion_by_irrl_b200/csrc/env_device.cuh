@@ -177,7 +177,7 @@ __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 // un-factorised blocks for the probe kernels: A (21 packed, replicated), B (18), D (6).
 __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm, const BaseModel& bm, const Base& b,
                                          f3 bx, f3 by, f3 bz, const LegKin& k, f3 qd, Dyn& d,
-                                         float* Aout = nullptr, S3* Dout = nullptr) {
+                                         float* Aout = nullptr, S3* Dout = nullptr, bool reduce_hb = true, int leg = 0) {
     S3 I1, I2, I3; leg_inertias(P, lm, bx, k, I1, I2, I3);
     const f3 w0 = b.w;
     // ---- velocities
@@ -208,7 +208,10 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
     f3 r0 = axpy(bm.com0.x, bx, axpy(bm.com0.y, by, bm.com0.z * bz));
     f3 F0 = bm.m0 * (cross(w0, cross(w0, r0)) + g);
     f3 N0 = cross(w0, mul(I0, w0)) + cross(r0, F0);
-    fb = qsum3(fb) + F0; nb = qsum3(nb) + N0;
+    // hb_part: this lane's share of the trunk bias wrench (lane 0 also carries the trunk body); callers reduce it together
+    // with whatever else they sum over the quad (integrate_substep: one 6-value reduction instead of two)
+    if (reduce_hb) { fb = qsum3(fb) + F0; nb = qsum3(nb) + N0; }
+    else if (leg == 0) { fb = fb + F0; nb = nb + N0; }
     d.hb[0] = fb.x; d.hb[1] = fb.y; d.hb[2] = fb.z; d.hb[3] = nb.x; d.hb[4] = nb.y; d.hb[5] = nb.z;
 
     // ---- composite inertias about the trunk origin: (mass, first moment, second moment)
@@ -447,14 +450,14 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     const float dt = P.sim_dt;
     f3 bx, by, bz; quat_cols(b.qw, b.qx, b.qy, b.qz, bx, by, bz);
     LegKin k; leg_fk(P, lm, bx, by, bz, q, k);
-    Dyn d; dynamics(P, lm, bm, b, bx, by, bz, k, qd, d);
+    Dyn d; dynamics(P, lm, bm, b, bx, by, bz, k, qd, d, nullptr, nullptr, false, leg);
 
     // ---- free acceleration in the factorised form:  t = Dinv r_l,  w = L^-1 (r_b - sum B t)
     f3 rl = mk(tau.x - P.joint_damping * qd.x - d.hl.x, tau.y - P.joint_damping * qd.y - d.hl.y, tau.z - P.joint_damping * qd.z - d.hl.z);
     f3 t = mul(d.Dinv, rl);
     float wv[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) wv[a] = -d.hb[a] - qsum(d.B[a][0] * t.x + d.B[a][1] * t.y + d.B[a][2] * t.z);
+    for (int a = 0; a < 6; ++a) wv[a] = -qsum(d.hb[a] + d.B[a][0] * t.x + d.B[a][1] * t.y + d.B[a][2] * t.z);
     fwd6(d.L, wv);
 
     // ---- collision detection against the plane z = 0 (ENV:268)
@@ -463,8 +466,9 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     cf.active = (b.p.z + k.toe.z - P.toe_r <= 0.f) ? 1 : 0;
     f3 Jl0 = cross(k.a1, xf - k.j1), Jl1 = cross(k.a2, xf - k.j2), Jl2 = cross(k.a2, xf - k.j3);
     // trunk box corners: lane l tests corners 2l and 2l+1, the quad then ranks the hits in corner order
-    int hit0, hit1; f3 xc0, xc1;
-    {
+    int hit0 = 0, hit1 = 0; f3 xc0 = mk(0.f, 0.f, 0.f), xc1 = xc0;
+    const float box_reach = sqrtf(P.box_half[0] * P.box_half[0] + P.box_half[1] * P.box_half[1] + P.box_half[2] * P.box_half[2]);
+    if (__any_sync(FULLMASK, b.p.z <= box_reach)) {
         int c0 = 2 * leg, c1 = 2 * leg + 1;
         f3 l0 = mk((c0 & 1) ? P.box_half[0] : -P.box_half[0], (c0 & 2) ? P.box_half[1] : -P.box_half[1], (c0 & 4) ? P.box_half[2] : -P.box_half[2]);
         f3 l1 = mk((c1 & 1) ? P.box_half[0] : -P.box_half[0], (c1 & 2) ? P.box_half[1] : -P.box_half[1], (c1 & 4) ? P.box_half[2] : -P.box_half[2]);

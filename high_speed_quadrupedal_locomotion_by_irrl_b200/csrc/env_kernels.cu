@@ -229,7 +229,10 @@ __device__ __forceinline__ void write_scaled_obs(const EnvParams& P, const DevSt
 }
 
 // ------------------------------------------------------------------ THE step kernel
-__global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__ StepArgs A) {
+#ifndef STEP_MINBLOCKS
+#define STEP_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const __grid_constant__ StepArgs A) {
     const EnvParams& P = A.P; const DevState& S = A.S;
     const int tid = blockIdx.x * BLOCK + threadIdx.x;
     int r = tid >> 2; const int leg = tid & 3;

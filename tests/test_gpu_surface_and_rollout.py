@@ -200,3 +200,18 @@ def test_fused_bptt_matches_autograd_reference():
             assert gb is None; continue
         scale = float(gb.abs().max()) + 1e-12
         assert float((ga - gb).abs().max()) < 2e-4 * scale + 1e-9, (n, float((ga - gb).abs().max()), scale)
+
+
+def test_bp5_155_policy_reproduces_the_references_robot_level_results():
+    """Statistical anchor for the RaiSim boundary: the reference's own trained policy, driven like
+    run_bp_v5.py --test with the command ramped to 5 m/s at friction 0.8, must trot in this simulator like it does in RaiSim:
+    reference z 0.2732 +- 0.0016 m, vx 4.964 m/s at cmd 5 (tracking error -0.066 +- 0.067), stride 5 Hz, vertical bounce 10 Hz."""
+    import importlib.util, os as _os
+    spec = importlib.util.spec_from_file_location("eval_bp5_155", _os.path.join(_os.path.dirname(_os.path.dirname(__file__)), "scripts", "eval_bp5_155.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    r = mod.run(vx_cmd=5.0, mu=0.8, n=4, seconds=6.0)
+    assert r["falls"] == 0
+    assert abs(r["z_mean"] - 0.2732) < 0.02 * 0.2732                   # within 2 % of the RaiSim rollout
+    assert abs(r["vx_mean"] - r["cmd_mean_second_half"]) < 0.35        # tracks the command like the reference (err ~ -0.07 +- 0.07)
+    assert abs(r["stride_hz"] - 5.0) < 0.26 and abs(r["bounce_hz"] - 10.0) < 0.51
+    assert abs(r["roll_mean"]) < 0.02 and abs(r["pitch_mean"]) < 0.02

@@ -51,13 +51,23 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-envs", type=int, default=200, help="reference CPU configuration (default_cfg.yaml:7)")
+    ap.add_argument("--workload", default="trot", choices=["trot", "relaxation", "stairs"],
+                    help="BASELINE.json configs[1] trot imitation (default) | configs[2] relaxation (mimic reward removed) | configs[4] stair heightfield + DR")
     return ap.parse_args()
 
 
+WORKLOAD = "trot"
+
+
 def workload_cfg(n_envs):
-    from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg, relaxation_cfg
     # BASELINE.json configs[1] / SURVEY.md 8d config 2: trot imitation coefficients, flat ground, ObsNoise 2.0, DR on
-    return trot_cfg(num_envs=n_envs, num_threads=os.cpu_count() or 1, StochasticDynamics=True, ObsNoise=2.0)
+    kw = dict(num_envs=n_envs, num_threads=os.cpu_count() or 1, StochasticDynamics=True, ObsNoise=2.0)
+    if WORKLOAD == "relaxation":      # configs[2]: JointRewardCoeff = EndEffectorRewardCoeff = 0
+        return relaxation_cfg(**kw)
+    if WORKLOAD == "stairs":          # configs[4]: stair heightfield (rise 0.08 / run 0.3 m) + mass/friction randomisation
+        return trot_cfg(Terrain=True, terrain_kind="stairs", stair_rise=0.08, stair_run=0.3, **kw)
+    return trot_cfg(**kw)
 
 
 def policy_weights():
@@ -323,8 +333,10 @@ def run_b200(args):
                         "frac": N * B_ACT_BYTES / (act_kernel_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_env": B_ACT_BYTES}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"bp5 trot imitation reward, {N} envs per B200 (BASELINE.json configs[1]) with fused LSTM act: act kernel + env step kernel "
-                                   "(PD, 8 physics substeps, obs, reward, done, auto-reset) + rollout stores",
+            "config": {"workload": {"trot": f"bp5 trot imitation reward, {N} envs per B200 (BASELINE.json configs[1])",
+                                     "relaxation": f"bp5 relaxation phase (mimic reward removed), {N} envs per B200 (BASELINE.json configs[2])",
+                                     "stairs": f"bp5 stair heightfield + domain randomisation, {N} envs per B200 (BASELINE.json configs[4])"}[WORKLOAD]
+                                    + " with fused LSTM act: act kernel + env step kernel (PD, 8 physics substeps, obs, reward, done, auto-reset) + rollout stores",
                        "envs_per_gpu": N, "total_envs": world * N, "substeps": 8, "policy": wname, "obs_noise": 2.0, "domain_randomisation": True,
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed (state << L2)",
                        "parallelism": f"env-shard x{world}, no data-path collective"},
@@ -343,7 +355,9 @@ def run_b200(args):
 
 
 def main():
+    global WORKLOAD
     args = parse()
+    WORKLOAD = args.workload
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -176,6 +176,23 @@ class FlexibleGymEnv:
             raise TypeError("reference table must be [rows,30] (Environment.hpp:17-21)")
         _lib.check(self._L.irrl_set_ref_traj(self._h, C.c_void_p(table.ctypes.data), int(table.shape[0])), "setRefTraj")
 
+    def setHeightfield(self, heights, x_size: float, y_size: float, cx: float = 0.0, cy: float = 0.0) -> None:
+        heights = np.ascontiguousarray(heights, np.float32)
+        if heights.ndim != 2:
+            raise TypeError("heights must be [nx, ny]")
+        _lib.check(self._L.irrl_set_heightfield(self._h, C.c_void_p(heights.ctypes.data), int(heights.shape[0]), int(heights.shape[1]),
+                                                float(x_size), float(y_size), float(cx), float(cy)), "setHeightfield")
+
+    def generateTerrain(self, kind: str = "perlin", nx: int = 5000, ny: int = 500, x_size: float = 500.0, y_size: float = 20.0) -> None:
+        _lib.check(self._L.irrl_generate_terrain(self._h, kind.encode(), int(nx), int(ny), float(x_size), float(y_size)), "generateTerrain")
+
+    def getHeightfield(self):
+        nx, ny = C.c_int(), C.c_int(); xs, ys, cx, cy = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        _lib.check(self._L.irrl_get_heightfield(self._h, None, C.byref(nx), C.byref(ny), C.byref(xs), C.byref(ys), C.byref(cx), C.byref(cy)), "getHeightfield")
+        h = np.zeros((nx.value, ny.value), np.float32)
+        _lib.check(self._L.irrl_get_heightfield(self._h, C.c_void_p(h.ctypes.data), None, None, None, None, None, None), "getHeightfield")
+        return h, xs.value, ys.value, cx.value, cy.value
+
     def lastEpisodeStats(self, ep_return, ep_length) -> None:
         _lib.check(self._L.irrl_last_episode_stats(self._h, self._ptr(ep_return, (self._n,), name="ep_return"),
                                                    self._ptr(ep_length, (self._n,), np.int32, name="ep_length")), "lastEpisodeStats")

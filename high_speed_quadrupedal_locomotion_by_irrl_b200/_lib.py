@@ -64,6 +64,9 @@ def load() -> C.CDLL:
     L.irrl_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.irrl_lstm_pw_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
     L.irrl_lstm_pw_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9
+    L.irrl_set_heightfield.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.irrl_generate_terrain.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.irrl_get_heightfield.argtypes = [C.c_void_p, C.c_void_p] + [C.c_void_p] * 6
     L.irrl_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.irrl_host_unregister.argtypes = [C.c_void_p]
     _lib = L

@@ -70,7 +70,9 @@ struct irrl_env_impl {
     uint32_t tick = 0;
     bool initialised = false;
     std::string resource_dir, ref_path;
-    double max_time_d = 0, control_dt_d = 0, sim_dt_d = 0;   // YAML values in double: integer counts are derived like the reference does
+    double max_time_d = 0, control_dt_d = 0, sim_dt_d = 0;
+    // heightfield (host copy + generator settings from the YAML)
+    std::vector<float> terrain_h; std::string terrain_kind = "perlin"; double stair_rise = 0.08, stair_run = 0.3, stair_start = 1.0; int terrain_seed = 0; float* d_terrain = nullptr;   // YAML values in double: integer counts are derived like the reference does
     std::vector<std::string> extra_names;
     // staging (device + pinned host)
     float *d_action = nullptr, *d_ob = nullptr, *d_reward = nullptr, *d_extra = nullptr, *d_ep_ret = nullptr, *d_scratch = nullptr;
@@ -159,14 +161,15 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         P.filter_para = P.flag_filter ? (float)(1.0 - freq * ctl_dt) : 0.f;                                      // ENV:396
         P.obs_filter_alpha = P.flag_obs_filter ? (float)(2.0 * 3.14 * ctl_dt * 20.0 / (2.0 * 3.14 * ctl_dt * 20.0 + 1.0)) : 1.f;   // ENV:425-426, 2026
         if (y.has("RefTraj")) E->ref_path = y.kv.at("RefTraj");
+        if (y.has("terrain_kind")) E->terrain_kind = y.kv.at("terrain_kind");
         // optional solver / model switches of this implementation
         auto opt = [&](const char* k, double dflt) { double v; return y.has(k) && num(k, v) ? v : dflt; };
         P.joint_damping = (float)opt("joint_damping", 0.01);                                                     // URDF:56
         P.solver_iters = (int)opt("solver_iters", 10); P.slide_iters = (int)opt("slide_iters", 1); P.solver_tol = (float)opt("solver_tol", 1e-5);
+        E->stair_rise = opt("stair_rise", 0.08); E->stair_run = opt("stair_run", 0.3); E->stair_start = opt("stair_start", 1.0); E->terrain_seed = (int)opt("terrain_seed", 0);
         P.mu = (float)opt("friction", 0.6); P.restitution = (float)opt("restitution", 0.2); P.rest_threshold = (float)opt("restitution_threshold", 0.01);   // ENV:433
     }
     if (P.N <= 0) return fail(-3, "num_envs must be positive");
-    if (P.flag_terrain) return fail(-3, "Terrain: True (RaiSim Perlin HeightMap, ENV:252-265) is not implemented in this build");
     if (P.flag_force_dist && P.flag_manual) return fail(-3, "ForceDisturbance with Manual (state_disturbance, ENV:912-940) is not implemented in this build");
     // ForceDisturbance without Manual: force_attack(random() < 0.0027) never fires -> zero external force.
     switch (P.gait_type) {                                                                                       // ENV:398-409
@@ -323,6 +326,9 @@ int irrl_init(irrl_env* env) {
     }
     if (!E->P.flag_manual_traj && !E->P.flag_manual && !E->d_ref)
         return fail(-3, "ManualTraj: False needs a reference table: RefTraj file with 30 columns (ENV:17-21) or irrl_set_ref_traj()");
+    if (E->P.flag_terrain && !E->d_terrain) {   // ENV:252-265: 500 x 20 m, 5000 x 500 samples
+        if (int r4 = irrl_generate_terrain(env, nullptr, 5000, 500, 500.0, 20.0)) return r4;
+    }
     launch_env_init(E->P, E->S, E->stream); CUDA_OK(cudaGetLastError());
     E->initialised = true;
     // VEC:172-182: every env is reset once during init
@@ -466,7 +472,18 @@ int irrl_is_terminal_state(irrl_env* env, uint8_t* terminal) {
     std::vector<float> s((size_t)E->P.N * STATE_DIM);
     if (int rc = irrl_get_state(env, s.data())) return rc;
     std::vector<uint8_t> t(E->P.N);
-    for (int i = 0; i < E->P.N; ++i) { const float* x = &s[(size_t)i * STATE_DIM]; t[i] = (x[2] < 0.15f || x[2] > 0.65f || x[109 + 31] < 0.5f) ? 1 : 0; }   // ENV:1560
+    for (int i = 0; i < E->P.N; ++i) {
+        const float* x = &s[(size_t)i * STATE_DIM]; float z = x[2];
+        if (!E->terrain_h.empty()) {   // height above the terrain under the trunk (same triangulation as the kernels)
+            const EnvParams& P = E->P; int nx = P.terrain_nx, ny = P.terrain_ny;
+            float fx = (x[0] - P.terrain_cx) / P.terrain_dx + 0.5f * (nx - 1), fy = (x[1] - P.terrain_cy) / P.terrain_dy + 0.5f * (ny - 1);
+            fx = std::min(std::max(fx, 0.f), (float)(nx - 1)); fy = std::min(std::max(fy, 0.f), (float)(ny - 1));
+            int ii = std::min((int)fx, nx - 2), jj = std::min((int)fy, ny - 2); float uu = fx - ii, vv = fy - jj;
+            const float* hh = &E->terrain_h[(size_t)ii * ny + jj]; float h00 = hh[0], h01 = hh[1], h10 = hh[ny], h11 = hh[ny + 1];
+            z -= (uu >= vv) ? h00 + (h10 - h00) * uu + (h11 - h10) * vv : h00 + (h11 - h01) * uu + (h01 - h00) * vv;
+        }
+        t[i] = (z < 0.15f || z > 0.65f || x[109 + 31] < 0.5f) ? 1 : 0;   // ENV:1560
+    }
     if (is_device_ptr(terminal)) { CUDA_OK(cudaMemcpy(terminal, t.data(), t.size(), cudaMemcpyHostToDevice)); } else memcpy(terminal, t.data(), t.size());
     return 0;
 }
@@ -538,6 +555,60 @@ int irrl_integrate(irrl_env* env, const float* tau, float* contact_out) {
     return 0;
 }
 int irrl_get_solver_sweeps(irrl_env* env, int32_t* out) { ENV(env); NEED_INIT(); return deliver(E, out, E->S.solver_sweeps, (size_t)E->P.N * sizeof(int)); }
+
+// ---- heightfield terrain.  The reference builds a RaiSim HeightMap from TerrainProperties (frequency 1, zScale 0.1, 500 x 20 m,
+// 5000 x 500 samples, 3 fractal octaves, lacunarity 2, gain 0.25; ENV:252-265).  RaiSim's noise generator is not available, so
+// "perlin" here is a fractal value-noise with the same parameters (new specification, unpinned); "stairs" is the stair course of
+// BASELINE.json config 5 (rise / run along +x).  Any other table can be supplied with irrl_set_heightfield.
+static inline float lattice(int ix, int iy, uint32_t seed) {
+    uint32_t h = (uint32_t)ix * 0x8da6b343u ^ (uint32_t)iy * 0xd8163841u ^ seed * 0xcb1ab31fu;
+    h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+    return (float)(h & 0xffffff) / 8388608.0f - 1.0f;
+}
+static inline float value_noise(float x, float y, uint32_t seed) {
+    int ix = (int)std::floor(x), iy = (int)std::floor(y); float fx = x - ix, fy = y - iy;
+    float sx = fx * fx * (3 - 2 * fx), sy = fy * fy * (3 - 2 * fy);
+    float a = lattice(ix, iy, seed), b = lattice(ix + 1, iy, seed), c2 = lattice(ix, iy + 1, seed), d = lattice(ix + 1, iy + 1, seed);
+    return (a + (b - a) * sx) + ((c2 + (d - c2) * sx) - (a + (b - a) * sx)) * sy;
+}
+int irrl_set_heightfield(irrl_env* env, const float* heights, int nx, int ny, double x_size, double y_size, double cx, double cy) {
+    ENV(env);
+    if (!heights || nx < 2 || ny < 2) return fail(-1, "heightfield needs at least 2 x 2 samples");
+    E->terrain_h.resize((size_t)nx * ny);
+    if (is_device_ptr(heights)) { CUDA_OK(cudaMemcpy(E->terrain_h.data(), heights, E->terrain_h.size() * 4, cudaMemcpyDeviceToHost)); } else memcpy(E->terrain_h.data(), heights, E->terrain_h.size() * 4);
+    float* d = nullptr; CUDA_OK(cudaMalloc((void**)&d, E->terrain_h.size() * 4)); E->allocs.push_back(d);
+    CUDA_OK(cudaMemcpy(d, E->terrain_h.data(), E->terrain_h.size() * 4, cudaMemcpyHostToDevice));
+    E->d_terrain = d; E->P.terrain = d; E->P.terrain_nx = nx; E->P.terrain_ny = ny; E->P.terrain_cx = (float)cx; E->P.terrain_cy = (float)cy;
+    E->P.terrain_dx = (float)(x_size / (nx - 1)); E->P.terrain_dy = (float)(y_size / (ny - 1)); E->P.flag_terrain = 1;
+    return 0;
+}
+int irrl_generate_terrain(irrl_env* env, const char* kind, int nx, int ny, double x_size, double y_size) {
+    ENV(env);
+    std::string k = kind ? kind : E->terrain_kind;
+    std::vector<float> h((size_t)nx * ny);
+    const double dx = x_size / (nx - 1), dy = y_size / (ny - 1);
+    for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) {
+        double x = -x_size / 2 + i * dx, yy = -y_size / 2 + j * dy; float v = 0.f;
+        if (k == "stairs") { if (x >= E->stair_start) v = (float)(E->stair_rise * (std::floor((x - E->stair_start) / E->stair_run) + 1.0)); }
+        else if (k == "flat") v = 0.f;
+        else {   // "perlin": TerrainProperties of ENV:254-263
+            float amp = 1.f, freq = 1.f, sum = 0.f;
+            for (int o = 0; o < 3; ++o) { sum += amp * value_noise((float)x * freq, (float)yy * freq, (uint32_t)(E->terrain_seed + 31 * o)); amp *= 0.25f; freq *= 2.0f; }
+            v = 0.1f * sum;
+        }
+        h[(size_t)i * ny + j] = v;
+    }
+    return irrl_set_heightfield(env, h.data(), nx, ny, x_size, y_size, 0.0, 0.0);
+}
+int irrl_get_heightfield(irrl_env* env, float* heights, int* nx, int* ny, double* x_size, double* y_size, double* cx, double* cy) {
+    ENV(env);
+    if (E->terrain_h.empty()) return fail(-3, "no heightfield is set (Terrain: False)");
+    if (nx) *nx = E->P.terrain_nx; if (ny) *ny = E->P.terrain_ny;
+    if (x_size) *x_size = (double)E->P.terrain_dx * (E->P.terrain_nx - 1); if (y_size) *y_size = (double)E->P.terrain_dy * (E->P.terrain_ny - 1);
+    if (cx) *cx = E->P.terrain_cx; if (cy) *cy = E->P.terrain_cy;
+    if (heights) memcpy(heights, E->terrain_h.data(), E->terrain_h.size() * 4);
+    return 0;
+}
 
 int irrl_set_ref_traj(irrl_env* env, const float* table, int rows) {
     ENV(env);

@@ -366,6 +366,27 @@ __device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Gin
     return mk(mu * lnz * dx, mu * lnz * dy, lnz);
 }
 
+// heightfield lookup (same triangulation as the oracle's Terrain::sample): height and unit normal under (x, y)
+__device__ __forceinline__ void terrain_sample(const EnvParams& P, float x, float y, float& height, f3& n) {
+    float fx = (x - P.terrain_cx) / P.terrain_dx + 0.5f * (float)(P.terrain_nx - 1), fy = (y - P.terrain_cy) / P.terrain_dy + 0.5f * (float)(P.terrain_ny - 1);
+    fx = fminf(fmaxf(fx, 0.f), (float)(P.terrain_nx - 1)); fy = fminf(fmaxf(fy, 0.f), (float)(P.terrain_ny - 1));
+    int i = min((int)fx, P.terrain_nx - 2), j = min((int)fy, P.terrain_ny - 2);
+    float u = fx - (float)i, v = fy - (float)j;
+    const float* h = P.terrain + (size_t)i * P.terrain_ny + j;
+    float h00 = __ldg(h), h01 = __ldg(h + 1), h10 = __ldg(h + P.terrain_ny), h11 = __ldg(h + P.terrain_ny + 1);
+    float a, b;
+    if (u >= v) { a = (h10 - h00) / P.terrain_dx; b = (h11 - h10) / P.terrain_dy; height = h00 + (h10 - h00) * u + (h11 - h10) * v; }
+    else        { a = (h11 - h01) / P.terrain_dx; b = (h01 - h00) / P.terrain_dy; height = h00 + (h11 - h01) * u + (h01 - h00) * v; }
+    float inv = 1.0f / sqrtf(1.0f + a * a + b * b);
+    n = mk(-a * inv, -b * inv, inv);
+}
+// contact frame rows (t1, t2, n): t1 = x-axis projected on the tangent plane, t2 = n x t1
+__device__ __forceinline__ void contact_frame(f3 n, f3& t1, f3& t2) {
+    t1 = mk(1.f - n.x * n.x, -n.x * n.y, -n.x * n.z);
+    float inv = 1.0f / sqrtf(dot(t1, t1)); t1 = inv * t1;
+    t2 = cross(n, t1);
+}
+
 // Per-contact data in the reduced trunk space: v_i = c_i + Q_i^T y + T_i lambda_i,  y = sum_j Q_j lambda_j
 struct Contact {
     float Q[6][3];   // L^-1 E_i^T
@@ -376,12 +397,22 @@ struct Contact {
 };
 // Build Q, G for a contact at point x (relative to the trunk origin).  Jl (3 columns) is the leg part of the
 // contact Jacobian (zero for a trunk contact).
-__device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1, f3 Jl2, bool on_leg, Contact& ct) {
+// `framed`: rows of the contact Jacobian are expressed in the contact frame (t1, t2, n) instead of world axes (heightfield);
+// Jl* must already be rotated by the caller in that case.
+__device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1, f3 Jl2, bool on_leg, Contact& ct,
+                                              bool framed = false, f3 t1 = f3{1, 0, 0}, f3 t2 = f3{0, 1, 0}, f3 nn = f3{0, 0, 1}) {
     // E = J_b - J_l Y^T : 3x6.  J_b = [1, -[x]x]
     float E[3][6];
     E[0][0] = 1.f; E[0][1] = 0.f; E[0][2] = 0.f; E[0][3] = 0.f;  E[0][4] = x.z;  E[0][5] = -x.y;
     E[1][0] = 0.f; E[1][1] = 1.f; E[1][2] = 0.f; E[1][3] = -x.z; E[1][4] = 0.f;  E[1][5] = x.x;
     E[2][0] = 0.f; E[2][1] = 0.f; E[2][2] = 1.f; E[2][3] = x.y;  E[2][4] = -x.x; E[2][5] = 0.f;
+    if (framed) {   // E <- D E with D rows (t1, t2, n)
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            f3 col = mk(E[0][a], E[1][a], E[2][a]);
+            E[0][a] = dot(t1, col); E[1][a] = dot(t2, col); E[2][a] = dot(nn, col);
+        }
+    }
     if (on_leg) {
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
@@ -460,20 +491,29 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     for (int a = 0; a < 6; ++a) wv[a] = -qsum(d.hb[a] + d.B[a][0] * t.x + d.B[a][1] * t.y + d.B[a][2] * t.z);
     fwd6(d.L, wv);
 
-    // ---- collision detection against the plane z = 0 (ENV:268)
+    // ---- collision detection against the plane z = 0 (ENV:268) or the heightfield (ENV:264)
     Contact cf;   // foot contact of this leg (slot 0 of this lane)
-    f3 xf = mk(k.toe.x, k.toe.y, k.toe.z - P.toe_r);                     // contact point on the sphere
-    cf.active = (b.p.z + k.toe.z - P.toe_r <= 0.f) ? 1 : 0;
+    const bool terr = P.terrain != nullptr;
+    f3 fn = mk(0.f, 0.f, 1.f), ft1 = mk(1.f, 0.f, 0.f), ft2 = mk(0.f, 1.f, 0.f); float fh = 0.f;
+    if (terr) { terrain_sample(P, b.p.x + k.toe.x, b.p.y + k.toe.y, fh, fn); contact_frame(fn, ft1, ft2); }
+    f3 xf = axpy(-P.toe_r, fn, k.toe);                                  // contact point on the sphere
+    cf.active = ((b.p.z + k.toe.z - fh) * fn.z - P.toe_r <= 0.f) ? 1 : 0;
     f3 Jl0 = cross(k.a1, xf - k.j1), Jl1 = cross(k.a2, xf - k.j2), Jl2 = cross(k.a2, xf - k.j3);
+    if (terr) {   // rows of the contact Jacobian in the contact frame
+        Jl0 = mk(dot(ft1, Jl0), dot(ft2, Jl0), dot(fn, Jl0)); Jl1 = mk(dot(ft1, Jl1), dot(ft2, Jl1), dot(fn, Jl1)); Jl2 = mk(dot(ft1, Jl2), dot(ft2, Jl2), dot(fn, Jl2));
+    }
     // trunk box corners: lane l tests corners 2l and 2l+1, the quad then ranks the hits in corner order
     int hit0 = 0, hit1 = 0; f3 xc0 = mk(0.f, 0.f, 0.f), xc1 = xc0;
     const float box_reach = sqrtf(P.box_half[0] * P.box_half[0] + P.box_half[1] * P.box_half[1] + P.box_half[2] * P.box_half[2]);
-    if (__any_sync(FULLMASK, b.p.z <= box_reach)) {
+    if (terr || __any_sync(FULLMASK, b.p.z <= box_reach)) {
         int c0 = 2 * leg, c1 = 2 * leg + 1;
         f3 l0 = mk((c0 & 1) ? P.box_half[0] : -P.box_half[0], (c0 & 2) ? P.box_half[1] : -P.box_half[1], (c0 & 4) ? P.box_half[2] : -P.box_half[2]);
         f3 l1 = mk((c1 & 1) ? P.box_half[0] : -P.box_half[0], (c1 & 2) ? P.box_half[1] : -P.box_half[1], (c1 & 4) ? P.box_half[2] : -P.box_half[2]);
         xc0 = axpy(l0.x, bx, axpy(l0.y, by, l0.z * bz)); xc1 = axpy(l1.x, bx, axpy(l1.y, by, l1.z * bz));
-        hit0 = (b.p.z + xc0.z <= 0.f) ? 1 : 0; hit1 = (b.p.z + xc1.z <= 0.f) ? 1 : 0;
+        if (terr) {
+            float h0, h1; f3 n0, n1; terrain_sample(P, b.p.x + xc0.x, b.p.y + xc0.y, h0, n0); terrain_sample(P, b.p.x + xc1.x, b.p.y + xc1.y, h1, n1);
+            hit0 = ((b.p.z + xc0.z - h0) * n0.z <= 0.f) ? 1 : 0; hit1 = ((b.p.z + xc1.z - h1) * n1.z <= 0.f) ? 1 : 0;
+        } else { hit0 = (b.p.z + xc0.z <= 0.f) ? 1 : 0; hit1 = (b.p.z + xc1.z <= 0.f) ? 1 : 0; }
     }
     int hits = hit0 | (hit1 << 1);
     int allhits = 0;
@@ -490,9 +530,11 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     cf.lam = mk(0.f, 0.f, 0.f);
     if (any_foot_or_box) {
         // ---- foot contact setup (every lane builds its own slot)
-        contact_setup(d, xf, Jl0, Jl1, Jl2, true, cf);
+        contact_setup(d, xf, Jl0, Jl1, Jl2, true, cf, terr, ft1, ft2, fn);
         {
-            f3 vpre = b.v + cross(b.w, xf) + qd.x * Jl0 + qd.y * Jl1 + qd.z * Jl2;        // J u (pre-step)
+            f3 vb_ = b.v + cross(b.w, xf);
+            if (terr) vb_ = mk(dot(ft1, vb_), dot(ft2, vb_), dot(fn, vb_));
+            f3 vpre = vb_ + qd.x * Jl0 + qd.y * Jl1 + qd.z * Jl2;                         // J u (pre-step)
             f3 jt = t.x * Jl0 + t.y * Jl1 + t.z * Jl2;                                    // J_l Dinv r_l
             f3 qw_ = mk(0.f, 0.f, 0.f);
 #pragma unroll
@@ -512,8 +554,11 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
                 if ((allhits >> c) & 1) { if (cnt == leg) { rank = c; xb = mk(px, py, pz); } cnt++; }
             }
             cb.active = (rank >= 0) ? 1 : 0;
-            contact_setup(d, xb, mk(0, 0, 0), mk(0, 0, 0), mk(0, 0, 0), false, cb);
+            f3 bn = mk(0.f, 0.f, 1.f), bt1 = mk(1.f, 0.f, 0.f), bt2 = mk(0.f, 1.f, 0.f);
+            if (terr) { float bh; terrain_sample(P, b.p.x + xb.x, b.p.y + xb.y, bh, bn); contact_frame(bn, bt1, bt2); }
+            contact_setup(d, xb, mk(0, 0, 0), mk(0, 0, 0), mk(0, 0, 0), false, cb, terr, bt1, bt2, bn);
             f3 vpre = b.v + cross(b.w, xb);
+            if (terr) vpre = mk(dot(bt1, vpre), dot(bt2, vpre), dot(bn, vpre));
             f3 qw_ = mk(0.f, 0.f, 0.f);
 #pragma unroll
             for (int a = 0; a < 6; ++a) { qw_.x = fmaf(cb.Q[a][0], wv[a], qw_.x); qw_.y = fmaf(cb.Q[a][1], wv[a], qw_.y); qw_.z = fmaf(cb.Q[a][2], wv[a], qw_.z); }

@@ -192,6 +192,7 @@ static __device__ __noinline__ void reset_env(const EnvParams& P, const DevState
         float a = u01(rr.x), bb = u01(rr.y);
         e.b.p = mk(a * 5.0f + (1.0f - a) * -5.0f, bb * 5.0f + (1.0f - bb) * -5.0f, 0.35f);
         e.b.v = mk(vx, vy, 0.f); e.b.w = mk(0.f, 0.f, wz); e.q = qi; e.qd = qdi;
+        if (P.terrain) { float gh; f3 gn; terrain_sample(P, e.b.p.x, e.b.p.y, gh, gn); e.b.p.z += gh; }   // drop height measured from the terrain
     }
     e.b.qw = 1.f; e.b.qx = e.b.qy = e.b.qz = 0.f;
     e.contact_flag = 0.f; e.impulse_norm = 0.f;                                     // contact list empty after setState
@@ -297,6 +298,8 @@ __global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const _
     float force_norm = imp / P.control_dt;        // ENV:1208 (control_dt, quirk 4)
     e.impulse_norm = imp;
 
+    float ground_z = 0.f;
+    if (P.terrain) { f3 gn; terrain_sample(P, e.b.p.x, e.b.p.y, ground_z, gn); }
     // ---- reward (ENV:1444-1548)
     float rew, r_ee, r_pos, r_att, r_joint, r_vel;
     {
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const _
         f3 de = ee - e.eeref;
         float ees = qsum(dot(de, de));
         r_ee = P.ee_coeff * expf(-40.f * ees);
-        float dz = e.b.p.z - P.stand_height;
+        float dz = e.b.p.z - ground_z - P.stand_height;              // height above the terrain under the trunk (flat ground: z)
         r_pos = P.pos_coeff * expf(-80.f * (dz * dz));
         r_att = P.atti_coeff * expf(-80.f * (o.ob29 * o.ob29 + o.ob30 * o.ob30));
         f3 dj = e.jref - e.q, dd = e.jdref - e.qd;
@@ -332,7 +335,8 @@ __global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const _
     e.contact_flag = contact_flag(P, e, leg, co.foot_active);
     e.frame_idx += 1;
     // ---- VEC::perAgentStep (VEC:352-372)
-    const bool done = (e.b.p.z < 0.15f) || (e.b.p.z > 0.65f) || (o.ob31 < 0.5f);   // ENV:1560
+    const float zrel = e.b.p.z - ground_z;
+    const bool done = (zrel < 0.15f) || (zrel > 0.65f) || (o.ob31 < 0.5f);   // ENV:1560 (relative to the terrain under the trunk)
     const float base_z = e.b.p.z;
     e.ep_len += 1;
     float ep_ret_out = 0.f; int ep_len_out = 0;

@@ -62,6 +62,8 @@ struct EnvParams {
     int N;
     const float* ref;             // optional [rows,30] reference table (ENV:17-21), device pointer
     int ref_rows, frame_max, frame_len;
+    // heightfield terrain (Terrain: True, ENV:252-265): [nx][ny] heights, grid centred on (cx, cy), device pointer
+    const float* terrain; int terrain_nx, terrain_ny; float terrain_cx, terrain_cy, terrain_dx, terrain_dy;
 };
 
 // Structure-of-arrays persistent state in HBM.  One robot is served by a group of 4 lanes (one per leg);

@@ -112,6 +112,14 @@ int irrl_get_solver_sweeps(irrl_env* env, int32_t* out /*[N]*/);
 /* reference-trajectory table mode (ManualTraj False): ref[rows,30] float32  VectorizedEnvironment.hpp:158-182, Environment.hpp:17-21 */
 int irrl_set_ref_traj(irrl_env* env, const float* table, int rows);
 
+/* ---- heightfield terrain (Terrain: True; the reference adds a RaiSim HeightMap, Environment.hpp:252-265).  heights[nx][ny] float32,
+ * grid of x_size x y_size metres centred on (cx, cy), cells split along the (i,j)-(i+1,j+1) diagonal.  With Terrain: True and no table
+ * supplied before irrl_init, the table of YAML key `terrain_kind` ("perlin" (default) | "stairs" | "flat"; `stair_rise`, `stair_run`,
+ * `stair_start`, `terrain_seed`) is generated with the reference's grid (5000 x 500 samples over 500 x 20 m). */
+int irrl_set_heightfield(irrl_env* env, const float* heights, int nx, int ny, double x_size, double y_size, double cx, double cy);
+int irrl_generate_terrain(irrl_env* env, const char* kind, int nx, int ny, double x_size, double y_size);
+int irrl_get_heightfield(irrl_env* env, float* heights, int* nx, int* ny, double* x_size, double* y_size, double* cx, double* cy);
+
 /* ---- LSTM policy act  (CustomLSTMPolicy.step  run_bp_v5.py:178-185)
  * params: the 19 arrays of the reference pkl in tf.trainable_variables() order, concatenated:
  * lstm_pi0{wx[35,192],wh[48,192],b[192]} lstm_pi1{wx[48,192],wh,b} lstm_v0{...} lstm_v1{...} vf{w[48,1],b[1]}

@@ -275,6 +275,27 @@ template <typename T> inline bool inv3(const T A[3][3], T R[3][3]) {
     return true;
 }
 
+// ------------------------------------------------------------------ heightfield terrain (ENV:252-265 RaiSim HeightMap; new spec in DESIGN.md)
+// Regular grid of nx x ny samples covering x_size x y_size metres centred on (cx, cy); every cell is split along the
+// (i,j)-(i+1,j+1) diagonal into two triangles; outside the grid the border value continues.
+struct Terrain {
+    const float* h = nullptr; int nx = 0, ny = 0; double cx = 0, cy = 0, dx = 1, dy = 1;
+    bool valid() const { return h != nullptr; }
+    template <typename T> void sample(T x, T y, T& height, V3<T>& n) const {
+        T fx = (x - T(cx)) / T(dx) + T(0.5) * T(nx - 1), fy = (y - T(cy)) / T(dy) + T(0.5) * T(ny - 1);   // centre-relative: small magnitudes in fp32
+        if (fx < T(0)) fx = T(0); if (fy < T(0)) fy = T(0);
+        if (fx > T(nx - 1)) fx = T(nx - 1); if (fy > T(ny - 1)) fy = T(ny - 1);
+        int i = (int)fx, j = (int)fy; if (i > nx - 2) i = nx - 2; if (j > ny - 2) j = ny - 2;
+        T u = fx - T(i), v = fy - T(j);
+        T h00 = T(h[(size_t)i * ny + j]), h10 = T(h[(size_t)(i + 1) * ny + j]), h01 = T(h[(size_t)i * ny + j + 1]), h11 = T(h[(size_t)(i + 1) * ny + j + 1]);
+        T a, b;   // slopes dh/dx, dh/dy of the triangle under (u,v)
+        if (u >= v) { a = (h10 - h00) / T(dx); b = (h11 - h10) / T(dy); height = h00 + (h10 - h00) * u + (h11 - h10) * v; }
+        else        { a = (h11 - h01) / T(dx); b = (h01 - h00) / T(dy); height = h00 + (h11 - h01) * u + (h01 - h00) * v; }
+        T inv = T(1) / std::sqrt(T(1) + a * a + b * b);
+        n = V3<T>(-a * inv, -b * inv, inv);
+    }
+};
+
 // ------------------------------------------------------------------ one robot ("ENVIRONMENT", ENV:212)
 template <typename T> struct Env {
     // ---- configuration (ENV:1594-1659)
@@ -328,6 +349,8 @@ template <typename T> struct Env {
     int last_solver_sweeps = 0;
     // optional reference table (ManualTraj False; ENV:17-21, VEC:158-182)
     const float* ref = nullptr; int ref_rows = 0, frame_max = 0, frame_len = 0;
+    Terrain terrain;               // valid() only when Terrain: True
+    T ground_height() const { if (!terrain.valid()) return T(0); T hh; V3<T> nn; terrain.sample(gc_[0], gc_[1], hh, nn); return hh; }
 
     T current_time() const { return t0_ + T(frame_idx) * control_dt_; }
 
@@ -498,23 +521,34 @@ template <typename T> struct Env {
     }
 
     struct Contact { int kind; /*0..3 foot, 4.. box corner*/ int body; V3<T> point; V3<T> n; };
-    // collision detection: toe spheres and trunk box corners against the plane z = 0 (ENV:268 addGround)
+    // collision detection: toe spheres and trunk box corners against the plane z = 0 (ENV:268 addGround) or the heightfield
+    // (ENV:264 addHeightMap): signed distance to the local triangle plane, contact point = centre - r n
     int detect_contacts(const T* gc, const Kin& k, Contact* cs) const {
         int n = 0;
         for (int l = 0; l < 4; ++l) {
-            T cz = gc[2] + k.toe[l].z;
-            if (cz - model.toe_radius <= T(0)) {
-                cs[n].kind = l; cs[n].body = 3 + 3 * l; cs[n].n = V3<T>(0, 0, 1);
-                cs[n].point = k.toe[l] + V3<T>(0, 0, -model.toe_radius); ++n;
+            T hh = 0; V3<T> nn(0, 0, 1);
+            if (terrain.valid()) terrain.sample(gc[0] + k.toe[l].x, gc[1] + k.toe[l].y, hh, nn);
+            T gap = (gc[2] + k.toe[l].z - hh) * nn.z - model.toe_radius;
+            if (gap <= T(0)) {
+                cs[n].kind = l; cs[n].body = 3 + 3 * l; cs[n].n = nn;
+                cs[n].point = k.toe[l] - model.toe_radius * nn; ++n;
             }
         }
         int nbox = 0;
         for (int c = 0; c < 8 && nbox < 4; ++c) {
             V3<T> loc((c & 1) ? model.box_half.x : -model.box_half.x, (c & 2) ? model.box_half.y : -model.box_half.y, (c & 4) ? model.box_half.z : -model.box_half.z);
             V3<T> w = k.R[0] * loc;
-            if (gc[2] + w.z <= T(0)) { cs[n].kind = 4 + c; cs[n].body = 0; cs[n].n = V3<T>(0, 0, 1); cs[n].point = w; ++n; ++nbox; }
+            T hh = 0; V3<T> nn(0, 0, 1);
+            if (terrain.valid()) terrain.sample(gc[0] + w.x, gc[1] + w.y, hh, nn);
+            if ((gc[2] + w.z - hh) * nn.z <= T(0)) { cs[n].kind = 4 + c; cs[n].body = 0; cs[n].n = nn; cs[n].point = w; ++n; ++nbox; }
         }
         return n;
+    }
+    // contact frame rows (t1, t2, n): t1 = x-axis projected on the tangent plane, t2 = n x t1 (identity on flat ground)
+    static void contact_frame(const V3<T>& n, V3<T> D[3]) {
+        V3<T> t1(T(1) - n.x * n.x, -n.x * n.y, -n.x * n.z);
+        T inv = T(1) / std::sqrt(dot(t1, t1)); t1 = inv * t1;
+        D[0] = t1; D[1] = cross(n, t1); D[2] = n;
     }
 
     // One world_->integrate() (ENV:768).  tau = joint torques (12).
@@ -540,6 +574,10 @@ template <typename T> struct Env {
             T G[3 * MAXC][3 * MAXC], c[3 * MAXC], vtarget[MAXC], lam[3 * MAXC];
             for (int i = 0; i < nc; ++i) {
                 point_jacobian(k, cs[i].body, cs[i].point, J[i]);
+                if (terrain.valid()) {   // express the three rows in the contact frame (t1, t2, n)
+                    V3<T> D[3]; contact_frame(cs[i].n, D);
+                    for (int a = 0; a < NV; ++a) { V3<T> col(J[i][0][a], J[i][1][a], J[i][2][a]); for (int r = 0; r < 3; ++r) J[i][r][a] = dot(D[r], col); }
+                }
                 for (int r = 0; r < 3; ++r) ch.solve(J[i][r], W[i][r]);
             }
             for (int i = 0; i < nc; ++i) for (int r = 0; r < 3; ++r) {
@@ -804,7 +842,7 @@ template <typename T> struct Env {
             for (int a = 0; a < 3; ++a) { EndEffector_[3 * i + a] = e[a]; T d = e[a] - EndEffectorRef_[3 * i + a]; ee += d * d; }
         }
         EndEffectorReward = EECoeff * std::exp(-40 * ee);                                              // ENV:1459-1460
-        T dz = gc_[2] - stand_height_;
+        T dz = gc_[2] - ground_height() - stand_height_;     // height above the terrain under the trunk (flat ground: z)
         BodyCenterReward = BodyPosCoeff * std::exp(-80 * (dz * dz));                                   // ENV:1467-1476
         BodyAttitudeReward = BodyAttiCoeff * std::exp(-80 * (obDouble_[29] * obDouble_[29] + obDouble_[30] * obDouble_[30]));  // ENV:1481-1483
         T jr = 0, jd = 0;
@@ -866,6 +904,7 @@ template <typename T> struct Env {
         }
         if (flag_manual) { for (int i = 0; i < NQ; ++i) gc_[i] = gc_init_[i]; for (int i = 0; i < NV; ++i) gv_[i] = 0; }   // ENV:616-619
         else { for (int i = 0; i < NQ; ++i) gc_[i] = random_init[i]; for (int i = 0; i < NV; ++i) gv_[i] = random_vel_init[i]; }  // ENV:620-623
+        if (terrain.valid()) gc_[2] += ground_height();   // drop height 0.35 m is measured from the terrain under the trunk (new spec)
         for (int i = 0; i < 4; ++i) { foot_impulse[i][0] = foot_impulse[i][1] = foot_impulse[i][2] = 0; }
         n_contacts = 0;
         updateObservation(P_IN_RESET);                                                         // ENV:625
@@ -906,7 +945,8 @@ template <typename T> struct Env {
     // ENV:1553-1578
     bool isTerminalState(float& terminalReward) const {
         terminalReward = float(terminalRewardCoeff_);
-        if (gc_[2] < T(0.15) || gc_[2] > T(0.65) || obDouble_[31] < T(0.5)) return true;
+        T zrel = gc_[2] - ground_height();
+        if (zrel < T(0.15) || zrel > T(0.65) || obDouble_[31] < T(0.5)) return true;
         terminalReward = 0.f; return false;
     }
     // ENV:1248-1262
@@ -935,12 +975,17 @@ template <typename T> struct VecEnv {
         uint32_t seed = (uint32_t)(int)c.get("seedd");   // VEC:171 (double truncated to int)
         envs.resize(n);
         for (int i = 0; i < n; ++i) envs[i].configure(c, (uint32_t)(env_offset + i), seed);
-        if (envs[0].flag_ManualTraj || envs[0].flag_manual) reset_all();   // VEC:172-182: init() resets every env once (tick 0)
+        if ((envs[0].flag_ManualTraj || envs[0].flag_manual) && !envs[0].flag_terrain) reset_all();   // VEC:172-182: init() resets every env once (tick 0); with a terrain the caller sets it first and then calls reset_all()
     }
     void set_ref(const float* data, int rows) {   // VEC:158-182
         ref.assign(data, data + (size_t)rows * 30); ref_rows = rows;
         for (auto& e : envs) { e.ref = ref.data(); e.ref_rows = rows; e.frame_max = rows / 2; e.frame_len = int(e.max_time / e.control_dt_); }   // ENV:538-539
         if (tick == 0 && !(envs[0].flag_ManualTraj || envs[0].flag_manual)) reset_all();   // table mode: the init reset needs the table
+    }
+    std::vector<float> hf;
+    void set_terrain(const float* h, int nx, int ny, double x_size, double y_size, double cx, double cy) {
+        hf.assign(h, h + (size_t)nx * ny);
+        for (auto& e : envs) { e.terrain.h = hf.data(); e.terrain.nx = nx; e.terrain.ny = ny; e.terrain.dx = x_size / (nx - 1); e.terrain.dy = y_size / (ny - 1); e.terrain.cx = cx; e.terrain.cy = cy; }
     }
     void reset_all() {   // VEC:201-207 (serial in the reference)
         #pragma omp parallel for schedule(dynamic) num_threads(num_threads)

@@ -115,6 +115,7 @@ int bp5o_num_envs(void* h) { return H(h)->precision == 0 ? (int)H(h)->d.envs.siz
 void bp5o_set_tick(void* h, unsigned tick) { DISPATCH(h, V.tick = tick, V.tick = tick); }
 unsigned bp5o_get_tick(void* h) { return H(h)->precision == 0 ? H(h)->d.tick : H(h)->f.tick; }
 void bp5o_set_ref(void* h, const float* ref, int rows) { DISPATCH(h, V.set_ref(ref, rows), V.set_ref(ref, rows)); }
+void bp5o_set_terrain(void* h, const float* hf, int nx, int ny, double xs, double ys, double cx, double cy) { DISPATCH(h, { V.set_terrain(hf, nx, ny, xs, ys, cx, cy); if (V.tick == 0) V.reset_all(); }, { V.set_terrain(hf, nx, ny, xs, ys, cx, cy); if (V.tick == 0) V.reset_all(); }); }
 void bp5o_reset(void* h, float* ob) { DISPATCH(h, { V.reset_all(); V.observe(ob); }, { V.reset_all(); V.observe(ob); }); }
 void bp5o_observe(void* h, float* ob) { DISPATCH(h, V.observe(ob), V.observe(ob)); }
 int bp5o_step(void* h, const float* action, float* ob, float* reward, uint8_t* done, float* extra) {

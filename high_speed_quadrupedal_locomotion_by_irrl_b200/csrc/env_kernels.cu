@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const _
     e.frame_idx += 1;
     // ---- VEC::perAgentStep (VEC:352-372)
     const float zrel = e.b.p.z - ground_z;
-    const bool done = (zrel < 0.15f) || (zrel > 0.65f) || (o.ob31 < 0.5f);   // ENV:1560 (relative to the terrain under the trunk)
+    // ENV:1560 (relative to the terrain under the trunk); written so that a non-finite state also terminates and resets the env
+    const bool done = !((zrel >= 0.15f) && (zrel <= 0.65f) && (o.ob31 >= 0.5f));
     const float base_z = e.b.p.z;
     e.ep_len += 1;
     float ep_ret_out = 0.f; int ep_len_out = 0;

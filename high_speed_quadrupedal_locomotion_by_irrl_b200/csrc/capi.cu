@@ -798,6 +798,14 @@ int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total,
     return 0;
 }
 
+int irrl_lstm_seq_fwd(void* cuda_stream, int T, int K, int n_env, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep,
+                      float* gates, float* Cs, float* Hs) {
+    launch_lstm_seq_fwd(T, K, n_env, xw, wh, c0, h0, keep, gates, Cs, Hs, reinterpret_cast<cudaStream_t>(cuda_stream)); CUDA_OK(cudaGetLastError()); return 0;
+}
+int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates,
+                      const float* Cs, float* dz) {
+    launch_lstm_seq_bwd(T, K, n_env, dH, wh, c0, keep, gates, Cs, dz, reinterpret_cast<cudaStream_t>(cuda_stream)); CUDA_OK(cudaGetLastError()); return 0;
+}
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,
                      float* c_out, float* h_out, float* hm_next, float* cm_next) {
     launch_lstm_pw_fwd(rows, n_env, z, c_prev_masked, keep_next, gates, c_out, h_out, hm_next, cm_next, reinterpret_cast<cudaStream_t>(cuda_stream));

@@ -250,6 +250,184 @@ __global__ void lstm_pw_bwd_kernel(int rows, int n_env, const float* __restrict_
     dr[2 * H + u] = dh * tc * o * (1.f - o); dr[3 * H + u] = dc * i * (1.f - g * g);
     dcm_prev[idx] = dc * f;
 }
+// ------------------------------------------------------------------ sequence-persistent BPTT kernels (one launch per layer and direction)
+// A CTA owns 32 environments of one tower for ALL T steps: W_h stays in shared memory, h(t-1) in shared memory, c(t-1) in
+// registers; per step it adds h W_h to the streamed input projection xw[t] (prefetched one step ahead), applies the cell and
+// streams gates / c / h out.  Environments are independent, so there is no inter-CTA dependency and no per-step launch.
+// Layouts (time-major, as the rollout stores them): xw, gates, dz [T,K,N,192] in the checkpoint's gate order i,f,o,g;
+// C, H, dH [T,K,N,48]; keep [T,N]; c0, h0 [K,N,48]; wh [K,48,192].
+constexpr int SEQ_TM = 32;
+constexpr int SEQ_THR = 192;        // 24 unit pairs x 8 env groups; thread = 4 envs x 2 units (x 4 gates)
+
+__global__ void __launch_bounds__(SEQ_THR) lstm_seq_fwd_kernel(int T, int K, int N, const float* __restrict__ xw, const float* __restrict__ wh,
+                                                               const float* __restrict__ c0, const float* __restrict__ h0, const float* __restrict__ keep,
+                                                               float* __restrict__ gates, float* __restrict__ Cs, float* __restrict__ Hs) {
+    __shared__ __align__(16) float Ws[H][G4];          // [k][unit pair][unit][gate]
+    __shared__ __align__(16) float hT[H][SEQ_TM];      // masked h(t-1), transposed
+    const int tower = blockIdx.y, e0 = blockIdx.x * SEQ_TM, t_ = threadIdx.x, eg = t_ & 7, cg = t_ >> 3;
+    const float* whk = wh + (size_t)tower * H * G4;
+    for (int i = t_; i < H * G4; i += SEQ_THR) { int k = i / G4, col = i % G4, g = col / H, u = col % H; Ws[k][(u >> 1) * 8 + (u & 1) * 4 + g] = whk[i]; }
+    float c[4][2];
+    int envs[4]; bool valid[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        envs[e] = min(e0 + 4 * eg + e, N - 1); valid[e] = (e0 + 4 * eg + e) < N;
+        const size_t o = ((size_t)tower * N + envs[e]) * H + 2 * cg;
+        const float k0 = keep[envs[e]];                                     // keep[0][env]
+        c[e][0] = c0[o] * k0; c[e][1] = c0[o + 1] * k0;
+        hT[2 * cg][4 * eg + e] = h0[o] * k0; hT[2 * cg + 1][4 * eg + e] = h0[o + 1] * k0;
+    }
+    // prefetch xw[0]
+    float2 xin[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xin[e][g] = *reinterpret_cast<const float2*>(xw + (((size_t)0 * K + tower) * N + envs[e]) * G4 + g * H + 2 * cg);
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        float acc[4][8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { acc[e][g] = xin[e][g].x; acc[e][4 + g] = xin[e][g].y; }
+        if (t + 1 < T) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xin[e][g] = *reinterpret_cast<const float2*>(xw + (((size_t)(t + 1) * K + tower) * N + envs[e]) * G4 + g * H + 2 * cg);
+        }
+#pragma unroll 8
+        for (int k = 0; k < H; ++k) {
+            const float4 x = *reinterpret_cast<const float4*>(&hT[k][4 * eg]);
+            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][8 * cg]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&Ws[k][8 * cg + 4]);
+            const float xe[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[e][0] = fmaf(xe[e], w0.x, acc[e][0]); acc[e][1] = fmaf(xe[e], w0.y, acc[e][1]); acc[e][2] = fmaf(xe[e], w0.z, acc[e][2]); acc[e][3] = fmaf(xe[e], w0.w, acc[e][3]);
+                acc[e][4] = fmaf(xe[e], w1.x, acc[e][4]); acc[e][5] = fmaf(xe[e], w1.y, acc[e][5]); acc[e][6] = fmaf(xe[e], w1.z, acc[e][6]); acc[e][7] = fmaf(xe[e], w1.w, acc[e][7]);
+            }
+        }
+        __syncthreads();                                                    // everybody has read h(t-1)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float kn = (t + 1 < T) ? keep[(size_t)(t + 1) * N + envs[e]] : 1.f;
+            float gi[2], gf[2], go[2], gg[2], hn[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                gi[u] = 1.f / (1.f + expf(-acc[e][4 * u + 0])); gf[u] = 1.f / (1.f + expf(-acc[e][4 * u + 1]));
+                go[u] = 1.f / (1.f + expf(-acc[e][4 * u + 2])); gg[u] = tanhf(acc[e][4 * u + 3]);
+                c[e][u] = gf[u] * c[e][u] + gi[u] * gg[u];
+                hn[u] = go[u] * tanhf(c[e][u]);
+            }
+            if (valid[e]) {
+                const size_t row = ((size_t)t * K + tower) * N + envs[e];
+                float* gr = gates + row * G4 + 2 * cg;
+                *reinterpret_cast<float2*>(gr) = make_float2(gi[0], gi[1]); *reinterpret_cast<float2*>(gr + H) = make_float2(gf[0], gf[1]);
+                *reinterpret_cast<float2*>(gr + 2 * H) = make_float2(go[0], go[1]); *reinterpret_cast<float2*>(gr + 3 * H) = make_float2(gg[0], gg[1]);
+                *reinterpret_cast<float2*>(Cs + row * H + 2 * cg) = make_float2(c[e][0], c[e][1]);
+                *reinterpret_cast<float2*>(Hs + row * H + 2 * cg) = make_float2(hn[0], hn[1]);
+            }
+            c[e][0] *= kn; c[e][1] *= kn;                                   // SB lstm(): c *= 1-m ; h *= 1-m before the next cell
+            hT[2 * cg][4 * eg + e] = hn[0] * kn; hT[2 * cg + 1][4 * eg + e] = hn[1] * kn;
+        }
+        __syncthreads();
+    }
+}
+
+// backward through time: dz[t] from (dH[t] + carry_h keep[t+1], carry_c keep[t+1]); carry_h = dz[t] W_h^T, carry_c = dc f
+__global__ void __launch_bounds__(SEQ_THR) lstm_seq_bwd_kernel(int T, int K, int N, const float* __restrict__ dH, const float* __restrict__ wh,
+                                                               const float* __restrict__ c0, const float* __restrict__ keep, const float* __restrict__ gates,
+                                                               const float* __restrict__ Cs, float* __restrict__ dz) {
+    extern __shared__ __align__(16) unsigned char seq_smem[];          // 60 KB: above the static limit, opt-in dynamic
+    float (*WT)[H] = reinterpret_cast<float (*)[H]>(seq_smem);                                   // [permuted col][unit k] = wh[k][col]
+    float (*dzT)[SEQ_TM] = reinterpret_cast<float (*)[SEQ_TM]>(seq_smem + sizeof(float) * G4 * H); // dz(t), permuted columns, transposed
+    const int tower = blockIdx.y, e0 = blockIdx.x * SEQ_TM, t_ = threadIdx.x, eg = t_ & 7, cg = t_ >> 3;
+    const float* whk = wh + (size_t)tower * H * G4;
+    for (int i = t_; i < H * G4; i += SEQ_THR) { int k = i / G4, col = i % G4, g = col / H, u = col % H; WT[(u >> 1) * 8 + (u & 1) * 4 + g][k] = whk[i]; }
+    int envs[4]; bool valid[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { envs[e] = min(e0 + 4 * eg + e, N - 1); valid[e] = (e0 + 4 * eg + e) < N; }
+    float ch[4][2], cc[4][2];                           // carries (gradient w.r.t. the masked h / c fed to step t+1)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ch[e][0] = ch[e][1] = cc[e][0] = cc[e][1] = 0.f; }
+    // per-step operands, loaded one step ahead
+    struct In { float2 dh, c, cp, gi, gf, go, gg; float ku, kt; };
+    In cur[4], nxt[4];
+    auto load_step = [&](int t, In* in) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const size_t row = ((size_t)t * K + tower) * N + envs[e];
+            in[e].ku = (t + 1 < T) ? keep[(size_t)(t + 1) * N + envs[e]] : 0.f;
+            in[e].kt = keep[(size_t)t * N + envs[e]];
+            in[e].dh = *reinterpret_cast<const float2*>(dH + row * H + 2 * cg);
+            in[e].c = *reinterpret_cast<const float2*>(Cs + row * H + 2 * cg);
+            in[e].cp = (t > 0) ? *reinterpret_cast<const float2*>(Cs + (((size_t)(t - 1) * K + tower) * N + envs[e]) * H + 2 * cg)
+                               : *reinterpret_cast<const float2*>(c0 + ((size_t)tower * N + envs[e]) * H + 2 * cg);
+            const float* gr = gates + row * G4 + 2 * cg;
+            in[e].gi = *reinterpret_cast<const float2*>(gr); in[e].gf = *reinterpret_cast<const float2*>(gr + H);
+            in[e].go = *reinterpret_cast<const float2*>(gr + 2 * H); in[e].gg = *reinterpret_cast<const float2*>(gr + 3 * H);
+        }
+    };
+    load_step(T - 1, cur);
+    __syncthreads();
+    for (int t = T - 1; t >= 0; --t) {
+        if (t > 0) load_step(t - 1, nxt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const size_t row = ((size_t)t * K + tower) * N + envs[e];
+            const float ku = cur[e].ku, kt = cur[e].kt;
+            const float dhv[2] = {cur[e].dh.x + ch[e][0] * ku, cur[e].dh.y + ch[e][1] * ku}, cv[2] = {cur[e].c.x, cur[e].c.y}, cpm[2] = {cur[e].cp.x * kt, cur[e].cp.y * kt};
+            const float iv[2] = {cur[e].gi.x, cur[e].gi.y}, fv[2] = {cur[e].gf.x, cur[e].gf.y}, ov[2] = {cur[e].go.x, cur[e].go.y}, gv[2] = {cur[e].gg.x, cur[e].gg.y};
+            float dzv[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float tc = tanhf(cv[u]);
+                const float dc = cc[e][u] * ku + dhv[u] * ov[u] * (1.f - tc * tc);
+                dzv[u][0] = dc * gv[u] * iv[u] * (1.f - iv[u]); dzv[u][1] = dc * cpm[u] * fv[u] * (1.f - fv[u]);
+                dzv[u][2] = dhv[u] * tc * ov[u] * (1.f - ov[u]); dzv[u][3] = dc * iv[u] * (1.f - gv[u] * gv[u]);
+                cc[e][u] = dc * fv[u];
+            }
+            if (valid[e]) {
+                float* dr = dz + row * G4 + 2 * cg;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(dr + g * H) = make_float2(dzv[0][g], dzv[1][g]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dzT[8 * cg + 4 * u + g][4 * eg + e] = dzv[u][g];
+        }
+        __syncthreads();
+        float acc[4][2];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e][0] = acc[e][1] = 0.f;
+#pragma unroll 8
+        for (int col = 0; col < G4; ++col) {
+            const float4 x = *reinterpret_cast<const float4*>(&dzT[col][4 * eg]);
+            const float2 w = *reinterpret_cast<const float2*>(&WT[col][2 * cg]);
+            acc[0][0] = fmaf(x.x, w.x, acc[0][0]); acc[0][1] = fmaf(x.x, w.y, acc[0][1]); acc[1][0] = fmaf(x.y, w.x, acc[1][0]); acc[1][1] = fmaf(x.y, w.y, acc[1][1]);
+            acc[2][0] = fmaf(x.z, w.x, acc[2][0]); acc[2][1] = fmaf(x.z, w.y, acc[2][1]); acc[3][0] = fmaf(x.w, w.x, acc[3][0]); acc[3][1] = fmaf(x.w, w.y, acc[3][1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ch[e][0] = acc[e][0]; ch[e][1] = acc[e][1]; cur[e] = nxt[e]; }
+        __syncthreads();
+    }
+}
+void launch_lstm_seq_fwd(int T, int K, int N, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep, float* gates, float* Cs,
+                         float* Hs, cudaStream_t st) {
+    dim3 grid((N + SEQ_TM - 1) / SEQ_TM, K);
+    lstm_seq_fwd_kernel<<<grid, SEQ_THR, 0, st>>>(T, K, N, xw, wh, c0, h0, keep, gates, Cs, Hs);
+}
+void launch_lstm_seq_bwd(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
+                         float* dz, cudaStream_t st) {
+    dim3 grid((N + SEQ_TM - 1) / SEQ_TM, K);
+    constexpr int smem = sizeof(float) * (G4 * H + G4 * SEQ_TM);
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+    lstm_seq_bwd_kernel<<<grid, SEQ_THR, smem, st>>>(T, K, N, dH, wh, c0, keep, gates, Cs, dz);
+}
+
 void launch_lstm_pw_fwd(int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates, float* c_out,
                         float* h_out, float* hm_next, float* cm_next, cudaStream_t st) {
     lstm_pw_fwd_kernel<<<(rows * H + 255) / 256, 256, 0, st>>>(rows, n_env, z, c_prev_masked, keep_next, gates, c_out, h_out, hm_next, cm_next);

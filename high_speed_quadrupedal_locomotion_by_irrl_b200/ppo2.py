@@ -77,11 +77,11 @@ class LstmActorCritic(torch.nn.Module):
     def forward_time_major(self, obs, keep, state, fused: Optional[bool] = None):
         """obs [T,N,35] (time-major, as the device rollout stores it), keep [T,N] = 1 - mask, state [N,384] at t = 0.
         Returns mean [T,N,12], value [T,N].  On CUDA the recurrence runs through the fused BPTT path (lstm_seq.LstmLayerSeq)."""
-        from .lstm_seq import LstmLayerSeq, lstm_layer_reference
+        from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, lstm_layer_reference
         T, N, _ = obs.shape
         H = 48
         fused = obs.is_cuda if fused is None else fused
-        layer = LstmLayerSeq.apply if fused else lstm_layer_reference
+        layer = lstm_layer_reference if not fused else (LstmLayerSeq.apply if fused == "stepwise" else LstmLayerSeqPersistent.apply)
         st = state.view(N, 2, 2, 2, H)                                  # [env, tower, layer, (c,h), unit]
         c0 = st[:, :, 0, 0].transpose(0, 1).contiguous(); h0 = st[:, :, 0, 1].transpose(0, 1).contiguous()
         c1 = st[:, :, 1, 0].transpose(0, 1).contiguous(); h1 = st[:, :, 1, 1].transpose(0, 1).contiguous()

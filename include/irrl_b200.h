@@ -150,6 +150,13 @@ typedef struct irrl_rollout_buffers {
     int32_t* ep_length;/* [T,N] (may be NULL) */
 } irrl_rollout_buffers;
 int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* buf, int deterministic);
+/* sequence-persistent BPTT through one LSTM layer of K towers (the PPO learner's recurrence, ppo2.py:136-197 over run_bp_v5.py:143-166):
+ * one launch per direction, a CTA owns 32 envs for all T steps.  Time-major device tensors: xw / gates / dz [T,K,N,192] (gate order
+ * i,f,o,g), Cs / Hs / dH [T,K,N,48], keep [T,N] = 1 - done mask, c0 / h0 [K,N,48] (state before step 0, unmasked), wh [K,48,192]. */
+int irrl_lstm_seq_fwd(void* cuda_stream, int T, int K, int n_env, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep,
+                      float* gates, float* Cs, float* Hs);
+int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates,
+                      const float* Cs, float* dz);
 /* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,
  * z / gates [rows,192] in gate order i,f,o,g, the rest [rows,48]; keep = 1 - done mask per env (run_bp_v5.py:151-153 lstm(..., masks, ...)) */
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,

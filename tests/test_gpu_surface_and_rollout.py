@@ -187,19 +187,20 @@ def test_fused_bptt_matches_autograd_reference():
     adv = torch.tensor(rng.normal(size=(T, N)).astype(np.float32), device=dev); ret = torch.tensor(rng.normal(size=(T, N)).astype(np.float32), device=dev)
     oldv = torch.tensor(rng.normal(size=(T, N)).astype(np.float32), device=dev); oldn = torch.tensor(rng.normal(-15, 1, size=(T, N)).astype(np.float32), device=dev)
     res = []
-    for fused in (True, False):
+    for fused in (True, False, "stepwise"):
         m = LstmActorCritic(W).to(dev)
         mean, val = m.forward_time_major(obs, 1.0 - masks, st, fused=fused)
         nlp = m.neglogp(mean, act)
         loss = ((val - ret) ** 2).mean() + (torch.exp(oldn - nlp).clamp(max=10.0) * adv).mean() * 0.0 + (nlp * adv).mean() * 1e-3
         grads = torch.autograd.grad(loss, m.param_list(), allow_unused=True)
         res.append((mean.detach(), val.detach(), grads))
-    assert torch.allclose(res[0][0], res[1][0], atol=2e-5) and torch.allclose(res[0][1], res[1][1], atol=2e-5)
-    for n, ga, gb in zip(PARAM_NAMES, res[0][2], res[1][2]):
-        if ga is None:
-            assert gb is None; continue
-        scale = float(gb.abs().max()) + 1e-12
-        assert float((ga - gb).abs().max()) < 2e-4 * scale + 1e-9, (n, float((ga - gb).abs().max()), scale)
+    for variant in (0, 2):       # persistent kernels and the step-wise fused path, each against plain autograd
+        assert torch.allclose(res[variant][0], res[1][0], atol=2e-5) and torch.allclose(res[variant][1], res[1][1], atol=2e-5)
+        for n, ga, gb in zip(PARAM_NAMES, res[variant][2], res[1][2]):
+            if ga is None:
+                assert gb is None; continue
+            scale = float(gb.abs().max()) + 1e-12
+            assert float((ga - gb).abs().max()) < 2e-4 * scale + 1e-9, (variant, n, float((ga - gb).abs().max()), scale)
 
 
 def test_bp5_155_policy_reproduces_the_references_robot_level_results():

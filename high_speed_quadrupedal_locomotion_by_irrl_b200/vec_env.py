@@ -1,13 +1,14 @@
-"""`RaisimGymVecEnv` -- the stable-baselines VecEnv adapter of the reference (flex_gym/env/RaisimGymVecEnv.py:6-189)
-with the same attributes, methods, return values and in-place buffer semantics, minus the imports that do not exist
-here (gym, stable_baselines) and minus the O(N) Python per step:
+"""`RaisimGymVecEnv`: the VecEnv adapter between the native vec-env and the RL code -- same public surface as the reference's
+flex_gym/env/RaisimGymVecEnv.py (attributes `wrapper, num_obs, num_acts, _observation, _reward, _done, _extraInfo, rewards`;
+`step / reset / reset_and_update_info`; the probe getters; window / video / curriculum pass-throughs; the `num_envs`,
+`observation_space`, `action_space`, `extra_info_names` properties), without gym / stable_baselines and without O(N) Python per step:
 
-  * `info` is a lazy sequence: the reference builds 6N one-key dicts every step (RaisimGymVecEnv.py:35-40) of which only
-    `info[i]['episode']` is ever consumed (ppo2.py:534-537).  Here entries materialise on access with the same content
-    (entry k < 6N holds extra-info j = k // N of env i = k % N; entry i additionally carries env i's `episode`).
-  * episode return / length bookkeeping (RaisimGymVecEnv.py:42-50) runs in the step kernel; `self.rewards` keeps the
-    reference's list-of-lists view only when `track_rewards=True`.
-  * numpy >= 1.24 names: `bool` / `np.inf` instead of the removed `np.bool` / `np.Inf`.
+  * `info` is a lazy sequence.  The reference materialises 6N one-key dicts per step (entry k holds extra-info j = k // N of env
+    i = k % N, and entry i also gets env i's `episode`), of which only `info[i]['episode']` is ever read (ppo2.py:534-537).
+    `LazyInfo` builds an entry only when it is indexed, with the same content.
+  * episode return / length bookkeeping happens in the step kernel; `self.rewards` keeps the reference's list-of-lists view only
+    with `track_rewards=True`.
+  * numpy >= 1.24 spellings (`bool`, `np.inf`).
 """
 from __future__ import annotations
 
@@ -17,195 +18,142 @@ import numpy as np
 
 
 class Box:
-    """Minimal stand-in for gym.spaces.Box (shape, low, high, dtype)."""
+    """Shape / bounds / dtype record standing in for gym.spaces.Box."""
 
     def __init__(self, low, high, dtype=np.float32):
-        self.low = np.asarray(low, dtype=dtype)
-        self.high = np.asarray(high, dtype=dtype)
-        self.shape = self.low.shape
-        self.dtype = np.dtype(dtype)
+        self.low, self.high = np.asarray(low, dtype=dtype), np.asarray(high, dtype=dtype)
+        self.shape, self.dtype = self.low.shape, np.dtype(dtype)
 
     def __repr__(self):
         return f"Box{self.shape}"
 
 
 class LazyInfo(Sequence):
-    """Materialises the reference's `info` list on demand."""
-
     def __init__(self, names: List[str], extra: np.ndarray, episodes: Dict[int, Dict[str, Any]]):
-        self._names, self._extra, self._episodes = names, extra, episodes
-        self._n = extra.shape[0]
+        self._names, self._extra, self._episodes, self._n = names, extra, episodes, extra.shape[0]
 
     def __len__(self):
-        return len(self._names) * self._n if self._names else self._n
+        return max(len(self._names), 1) * self._n
 
     def __getitem__(self, k):
         if isinstance(k, slice):
             return [self[i] for i in range(*k.indices(len(self)))]
-        if k < 0:
-            k += len(self)
+        k = k + len(self) if k < 0 else k
         if not 0 <= k < len(self):
             raise IndexError(k)
-        d: Dict[str, Any] = {}
+        entry: Dict[str, Any] = {}
         if self._names:
             j, i = divmod(k, self._n)
-            d["extra_info"] = {self._names[j]: self._extra[i, j]}
+            entry["extra_info"] = {self._names[j]: self._extra[i, j]}
         if k in self._episodes:
-            d["episode"] = self._episodes[k]
-        return d
+            entry["episode"] = self._episodes[k]
+        return entry
 
     def copy(self):
         return self
 
     def episodes(self):
-        """only the entries that carry an `episode` key (what ppo2.py:534-537 scans for)"""
+        """the `episode` records only, by env index"""
         return [self._episodes[i] for i in sorted(self._episodes)]
+
+
+_UNSUPPORTED = ("render", "step_async", "step_wait", "get_attr", "set_attr", "env_method")
+# probe getter -> (native method, row width as a function of the action count)
+_PROBES = {
+    "ReferenceState": ("ReferenceState", lambda a: 2 * a),
+    "GetJointEffort": ("GetJointEffort", lambda a: a),
+    "GetGeneralizedForce": ("GetGeneralizedForce", lambda a: a + 6),          # floating base: 6 + joints
+    "GetInverseMassMatrix": ("GetInverseMassMatrix", lambda a: (a + 6) ** 2),
+    "GetNonlinear": ("GetNonlinear", lambda a: a + 6),
+    "GetSphereInfo": ("GetSphereInfo", lambda a: 4),
+}
+_PASSTHROUGH = {"close": "close", "start_recording_video": "startRecordingVideo", "stop_recording_video": "stopRecordingVideo",
+                "curriculum_callback": "curriculumUpdate", "show_window": "showWindow", "hide_window": "hideWindow"}
 
 
 class RaisimGymVecEnv:
     def __init__(self, impl, track_rewards: bool = False):
         self.wrapper = impl
-        self.wrapper.init()
-        self.num_obs = self.wrapper.getObDim()
-        self.num_acts = self.wrapper.getActionDim()
-        self._observation_space = Box(np.ones(self.num_obs) * -np.inf, np.ones(self.num_obs) * np.inf, dtype=np.float32)
-        self._action_space = Box(np.ones(self.num_acts) * -1., np.ones(self.num_acts) * 1., dtype=np.float32)
-        self._observation = np.zeros([self.num_envs, self.num_obs], dtype=np.float32)
-        self._reward = np.zeros(self.num_envs, dtype=np.float32)
-        self._done = np.zeros((self.num_envs), dtype=bool)
-        self._extraInfoNames = self.wrapper.getExtraInfoNames()
-        self._extraInfo = np.zeros([self.num_envs, len(self._extraInfoNames)], dtype=np.float32)
-        self._ep_ret = np.zeros(self.num_envs, dtype=np.float32)
-        self._ep_len = np.zeros(self.num_envs, dtype=np.int32)
-        # the wrapper owns these buffers (as in the reference): page-lock them once so step() DMAs straight into them
-        try:
+        impl.init()
+        n = impl.getNumOfEnvs()
+        self.num_obs, self.num_acts = impl.getObDim(), impl.getActionDim()
+        self._observation_space = Box(np.full(self.num_obs, -np.inf), np.full(self.num_obs, np.inf))
+        self._action_space = Box(-np.ones(self.num_acts), np.ones(self.num_acts))
+        self._extraInfoNames = impl.getExtraInfoNames()
+        self._observation = np.zeros((n, self.num_obs), np.float32)
+        self._reward = np.zeros(n, np.float32)
+        self._done = np.zeros(n, bool)
+        self._extraInfo = np.zeros((n, len(self._extraInfoNames)), np.float32)
+        self._ep_ret, self._ep_len = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        try:   # the adapter owns these buffers: page-lock them once so the native step DMAs straight into them
             from . import _lib
             for buf in (self._observation, self._reward, self._done, self._extraInfo):
                 _lib.pin(buf)
         except Exception:
             pass
         self._track = track_rewards
-        self.rewards = [[] for _ in range(self.num_envs)] if track_rewards else None
+        self.rewards = [[] for _ in range(n)] if track_rewards else None
 
-    def seed(self, seed=None):
-        # the reference calls a non-existent wrapper.seed (RaisimGymVecEnv.py:24); setSeed is the bound name
-        self.wrapper.setSeed(0 if seed is None else int(seed))
-
+    # ------------------------------------------------------------------ hot path
     def step(self, action, visualize=False):
-        action = np.ascontiguousarray(action, dtype=np.float32)
-        if not visualize:
-            self.wrapper.step(action, self._observation, self._reward, self._done, self._extraInfo)
-        else:
-            self.wrapper.testStep(action, self._observation, self._reward, self._done, self._extraInfo)
+        native = self.wrapper.testStep if visualize else self.wrapper.step
+        native(np.ascontiguousarray(action, np.float32), self._observation, self._reward, self._done, self._extraInfo)
         episodes: Dict[int, Dict[str, Any]] = {}
         if self._done.any():
             self.wrapper.lastEpisodeStats(self._ep_ret, self._ep_len)
-            for i in np.flatnonzero(self._done):
-                episodes[int(i)] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i])}
+            episodes = {int(i): {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i])} for i in np.flatnonzero(self._done)}
         if self._track:
-            for i in range(self.num_envs):
-                self.rewards[i].append(self._reward[i])
+            for i, r in enumerate(self._reward):
+                self.rewards[i].append(r)
                 if self._done[i]:
                     self.rewards[i].clear()
-        info = LazyInfo(self._extraInfoNames, self._extraInfo.copy(), episodes)
-        return self._observation.copy(), self._reward.copy(), self._done.copy(), info
-
-    def _probe(self, fn, width):
-        temp = np.zeros([self.num_envs, width], dtype=np.float32)
-        fn(temp)
-        return temp
-
-    def OriginState(self):
-        return self._probe(self.wrapper.OriginState, self.wrapper.GetOriginStateDim())
-
-    def ReferenceState(self):
-        return self._probe(self.wrapper.ReferenceState, self.num_acts * 2)
-
-    def GetJointEffort(self):
-        return self._probe(self.wrapper.GetJointEffort, self.num_acts)
-
-    def GetGeneralizedForce(self):
-        return self._probe(self.wrapper.GetGeneralizedForce, self.num_acts + 6)
-
-    def GetInverseMassMatrix(self):
-        return self._probe(self.wrapper.GetInverseMassMatrix, (self.num_acts + 6) * (self.num_acts + 6))
-
-    def GetNonlinear(self):
-        return self._probe(self.wrapper.GetNonlinear, self.num_acts + 6)
-
-    def GetSphereInfo(self):
-        return self._probe(self.wrapper.GetSphereInfo, 4)
-
-    def SetContactCoefficient(self, contact_coeff):
-        self.wrapper.SetContactCoefficient(np.ascontiguousarray(contact_coeff, dtype=np.float32))
+        return self._observation.copy(), self._reward.copy(), self._done.copy(), LazyInfo(self._extraInfoNames, self._extraInfo.copy(), episodes)
 
     def reset(self):
-        self._reward = np.zeros(self.num_envs, dtype=np.float32)
+        self._reward = np.zeros(self.num_envs, np.float32)
         self.wrapper.reset(self._observation)
         return self._observation.copy()
 
     def reset_and_update_info(self):
-        # the reference resets first and reads the running episode statistics afterwards (RaisimGymVecEnv.py:100-101);
-        # the device counters are cleared by reset, so they are read first here -- same values
+        # the device counters are cleared by the reset, so they are read first (the reference reads its Python lists afterwards)
         info = self._update_epi_info()
         return self.reset(), info
 
     def _update_epi_info(self):
         self.wrapper.runningEpisodeStats(self._ep_ret, self._ep_len, True)
-        info = [{"episode": {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i])}} for i in range(self.num_envs)]
         if self._track:
             for r in self.rewards:
                 r.clear()
-        return info
+        return [{"episode": {"r": float(r), "l": int(l)}} for r, l in zip(self._ep_ret, self._ep_len)]
 
-    def render(self, mode='human'):
-        raise RuntimeError('This method is not implemented')
+    def seed(self, seed=None):
+        self.wrapper.setSeed(0 if seed is None else int(seed))      # the reference calls a non-existent wrapper.seed here
 
-    def close(self):
-        self.wrapper.close()
+    # ------------------------------------------------------------------ probes and pass-throughs
+    def _fetch(self, native_name: str, width: int):
+        out = np.zeros((self.num_envs, width), np.float32)
+        getattr(self.wrapper, native_name)(out)
+        return out
 
-    def start_recording_video(self, file_name):
-        self.wrapper.startRecordingVideo(file_name)
+    def OriginState(self):
+        return self._fetch("OriginState", self.wrapper.GetOriginStateDim())
 
-    def stop_recording_video(self):
-        self.wrapper.stopRecordingVideo()
+    def SetContactCoefficient(self, contact_coeff):
+        self.wrapper.SetContactCoefficient(np.ascontiguousarray(contact_coeff, np.float32))
 
-    def curriculum_callback(self):
-        self.wrapper.curriculumUpdate()
+    def __getattr__(self, name):
+        if name in _PROBES:
+            native, width = _PROBES[name]
+            return lambda: self._fetch(native, width(self.num_acts))
+        if name in _PASSTHROUGH:
+            return getattr(self.wrapper, _PASSTHROUGH[name])
+        if name in _UNSUPPORTED:
+            def _raise(*a, **k):
+                raise RuntimeError('This method is not implemented')
+            return _raise
+        raise AttributeError(name)
 
-    def step_async(self):
-        raise RuntimeError('This method is not implemented')
-
-    def step_wait(self):
-        raise RuntimeError('This method is not implemented')
-
-    def get_attr(self, attr_name, indices=None):
-        raise RuntimeError('This method is not implemented')
-
-    def set_attr(self, attr_name, value, indices=None):
-        raise RuntimeError('This method is not implemented')
-
-    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
-        raise RuntimeError('This method is not implemented')
-
-    def show_window(self):
-        self.wrapper.showWindow()
-
-    def hide_window(self):
-        self.wrapper.hideWindow()
-
-    @property
-    def num_envs(self):
-        return self.wrapper.getNumOfEnvs()
-
-    @property
-    def observation_space(self):
-        return self._observation_space
-
-    @property
-    def action_space(self):
-        return self._action_space
-
-    @property
-    def extra_info_names(self):
-        return self._extraInfoNames
+    num_envs = property(lambda self: self.wrapper.getNumOfEnvs())
+    observation_space = property(lambda self: self._observation_space)
+    action_space = property(lambda self: self._action_space)
+    extra_info_names = property(lambda self: self._extraInfoNames)

@@ -87,6 +87,7 @@ struct irrl_policy_impl {
     int device = 0;
     float* d_params = nullptr;
     float* d_derived = nullptr;   // 4 x ([96][192] + [192]) gate-interleaved copies for the act kernel
+    unsigned char* d_tcblob = nullptr;   // 2 x TC_BLOB_BYTES hi/lo-split UMMA-layout weights for the tcgen05 act kernel
     PolicyWeights W{};
     // staging for host callers
     int cap = 0; float *d_obs = nullptr, *d_state = nullptr, *d_action = nullptr, *d_clipped = nullptr, *d_value = nullptr, *d_nlp = nullptr; uint8_t* d_done = nullptr;
@@ -657,6 +658,7 @@ static void bind_weights(irrl_policy_impl* Pn) {
     for (int i = 0; i < 4; ++i) { W.wx[i] = p; p += in[i] * 192; W.wh[i] = p; p += 48 * 192; W.b[i] = p; p += 192; }
     W.vf_w = p; p += 48; W.vf_b = p; p += 1; W.pi_w = p; p += 48 * 12; W.pi_b = p; p += 12; W.logstd = p; p += 12; /* q head (unused by act) follows */
     for (int i = 0; i < 4; ++i) { W.wcat[i] = Pn->d_derived + (size_t)i * (96 * 192 + 192); W.bperm[i] = W.wcat[i] + 96 * 192; }
+    W.tcblob = Pn->d_tcblob;
 }
 // gate-interleaved, zero-padded [x ; h] weight blocks: new column (u/2)*8 + (u%2)*4 + g  <-  original column g*48 + u
 static int upload_derived(irrl_policy_impl* Pn, const float* host_params) {
@@ -673,6 +675,15 @@ static int upload_derived(irrl_policy_impl* Pn, const float* host_params) {
         }
     }
     CUDA_OK(cudaMemcpy(Pn->d_derived, d.data(), d.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {   // tensor-core layout (policy_tc_kernels.cu): tower 0 = pi cells + mean head, tower 1 = V cells + value head
+        std::vector<unsigned char> blob((size_t)2 * TC_BLOB_BYTES);
+        const float* q = host_params; const float* wx[4]; const float* wh[4];
+        for (int i = 0; i < 4; ++i) { wx[i] = q; q += in[i] * 192; wh[i] = q; q += 48 * 192; q += 192; }
+        const float* vf_w = q; q += 48 + 1; const float* pi_w = q;
+        pack_tc_blob(wx[0], wh[0], wx[1], wh[1], pi_w, 12, blob.data());
+        pack_tc_blob(wx[2], wh[2], wx[3], wh[3], vf_w, 1, blob.data() + TC_BLOB_BYTES);
+        CUDA_OK(cudaMemcpy(Pn->d_tcblob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 int irrl_policy_create(int device, const float* params, irrl_policy** out) {
@@ -682,6 +693,7 @@ int irrl_policy_create(int device, const float* params, irrl_policy** out) {
     irrl_policy_impl* Pn = new irrl_policy_impl(); Pn->device = device;
     CUDA_OK(cudaMalloc((void**)&Pn->d_params, IRRL_POLICY_NUM_PARAMS * sizeof(float)));
     CUDA_OK(cudaMalloc((void**)&Pn->d_derived, (size_t)4 * (96 * 192 + 192) * sizeof(float)));
+    CUDA_OK(cudaMalloc((void**)&Pn->d_tcblob, (size_t)2 * TC_BLOB_BYTES));
     bind_weights(Pn);
     *out = reinterpret_cast<irrl_policy*>(Pn);
     return irrl_policy_set_params(*out, params);
@@ -694,10 +706,27 @@ int irrl_policy_set_params(irrl_policy* pol, const float* params) {
     CUDA_OK(cudaMemcpy(hp.data(), Pn->d_params, hp.size() * sizeof(float), cudaMemcpyDeviceToHost));
     return upload_derived(Pn, hp.data());
 }
+int irrl_policy_set_act_path(int mode) {
+    if (mode < 0 || mode > 2) return fail(-1, "irrl_policy_set_act_path: mode must be 0 (auto), 1 (fp32 FMA kernel) or 2 (tcgen05 kernel)");
+    g_act_path = mode; return 0;
+}
+int irrl_tc_timeline(int enable, long long* out16) { tc_timeline(enable, out16); return 0; }
+int irrl_tc_gemm_probe(const float* a, const float* b, float* d, int k, int n, int variant) {
+    if (!a || !b || !d) return fail(-1, "null argument");
+    float *da = nullptr, *db = nullptr, *dd = nullptr;
+    CUDA_OK(cudaMalloc((void**)&da, 128 * k * 4)); CUDA_OK(cudaMalloc((void**)&db, (size_t)n * k * 4)); CUDA_OK(cudaMalloc((void**)&dd, (size_t)128 * n * 4));
+    CUDA_OK(cudaMemcpy(da, a, 128 * k * 4, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(db, b, (size_t)n * k * 4, cudaMemcpyHostToDevice));
+    int rc = launch_tc_gemm_probe(da, db, dd, k, n, variant, 0);
+    if (rc) { cudaFree(da); cudaFree(db); cudaFree(dd); return fail(-1, "irrl_tc_gemm_probe: k must be a multiple of 8 in [8,64], n a multiple of 16 in [16,256]"); }
+    CUDA_OK(cudaGetLastError()); CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(d, dd, (size_t)128 * n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return 0;
+}
 void irrl_policy_destroy(irrl_policy* pol) {
     irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return;
     cudaSetDevice(Pn->device); cudaDeviceSynchronize();
-    cudaFree(Pn->d_params); cudaFree(Pn->d_derived); cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
+    cudaFree(Pn->d_params); cudaFree(Pn->d_derived); cudaFree(Pn->d_tcblob); cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
     if (Pn->h_pin) cudaFreeHost(Pn->h_pin);
     delete Pn;
 }

@@ -39,7 +39,9 @@ struct PolicyWeights {      // device pointers, fp32, layouts as in the referenc
     const float* logstd;    // [12]
     const float* wcat[4];   // derived: [96][192] = [wx ; wh ; 0-pad] with gate-interleaved columns (unit pair, unit, gate)
     const float* bperm[4];  // derived: [192] biases in the same column order
+    const unsigned char* tcblob;   // derived: 2 towers x TC_BLOB_BYTES, hi/lo-split UMMA-layout weights (policy_tc_kernels.cu)
 };
+constexpr int TC_BLOB_BYTES = (11 + 12) * 12288 + 6 * 1024;
 struct ActArgs {
     PolicyWeights W;
     const float* obs;       // [N,35]
@@ -55,7 +57,13 @@ struct ActArgs {
     int N; int deterministic;
     uint32_t seed, env_offset, tick;
 };
-void launch_lstm_act(const ActArgs& a, cudaStream_t st);
+void launch_lstm_act(const ActArgs& a, cudaStream_t st);          // dispatches on N and g_act_path
+void launch_lstm_act_fma(const ActArgs& a, cudaStream_t st);      // fp32 FMA kernel (policy_kernels.cu)
+void launch_lstm_act_tc(const ActArgs& a, cudaStream_t st);       // tcgen05 kernel (policy_tc_kernels.cu)
+extern int g_act_path;                                             // 0 auto (tensor cores from 256 envs), 1 FMA, 2 tensor cores
+int launch_tc_gemm_probe(const float* dA, const float* dB, float* dD, int K, int N, int variant, cudaStream_t st);
+void tc_timeline(int enable, long long* out16);
+void pack_tc_blob(const float* wx0, const float* wh0, const float* wx1, const float* wh1, const float* head_w, int head_cols, unsigned char* out);
 void launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, const uint8_t* last_dones,
                 float* adv, float* ret, int T, int N, float gamma, float lam, cudaStream_t st);
 

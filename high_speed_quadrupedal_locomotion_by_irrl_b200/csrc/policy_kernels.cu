@@ -186,7 +186,12 @@ __global__ void __launch_bounds__(NTHR, 2) lstm_act_kernel(const __grid_constant
     }
 }
 
+int g_act_path = 0;
 void launch_lstm_act(const ActArgs& a, cudaStream_t st) {
+    const bool tc = g_act_path == 2 || (g_act_path == 0 && a.N >= 256);
+    if (tc) launch_lstm_act_tc(a, st); else launch_lstm_act_fma(a, st);
+}
+void launch_lstm_act_fma(const ActArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(lstm_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ActSmem)); configured = true; }
     int grid = (a.N + TM - 1) / TM;

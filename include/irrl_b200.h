@@ -128,6 +128,15 @@ int irrl_get_heightfield(irrl_env* env, float* heights, int* nx, int* ny, double
 int irrl_policy_create(int device, const float* params, irrl_policy** out);
 int irrl_policy_set_params(irrl_policy* pol, const float* params);
 void irrl_policy_destroy(irrl_policy* pol);
+/* Which act kernel irrl_policy_act / irrl_rollout launch: 0 = automatic (tcgen05 tensor-core kernel from 256 environments,
+ * fp32 FMA kernel below), 1 = always the fp32 FMA kernel, 2 = always the tcgen05 kernel.  Both follow run_bp_v5.py:143-176. */
+int irrl_policy_set_act_path(int mode);
+/* Probe of the tcgen05 path: d[128,n] = a[128,k] b[n,k]^T (host pointers) with the 3xTF32 split of the act kernel.
+ * variant bit 0 = single tf32 pass (accuracy control). */
+/* Diagnostic: SM-clock timestamps of CTA (0,0) of the last tcgen05 act launch (16 slots, policy_tc_kernels.cu TC_MARK);
+ * enable != 0 turns recording on for the following launches.  out16 may be NULL. */
+int irrl_tc_timeline(int enable, long long* out16);
+int irrl_tc_gemm_probe(const float* a, const float* b, float* d, int k, int n, int variant);
 /* obs[N,35], done[N] (mask = done of the previous step, may be NULL), state[N,384] in/out, action[N,12] (unclipped),
  * clipped[N,12] (may be NULL), value[N], neglogp[N]; deterministic != 0 -> action = mean.  seed/env_offset/tick key the
  * Gaussian draws. */

@@ -330,7 +330,9 @@ def run_b200(args):
     else:
         roof.update({"achieved": None, "frac": None, "flop_per_env_step": None, "flop_source": "profiles/kernel_counts.json missing"})
     roof["lstm_act"] = {"kernel_ms": act_kernel_ms, "bound": "hbm", "achieved": N * B_ACT_BYTES / (act_kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": N * B_ACT_BYTES / (act_kernel_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_env": B_ACT_BYTES}
+                        "frac": N * B_ACT_BYTES / (act_kernel_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_env": B_ACT_BYTES,
+                        "kernel": "lstm_act_tc_kernel: tcgen05.mma kind::tf32 x3 split, TMEM accumulators, cp.async.bulk operand/state staging" if N >= 256 else "lstm_act_kernel (fp32 FMA)",
+                        "tensor_tflops_issued": N * 2 * 3 * 2 * (88 * 192 + 96 * 192 + 48 * 16) / (act_kernel_ms * 1e-3) / 1e12 if N >= 256 else None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": {"trot": f"bp5 trot imitation reward, {N} envs per B200 (BASELINE.json configs[1])",
@@ -342,7 +344,7 @@ def run_b200(args):
                        "parallelism": f"env-shard x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "path": "irrl_policy_act + irrl_step with page-locked host numpy buffers (as RaisimGymVecEnv owns them), 2 blocking calls per step; LSTM state device-resident"},
-            "gpu_launches": 2 * K, "kernels": ["lstm_act_kernel", "env_step_kernel"], "memcpy_d2d_per_step": 0,
+            "gpu_launches": 2 * K, "kernels": ["lstm_act_tc_kernel (tcgen05 3xTF32)" if N >= 256 else "lstm_act_kernel", "env_step_kernel"], "memcpy_d2d_per_step": 0,
             "roofline": roof, "clocks": clocks, "wall_s": wall,
             "sanity": {"mean_reward": mean_rew, "episodes_finished": episodes_done, "gs_sweeps_last_substep": {"mean": float(sw.mean()), "max": int(sw.max()), "hist": np.bincount(sw, minlength=9).tolist()}}}
     if not args.no_cpu_baseline:

@@ -59,6 +59,7 @@ def load() -> C.CDLL:
     L.irrl_policy_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     L.irrl_policy_set_act_path.argtypes = [C.c_int]
     L.irrl_tc_timeline.argtypes = [C.c_int, C.c_void_p]
+    L.irrl_tc_mma_rate.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
     L.irrl_tc_gemm_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.irrl_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RolloutBuffers), C.c_int]
     L.irrl_gae.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]

@@ -677,11 +677,11 @@ static int upload_derived(irrl_policy_impl* Pn, const float* host_params) {
     CUDA_OK(cudaMemcpy(Pn->d_derived, d.data(), d.size() * sizeof(float), cudaMemcpyHostToDevice));
     {   // tensor-core layout (policy_tc_kernels.cu): tower 0 = pi cells + mean head, tower 1 = V cells + value head
         std::vector<unsigned char> blob((size_t)2 * TC_BLOB_BYTES);
-        const float* q = host_params; const float* wx[4]; const float* wh[4];
-        for (int i = 0; i < 4; ++i) { wx[i] = q; q += in[i] * 192; wh[i] = q; q += 48 * 192; q += 192; }
-        const float* vf_w = q; q += 48 + 1; const float* pi_w = q;
-        pack_tc_blob(wx[0], wh[0], wx[1], wh[1], pi_w, 12, blob.data());
-        pack_tc_blob(wx[2], wh[2], wx[3], wh[3], vf_w, 1, blob.data() + TC_BLOB_BYTES);
+        const float* q = host_params; const float* wx[4]; const float* wh[4]; const float* bb[4];
+        for (int i = 0; i < 4; ++i) { wx[i] = q; q += in[i] * 192; wh[i] = q; q += 48 * 192; bb[i] = q; q += 192; }
+        const float* vf_w = q; q += 48; const float* vf_b = q; q += 1; const float* pi_w = q; q += 48 * 12; const float* pi_b = q; q += 12; const float* logstd = q;
+        pack_tc_blob(wx[0], wh[0], bb[0], wx[1], wh[1], bb[1], pi_w, pi_b, 12, logstd, blob.data());
+        pack_tc_blob(wx[2], wh[2], bb[2], wx[3], wh[3], bb[3], vf_w, vf_b, 1, nullptr, blob.data() + TC_BLOB_BYTES);
         CUDA_OK(cudaMemcpy(Pn->d_tcblob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     }
     return 0;
@@ -711,6 +711,14 @@ int irrl_policy_set_act_path(int mode) {
     g_act_path = mode; return 0;
 }
 int irrl_tc_timeline(int enable, long long* out16) { tc_timeline(enable, out16); return 0; }
+int irrl_tc_mma_rate(int n, int reps, unsigned layout_type, unsigned lbo, unsigned sbo, unsigned kadv, long long* cycles2) {
+    long long* d = nullptr; CUDA_OK(cudaMalloc((void**)&d, 16));
+    int rc = launch_tc_mma_rate(n, reps, layout_type, lbo, sbo, kadv, d, 0);
+    if (rc) { cudaFree(d); return fail(-1, "irrl_tc_mma_rate: launch failed"); }
+    CUDA_OK(cudaGetLastError()); CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(cycles2, d, 16, cudaMemcpyDeviceToHost)); cudaFree(d);
+    return 0;
+}
 int irrl_tc_gemm_probe(const float* a, const float* b, float* d, int k, int n, int variant) {
     if (!a || !b || !d) return fail(-1, "null argument");
     float *da = nullptr, *db = nullptr, *dd = nullptr;

@@ -41,7 +41,8 @@ struct PolicyWeights {      // device pointers, fp32, layouts as in the referenc
     const float* bperm[4];  // derived: [192] biases in the same column order
     const unsigned char* tcblob;   // derived: 2 towers x TC_BLOB_BYTES, hi/lo-split UMMA-layout weights (policy_tc_kernels.cu)
 };
-constexpr int TC_BLOB_BYTES = (11 + 12) * 12288 + 6 * 1024;
+constexpr int TC_BIAS_BYTES = 2048;   // [2][192] gate biases (gate-interleaved), [16] head bias, [16] logstd, zero pad
+constexpr int TC_BLOB_BYTES = (11 + 12) * 12288 + 6 * 1024 + TC_BIAS_BYTES;
 struct ActArgs {
     PolicyWeights W;
     const float* obs;       // [N,35]
@@ -63,7 +64,9 @@ void launch_lstm_act_tc(const ActArgs& a, cudaStream_t st);       // tcgen05 ker
 extern int g_act_path;                                             // 0 auto (tensor cores from 256 envs), 1 FMA, 2 tensor cores
 int launch_tc_gemm_probe(const float* dA, const float* dB, float* dD, int K, int N, int variant, cudaStream_t st);
 void tc_timeline(int enable, long long* out16);
-void pack_tc_blob(const float* wx0, const float* wh0, const float* wx1, const float* wh1, const float* head_w, int head_cols, unsigned char* out);
+int launch_tc_mma_rate(int N, int reps, unsigned layout_type, unsigned lbo, unsigned sbo, unsigned kadv, long long* d_out, cudaStream_t st);
+void pack_tc_blob(const float* wx0, const float* wh0, const float* b0, const float* wx1, const float* wh1, const float* b1, const float* head_w, const float* head_b,
+                  int head_cols, const float* logstd, unsigned char* out);
 void launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, const uint8_t* last_dones,
                 float* adv, float* ret, int T, int N, float gamma, float lam, cudaStream_t st);
 

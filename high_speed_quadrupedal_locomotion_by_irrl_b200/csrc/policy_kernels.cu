@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(NTHR, 2) lstm_act_kernel(const __grid_constant
 
 int g_act_path = 0;
 void launch_lstm_act(const ActArgs& a, cudaStream_t st) {
-    const bool tc = g_act_path == 2 || (g_act_path == 0 && a.N >= 256);
+    // the tensor-core kernel moves state rows with the bulk-copy engine: 16-byte aligned rows required (always true for [N,384] allocations)
+    const bool tc = (g_act_path == 2 || (g_act_path == 0 && a.N >= 256)) && (reinterpret_cast<uintptr_t>(a.state) & 15) == 0;
     if (tc) launch_lstm_act_tc(a, st); else launch_lstm_act_fma(a, st);
 }
 void launch_lstm_act_fma(const ActArgs& a, cudaStream_t st) {

@@ -4,22 +4,32 @@
 // run_bp_v5.py:143-176): both layers of one tower, the pi / V head, the Gaussian sample and neglogp in one launch.
 //
 // Mapping.  A CTA owns 128 environments (the MMA M dimension, one TMEM lane per environment) and one tower
-// (blockIdx.y).  Every layer is one GEMM  gates[128 x 192] = [x ; h][128 x K] * W^T[K x 192]  issued by a single
-// thread as tcgen05.mma.kind::tf32 instructions (M128 N192 K8) with the fp32 accumulator in tensor memory.
-//   * fp32 accuracy on tf32 hardware: both operands are split x = hi + lo (hi = the 19 leading bits, exactly a tf32
-//     number; lo = x - hi) and three products are accumulated, lo*hi + hi*lo + hi*hi ("3xTF32"); the dropped lo*lo
-//     term is 2^-22 relative.  Agreement with the fp32 FMA kernel and the float64 oracle stays inside the 2e-5 bar.
+// (blockIdx.y).  Every layer is one GEMM  gates[128 x 192] = [x ; h][128 x K] * W^T[K x 192]  issued by one elected lane
+// as tcgen05.mma.kind::tf32 instructions (M128 N192 K8) with the fp32 accumulator in tensor memory.
+//   * fp32 accuracy on tf32 hardware: both operands are split x = hi + lo (hi = nearest tf32 number, lo = x - hi, both
+//     exact in fp32) and three products are accumulated, lo*hi + hi*lo + hi*hi ("3xTF32"); the dropped lo*lo term is
+//     2^-24 relative.  Agreement with the fp32 FMA kernel and the float64 oracle stays inside the 2e-5 bar
+//     (tests/test_gpu_policy_parity.py).
 //   * operands live in shared memory in the UMMA canonical K-major no-swizzle layout
 //     [k-step of 8][hi|lo][16-byte k-chunk (2)][row][4 floats]  (core matrix = 8 rows x 16 B, SBO = 128 B,
 //     LBO = rows * 16 B), so a thread that owns one environment row writes its 4 new hidden units as one float4.
+//     The measured MMA rate does not depend on the layout type (irrl_tc_mma_rate: 98 cycles per M128 N192 K8).
 //   * the weights are stored once (irrl_policy_set_params) in exactly that layout, hi and lo pre-split, and stream
-//     L2 -> shared memory through a 6-stage ring of 12 KB cp.async.bulk copies completing on mbarriers (TMA engine);
-//     tcgen05.commit releases a stage as soon as its three MMAs have read it.
-//   * epilogue: 8 warps; warp w reads TMEM lanes 32 (w%4).., gate columns 96 (w/4).. with tcgen05.ld.32x32b.x16 --
+//     L2 -> shared memory as 12 KB cp.async.bulk copies completing on mbarriers (TMA engine) through a ring of 3 slots,
+//     6 for layer 1 (3 more slots overlay the part of the layer-0 A tile that is dead by then); tcgen05.commit
+//     releases a slot as soon as its three MMAs have read it.  Biases / logstd ride in the same blob.
+//   * recurrent state: one 384-byte bulk copy per environment row and layer ([c | h], contiguous in the [N,384] state)
+//     into a padded staging tile (pitch 400 B: conflict-free for row-per-lane access), and one bulk store per row back.
+//     No thread ever issues a strided global access; global stores are only issued behind a hand-off because
+//     fence.proxy.async is a full memory barrier for the issuing thread.
+//   * epilogue: 16 warps; warp w reads TMEM lanes 32 (w%4).., gate columns 48 (w/4).. with tcgen05.ld.32x32b.x16 --
 //     columns are gate-interleaved (4 unit + gate), so 16 columns = 4 hidden units x (i,f,o,g): the cell update is done
-//     in registers, c/h go to HBM and h (hi/lo) straight back into the A-operand tile of the next GEMM.
-//   * the heads are a third GEMM (N = 16) on h of the top layer; lanes then sample / write their own environment.
-// Roles: warps 0-7 stage + epilogue, warp 8 lane 0 = bulk-copy producer, warp 9 lane 0 = MMA issuer (warp 9 owns TMEM).
+//     in registers (5 ex2 + 3 rcp per unit: MUFU-bound), h (hi/lo) goes straight into the A-operand tile of the next GEMM.
+//   * the heads are a third GEMM (N = 16) on h of the top layer (weights: one 6 KB copy over the dead layer-1 tile);
+//     the Gaussian draws, sigma and neglogp are computed while it runs; lanes then write their own environment.
+// Roles: warps 0-15 stage + epilogue, warp 16 lane 0 = bulk-copy producer, warp 17 = MMA issuer (owns TMEM).
+// Measured (B200, L2 flushed): 25 us at 4096 and 8192 environments, 44 us at 16384, 80 us at 32768
+// (fp32 FMA kernel: 40 / 57 / 103 / 174 us).
 #include <cstring>
 #include "env_device.cuh"
 #include "env_kernels.h"
@@ -37,18 +47,26 @@ constexpr int B_HALF = 2 * NG * 16;              // 6144
 constexpr int B_KSTEP = 2 * B_HALF;              // 12288
 constexpr int H_HALF = 2 * NHEAD * 16;           // 512
 constexpr int H_KSTEP = 2 * H_HALF;              // 1024
-constexpr int NST = 6;                           // ring stages
+constexpr int NST = 3;                           // weight ring stages in their own shared memory
+constexpr int NSLOT = 6;                         // + 3 more for layer 1, carved out of the part of the layer-0 A tile that is dead by then
 constexpr int NWORK = 512;                       // staging / epilogue threads (16 warps: TMEM lane quarter w%4, 48-column block w/4)
 constexpr int NTHR = NWORK + 64;
 constexpr int TMEM_COLS = 512;                   // 192 (layer 0) + 192 (layer 1) + 16 (head) -> next power of two
+constexpr int STG_PITCH = 400;                   // bytes per row of the state staging tile: [c(48) h(48)] = 384 B + 16 B (odd number of 16-byte groups: no bank conflicts)
 constexpr int OFF_A1 = 0;
-constexpr int OFF_A2 = OFF_A1 + KS1 * A_KSTEP;   // 90112 : h(t-1) of layer 1
+constexpr int OFF_A2 = OFF_A1 + KS1 * A_KSTEP;   // 90112 : h(t-1) of layer 1 (and, before that, the raw observation tile)
 constexpr int OFF_RING = OFF_A2 + 6 * A_KSTEP;   // 139264
-constexpr int OFF_BIAS = OFF_RING + NST * B_KSTEP;   // 212992 : 2 x 192 gate biases, 16 head biases, 16 logstd
-constexpr int OFF_BAR = OFF_BIAS + (2 * NG + 32) * 4;
-constexpr int SMEM_BYTES = OFF_BAR + (2 * NST + 4) * 8 + 16;
-static_assert((KS1 + KS2) * B_KSTEP + KSH * H_KSTEP == TC_BLOB_BYTES, "blob size");
+constexpr int OFF_STG = OFF_RING + NST * B_KSTEP;    // 176128 : [row][c | h] of one layer, in (bulk loads) and out (bulk stores)
+constexpr int OFF_BIAS = OFF_STG + TM * STG_PITCH;   // 227328 : TC_BIAS_BYTES = 2 x 192 gate biases, 16 head biases, 16 logstd (+ pad)
+constexpr int OFF_BAR = OFF_BIAS + TC_BIAS_BYTES;
+constexpr int NBAR = 2 * NSLOT + 1 + 3 + 5;      // full, empty, a_ready, d_full[3], in_bar[2], obs_bar, bias_bar, head_full
+constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+static_assert((KS1 + KS2) * B_KSTEP + KSH * H_KSTEP + TC_BIAS_BYTES == TC_BLOB_BYTES, "blob size");
 static_assert(SMEM_BYTES <= 232448, "shared memory");
+static_assert(6 * A_KSTEP + 3 * B_KSTEP <= KS1 * A_KSTEP, "extra ring slots must fit behind the h_new columns of the layer-0 A tile");
+// weight k-step i (0..22) lives in ring slot: layer 0 cycles through the 3 dedicated slots, layer 1 through all 6
+__device__ __forceinline__ int slot_of(int i) { return i < KS1 ? i % NST : (i - KS1) % NSLOT; }
+__device__ __forceinline__ uint32_t slot_addr(uint32_t ring, uint32_t a1, int s) { return s < NST ? ring + s * B_KSTEP : a1 + 6 * A_KSTEP + (s - NST) * B_KSTEP; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
@@ -87,6 +105,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
                  "r"(accumulate)
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
@@ -120,122 +143,154 @@ __device__ __forceinline__ void store_hilo(unsigned char* tile, uint32_t off, ui
 }
 
 // optional timeline of CTA (0,0) in SM clocks (irrl_tc_timeline): a cheap way to see which hand-off paces the kernel
-__device__ long long g_timeline[16];
+__device__ long long g_timeline[32];
 __device__ int g_timeline_on = 0;
-#define TC_MARK(slot) do { if (g_timeline_on && blockIdx.x == 0 && blockIdx.y == 0) g_timeline[slot] = clock64(); } while (0)
+#define TC_MARK(slot) do { if (dbg) g_timeline[slot] = clock64(); } while (0)      // dbg is read once per thread
+
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); }
 
 __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_constant__ ActArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int tower = blockIdx.y, e0 = blockIdx.x * TM;
+    const int dbg = (blockIdx.x == 0 && blockIdx.y == 0) ? g_timeline_on : 0;
+    if (t == 0) TC_MARK(23);
     unsigned char* sA1 = smem + OFF_A1;
     unsigned char* sA2 = smem + OFF_A2;
-    float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);      // [2][192] gate biases, [16] head bias, [16] logstd
+    unsigned char* sSTG = smem + OFF_STG;
+    const float* sbias = reinterpret_cast<const float*>(smem + OFF_BIAS);      // [2][192] gate biases, [16] head bias, [16] logstd
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* empty = full + NST;
-    uint64_t* a_ready = empty + NST;
+    uint64_t* empty = full + NSLOT;
+    uint64_t* a_ready = empty + NSLOT;
     uint64_t* d_full = a_ready + 1;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_full + 3);
+    uint64_t* in_bar = d_full + 3;          // [2] : state rows of layer 0 / layer 1 have landed in the staging tile
+    uint64_t* obs_bar = in_bar + 2;
+    uint64_t* bias_bar = obs_bar + 1;
+    uint64_t* head_full = bias_bar + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(head_full + 1);
+    const int rows = min(TM, A.N - e0);
+    // the observation tile is one contiguous block; the bulk engine wants 16-byte granularity on both ends
+    const bool obs_bulk = ((reinterpret_cast<uintptr_t>(A.obs) & 15) == 0) && ((rows & 3) == 0);
+    const unsigned char* blob = A.W.tcblob + (size_t)tower * TC_BLOB_BYTES;
 
     if (t == NWORK) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(a_ready, NWORK);
         for (int i = 0; i < 3; ++i) mbar_init(&d_full[i], 1);
+        mbar_init(head_full, 1);
+        mbar_init(&in_bar[0], TM); mbar_init(&in_bar[1], TM);
+        mbar_init(obs_bar, 1); mbar_init(bias_bar, 1);
         fence_mbar_init();
+        // everything that does not depend on another thread is requested right here
+        mbar_expect_tx(bias_bar, TC_BIAS_BYTES);
+        bulk_g2s(smem_u32(smem + OFF_BIAS), blob + TC_BLOB_BYTES - TC_BIAS_BYTES, TC_BIAS_BYTES, bias_bar);
+        if (obs_bulk) {
+            mbar_expect_tx(obs_bar, rows * OB_DIM * 4);
+            bulk_g2s(smem_u32(sA2), A.obs + (size_t)e0 * OB_DIM, rows * OB_DIM * 4, obs_bar);
+        }
     }
     if (warp == NWORK / 32 + 1) { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
-    if (t < NWORK) {
-        for (int i = t; i < 2 * NG; i += NWORK) sbias[i] = A.W.bperm[tower * 2 + i / NG][i % NG];
-        if (t < 16) sbias[2 * NG + t] = tower == 0 ? (t < ACT_DIM ? A.W.pi_b[t] : 0.f) : (t == 0 ? A.W.vf_b[0] : 0.f);
-        else if (t < 32) sbias[2 * NG + t] = (t - 16) < ACT_DIM ? A.W.logstd[t - 16] : 0.f;
-    }
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     if (t == 0) TC_MARK(0);
 
     if (t < NWORK) {
-        // ------------------------------------------------------------ stage the A operands (hi/lo split)
-        // every global load of a thread is issued before its first use, so one HBM latency is exposed, not a chain of them
-        const int nvalid = min(TM, A.N - e0) * OB_DIM;                // this tile's observations are one contiguous block
-        float* stage = reinterpret_cast<float*>(sA2);                 // layer-1 tile doubles as the obs staging buffer until h1 is stored
-        float ov[9]; float4 h0[3], h1[3]; float kp[3];
-#pragma unroll
-        for (int it = 0; it < 9; ++it) { const int i = t + it * NWORK; ov[it] = (i < nvalid) ? __ldg(A.obs + (size_t)e0 * OB_DIM + i) : 0.f; }
-#pragma unroll
-        for (int it = 0; it < 3; ++it) {                             // h(t-1) of both layers: item = (row, 4 units)
-            const int idx = t + it * NWORK, r = idx & (TM - 1), q = idx >> 7, env = min(e0 + r, A.N - 1);
-            const float* st = A.state + (size_t)env * LSTM_STATE + tower * 4 * LSTM_H;
-            h0[it] = *reinterpret_cast<const float4*>(st + LSTM_H + 4 * q);
-            h1[it] = *reinterpret_cast<const float4*>(st + 3 * LSTM_H + 4 * q);
-            kp[it] = (A.done && A.done[env]) ? 0.f : 1.f;
-        }
         const int wq = warp & 3, part = warp >> 2, row = 32 * wq + lane, env = e0 + row, envc = min(env, A.N - 1);
         const bool valid = env < A.N;
+        float* strow = A.state + (size_t)min(e0 + t, A.N - 1) * LSTM_STATE + tower * 4 * LSTM_H;     // row t of the tile (t < 128 only)
+        // ------------------------------------------------------------ state rows [c0 h0] -> staging tile (one 384-byte bulk copy per row)
+        if (t < TM) { mbar_expect_tx(&in_bar[0], 2 * LSTM_H * 4); bulk_g2s(smem_u32(sSTG + t * STG_PITCH), strow, 2 * LSTM_H * 4, &in_bar[0]); }
         const float keep = (A.done && A.done[envc]) ? 0.f : 1.f;
-        float4 cprev[2][3];                                           // c(t-1) of this lane's 12 units, both layers (needed after the first GEMM)
+        float kp[3];
 #pragma unroll
-        for (int l = 0; l < 2; ++l)
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                cprev[l][i] = *reinterpret_cast<const float4*>(A.state + (size_t)envc * LSTM_STATE + tower * 4 * LSTM_H + l * 2 * LSTM_H + 12 * part + 4 * i);
-#pragma unroll
-        for (int it = 0; it < 9; ++it) {
-            const int i = t + it * NWORK;
-            if (i < TM * OB_DIM) stage[i] = ov[it];
-            if (tower == 0 && A.obs_store && i < nvalid) A.obs_store[(size_t)e0 * OB_DIM + i] = ov[it];      // mb_obs (ppo2.py:522)
+        for (int it = 0; it < 3; ++it) { const int r = (t + it * NWORK) & (TM - 1); kp[it] = (A.done && A.done[min(e0 + r, A.N - 1)]) ? 0.f : 1.f; }
+        float* stage = reinterpret_cast<float*>(sA2);                 // layer-1 tile doubles as the observation staging buffer until h1 is stored
+        if (obs_bulk) {
+            mbar_wait(obs_bar, 0);
+        } else {                                                      // unaligned / ragged tile: plain loads
+            for (int i = t; i < TM * OB_DIM; i += NWORK) stage[i] = (i < rows * OB_DIM) ? __ldg(A.obs + (size_t)e0 * OB_DIM + i) : 0.f;
+            worker_sync();
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");
+        if (t == 0) TC_MARK(16);
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {                             // observations: item = (row, 4 k), zero padded 35 -> 40
+        for (int it = 0; it < 3; ++it) {                             // observations: item = (row, 4 k), zero padded 35 -> 40, rows past N zero
             const int idx = t + it * NWORK, r = idx & (TM - 1), q = idx >> 7;
             if (q < 10) {
                 float v[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = (4 * q + j < OB_DIM) ? stage[r * OB_DIM + 4 * q + j] : 0.f;
+                for (int j = 0; j < 4; ++j) v[j] = (4 * q + j < OB_DIM && r < rows) ? stage[r * OB_DIM + 4 * q + j] : 0.f;
                 store_hilo(sA1, op_off(4 * q, r, TM), A_HALF, v);
             }
         }
+        if (t == 0) TC_MARK(17);
+        mbar_wait(&in_bar[0], 0);
+        if (t == 0) TC_MARK(18);
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {                             // masked (SB lstm(): h *= 1-m)
+        for (int it = 0; it < 3; ++it) {                             // h(t-1) of layer 0, masked (SB lstm(): h *= 1-m)
             const int idx = t + it * NWORK, r = idx & (TM - 1), q = idx >> 7;
-            const float v0[4] = {h0[it].x * kp[it], h0[it].y * kp[it], h0[it].z * kp[it], h0[it].w * kp[it]};
+            const float4 h = *reinterpret_cast<const float4*>(sSTG + r * STG_PITCH + (LSTM_H + 4 * q) * 4);
+            const float v0[4] = {h.x * kp[it], h.y * kp[it], h.z * kp[it], h.w * kp[it]};
             store_hilo(sA1, op_off(40 + 4 * q, r, TM), A_HALF, v0);
         }
-        if (tower == 0 && A.done_store && t < TM && e0 + t < A.N) A.done_store[e0 + t] = A.done ? A.done[e0 + t] : 0;   // mb_dones (ppo2.py:526)
+        float4 ca, cb, cc;                                            // c(t-1) of this lane's 12 units (TMEM lane = row)
+        ca = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part) * 4);
+        cb = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part + 4) * 4);
+        cc = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part + 8) * 4);
+        if (t == 0) TC_MARK(19);
         fence_proxy_async();
         mbar_arrive(a_ready);
         if (t == 0) TC_MARK(1);
-        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");      // everyone is done reading the staging buffer
+        worker_sync();                                                // staging tile and observation buffer are free again
+        // ---- behind the first GEMM: rows [c1 h1] -> staging tile -> A tile of layer 1 / registers; rollout copies of obs and mask
+        if (t < TM) { mbar_expect_tx(&in_bar[1], 2 * LSTM_H * 4); bulk_g2s(smem_u32(sSTG + t * STG_PITCH), strow + 2 * LSTM_H, 2 * LSTM_H * 4, &in_bar[1]); }
+        if (tower == 0 && A.obs_store) {                              // mb_obs (ppo2.py:522): global stores only ever follow a hand-off,
+            for (int i = t; i < rows * OB_DIM; i += NWORK) A.obs_store[(size_t)e0 * OB_DIM + i] = stage[i];      // fence.proxy.async would wait for them
+        }
+        if (tower == 0 && A.done_store && t < rows) A.done_store[e0 + t] = A.done ? A.done[e0 + t] : 0;       // mb_dones (ppo2.py:526)
+        mbar_wait(&in_bar[1], 0);
+        worker_sync();                                                // obs_store has finished reading the buffer that h1 overwrites
+        float4 da, db, dc;
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {                             // h(t-1) of layer 1 (consumed by the second GEMM only)
+        for (int it = 0; it < 3; ++it) {
             const int idx = t + it * NWORK, r = idx & (TM - 1), q = idx >> 7;
-            const float v1[4] = {h1[it].x * kp[it], h1[it].y * kp[it], h1[it].z * kp[it], h1[it].w * kp[it]};
+            const float4 h = *reinterpret_cast<const float4*>(sSTG + r * STG_PITCH + (LSTM_H + 4 * q) * 4);
+            const float v1[4] = {h.x * kp[it], h.y * kp[it], h.z * kp[it], h.w * kp[it]};
             store_hilo(sA2, op_off(4 * q, r, TM), A_HALF, v1);
         }
+        da = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part) * 4);
+        db = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part + 4) * 4);
+        dc = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part + 8) * 4);
+        mbar_wait(bias_bar, 0);
+        worker_sync();                                                // staging tile free for the epilogue's output rows
 
         // ------------------------------------------------------------ cell updates straight out of tensor memory
-#pragma unroll
+        // Rolled loops on purpose: every warp runs this code once per launch, so its size is paid in instruction fetches.
+#pragma unroll 1
         for (int l = 0; l < 2; ++l) {
             mbar_wait(&d_full[l], 0);
             tc_fence_after();
             if (t == 0) TC_MARK(5 + 4 * l);
-            float* st = A.state + (size_t)envc * LSTM_STATE + tower * 4 * LSTM_H + l * 2 * LSTM_H;
             const uint32_t taddr = tmem + ((uint32_t)(32 * wq) << 16) + l * NG + 48 * part;
             const float* bl = sbias + l * NG + 48 * part;
-            uint32_t v[3][16];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) tmem_ld16(taddr + 16 * i, v[i]);
-            tmem_ld_wait();
-#pragma unroll
+            unsigned char* orow = sSTG + row * STG_PITCH + (12 * part) * 4;
+#pragma unroll 1
             for (int i = 0; i < 3; ++i) {
-                const int u = 12 * part + 4 * i;
-                const float cold[4] = {cprev[l][i].x, cprev[l][i].y, cprev[l][i].z, cprev[l][i].w};
+                uint32_t v[16];
+                tmem_ld16(taddr + 16 * i, v);
+                tmem_ld_wait();
+                const float cold[4] = {ca.x, ca.y, ca.z, ca.w};
                 float cn[4], hn[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {      // gate order i,f,o,g (CustomerLstmNN.py:119-126); reciprocals shared pairwise
                     const float4 b4 = *reinterpret_cast<const float4*>(bl + 16 * i + 4 * j);
-                    const float zi = __uint_as_float(v[i][4 * j + 0]) + b4.x, zf = __uint_as_float(v[i][4 * j + 1]) + b4.y;
-                    const float zo = __uint_as_float(v[i][4 * j + 2]) + b4.z, zg = __uint_as_float(v[i][4 * j + 3]) + b4.w;
+                    const float zi = __uint_as_float(v[4 * j + 0]) + b4.x, zf = __uint_as_float(v[4 * j + 1]) + b4.y;
+                    const float zo = __uint_as_float(v[4 * j + 2]) + b4.z, zg = __uint_as_float(v[4 * j + 3]) + b4.w;
                     const float ei = __expf(-zi), ef = __expf(-zf), eo = __expf(-zo), eg = __expf(-2.0f * fabsf(zg));
                     const float ig_gg = copysignf(__fdividef(1.0f - eg, (1.0f + ei) * (1.0f + eg)), zg);       // sigmoid(zi) * tanh(zg)
                     const float fg = __fdividef(1.0f, 1.0f + ef);
@@ -243,18 +298,38 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
                     const float ec = __expf(-2.0f * fabsf(cn[j]));
                     hn[j] = copysignf(__fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec)), cn[j]);                 // sigmoid(zo) * tanh(c)
                 }
-                if (valid) {
-                    *reinterpret_cast<float4*>(st + u) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                    *reinterpret_cast<float4*>(st + LSTM_H + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                }
-                store_hilo(sA1, op_off(u, row, TM), A_HALF, hn);      // A operand of the next GEMM (k = unit index)
+                store_hilo(sA1, op_off(12 * part + 4 * i, row, TM), A_HALF, hn);      // A operand of the next GEMM (k = unit index)
+                *reinterpret_cast<float4*>(orow + 16 * i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                *reinterpret_cast<float4*>(orow + LSTM_H * 4 + 16 * i) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                ca = cb; cb = cc;
             }
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(a_ready);
             if (t == 0) TC_MARK(6 + 4 * l);
+            worker_sync();                                            // all output rows of this layer are in the staging tile
+            if (t < rows) { bulk_s2g(strow + l * 2 * LSTM_H, smem_u32(sSTG + t * STG_PITCH), 2 * LSTM_H * 4); bulk_commit(); }
+            if (l == 0) {
+                ca = da; cb = db; cc = dc;
+                if (t < rows) bulk_wait_read0();                      // the engine has read the rows: the tile may be overwritten
+                worker_sync();
+            }
         }
         // ------------------------------------------------------------ heads: lanes of warps 0-3 own one environment each
+        // the 12 Gaussian draws, sigma = exp(logstd) and neglogp = sum(0.5 z^2 + logstd) + 6 ln(2 pi) (z = the draw itself) do not
+        // depend on the head GEMM: they are computed while it runs
+        const float* hb = sbias + 2 * NG;
+        float sg[3][4];                                               // sigma * z per action
+        float nlp = 0.5f * 1.8378770664093453f * ACT_DIM;
+        if (part == 0 && tower == 0) {
+#pragma unroll
+            for (int g3 = 0; g3 < 3; ++g3) {
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!A.deterministic) gauss4(A.seed, (uint32_t)envc + A.env_offset, A.tick, P_POLICY_EPS + g3, g);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float ls = hb[16 + 4 * g3 + j]; sg[g3][j] = expf(ls) * g[j]; nlp += 0.5f * g[j] * g[j] + ls; }
+            }
+        }
         mbar_wait(&d_full[2], 0);
         tc_fence_after();
         if (t == 0) TC_MARK(12);
@@ -262,87 +337,90 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
             uint32_t v[16];
             tmem_ld16(tmem + ((uint32_t)(32 * wq) << 16) + 2 * NG, v);
             tmem_ld_wait();
-            const float* hb = sbias + 2 * NG;
             if (tower == 0) {
-                float act[ACT_DIM], mean[ACT_DIM];
-                float nlp[ACT_DIM];
-#pragma unroll
-                for (int g3 = 0; g3 < 3; ++g3) {
-                    float g[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (!A.deterministic) gauss4(A.seed, (uint32_t)envc + A.env_offset, A.tick, P_POLICY_EPS + g3, g);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int a = 4 * g3 + j;
-                        const float m = __uint_as_float(v[a]) + hb[a], ls = hb[16 + a], sd = expf(ls);
-                        const float x = fmaf(sd, g[j], m), z = (x - m) / sd;
-                        mean[a] = m; act[a] = x; nlp[a] = 0.5f * z * z + ls;
-                    }
-                }
-                float acc = 0.5f * 1.8378770664093453f * ACT_DIM;     // 0.5 * ln(2 pi) * 12
-#pragma unroll
-                for (int a = 0; a < ACT_DIM; ++a) acc += nlp[a];
                 if (valid) {
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        reinterpret_cast<float4*>(A.action + (size_t)env * ACT_DIM)[q] = make_float4(act[4 * q], act[4 * q + 1], act[4 * q + 2], act[4 * q + 3]);
-                        if (A.clipped)
-                            reinterpret_cast<float4*>(A.clipped + (size_t)env * ACT_DIM)[q] =
-                                make_float4(fminf(fmaxf(act[4 * q], -1.f), 1.f), fminf(fmaxf(act[4 * q + 1], -1.f), 1.f), fminf(fmaxf(act[4 * q + 2], -1.f), 1.f),
-                                            fminf(fmaxf(act[4 * q + 3], -1.f), 1.f));                                   // ppo2.py:529-531
-                        if (A.mean) reinterpret_cast<float4*>(A.mean + (size_t)env * ACT_DIM)[q] = make_float4(mean[4 * q], mean[4 * q + 1], mean[4 * q + 2], mean[4 * q + 3]);
+                    for (int g3 = 0; g3 < 3; ++g3) {
+                        float x[4], mean[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { mean[j] = __uint_as_float(v[4 * g3 + j]) + hb[4 * g3 + j]; x[j] = mean[j] + sg[g3][j]; }
+                        reinterpret_cast<float4*>(A.action + (size_t)env * ACT_DIM)[g3] = make_float4(x[0], x[1], x[2], x[3]);
+                        if (A.clipped)                                                                                   // ppo2.py:529-531
+                            reinterpret_cast<float4*>(A.clipped + (size_t)env * ACT_DIM)[g3] =
+                                make_float4(fminf(fmaxf(x[0], -1.f), 1.f), fminf(fmaxf(x[1], -1.f), 1.f), fminf(fmaxf(x[2], -1.f), 1.f), fminf(fmaxf(x[3], -1.f), 1.f));
+                        if (A.mean) reinterpret_cast<float4*>(A.mean + (size_t)env * ACT_DIM)[g3] = make_float4(mean[0], mean[1], mean[2], mean[3]);
                     }
-                    A.neglogp[env] = acc;
+                    A.neglogp[env] = nlp;
                 }
             } else if (valid) {
                 A.value[env] = __uint_as_float(v[0]) + hb[0];
             }
         }
+        if (t == 0) TC_MARK(21);
+        if (t < rows) bulk_wait0();                                   // state rows are in HBM before the CTA retires
+        if (t == 0) TC_MARK(22);
     } else if (t == NWORK) {
         // ------------------------------------------------------------ weight producer: bulk copies through the ring
-        const unsigned char* src = A.W.tcblob + (size_t)tower * TC_BLOB_BYTES;
-        const uint32_t ring = smem_u32(smem + OFF_RING);
-        for (int off = 0; off < TC_BLOB_BYTES; off += 6 * B_KSTEP) {          // whole blob HBM -> L2 up front: the ring then runs at L2-hit latency
-            const uint32_t bytes = min(6 * B_KSTEP, TC_BLOB_BYTES - off);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(bytes) : "memory");
-        }
-        for (int i = 0; i < KS1 + KS2 + KSH; ++i) {
-            const int s = i % NST, use = i / NST;
-            if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-            const uint32_t bytes = i < KS1 + KS2 ? B_KSTEP : H_KSTEP;
-            mbar_expect_tx(&full[s], bytes);
-            bulk_g2s(ring + s * B_KSTEP, src, bytes, &full[s]);
-            src += bytes;
+        const unsigned char* src = blob;
+        const uint32_t ring = smem_u32(smem + OFF_RING), a1 = smem_u32(sA1);
+        uint32_t used = 0, phase = 0;                                 // per-slot: has been filled before / parity of its next `empty` completion
+        for (int i = 0; i < KS1 + KS2; ++i) {
+            const int sl = slot_of(i);
+            if (i == KS1 + NST) mbar_wait(&d_full[0], 0);             // slots 3-5 overlay A-tile columns the first GEMM reads
+            if (used & (1u << sl)) { mbar_wait(&empty[sl], (phase >> sl) & 1); phase ^= 1u << sl; }
+            used |= 1u << sl;
+            mbar_expect_tx(&full[sl], B_KSTEP);
+            bulk_g2s(slot_addr(ring, a1, sl), src, B_KSTEP, &full[sl]);
+            src += B_KSTEP;
             if (i == NST - 1) TC_MARK(14);
         }
+        mbar_wait(&d_full[1], 0);                                     // head weights (6 KB, one copy) overlay the layer-1 A tile once its GEMM is done
+        mbar_expect_tx(head_full, KSH * H_KSTEP);
+        bulk_g2s(smem_u32(sA2), src, KSH * H_KSTEP, head_full);
         TC_MARK(15);
-    } else if (t == NWORK + 32) {
-        // ------------------------------------------------------------ MMA issuer
+    } else if (warp == NWORK / 32 + 1) {
+        // ------------------------------------------------------------ MMA issuer: the whole warp walks the loop (warp-uniform control flow keeps
+        // descriptors in uniform registers), one elected lane issues
         const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), ring = smem_u32(smem + OFF_RING);
+        constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);        // SBO = 128 B, descriptor version 1
+        constexpr uint32_t A_LBO = (uint32_t)(TM * 16 >> 4) << 16, G_LBO = (uint32_t)(NG * 16 >> 4) << 16, H_LBO = (uint32_t)(NHEAD * 16 >> 4) << 16;
+        uint32_t phase = 0;                                           // per-slot parity of the next `full` completion
         int i = 0;
+#pragma unroll 1
         for (int layer = 0; layer < 3; ++layer) {
             mbar_wait(a_ready, layer & 1);
+            if (layer == 2) mbar_wait(head_full, 0);
             tc_fence_after();
-            TC_MARK(layer == 0 ? 2 : layer == 1 ? 7 : 11);
+            if (lane == 0) TC_MARK(layer == 0 ? 2 : layer == 1 ? 7 : 11);
             const int nks = layer == 0 ? KS1 : layer == 1 ? KS2 : KSH;
             const uint32_t d = tmem + layer * NG;
             const uint32_t idesc = layer == 2 ? make_idesc(TM, NHEAD) : make_idesc(TM, NG);
-            const uint32_t bhalf = layer == 2 ? H_HALF : B_HALF, blbo = layer == 2 ? NHEAD * 16 : NG * 16;
+            const uint32_t bhalf = (layer == 2 ? H_HALF : B_HALF) >> 4, blbo = layer == 2 ? H_LBO : G_LBO;
+#pragma unroll 1
             for (int ks = 0; ks < nks; ++ks, ++i) {
-                const int s = i % NST;
-                mbar_wait(&full[s], (i / NST) & 1);
-                tc_fence_after();
-                if (i == 0) TC_MARK(3);
+                uint32_t bb; int sl = 0;
+                if (layer < 2) {
+                    sl = slot_of(i);
+                    mbar_wait(&full[sl], (phase >> sl) & 1); phase ^= 1u << sl;
+                    tc_fence_after();
+                    bb = slot_addr(ring, a1, sl);
+                } else {
+                    bb = a2 + ks * H_KSTEP;
+                }
                 const uint32_t ab = (layer == 1 && ks >= 6) ? a2 + (ks - 6) * A_KSTEP : a1 + ks * A_KSTEP;
-                const uint32_t bb = ring + s * B_KSTEP;
-                const uint64_t ah = make_desc(ab, TM * 16, 128), al = make_desc(ab + A_HALF, TM * 16, 128);
-                const uint64_t bh = make_desc(bb, blbo, 128), bl = make_desc(bb + bhalf, blbo, 128);
-                mma_tf32(d, al, bh, idesc, ks > 0);
-                mma_tf32(d, ah, bl, idesc, 1);
-                mma_tf32(d, ah, bh, idesc, 1);
-                umma_commit(&empty[s]);
+                const uint32_t alo = (ab >> 4) | A_LBO, blo = (bb >> 4) | blbo;
+                const uint64_t ah = ((uint64_t)DESC_HI << 32) | alo, al = ((uint64_t)DESC_HI << 32) | (alo + (A_HALF >> 4));
+                const uint64_t bh = ((uint64_t)DESC_HI << 32) | blo, bl = ((uint64_t)DESC_HI << 32) | (blo + bhalf);
+                if (elect_one()) {
+                    mma_tf32(d, al, bh, idesc, ks > 0);
+                    mma_tf32(d, ah, bl, idesc, 1);
+                    mma_tf32(d, ah, bh, idesc, 1);
+                    if (layer < 2) umma_commit(&empty[sl]);
+                    if (ks == nks - 1) umma_commit(&d_full[layer]);
+                }
+                __syncwarp();
             }
-            umma_commit(&d_full[layer]);
-            TC_MARK(layer == 0 ? 4 : layer == 1 ? 8 : 13);
+            if (lane == 0) TC_MARK(layer == 0 ? 4 : layer == 1 ? 8 : 13);
         }
     }
     tc_fence_before();
@@ -408,6 +486,41 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_probe_kernel(const float* __re
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
 }
 
+// Issue-rate probe: `reps` back-to-back M128 x N x K8 tf32 MMAs on one accumulator, operands described with the given
+// shared-memory layout type / strides (contents are irrelevant); returns SM cycles from first issue to completion.
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int N, int reps, uint32_t layout_type, uint32_t lbo, uint32_t sbo, uint32_t kadv, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar; __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < 64 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+    if (t == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(&tmem_slot, 256); tmem_relinquish(); }
+    fence_proxy_async();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 1) {
+        const uint32_t idesc = make_idesc(TM, N);
+        const uint32_t a0 = smem_u32(smem), b0 = a0 + 32 * 1024;
+        const uint32_t hi = (sbo >> 4) | (1u << 14) | (layout_type << 29);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint32_t off = (uint32_t)(r & 3) * kadv;
+            const uint64_t ad = ((uint64_t)hi << 32) | (((a0 + off) >> 4) | ((lbo >> 4) << 16));
+            const uint64_t bd = ((uint64_t)hi << 32) | (((b0 + off) >> 4) | ((lbo >> 4) << 16));
+            if (elect_one()) mma_tf32(tmem, ad, bd, idesc, r > 0);
+            __syncwarp();
+        }
+        long long t1 = clock64();
+        if (elect_one()) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        if (t == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
+}
+
 }  // namespace tc
 
 void launch_lstm_act_tc(const ActArgs& a, cudaStream_t st) {
@@ -419,8 +532,14 @@ void launch_lstm_act_tc(const ActArgs& a, cudaStream_t st) {
 
 void tc_timeline(int enable, long long* out16) {
     cudaDeviceSynchronize();
-    if (out16) cudaMemcpyFromSymbol(out16, tc::g_timeline, sizeof(long long) * 16);
+    if (out16) cudaMemcpyFromSymbol(out16, tc::g_timeline, sizeof(long long) * 32);
     cudaMemcpyToSymbol(tc::g_timeline_on, &enable, sizeof(int));
+}
+
+int launch_tc_mma_rate(int N, int reps, unsigned layout_type, unsigned lbo, unsigned sbo, unsigned kadv, long long* d_out, cudaStream_t st) {
+    if (cudaFuncSetAttribute(tc::tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) return -2;
+    tc::tc_mma_rate_kernel<<<1, 128, 64 * 1024, st>>>(N, reps, layout_type, lbo, sbo, kadv, d_out);
+    return 0;
 }
 
 int launch_tc_gemm_probe(const float* dA, const float* dB, float* dD, int K, int N, int variant, cudaStream_t st) {
@@ -434,7 +553,8 @@ int launch_tc_gemm_probe(const float* dA, const float* dB, float* dD, int K, int
 // Host-side packing of one tower's weights into the streamed layout (called by irrl_policy_set_params):
 // k-steps of layer 0 (11), layer 1 (12) and the head (6); each = [hi: chunk(2) x row x 16 B][lo: same].
 // Row n of a gate block is column 4*unit + gate of the reference's [in,192] matrices (their column = gate*48 + unit).
-void pack_tc_blob(const float* wx0, const float* wh0, const float* wx1, const float* wh1, const float* head_w, int head_cols, unsigned char* out) {
+void pack_tc_blob(const float* wx0, const float* wh0, const float* b0, const float* wx1, const float* wh1, const float* b1, const float* head_w, const float* head_b,
+                  int head_cols, const float* logstd, unsigned char* out) {
     auto put = [](unsigned char* base, uint32_t off, uint32_t lo_off, float v) {
         float hi = tc::tf32_hi(v); float lo = v - hi;
         memcpy(base + off, &hi, 4); memcpy(base + off + lo_off, &lo, 4);
@@ -451,6 +571,10 @@ void pack_tc_blob(const float* wx0, const float* wh0, const float* wx1, const fl
     unsigned char* hd = out + (tc::KS1 + tc::KS2) * tc::B_KSTEP;
     for (int n = 0; n < head_cols; ++n)
         for (int k = 0; k < LSTM_H; ++k) put(hd, tc::op_off(k, n, tc::NHEAD), tc::H_HALF, head_w[(size_t)k * head_cols + n]);
+    float* bias = reinterpret_cast<float*>(out + TC_BLOB_BYTES - TC_BIAS_BYTES);      // [2][192] gate biases, [16] head bias, [16] logstd
+    for (int n = 0; n < tc::NG; ++n) { const int src = (n & 3) * LSTM_H + (n >> 2); bias[n] = b0[src]; bias[tc::NG + n] = b1[src]; }
+    for (int n = 0; n < head_cols; ++n) bias[2 * tc::NG + n] = head_b[n];
+    if (logstd) for (int n = 0; n < ACT_DIM; ++n) bias[2 * tc::NG + 16 + n] = logstd[n];
 }
 
 }  // namespace irrl

@@ -13,6 +13,7 @@ from high_speed_quadrupedal_locomotion_by_irrl_b200 import _lib
 from high_speed_quadrupedal_locomotion_by_irrl_b200.policy import FusedLstmPolicy, PARAM_NAMES
 
 L = _lib.load()
+NOFLUSH = "noflush" in sys.argv
 G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
@@ -57,7 +58,7 @@ def timing():
     z = np.load(os.path.join(G, "bp5_155_params.npz")); W = [z[k] for k in PARAM_NAMES]
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for n in (4096, 8192, 16384, 32768):
+    for n in ((4096, 8192) if NOFLUSH else (4096, 8192, 16384, 32768)):
         pol = FusedLstmPolicy(W, n_env=n)
         obs = torch.randn(n, 35, device=dev) * 0.7; state = torch.randn(n, 384, device=dev) * 0.4
         act = torch.empty(n, 12, device=dev); clip = torch.empty(n, 12, device=dev); val = torch.empty(n, device=dev); nlp = torch.empty(n, device=dev)
@@ -67,7 +68,7 @@ def timing():
             _lib.check(L.irrl_policy_set_act_path(mode))
             ts = []
             for it in range(30):
-                flush.zero_()
+                if not NOFLUSH: flush.zero_()
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
                 _lib.check(L.irrl_policy_act(pol.handle, C.c_void_p(st), n, C.c_void_p(obs.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(state.data_ptr()),
@@ -77,18 +78,29 @@ def timing():
             ts = np.array(ts[5:])
             print(f"n={n} mode={'fma' if mode == 1 else 'tc '}: {np.median(ts):.1f} us (min {ts.min():.1f})", flush=True)
             if mode == 2 and n == 4096:
-                tl = np.zeros(16, np.int64)
-                L.irrl_tc_timeline(1, None)
-                for rep_ in range(3):
-                    flush.zero_()
+                tl = np.zeros(32, np.int64)
+                for rep_ in (1, 1, 1):
+                    L.irrl_tc_timeline(rep_, None)
+                    if not NOFLUSH: flush.zero_()
                     _lib.check(L.irrl_policy_act(pol.handle, C.c_void_p(st), n, C.c_void_p(obs.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(state.data_ptr()),
                                                  C.c_void_p(act.data_ptr()), C.c_void_p(clip.data_ptr()), C.c_void_p(val.data_ptr()), C.c_void_p(nlp.data_ptr()), 0, 1, 0, 99))
-                    L.irrl_tc_timeline(1, C.c_void_p(tl.ctypes.data))
+                    L.irrl_tc_timeline(rep_, C.c_void_p(tl.ctypes.data))
                     names = ["start", "A staged", "mma: A0 seen", "mma: W0 seen", "mma: L0 issued", "epi: D0 seen", "epi: L0 done", "mma: A1 seen", "mma: L1 issued",
-                             "epi: D1 seen", "epi: L1 done", "mma: A2 seen", "epi: D2 seen", "mma: head issued", "prod: ring filled", "prod: all issued"]
-                    print("timeline (cycles from start):", ", ".join(f"{nm}={int(tl[i] - tl[0])}" for i, nm in sorted(enumerate(names), key=lambda kv: tl[kv[0]])), flush=True)
+                             "epi: D1 seen", "epi: L1 done", "mma: A2 seen", "epi: D2 seen", "mma: head issued", "prod: ring filled", "prod: all issued",
+                             "pro: obs in", "pro: obs->A", "pro: rows in", "pro: h0->A", "-", "head stored", "stores drained", "entry"]
+                    print(f"dbg={rep_} timeline (cycles from start):", ", ".join(f"{nm}={int(tl[i] - tl[0])}" for i, nm in sorted(enumerate(names), key=lambda kv: tl[kv[0]])), flush=True)
                 L.irrl_tc_timeline(0, None)
 
 
+def rate():
+    out = np.zeros(2, np.int64)
+    for n in (16, 96, 192, 256):
+        for name, lt, lbo, sbo, kadv in [("none lbo=2048 sbo=128", 0, 2048, 128, 4096), ("none lbo=128 sbo=256", 0, 128, 256, 0), ("none same-op", 0, 2048, 128, 0),
+                                         ("sw32 sbo=256", 6, 0, 256, 4096), ("sw64 sbo=512", 4, 0, 512, 32), ("sw128 sbo=1024", 2, 0, 1024, 32)]:
+            for reps in (32, 128):
+                _lib.check(L.irrl_tc_mma_rate(n, reps, lt, lbo, sbo, kadv, C.c_void_p(out.ctypes.data)))
+                print(f"N={n:3d} {name:24s} reps={reps:3d}: issue {out[0] / reps:6.1f} cyc/MMA, complete {out[1] / reps:6.1f} cyc/MMA", flush=True)
+
+
 if __name__ == "__main__":
-    {"probe": probe, "act": act, "time": timing}[sys.argv[1]]()
+    {"probe": probe, "act": act, "time": timing, "rate": rate}[sys.argv[1]]()

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -113,6 +114,27 @@ bool is_pinned_host_ptr(const void* p, size_t bytes = 1) {
     }
     return true;
 }
+
+// Registry of the ranges page-locked through irrl_host_register.  With IRRL_ZERO_COPY=1 (outputs and inputs) or 2 (inputs only)
+// the kernels use those buffers in place (mapped pinned memory) instead of cudaMemcpy staging.  Measured on B200 / PCIe 5:
+// in-place outputs are 35 % SLOWER end to end (the step kernel's scalar observation stores become small PCIe writes) and
+// in-place inputs are neutral, so the default is 0 = DMA copies; the switch stays for experiments.
+struct PinnedRange { size_t bytes; char* dev; };
+static std::map<uintptr_t, PinnedRange> g_pinned;
+static std::mutex g_pinned_mu;
+static int zero_copy_mode() { static int m = [] { const char* e = getenv("IRRL_ZERO_COPY"); return e ? atoi(e) : 0; }(); return m; }
+// device-visible alias of [p, p+bytes) if the range lies inside one registered block, else nullptr
+template <typename T> static T* mapped_alias(T* p, size_t bytes) {
+    if (!p || zero_copy_mode() == 0) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    auto it = g_pinned.upper_bound(a);
+    if (it == g_pinned.begin()) return nullptr;
+    --it;
+    if (a + bytes > it->first + it->second.bytes) return nullptr;
+    return reinterpret_cast<T*>(it->second.dev + (a - it->first));
+}
+static cudaError_t wait_stream(cudaStream_t st) { return cudaStreamSynchronize(st); }
 
 template <typename T> int dev_alloc(irrl_env_impl* E, T** p, size_t n) {
     void* q = nullptr; CUDA_OK(cudaMalloc(&q, n * sizeof(T))); CUDA_OK(cudaMemset(q, 0, n * sizeof(T)));
@@ -384,22 +406,32 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
     unsigned char* pin = E->h_pin;
     float* p_act = reinterpret_cast<float*>(pin);
     float* p_ob = p_act + N * 12; float* p_rew = p_ob + N * 35; float* p_ext = p_rew + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_ext + N * 6);
-    const bool pa = is_pinned_host_ptr(action, N * 48), po = ob && is_pinned_host_ptr(ob, N * 140), pr = is_pinned_host_ptr(reward, N * 4), pd = is_pinned_host_ptr(done, N), pe = extra && is_pinned_host_ptr(extra, N * 24);
-    if (!pa) memcpy(p_act, action, N * 12 * sizeof(float));
-    CUDA_OK(cudaMemcpyAsync(E->d_action, pa ? action : p_act, N * 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
-    StepArgs a = make_args(E, E->d_action, E->P.flag_obs_filter ? nullptr : E->d_ob, E->d_reward, E->d_done, E->d_extra);
+    // buffers registered with irrl_host_register are used in place by the kernel (zero copy); other page-locked buffers are DMA
+    // targets; pageable ones go through pinned staging
+    const bool outs_ok = zero_copy_mode() == 1;
+    const float* z_act = mapped_alias(action, N * 48);
+    float* z_ob = outs_ok && !E->P.flag_obs_filter ? mapped_alias(ob, N * 140) : nullptr; float* z_rew = outs_ok ? mapped_alias(reward, N * 4) : nullptr;
+    uint8_t* z_done = outs_ok ? mapped_alias(done, N) : nullptr; float* z_ext = outs_ok ? mapped_alias(extra, N * 24) : nullptr;
+    const bool pa = !z_act && is_pinned_host_ptr(action, N * 48), po = ob && !z_ob && is_pinned_host_ptr(ob, N * 140), pr = !z_rew && is_pinned_host_ptr(reward, N * 4),
+               pd = !z_done && is_pinned_host_ptr(done, N), pe = extra && !z_ext && is_pinned_host_ptr(extra, N * 24);
+    if (!z_act) {
+        if (!pa) memcpy(p_act, action, N * 12 * sizeof(float));
+        CUDA_OK(cudaMemcpyAsync(E->d_action, pa ? action : p_act, N * 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
+    }
+    StepArgs a = make_args(E, z_act ? z_act : E->d_action, E->P.flag_obs_filter ? nullptr : (z_ob ? z_ob : E->d_ob), z_rew ? z_rew : E->d_reward, z_done ? z_done : E->d_done,
+                           extra ? (z_ext ? z_ext : E->d_extra) : E->d_extra);
     launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
     E->tick++;
     if (E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, E->d_ob, E->stream); CUDA_OK(cudaGetLastError()); }
-    if (ob) CUDA_OK(cudaMemcpyAsync(po ? ob : p_ob, E->d_ob, N * 35 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    CUDA_OK(cudaMemcpyAsync(pr ? reward : p_rew, E->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    if (extra) CUDA_OK(cudaMemcpyAsync(pe ? extra : p_ext, E->d_extra, N * 6 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    CUDA_OK(cudaMemcpyAsync(pd ? done : p_done, E->d_done, N, cudaMemcpyDeviceToHost, E->stream));
-    CUDA_OK(cudaStreamSynchronize(E->stream));
-    if (ob && !po) memcpy(ob, p_ob, N * 35 * sizeof(float));
-    if (!pr) memcpy(reward, p_rew, N * sizeof(float));
-    if (extra && !pe) memcpy(extra, p_ext, N * 6 * sizeof(float));
-    if (!pd) memcpy(done, p_done, N);
+    if (ob && !z_ob) CUDA_OK(cudaMemcpyAsync(po ? ob : p_ob, E->d_ob, N * 35 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (!z_rew) CUDA_OK(cudaMemcpyAsync(pr ? reward : p_rew, E->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (extra && !z_ext) CUDA_OK(cudaMemcpyAsync(pe ? extra : p_ext, E->d_extra, N * 6 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+    if (!z_done) CUDA_OK(cudaMemcpyAsync(pd ? done : p_done, E->d_done, N, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_OK(wait_stream(E->stream));
+    if (ob && !z_ob && !po) memcpy(ob, p_ob, N * 35 * sizeof(float));
+    if (!z_rew && !pr) memcpy(reward, p_rew, N * sizeof(float));
+    if (extra && !z_ext && !pe) memcpy(extra, p_ext, N * 6 * sizeof(float));
+    if (!z_done && !pd) memcpy(done, p_done, N);
     return 0;
 }
 
@@ -761,27 +793,34 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
     }
     float* p_obs = reinterpret_cast<float*>(Pn->h_pin); float* p_state = p_obs + N * 35; float* p_act = p_state + N * 384; float* p_clip = p_act + N * 12;
     float* p_val = p_clip + N * 12; float* p_nlp = p_val + N; uint8_t* p_done = reinterpret_cast<uint8_t*>(p_nlp + N);
-    const bool q_obs = h_obs && is_pinned_host_ptr(obs, N * 140), q_done = h_done && is_pinned_host_ptr(done, N), q_state = h_state && is_pinned_host_ptr(state, N * 1536),
-               q_act = h_act && is_pinned_host_ptr(action, N * 48), q_clip = h_clip && is_pinned_host_ptr(clipped, N * 48), q_val = h_val && is_pinned_host_ptr(value, N * 4), q_nlp = h_nlp && is_pinned_host_ptr(neglogp, N * 4);
-    if (h_obs) { if (!q_obs) memcpy(p_obs, obs, N * 35 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_obs, q_obs ? obs : p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st)); }
+    // zero copy for buffers registered with irrl_host_register (see step_impl); the LSTM state is read-modify-write and
+    // always staged when it lives on the host
+    const bool outs_ok = zero_copy_mode() == 1;
+    const float* z_obs = h_obs ? mapped_alias(obs, N * 140) : nullptr; const uint8_t* z_done = h_done ? mapped_alias(done, N) : nullptr;
+    float* z_act = h_act && outs_ok ? mapped_alias(action, N * 48) : nullptr; float* z_clip = h_clip && outs_ok ? mapped_alias(clipped, N * 48) : nullptr;
+    float* z_val = h_val && outs_ok ? mapped_alias(value, N * 4) : nullptr; float* z_nlp = h_nlp && outs_ok ? mapped_alias(neglogp, N * 4) : nullptr;
+    const bool q_obs = h_obs && !z_obs && is_pinned_host_ptr(obs, N * 140), q_done = h_done && !z_done && is_pinned_host_ptr(done, N), q_state = h_state && is_pinned_host_ptr(state, N * 1536),
+               q_act = h_act && !z_act && is_pinned_host_ptr(action, N * 48), q_clip = h_clip && !z_clip && is_pinned_host_ptr(clipped, N * 48),
+               q_val = h_val && !z_val && is_pinned_host_ptr(value, N * 4), q_nlp = h_nlp && !z_nlp && is_pinned_host_ptr(neglogp, N * 4);
+    if (h_obs && !z_obs) { if (!q_obs) memcpy(p_obs, obs, N * 35 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_obs, q_obs ? obs : p_obs, N * 35 * 4, cudaMemcpyHostToDevice, st)); }
     if (h_state) { if (!q_state) memcpy(p_state, state, N * 384 * 4); CUDA_OK(cudaMemcpyAsync(Pn->d_state, q_state ? state : p_state, N * 384 * 4, cudaMemcpyHostToDevice, st)); }
-    if (h_done) { if (!q_done) memcpy(p_done, done, N); CUDA_OK(cudaMemcpyAsync(Pn->d_done, q_done ? done : p_done, N, cudaMemcpyHostToDevice, st)); }
-    a.obs = h_obs ? Pn->d_obs : obs; a.done = done ? (h_done ? Pn->d_done : done) : nullptr; a.state = h_state ? Pn->d_state : state;
-    a.action = h_act ? Pn->d_action : action; a.clipped = clipped ? (h_clip ? Pn->d_clipped : clipped) : nullptr;
-    a.value = h_val ? Pn->d_value : value; a.neglogp = h_nlp ? Pn->d_nlp : neglogp;
+    if (h_done && !z_done) { if (!q_done) memcpy(p_done, done, N); CUDA_OK(cudaMemcpyAsync(Pn->d_done, q_done ? done : p_done, N, cudaMemcpyHostToDevice, st)); }
+    a.obs = h_obs ? (z_obs ? z_obs : Pn->d_obs) : obs; a.done = done ? (h_done ? (z_done ? z_done : Pn->d_done) : done) : nullptr; a.state = h_state ? Pn->d_state : state;
+    a.action = h_act ? (z_act ? z_act : Pn->d_action) : action; a.clipped = clipped ? (h_clip ? (z_clip ? z_clip : Pn->d_clipped) : clipped) : nullptr;
+    a.value = h_val ? (z_val ? z_val : Pn->d_value) : value; a.neglogp = h_nlp ? (z_nlp ? z_nlp : Pn->d_nlp) : neglogp;
     launch_lstm_act(a, st); CUDA_OK(cudaGetLastError());
     if (!any_host) return 0;
     if (h_state) CUDA_OK(cudaMemcpyAsync(q_state ? state : p_state, Pn->d_state, N * 384 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_act) CUDA_OK(cudaMemcpyAsync(q_act ? action : p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_clip) CUDA_OK(cudaMemcpyAsync(q_clip ? clipped : p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_val) CUDA_OK(cudaMemcpyAsync(q_val ? value : p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
-    if (h_nlp) CUDA_OK(cudaMemcpyAsync(q_nlp ? neglogp : p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    if (h_act && !z_act) CUDA_OK(cudaMemcpyAsync(q_act ? action : p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_clip && !z_clip) CUDA_OK(cudaMemcpyAsync(q_clip ? clipped : p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_val && !z_val) CUDA_OK(cudaMemcpyAsync(q_val ? value : p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
+    if (h_nlp && !z_nlp) CUDA_OK(cudaMemcpyAsync(q_nlp ? neglogp : p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(wait_stream(st));
     if (h_state && !q_state) memcpy(state, p_state, N * 384 * 4);
-    if (h_act && !q_act) memcpy(action, p_act, N * 12 * 4);
-    if (h_clip && !q_clip) memcpy(clipped, p_clip, N * 12 * 4);
-    if (h_val && !q_val) memcpy(value, p_val, N * 4);
-    if (h_nlp && !q_nlp) memcpy(neglogp, p_nlp, N * 4);
+    if (h_act && !z_act && !q_act) memcpy(action, p_act, N * 12 * 4);
+    if (h_clip && !z_clip && !q_clip) memcpy(clipped, p_clip, N * 12 * 4);
+    if (h_val && !z_val && !q_val) memcpy(value, p_val, N * 4);
+    if (h_nlp && !z_nlp && !q_nlp) memcpy(neglogp, p_nlp, N * 4);
     return 0;
 }
 
@@ -856,9 +895,19 @@ int irrl_lstm_pw_bwd(void* cuda_stream, int rows, int n_env, const float* dh_out
 int irrl_host_register(void* ptr, size_t bytes) {
     if (!ptr || !bytes) return fail(-1, "irrl_host_register: null argument");
     if (is_pinned_host_ptr(ptr, bytes)) return 0;
-    CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0;
+    CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, ptr, 0) == cudaSuccess && dev) {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        g_pinned[reinterpret_cast<uintptr_t>(ptr)] = PinnedRange{bytes, static_cast<char*>(dev)};
+    } else cudaGetLastError();
+    return 0;
 }
-int irrl_host_unregister(void* ptr) { if (!ptr) return 0; cudaError_t e = cudaHostUnregister(ptr); if (e != cudaSuccess) cudaGetLastError(); return 0; }
+int irrl_host_unregister(void* ptr) {
+    if (!ptr) return 0;
+    { std::lock_guard<std::mutex> lk(g_pinned_mu); g_pinned.erase(reinterpret_cast<uintptr_t>(ptr)); }
+    cudaError_t e = cudaHostUnregister(ptr); if (e != cudaSuccess) cudaGetLastError(); return 0;
+}
 
 int irrl_gae(void* cuda_stream, int T, int n, const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
              const uint8_t* last_dones, float gamma, float lam, float* adv, float* returns) {

@@ -263,10 +263,10 @@ def run_b200(args):
 
     # ---- e2e: the reference-facing calls with HOST buffers (model.step + env.step), copies inside the timed region
     Ke = max(10, min(args.e2e_steps, K))
-    h_obs = np.zeros((N, 35), np.float32); h_rew = np.zeros(N, np.float32); h_done = np.zeros(N, np.bool_); h_extra = np.zeros((N, 6), np.float32)
-    h_act = np.zeros((N, 12), np.float32); h_clip = np.zeros((N, 12), np.float32); h_val = np.zeros(N, np.float32); h_nlp = np.zeros(N, np.float32)
-    for hb in (h_obs, h_rew, h_done, h_extra, h_act, h_clip, h_val, h_nlp):   # RaisimGymVecEnv / the policy object page-lock the buffers they own
-        _lib.pin(hb)
+    # RaisimGymVecEnv / the policy object own their host buffers as one page-locked block each, laid out like the native output
+    # blocks (vec_env.py, _lib.pinned_block), so every call returns its results in a single DMA copy
+    h_obs, h_rew, h_extra, h_done = _lib.pinned_block(((N, 35), np.float32), ((N,), np.float32), ((N, 6), np.float32), ((N,), np.bool_))
+    h_act, h_clip, h_val, h_nlp = _lib.pinned_block(((N, 12), np.float32), ((N, 12), np.float32), ((N,), np.float32), ((N,), np.float32))
     env.reset(h_obs)
     state.zero_()
 
@@ -343,7 +343,7 @@ def run_b200(args):
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed (state << L2)",
                        "parallelism": f"env-shard x{world}, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "path": "irrl_policy_act + irrl_step with page-locked host numpy buffers (as RaisimGymVecEnv owns them), 2 blocking calls per step; LSTM state device-resident"},
+                    "path": "irrl_policy_act + irrl_step with page-locked host numpy buffers (as RaisimGymVecEnv owns them: one block per call, one DMA copy back), 2 blocking calls per step; LSTM state device-resident"},
             "gpu_launches": 2 * K, "kernels": ["lstm_act_tc_kernel (tcgen05 3xTF32)" if N >= 256 else "lstm_act_kernel", "env_step_kernel"], "memcpy_d2d_per_step": 0,
             "roofline": roof, "clocks": clocks, "wall_s": wall,
             "sanity": {"mean_reward": mean_rew, "episodes_finished": episodes_done, "gs_sweeps_last_substep": {"mean": float(sw.mean()), "max": int(sw.max()), "hist": np.bincount(sw, minlength=9).tolist()}}}

@@ -98,3 +98,19 @@ def pin(array) -> bool:
         return True
     except Exception:
         return False
+
+
+def pinned_block(*specs):
+    """One page-locked block carved into back-to-back arrays: `specs` = (shape, dtype) pairs, each array 4-byte aligned by
+    construction when the leading ones are float32.  The C ABI recognises buffers laid out like its device-side output
+    blocks ([ob | reward | extra | done] for irrl_step, [action | clipped | value | neglogp] for irrl_policy_act) and moves
+    them with a single DMA copy.  Falls back to separate pageable arrays when page-locking is impossible."""
+    import numpy as np
+    sizes = [int(np.prod(shape)) * np.dtype(dt).itemsize for shape, dt in specs]
+    block = np.zeros(sum(sizes), np.uint8)
+    pin(block)
+    out, off = [], 0
+    for (shape, dt), nb in zip(specs, sizes):
+        out.append(block[off:off + nb].view(dt).reshape(shape))
+        off += nb
+    return out

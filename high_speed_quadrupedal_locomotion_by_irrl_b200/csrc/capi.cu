@@ -161,7 +161,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         E->control_dt_d = ctl_dt; E->sim_dt_d = sim_dt;
         if (!num("seedd", d)) goto bad; P.seed = (uint32_t)(int)d;                                               // VEC:171
         // ENV:1598-1613
-        NUM("abad", P.abad) NUM("period", P.period) NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
+        NUM("abad", P.abad) NUM("period", P.period) P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
         IGN("down_height") IGN("gait_step")
         NUM("Vx", P.Vx_max) P.Vx_min = 0.f;                                                                      // ENV:1606-1607, 2054
         NUM("Vy", P.Vy_max) P.Vy_min = -P.Vy_max; NUM("Omega", P.omega_max) P.omega_min = -P.omega_max;
@@ -193,8 +193,8 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         P.mu = (float)opt("friction", 0.6); P.restitution = (float)opt("restitution", 0.2); P.rest_threshold = (float)opt("restitution_threshold", 0.01);   // ENV:433
     }
     if (P.N <= 0) return fail(-3, "num_envs must be positive");
-    if (P.flag_force_dist && P.flag_manual) return fail(-3, "ForceDisturbance with Manual (state_disturbance, ENV:912-940) is not implemented in this build");
-    // ForceDisturbance without Manual: force_attack(random() < 0.0027) never fires -> zero external force.
+    // ForceDisturbance: with Manual the step kernel perturbs the base state every 10 gait periods (state_disturbance, ENV:912-940);
+    // without Manual force_attack(random() < 0.0027) never fires -> zero external force.
     switch (P.gait_type) {                                                                                       // ENV:398-409
         case 0: P.phase[0] = 0.5f; P.phase[1] = 0.f; P.phase[2] = 0.f; P.phase[3] = 0.5f; break;
         case 1: P.phase[0] = 0.5f; P.phase[1] = 0.5f; P.phase[2] = 0.f; P.phase[3] = 0.f; break;
@@ -338,8 +338,11 @@ int irrl_init(irrl_env* env) {
     rc |= dev_alloc(E, &E->S.legmodel, N * 64); rc |= dev_alloc(E, &E->S.basemodel, N * 8);
     rc |= dev_alloc(E, &E->S.frame_idx, N); rc |= dev_alloc(E, &E->S.itera, N); rc |= dev_alloc(E, &E->S.ep_len, N);
     rc |= dev_alloc(E, &E->S.ep_ret, N); rc |= dev_alloc(E, &E->S.solver_sweeps, N);
-    rc |= dev_alloc(E, &E->d_action, N * 12); rc |= dev_alloc(E, &E->d_ob, N * 35); rc |= dev_alloc(E, &E->d_reward, N);
-    rc |= dev_alloc(E, &E->d_extra, N * 6); rc |= dev_alloc(E, &E->d_done, N); rc |= dev_alloc(E, &E->d_ep_ret, N); rc |= dev_alloc(E, &E->d_ep_len, N);
+    rc |= dev_alloc(E, &E->d_action, N * 12);
+    {   // step outputs live in one block [ob | reward | extra | done]: a caller that lays its host buffers out the same way gets them in one copy
+        unsigned char* blk = nullptr; rc |= dev_alloc(E, &blk, N * (35 + 1 + 6) * 4 + N);
+        if (!rc) { E->d_ob = reinterpret_cast<float*>(blk); E->d_reward = E->d_ob + N * 35; E->d_extra = E->d_reward + N; E->d_done = reinterpret_cast<uint8_t*>(E->d_extra + N * 6); }
+    } rc |= dev_alloc(E, &E->d_ep_ret, N); rc |= dev_alloc(E, &E->d_ep_len, N);
     if (rc) return rc;
     if (int r2 = ensure_pin(E, N * (35 + 12 + 1 + 6 + 2) * sizeof(float) + N)) return r2;
     // optional reference table (VEC:158-169); a missing file is only a warning there (VEC:71-73)
@@ -423,10 +426,16 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
     launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
     E->tick++;
     if (E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, E->d_ob, E->stream); CUDA_OK(cudaGetLastError()); }
-    if (ob && !z_ob) CUDA_OK(cudaMemcpyAsync(po ? ob : p_ob, E->d_ob, N * 35 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    if (!z_rew) CUDA_OK(cudaMemcpyAsync(pr ? reward : p_rew, E->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    if (extra && !z_ext) CUDA_OK(cudaMemcpyAsync(pe ? extra : p_ext, E->d_extra, N * 6 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
-    if (!z_done) CUDA_OK(cudaMemcpyAsync(pd ? done : p_done, E->d_done, N, cudaMemcpyDeviceToHost, E->stream));
+    // host buffers laid out like the device block (ob | reward | extra | done back to back, all page-locked): one copy instead of four
+    const bool packed = ob && extra && po && pr && pe && pd && reward == ob + N * 35 && extra == reward + N && done == reinterpret_cast<uint8_t*>(extra + N * 6);
+    if (packed) {
+        CUDA_OK(cudaMemcpyAsync(ob, E->d_ob, N * (35 + 1 + 6) * sizeof(float) + N, cudaMemcpyDeviceToHost, E->stream));
+    } else {
+        if (ob && !z_ob) CUDA_OK(cudaMemcpyAsync(po ? ob : p_ob, E->d_ob, N * 35 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+        if (!z_rew) CUDA_OK(cudaMemcpyAsync(pr ? reward : p_rew, E->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+        if (extra && !z_ext) CUDA_OK(cudaMemcpyAsync(pe ? extra : p_ext, E->d_extra, N * 6 * sizeof(float), cudaMemcpyDeviceToHost, E->stream));
+        if (!z_done) CUDA_OK(cudaMemcpyAsync(pd ? done : p_done, E->d_done, N, cudaMemcpyDeviceToHost, E->stream));
+    }
     CUDA_OK(wait_stream(E->stream));
     if (ob && !z_ob && !po) memcpy(ob, p_ob, N * 35 * sizeof(float));
     if (!z_rew && !pr) memcpy(reward, p_rew, N * sizeof(float));
@@ -766,7 +775,7 @@ int irrl_tc_gemm_probe(const float* a, const float* b, float* d, int k, int n, i
 void irrl_policy_destroy(irrl_policy* pol) {
     irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return;
     cudaSetDevice(Pn->device); cudaDeviceSynchronize();
-    cudaFree(Pn->d_params); cudaFree(Pn->d_derived); cudaFree(Pn->d_tcblob); cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
+    cudaFree(Pn->d_params); cudaFree(Pn->d_derived); cudaFree(Pn->d_tcblob); cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_done);
     if (Pn->h_pin) cudaFreeHost(Pn->h_pin);
     delete Pn;
 }
@@ -784,10 +793,11 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
                h_clip = clipped && !is_device_ptr(clipped), h_val = !is_device_ptr(value), h_nlp = !is_device_ptr(neglogp);
     const bool any_host = h_obs || h_done || h_state || h_act || h_clip || h_val || h_nlp;
     if (any_host && n > Pn->cap) {
-        cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_clipped); cudaFree(Pn->d_value); cudaFree(Pn->d_nlp); cudaFree(Pn->d_done);
+        cudaFree(Pn->d_obs); cudaFree(Pn->d_state); cudaFree(Pn->d_action); cudaFree(Pn->d_done);
         if (Pn->h_pin) cudaFreeHost(Pn->h_pin);
-        CUDA_OK(cudaMalloc((void**)&Pn->d_obs, N * 35 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_state, N * 384 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_action, N * 12 * 4));
-        CUDA_OK(cudaMalloc((void**)&Pn->d_clipped, N * 12 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_value, N * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_nlp, N * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_done, N));
+        CUDA_OK(cudaMalloc((void**)&Pn->d_obs, N * 35 * 4)); CUDA_OK(cudaMalloc((void**)&Pn->d_state, N * 384 * 4));
+        CUDA_OK(cudaMalloc((void**)&Pn->d_action, N * (12 + 12 + 1 + 1) * 4));      // one block [action | clipped | value | neglogp]: one copy for callers laid out the same way
+        Pn->d_clipped = Pn->d_action + N * 12; Pn->d_value = Pn->d_clipped + N * 12; Pn->d_nlp = Pn->d_value + N; CUDA_OK(cudaMalloc((void**)&Pn->d_done, N));
         CUDA_OK(cudaMallocHost((void**)&Pn->h_pin, N * (35 + 384 + 12 + 12 + 1 + 1) * 4 + N));
         Pn->cap = n;
     }
@@ -811,10 +821,15 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
     launch_lstm_act(a, st); CUDA_OK(cudaGetLastError());
     if (!any_host) return 0;
     if (h_state) CUDA_OK(cudaMemcpyAsync(q_state ? state : p_state, Pn->d_state, N * 384 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_act && !z_act) CUDA_OK(cudaMemcpyAsync(q_act ? action : p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_clip && !z_clip) CUDA_OK(cudaMemcpyAsync(q_clip ? clipped : p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_val && !z_val) CUDA_OK(cudaMemcpyAsync(q_val ? value : p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
-    if (h_nlp && !z_nlp) CUDA_OK(cudaMemcpyAsync(q_nlp ? neglogp : p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
+    const bool packed = q_act && q_clip && q_val && q_nlp && clipped == action + N * 12 && value == clipped + N * 12 && neglogp == value + N;
+    if (packed) {
+        CUDA_OK(cudaMemcpyAsync(action, Pn->d_action, N * (12 + 12 + 1 + 1) * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (h_act && !z_act) CUDA_OK(cudaMemcpyAsync(q_act ? action : p_act, Pn->d_action, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+        if (h_clip && !z_clip) CUDA_OK(cudaMemcpyAsync(q_clip ? clipped : p_clip, Pn->d_clipped, N * 12 * 4, cudaMemcpyDeviceToHost, st));
+        if (h_val && !z_val) CUDA_OK(cudaMemcpyAsync(q_val ? value : p_val, Pn->d_value, N * 4, cudaMemcpyDeviceToHost, st));
+        if (h_nlp && !z_nlp) CUDA_OK(cudaMemcpyAsync(q_nlp ? neglogp : p_nlp, Pn->d_nlp, N * 4, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_OK(wait_stream(st));
     if (h_state && !q_state) memcpy(state, p_state, N * 384 * 4);
     if (h_act && !z_act && !q_act) memcpy(action, p_act, N * 12 * 4);

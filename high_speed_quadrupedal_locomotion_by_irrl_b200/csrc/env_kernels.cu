@@ -257,6 +257,19 @@ __global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const _
         pt = mk(p0 * k + p0, p1 * k + p1, p2 * k + p2);
     }
     e.ptl = pt;
+    // ---- ForceDisturbance + Manual: state_disturbance every 10 gait periods (ENV:744-747, 912-940); without Manual the
+    // reference's force_attack never fires
+    if (P.flag_force_dist && P.flag_manual) {
+        if (P.disturb_every > 0 && e.frame_idx % P.disturb_every == 0) {
+            const uint4 ra = philox(P.seed, gid, A.tick, P_DISTURB), rb = philox(P.seed, gid, A.tick, P_DISTURB + 1);
+            const float ratio = 0.5f;
+            e.b.p.z += 0.03f * usym(ra.x) * ratio;
+            e.b.qw += 0.1f * usym(ra.y) * ratio; e.b.qx += 0.1f * usym(ra.z) * ratio; e.b.qy += 0.1f * usym(ra.w) * ratio; e.b.qz += 0.1f * usym(rb.x) * ratio;
+            const float qn = 1.0f / sqrtf(e.b.qw * e.b.qw + e.b.qx * e.b.qx + e.b.qy * e.b.qy + e.b.qz * e.b.qz);
+            e.b.qw *= qn; e.b.qx *= qn; e.b.qy *= qn; e.b.qz *= qn;
+            e.b.v.z += 0.1f * usym(rb.y) * ratio; e.b.w.x += 0.3f * usym(rb.z) * ratio; e.b.w.y += 0.3f * usym(rb.w) * ratio;
+        }
+    }
     // ---- PD + torque filter + clamp + integrate, loop_count times (ENV:758-774)
     const float kp0 = P.stiffness * P.abad_ratio, kd0 = P.damping * P.abad_ratio;
     const float rr_ = P.motor_max_torque / (P.motor_max_speed - P.motor_crit_speed);

@@ -18,7 +18,7 @@ constexpr int LSTM_STATE = 384;  // run_bp_v5.py:136-137
 // RNG stream ids (Philox4x32-10 counter = (global env id, tick, purpose, 0), key = (seed, 0x1BD11BDA))
 enum : uint32_t {
     P_OBS_Q0 = 0, P_OBS_QD0 = 3, P_OBS_POSTURE = 6, P_OBS_OMEGA = 7, P_CMD = 8, P_ACT = 9,
-    P_RST_TIME_CMD = 16, P_RST_INIT = 17, P_RST_BASEVEL = 18, P_RST_XY = 19, P_IN_RESET = 32,
+    P_RST_TIME_CMD = 16, P_RST_INIT = 17, P_RST_BASEVEL = 18, P_RST_XY = 19, P_DISTURB = 20, P_IN_RESET = 32,
     P_DR_MATERIAL = 64, P_DR_MASS = 65, P_DR_COM = 80, P_DR_CALF = 96,
     P_POLICY_EPS = 128,   // +0..2 : 12 standard normals of the Gaussian policy sample
 };
@@ -34,6 +34,7 @@ struct EnvParams {
     float motor_max_torque, motor_crit_speed, motor_max_speed;
     float sim_dt, control_dt;
     int loop_count;               // ENV:711
+    int disturb_every;            // ENV:746 : control steps between state disturbances = int(period / control_dt * 10)
     int gait_type;
     float phase[4];               // ENV:398-409
     float filter_para;            // ENV:396

@@ -80,17 +80,16 @@ class RaisimGymVecEnv:
         self._observation_space = Box(np.full(self.num_obs, -np.inf), np.full(self.num_obs, np.inf))
         self._action_space = Box(-np.ones(self.num_acts), np.ones(self.num_acts))
         self._extraInfoNames = impl.getExtraInfoNames()
-        self._observation = np.zeros((n, self.num_obs), np.float32)
-        self._reward = np.zeros(n, np.float32)
-        self._done = np.zeros(n, bool)
-        self._extraInfo = np.zeros((n, len(self._extraInfoNames)), np.float32)
         self._ep_ret, self._ep_len = np.zeros(n, np.float32), np.zeros(n, np.int32)
-        try:   # the adapter owns these buffers: page-lock them once so the native step DMAs straight into them
+        try:   # the adapter owns these buffers: one page-locked block laid out like the native output block -> one DMA copy per step
             from . import _lib
-            for buf in (self._observation, self._reward, self._done, self._extraInfo):
-                _lib.pin(buf)
+            self._observation, self._reward, self._extraInfo, self._done = _lib.pinned_block(
+                ((n, self.num_obs), np.float32), ((n,), np.float32), ((n, len(self._extraInfoNames)), np.float32), ((n,), np.bool_))
         except Exception:
-            pass
+            self._observation = np.zeros((n, self.num_obs), np.float32)
+            self._reward = np.zeros(n, np.float32)
+            self._done = np.zeros(n, bool)
+            self._extraInfo = np.zeros((n, len(self._extraInfoNames)), np.float32)
         self._track = track_rewards
         self.rewards = [[] for _ in range(n)] if track_rewards else None
 
@@ -110,7 +109,7 @@ class RaisimGymVecEnv:
         return self._observation.copy(), self._reward.copy(), self._done.copy(), LazyInfo(self._extraInfoNames, self._extraInfo.copy(), episodes)
 
     def reset(self):
-        self._reward = np.zeros(self.num_envs, np.float32)
+        self._reward[:] = 0
         self.wrapper.reset(self._observation)
         return self._observation.copy()
 

@@ -72,7 +72,7 @@ static inline float usym(uint32_t x) { return (float)(x >> 8) * (1.0f / 8388608.
 enum : uint32_t {
     P_OBS_Q0 = 0, P_OBS_Q1 = 1, P_OBS_Q2 = 2, P_OBS_QD0 = 3, P_OBS_QD1 = 4, P_OBS_QD2 = 5,
     P_OBS_POSTURE = 6, P_OBS_OMEGA = 7, P_CMD = 8, P_ACT = 9,
-    P_RST_TIME_CMD = 16, P_RST_INIT = 17, P_RST_BASEVEL = 18, P_RST_XY = 19,
+    P_RST_TIME_CMD = 16, P_RST_INIT = 17, P_RST_BASEVEL = 18, P_RST_XY = 19, P_DISTURB = 20,
     P_IN_RESET = 32,
     P_DR_MATERIAL = 64, P_DR_MASS = 65 /* +body (13) */, P_DR_COM = 80 /* +body (13) */, P_DR_CALF = 96,
 };
@@ -925,6 +925,22 @@ template <typename T> struct Env {
             pTarget12_[j] = p; pTarget12Last_[j] = p;                                          // ENV:706-707
         }
         int loopCount = int(control_dt_ / simulation_dt_ + T(1e-10));                          // ENV:711
+        // ENV:744-754: ForceDisturbance.  With Manual the base state is perturbed every 10 gait periods (state_disturbance,
+        // ENV:912-940, ratio 0.5; the quaternion is re-normalised here, RaiSim's setState is assumed to do the same);
+        // without Manual force_attack(random() < 0.0027) never fires: no external force.
+        if (flag_ForceDisturbance && flag_manual) {
+            int every = int(period_ / control_dt_ * T(10));
+            if (every > 0 && frame_idx % every == 0) {
+                uint32_t ra[4], rb[4]; Philox::gen(seed, env_id, tick, P_DISTURB, ra); Philox::gen(seed, env_id, tick, P_DISTURB + 1, rb);
+                const T ratio = T(0.5);
+                gc_[2] += T(0.03) * T(usym(ra[0])) * ratio;
+                gc_[3] += T(0.1) * T(usym(ra[1])) * ratio; gc_[4] += T(0.1) * T(usym(ra[2])) * ratio;
+                gc_[5] += T(0.1) * T(usym(ra[3])) * ratio; gc_[6] += T(0.1) * T(usym(rb[0])) * ratio;
+                T qn = std::sqrt(gc_[3] * gc_[3] + gc_[4] * gc_[4] + gc_[5] * gc_[5] + gc_[6] * gc_[6]);
+                for (int i = 3; i < 7; ++i) gc_[i] /= qn;
+                gv_[2] += T(0.1) * T(usym(rb[1])) * ratio; gv_[3] += T(0.3) * T(usym(rb[2])) * ratio; gv_[4] += T(0.3) * T(usym(rb[3])) * ratio;
+            }
+        }
         const T afp = T(0.99);                                                                 // ENV:756
         for (int i = 0; i < loopCount; ++i) {                                                  // ENV:758-774
             for (int j = 0; j < NJ; ++j) {

@@ -88,6 +88,24 @@ def test_manual_teleop_configuration():      # bp5_test.yaml: Manual True -> fix
     assert np.abs(sg[:, S["command"]]).max() == 0 and np.abs(sg[:, S["joint_dot_ref"]]).max() == 0
 
 
+def test_state_disturbance_every_ten_periods():   # ENV:744-747, 912-940 (ForceDisturbance + Manual)
+    cfg = manual_test_cfg(num_envs=64, render=False, ForceDisturbance=True)
+    o, c = _run(cfg, steps=3, sigma=0.1)
+    # frame_idx = 1000 = int(period / control_dt * 10) fires the disturbance: kernel and oracle draw the same Philox numbers
+    s0 = o.get_state().copy(); s0[:, S["frame_idx"]] = 1000
+    for e in range(o.n):
+        o.set_state(e, s0[e])
+    c.set_state(s0.astype(np.float32))
+    before = s0[:, S["gc"]][:, 3:7].copy()
+    a = np.zeros((o.n, 12), np.float32)
+    obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
+    so, sg = o.get_state(), c.get_state()
+    assert np.abs(so[:, S["gc"]][:, 3:7] - before).max() > 1e-3                     # it fired
+    ok = (sg[:, S["contact"]] == so[:, S["contact"]]).all(axis=1) & (do == dg)
+    assert ok.sum() >= o.n - 1
+    assert rel(sg[ok][:, S["gc"]], so[ok][:, S["gc"]]) < 2e-5 and rel(obg[ok], obo[ok]) < 2e-5 and rel(rg[ok], ro[ok]) < 2e-5
+
+
 def test_other_time_steps_loop_count():      # ENV:711
     o, c = _run(_cfg(simulation_dt=0.0005, control_dt=0.004), steps=6)
 

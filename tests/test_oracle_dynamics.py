@@ -197,3 +197,26 @@ def test_drop_with_restitution_bounces_below_drop_height():
     zs = np.array(zs)
     assert zs.min() > 0.15 and zs.max() <= 0.45 + 1e-9
     assert abs(zs[-1] - zs[-200]) < 2e-3      # came to rest
+
+
+def test_state_disturbance_fires_every_ten_periods_only():
+    """ENV:744-747, 912-940: ForceDisturbance + Manual perturbs z, the quaternion, v_z and omega_xy when
+    frame_idx % int(period / control_dt * 10) == 0 (frame 1000 at the test time steps) and at no other frame"""
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import test_cfg as manual_cfg
+    on, off = Oracle(manual_cfg(num_envs=4, render=False, ForceDisturbance=True)), Oracle(manual_cfg(num_envs=4, render=False, ForceDisturbance=False))
+    for o in (on, off):
+        o.set_tick(1); o.reset()
+    a = np.zeros((4, 12), np.float32)
+    s0 = on.get_state().copy()
+    assert (s0[:, S["frame_idx"]] == 1).all()                  # reset leaves frame_idx at 1 (ENV:630-631)
+    on.step(a); off.step(a)
+    assert np.abs(on.get_state() - off.get_state()).max() < 1e-12      # frame 1: nothing happens
+    s0[:, S["frame_idx"]] = 1000
+    for e in range(4):
+        on.set_state(e, s0[e]); off.set_state(e, s0[e])
+    on.step(a); off.step(a)
+    s_on, s_off = on.get_state(), off.get_state()
+    q_on, q_off = s_on[:, S["gc"]][:, 3:7], s_off[:, S["gc"]][:, 3:7]
+    dq = np.abs(q_on - q_off).max(axis=1)
+    assert (dq > 1e-4).all() and (dq < 0.12).all()
+    assert np.allclose(np.linalg.norm(q_on, axis=1), 1.0, atol=1e-9)

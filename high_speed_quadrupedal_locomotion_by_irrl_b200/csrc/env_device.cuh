@@ -474,14 +474,21 @@ __device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int own
 
 struct ContactOut { int foot_active; f3 foot_impulse; int sweeps; };
 
+// PHASE_SYNC (template flag SYNC): block-wide barriers that keep the warps of a CTA in the same stretch of the substep code
+// (39 KB of straight-line SASS, more than the 32 KB instruction cache), so that one instruction fetch serves all of them.
+// Measured: -7 % kernel time from 8192 robots per GPU with 128-thread CTAs, neutral to slightly negative at 4096.
+#define PHASE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
 // ------------------------------------------------------------------ one world.integrate() (ENV:768)
 // tau: this leg's joint torques.  fext: optional external generalised force on the trunk (6).
+template <bool SYNC = false>
 __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegModel& lm, const BaseModel& bm, int leg,
                                                   Base& b, f3& q, f3& qd, f3 tau, ContactOut& out) {
     const float dt = P.sim_dt;
+    PHASE_SYNC();
     f3 bx, by, bz; quat_cols(b.qw, b.qx, b.qy, b.qz, bx, by, bz);
     LegKin k; leg_fk(P, lm, bx, by, bz, q, k);
     Dyn d; dynamics(P, lm, bm, b, bx, by, bz, k, qd, d, nullptr, nullptr, false, leg);
+    PHASE_SYNC();
 
     // ---- free acceleration in the factorised form:  t = Dinv r_l,  w = L^-1 (r_b - sum B t)
     f3 rl = mk(tau.x - P.joint_damping * qd.x - d.hl.x, tau.y - P.joint_damping * qd.y - d.hl.y, tau.z - P.joint_damping * qd.z - d.hl.z);
@@ -528,6 +535,7 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     f3 lam_leg = mk(0.f, 0.f, 0.f);
     out.sweeps = 0;
     cf.lam = mk(0.f, 0.f, 0.f);
+    PHASE_SYNC();
     if (any_foot_or_box) {
         // ---- foot contact setup (every lane builds its own slot)
         contact_setup(d, xf, Jl0, Jl1, Jl2, true, cf, terr, ft1, ft2, fn);
@@ -603,6 +611,7 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
         lam_leg = cf.lam;
     }
     out.foot_active = cf.active; out.foot_impulse = cf.lam;
+    PHASE_SYNC();
 
     // ---- new velocity: u+ = u + M^-1 (dt r + J^T lambda)
     bwd6(d.L, ytot);                                                    // trunk increment

@@ -233,9 +233,12 @@ __device__ __forceinline__ void write_scaled_obs(const EnvParams& P, const DevSt
 #ifndef STEP_MINBLOCKS
 #define STEP_MINBLOCKS 1
 #endif
-__global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const __grid_constant__ StepArgs A) {
+// BLK / SYNC: 64-thread CTAs without phase barriers up to ~6k robots (one warp per scheduler: pure latency), 128-thread CTAs with
+// phase barriers above (launch_env_step)
+template <int BLK, bool SYNC>
+__global__ void __launch_bounds__(BLK, STEP_MINBLOCKS) env_step_kernel(const __grid_constant__ StepArgs A) {
     const EnvParams& P = A.P; const DevState& S = A.S;
-    const int tid = blockIdx.x * BLOCK + threadIdx.x;
+    const int tid = blockIdx.x * BLK + threadIdx.x;
     int r = tid >> 2; const int leg = tid & 3;
     const bool valid = r < P.N;
     if (!valid) r = P.N - 1;                      // tail lanes shadow the last robot (no stores) so quads stay convergent
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(BLOCK, STEP_MINBLOCKS) env_step_kernel(const _
             tt[k] = fmaxf(fminf(tt[k], up), low);
         }
         tau = mk(tt[0], tt[1], tt[2]);
-        integrate_substep(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co);
+        integrate_substep<SYNC>(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co);
     }
     e.tau_applied = tau;
 
@@ -566,7 +569,10 @@ __global__ void env_init_kernel(EnvParams P, DevState S) {
 
 // ------------------------------------------------------------------ host launchers
 static inline int quad_grid(int N) { return (N * 4 + BLOCK - 1) / BLOCK; }
-void launch_env_step(const StepArgs& a, cudaStream_t st) { env_step_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a); }
+void launch_env_step(const StepArgs& a, cudaStream_t st) {
+    if (a.P.N > 6144) env_step_kernel<128, true><<<(a.P.N * 4 + 127) / 128, 128, 0, st>>>(a);
+    else env_step_kernel<64, false><<<quad_grid(a.P.N), 64, 0, st>>>(a);
+}
 void launch_env_reset(const StepArgs& a, cudaStream_t st) { env_reset_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a); }
 void launch_env_observe(const EnvParams& P, const DevState& S, float* ob, cudaStream_t st) { env_observe_kernel<<<(P.N + 127) / 128, 128, 0, st>>>(P, S, ob); }
 void launch_env_probe(const EnvParams& P, const DevState& S, float* M, float* Minv, float* h, cudaStream_t st) { env_probe_kernel<<<quad_grid(P.N), BLOCK, 0, st>>>(P, S, M, Minv, h); }

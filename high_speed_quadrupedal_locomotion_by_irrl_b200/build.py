@@ -13,6 +13,10 @@ SOURCES = ["env_kernels.cu", "policy_kernels.cu", "policy_tc_kernels.cu", "capi.
 HEADERS = ["env_device.cuh", "env_kernels.h", "irrl_params.h", os.path.join("..", "..", "include", "irrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+if os.environ.get("IRRL_FASTDIV"):
+    NVCC_FLAGS += ["-DIRRL_FASTDIV=" + os.environ["IRRL_FASTDIV"]]
+if os.environ.get("IRRL_SINCOS"):               # 0 libdevice sincosf, 1 MUFU, 2 (default) Cody-Waite polynomial
+    NVCC_FLAGS += ["-DIRRL_SINCOS=" + os.environ["IRRL_SINCOS"]]
 if os.environ.get("IRRL_STEP_MINBLOCKS"):      # tuning knob: register cap of the step kernel = 65536 / (64 * minblocks)
     NVCC_FLAGS += ["-DSTEP_MINBLOCKS=" + os.environ["IRRL_STEP_MINBLOCKS"]]
 

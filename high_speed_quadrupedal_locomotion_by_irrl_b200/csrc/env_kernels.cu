@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(BLK, STEP_MINBLOCKS) env_step_kernel(const __g
     // ---- PD + torque filter + clamp + integrate, loop_count times (ENV:758-774)
     const float kp0 = P.stiffness * P.abad_ratio, kd0 = P.damping * P.abad_ratio;
     const float rr_ = P.motor_max_torque / (P.motor_max_speed - P.motor_crit_speed);
+    const float ilow_ = 1.0f / (-P.motor_max_speed + P.motor_crit_speed);      // hoisted out of the substep loop
     f3 tau = mk(0.f, 0.f, 0.f);
     ContactOut co; co.foot_active = 0; co.foot_impulse = mk(0, 0, 0); co.sweeps = 0;
     for (int it = 0; it < P.loop_count; ++it) {
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(BLK, STEP_MINBLOCKS) env_step_kernel(const __g
             float s = qv[k] * ratio;
             float up = (s > P.motor_crit_speed) ? (P.motor_max_torque - (s - P.motor_crit_speed) * rr_) : P.motor_max_torque;
             up = up * ratio;
-            float low = (s < -P.motor_crit_speed) ? ((-P.motor_max_speed - s) / (-P.motor_max_speed + P.motor_crit_speed) * -P.motor_max_torque) : -P.motor_max_torque;
+            float low = (s < -P.motor_crit_speed) ? ((-P.motor_max_speed - s) * ilow_ * -P.motor_max_torque) : -P.motor_max_torque;
             low = low * ratio;
             tt[k] = fmaxf(fminf(tt[k], up), low);
         }

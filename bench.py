@@ -43,7 +43,7 @@ B_ACT_BYTES = 3.3e3                                      # obs 140
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=4096, help="BASELINE.json configs[1]: 4096 envs on 1xB200")
@@ -101,7 +101,7 @@ class ClockSampler:
                 for bit, n in names.items():
                     if r & bit:
                         self.reasons.add(n)
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as e:   # NVML missing: fall back to one nvidia-smi query
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.dev}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],

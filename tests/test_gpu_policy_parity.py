@@ -63,7 +63,7 @@ def test_act_matches_numpy_oracle(n):
     assert np.abs(s - rs).max() < TOL
 
 
-@pytest.mark.parametrize("n", [128, 300, 4096])
+@pytest.mark.parametrize("n", [128, 300, 301, 4096])     # 301: last tile of 45 rows -> observation tile not 16-byte granular (plain-load path)
 def test_tensor_core_kernel_matches_fma_kernel_and_oracle(n):
     """both act kernels forced on the same inputs (irrl_policy_set_act_path): same Philox draws, same outputs"""
     L = _lib.load()

@@ -80,9 +80,10 @@ def test_test_step_advances_only_env0():
     assert (ob[1:] == 7.0).all() and (rew[1:] == 7.0).all() and rew[0] != 7.0      # VEC:280-290 touches row 0 only
 
 
-def test_device_rollout_equals_step_by_step_host_calls():
+@pytest.mark.parametrize("n", [96, 300])     # 96: fp32 FMA act kernel, 300: tcgen05 act kernel with a ragged last tile
+def test_device_rollout_equals_step_by_step_host_calls(n):
     import torch
-    n, T = 96, 12
+    T = 12
     cfg = trot_cfg(num_envs=n, StochasticDynamics=True, ObsNoise=2.0)
     W = _weights()
     L = _lib.load()

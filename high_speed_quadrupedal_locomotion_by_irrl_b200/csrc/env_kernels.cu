@@ -230,13 +230,14 @@ __device__ __forceinline__ void write_scaled_obs(const EnvParams& P, const DevSt
 }
 
 // ------------------------------------------------------------------ THE step kernel
-#ifndef STEP_MINBLOCKS
-#define STEP_MINBLOCKS 1
+// register cap of the step kernel: STEP_MINWARPS resident warps per SM -> 65536 / (32 * STEP_MINWARPS) registers per thread
+#ifndef STEP_MINWARPS
+#define STEP_MINWARPS 8
 #endif
 // BLK / SYNC: 64-thread CTAs without phase barriers up to ~6k robots (one warp per scheduler: pure latency), 128-thread CTAs with
 // phase barriers above (launch_env_step)
 template <int BLK, bool SYNC>
-__global__ void __launch_bounds__(BLK, STEP_MINBLOCKS) env_step_kernel(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env_step_kernel(const __grid_constant__ StepArgs A) {
     const EnvParams& P = A.P; const DevState& S = A.S;
     const int tid = blockIdx.x * BLK + threadIdx.x;
     int r = tid >> 2; const int leg = tid & 3;

@@ -152,6 +152,13 @@ class FlexibleGymEnv:
         _lib.check(self._L.irrl_get_sphere_info(self._h, self._ptr(sphere_info, (self._n, 4), name="sphere_info")), "GetSphereInfo")
 
     # ---- additions
+    def getMeteor(self, out) -> None:
+        """[N,9] float32 host array: sphere position, velocity, mode (0 placed / 1 falling), radius, mass (Crutial: True)"""
+        _lib.check(self._L.irrl_get_meteor(self._h, self._ptr(out, (self._n, 9), name="meteor")), "getMeteor")
+
+    def setMeteor(self, m) -> None:
+        _lib.check(self._L.irrl_set_meteor(self._h, self._ptr(m, (self._n, 9), name="meteor")), "setMeteor")
+
     def GetMassMatrix(self, mass) -> None:
         _lib.check(self._L.irrl_get_mass_matrix(self._h, self._ptr(mass, (self._n, 324), name="mass")), "GetMassMatrix")
 

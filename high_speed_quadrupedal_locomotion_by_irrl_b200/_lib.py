@@ -40,7 +40,7 @@ def load() -> C.CDLL:
         getattr(L, "irrl_" + name).argtypes = [C.c_void_p]
     for name in ("reset", "observe", "is_terminal_state", "origin_state", "reference_state", "get_joint_effort", "get_generalized_force",
                  "get_inverse_mass_matrix", "get_nonlinear", "get_mass_matrix", "set_contact_coefficient", "get_sphere_info",
-                 "get_model_params", "get_state", "set_state", "get_solver_sweeps", "set_stream"):
+                 "get_model_params", "get_state", "set_state", "get_solver_sweeps", "set_stream", "get_meteor", "set_meteor"):
         getattr(L, "irrl_" + name).argtypes = [C.c_void_p, C.c_void_p]
     L.irrl_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.irrl_test_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5

@@ -161,13 +161,13 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         E->control_dt_d = ctl_dt; E->sim_dt_d = sim_dt;
         if (!num("seedd", d)) goto bad; P.seed = (uint32_t)(int)d;                                               // VEC:171
         // ENV:1598-1613
-        NUM("abad", P.abad) NUM("period", P.period) P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
+        NUM("abad", P.abad) NUM("period", P.period) P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ P.meteor_every = int(5.0 * d / ctl_dt);   /* ENV:731 */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
         IGN("down_height") IGN("gait_step")
         NUM("Vx", P.Vx_max) P.Vx_min = 0.f;                                                                      // ENV:1606-1607, 2054
         NUM("Vy", P.Vy_max) P.Vy_min = -P.Vy_max; NUM("Omega", P.omega_max) P.omega_min = -P.omega_max;
         NUM("LeanFront", P.lean_front) NUM("LeanHind", P.lean_hind)
         // ENV:1616-1629
-        FLG("Terrain", P.flag_terrain) FLG("Manual", P.flag_manual) { int crucial; FLG("Crutial", crucial) if (crucial) return fail(-3, "Crutial: True (meteor spheres, ENV:815-861) is not implemented in this build"); }
+        FLG("Terrain", P.flag_terrain) FLG("Manual", P.flag_manual) FLG("Crutial", P.flag_crucial)
         FLG("Filter", P.flag_filter) IGN("Camera") FLG("StochasticDynamics", P.flag_stochastic) FLG("HeightVariable", P.flag_height_variable)
         FLG("TimeBasedContact", P.flag_time_contact) FLG("ManualTraj", P.flag_manual_traj) IGN("MotorDynamics") FLG("ObsFilter", P.flag_obs_filter)
         FLG("WILDCAT", P.flag_wildcat) FLG("ForceDisturbance", P.flag_force_dist) IGN("Convert2Torque")
@@ -178,7 +178,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         // ENV:1643-1658
         NUM("Stiffness", P.stiffness) IGN("Stiffness_Low") NUM("AbadRatio", P.abad_ratio) NUM("Damping", P.damping)
         double freq; if (!num("Freq", freq)) goto bad;
-        NUM("max_time", P.max_time) E->max_time_d = d; IGN("CubeNum") IGN("FPS") NUM("ActionNoise", P.action_noise) NUM("ObsNoise", P.noise_flag)
+        NUM("max_time", P.max_time) E->max_time_d = d; if (!num("CubeNum", d)) goto bad; P.num_cube = (int)d; IGN("FPS") NUM("ActionNoise", P.action_noise) NUM("ObsNoise", P.noise_flag)
         if (!num("GaitType", d)) goto bad; P.gait_type = (int)d;
         NUM("MotorMaxTorque", P.motor_max_torque) NUM("MotorCriticalSpeed", P.motor_crit_speed) NUM("MotorMaxSpeed", P.motor_max_speed)
         P.filter_para = P.flag_filter ? (float)(1.0 - freq * ctl_dt) : 0.f;                                      // ENV:396
@@ -338,6 +338,7 @@ int irrl_init(irrl_env* env) {
     rc |= dev_alloc(E, &E->S.legmodel, N * 64); rc |= dev_alloc(E, &E->S.basemodel, N * 8);
     rc |= dev_alloc(E, &E->S.frame_idx, N); rc |= dev_alloc(E, &E->S.itera, N); rc |= dev_alloc(E, &E->S.ep_len, N);
     rc |= dev_alloc(E, &E->S.ep_ret, N); rc |= dev_alloc(E, &E->S.solver_sweeps, N);
+    if (E->P.flag_crucial) rc |= dev_alloc(E, &E->S.meteor, N * 12); else E->S.meteor = nullptr;
     rc |= dev_alloc(E, &E->d_action, N * 12);
     {   // step outputs live in one block [ob | reward | extra | done]: a caller that lays its host buffers out the same way gets them in one copy
         unsigned char* blk = nullptr; rc |= dev_alloc(E, &blk, N * (35 + 1 + 6) * 4 + N);
@@ -360,6 +361,7 @@ int irrl_init(irrl_env* env) {
     // VEC:172-182: every env is reset once during init
     StepArgs a = make_args(E, nullptr, nullptr, nullptr, nullptr, nullptr);
     launch_env_reset(a, E->stream); CUDA_OK(cudaGetLastError());
+    if (E->P.flag_crucial) { launch_env_meteor(a, 1, E->stream); CUDA_OK(cudaGetLastError()); }     // ENV:608-611
     E->tick++;
     CUDA_OK(cudaStreamSynchronize(E->stream));
     return 0;
@@ -379,6 +381,7 @@ int irrl_reset(irrl_env* env, float* ob) {
     bool dev = is_device_ptr(ob);
     StepArgs a = make_args(E, nullptr, E->P.flag_obs_filter ? nullptr : (dev ? ob : E->d_ob), nullptr, nullptr, nullptr);
     launch_env_reset(a, E->stream); CUDA_OK(cudaGetLastError());
+    if (E->P.flag_crucial) { launch_env_meteor(a, 1, E->stream); CUDA_OK(cudaGetLastError()); }     // ENV:608-611
     E->tick++;
     if (E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, dev ? ob : E->d_ob, E->stream); CUDA_OK(cudaGetLastError()); }
     if (!dev) return deliver(E, ob, E->d_ob, (size_t)E->P.N * OB_DIM * sizeof(float));
@@ -398,6 +401,7 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
             return fail(-1, "irrl_step: action is device memory, so every output must be device memory too");
         if (!reward || !done) return fail(-1, "irrl_step: reward and done are required");
         StepArgs a = make_args(E, action, E->P.flag_obs_filter ? nullptr : ob, reward, done, extra);
+        if (E->P.flag_crucial) launch_env_meteor(a, 0, E->stream);
         launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
         E->tick++;
         if (E->P.flag_obs_filter && ob) { launch_env_observe(E->P, E->S, ob, E->stream); CUDA_OK(cudaGetLastError()); }
@@ -423,6 +427,7 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
     }
     StepArgs a = make_args(E, z_act ? z_act : E->d_action, E->P.flag_obs_filter ? nullptr : (z_ob ? z_ob : E->d_ob), z_rew ? z_rew : E->d_reward, z_done ? z_done : E->d_done,
                            extra ? (z_ext ? z_ext : E->d_extra) : E->d_extra);
+    if (E->P.flag_crucial) launch_env_meteor(a, 0, E->stream);
     launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
     E->tick++;
     if (E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, E->d_ob, E->stream); CUDA_OK(cudaGetLastError()); }
@@ -459,6 +464,7 @@ int irrl_test_step(irrl_env* env, const float* action, float* ob, float* reward,
     // stage only row 0
     CUDA_OK(cudaMemcpyAsync(E->d_action, action, 12 * sizeof(float), cudaMemcpyHostToDevice, E->stream));
     StepArgs a = make_args(E, E->d_action, E->P.flag_obs_filter ? nullptr : E->d_ob, E->d_reward, E->d_done, E->d_extra);
+    if (E->P.flag_crucial) launch_env_meteor(a, 0, E->stream);
     launch_env_step(a, E->stream); cudaError_t ce = cudaGetLastError();
     if (ce == cudaSuccess && E->P.flag_obs_filter) { launch_env_observe(E->P, E->S, E->d_ob, E->stream); ce = cudaGetLastError(); }
     E->P = saved; E->tick++;
@@ -563,7 +569,34 @@ int irrl_set_contact_coefficient(irrl_env* env, const float* coeff) {
     CUDA_OK(cudaMemcpy(E->S.basemodel, bm.data(), bm.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
-int irrl_get_sphere_info(irrl_env* env, float*) { ENV(env); return fail(-3, "Please make sure the [Flag_Crucial] is True (not implemented in this build)"); }   // ENV:1434
+// ENV:1423-1436: position and radius of the (first) attack sphere
+int irrl_get_sphere_info(irrl_env* env, float* out) {
+    ENV(env); NEED_INIT();
+    if (!E->P.flag_crucial) return fail(-3, "Please make sure the [Flag_Crucial] is True");   // ENV:1434
+    const size_t N = (size_t)E->P.N;
+    std::vector<float> m(N * 12), o(N * 4);
+    CUDA_OK(cudaStreamSynchronize(E->stream)); CUDA_OK(cudaMemcpy(m.data(), E->S.meteor, m.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < N; ++i) { o[4 * i] = m[12 * i]; o[4 * i + 1] = m[12 * i + 1]; o[4 * i + 2] = m[12 * i + 2]; o[4 * i + 3] = m[12 * i + 7]; }
+    if (is_device_ptr(out)) { CUDA_OK(cudaMemcpy(out, o.data(), o.size() * 4, cudaMemcpyHostToDevice)); } else memcpy(out, o.data(), o.size() * 4);
+    return 0;
+}
+// test access to the meteor state: [N,9] = p(3) v(3) mode radius mass (host memory)
+int irrl_get_meteor(irrl_env* env, float* out) {
+    ENV(env); NEED_INIT();
+    if (!E->P.flag_crucial) return fail(-3, "irrl_get_meteor: Crutial is False");
+    const size_t N = (size_t)E->P.N; std::vector<float> m(N * 12);
+    CUDA_OK(cudaStreamSynchronize(E->stream)); CUDA_OK(cudaMemcpy(m.data(), E->S.meteor, m.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < N; ++i) for (int k = 0; k < 9; ++k) out[9 * i + k] = m[12 * i + k];
+    return 0;
+}
+int irrl_set_meteor(irrl_env* env, const float* in) {
+    ENV(env); NEED_INIT();
+    if (!E->P.flag_crucial) return fail(-3, "irrl_set_meteor: Crutial is False");
+    const size_t N = (size_t)E->P.N; std::vector<float> m(N * 12, 0.f);
+    for (size_t i = 0; i < N; ++i) for (int k = 0; k < 9; ++k) m[12 * i + k] = in[9 * i + k];
+    CUDA_OK(cudaStreamSynchronize(E->stream)); CUDA_OK(cudaMemcpy(E->S.meteor, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
 int irrl_get_model_params(irrl_env* env, float* out) {
     ENV(env); NEED_INIT();
     const int N = E->P.N; std::vector<float> bm((size_t)N * 8), lm((size_t)N * 64), o((size_t)N * 94);
@@ -860,6 +893,7 @@ int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buff
         if (E->profiling) CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 1], E->stream));
         StepArgs s = make_args(E, E->d_action, b->cur_obs, b->rewards + (size_t)t * N, b->cur_done, nullptr);
         if (b->ep_return && b->ep_length) { s.ep_ret_out = b->ep_return + (size_t)t * N; s.ep_len_out = b->ep_length + (size_t)t * N; }
+        if (E->P.flag_crucial) launch_env_meteor(s, 0, E->stream);
         launch_env_step(s, E->stream);
         if (E->profiling) { CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 2], E->stream)); E->prof_cursor += 3; }
         E->tick++;

@@ -457,6 +457,85 @@ __global__ void __launch_bounds__(BLOCK) env_probe_kernel(EnvParams P, DevState 
     }
 }
 
+// ------------------------------------------------------------------ Crutial: True -- meteor sphere (ENV:717-741, 815-861)
+// Same specification as the oracle (oracle/bp5_oracle.hpp, meteor_update): the CubeNum coincident steel spheres of the reference are
+// one sphere of CubeNum times the mass; sphere <-> trunk box (frictionless, restitution 0.95 above 1 mm/s) and sphere <-> ground are
+// resolved once per control step, before the physics substeps, against the trunk pose at the start of the step.  The impulse on the
+// robot goes through the same factorised mass matrix as the contact solver: du = -lambda M^-1 J^T n.
+// respawn_only: called after irrl_reset so that GetSphereInfo sees the sphere the reset placed (ENV:608-611).
+__global__ void __launch_bounds__(BLOCK) env_meteor_kernel(const __grid_constant__ StepArgs A, int respawn_only) {
+    const EnvParams& P = A.P; const DevState& S = A.S;
+    const int tid = blockIdx.x * BLOCK + threadIdx.x;
+    int r = tid >> 2; const int leg = tid & 3;
+    const bool valid = r < P.N; if (!valid) r = P.N - 1;
+    EnvRegs e; load_env(S, r, leg, e);
+    float* mp = S.meteor + (size_t)r * 12;
+    float4 m0 = ld4(mp), m1 = ld4(mp + 4); const float m8 = mp[8];
+    f3 sp = mk(m0.x, m0.y, m0.z), sv = mk(m0.w, m1.x, m1.y); int mode = (int)m1.z; float rad = m1.w, mass = m8;
+    const bool periodic = P.meteor_every > 0 && (e.frame_idx % P.meteor_every) == 0;
+    if (respawn_only || periodic || e.frame_idx == 1) {            // ENV:827-838 (frame_idx == 1: the env was reset since its last step)
+        const float t = cur_time(P, e);
+        rad = (t / 5.0f + 1.0f) * 0.08f; mass = (float)P.num_cube * (t / 5.0f + 0.2f);
+        sp = mk(e.b.p.x + 0.05f, e.b.p.y, e.b.p.z + 1.0f); sv = mk(0.f, 0.f, 0.f); mode = 0;
+    }
+    if (!(respawn_only || periodic)) {
+        if (mode == 0) { mode = 1; sv = mk(e.b.v.x, e.b.v.y, -5.0f); }             // ENV:849-858
+        f3 bx, by, bz; quat_cols(e.b.qw, e.b.qx, e.b.qy, e.b.qz, bx, by, bz);
+        LegKin k; leg_fk(P, e.lm, bx, by, bz, e.q, k);
+        Dyn d; dynamics(P, e.lm, e.bm, e.b, bx, by, bz, k, e.qd, d, nullptr, nullptr, false, leg);
+        float du[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; f3 dq = mk(0.f, 0.f, 0.f);
+        const float dt = P.sim_dt;
+        for (int sub = 0; sub < P.loop_count; ++sub) {
+            sv.z -= P.gravity * dt;
+            f3 dw = sp - e.b.p;
+            f3 dl = mk(dot(bx, dw), dot(by, dw), dot(bz, dw));
+            f3 q = mk(fminf(fmaxf(dl.x, -P.box_half[0]), P.box_half[0]), fminf(fmaxf(dl.y, -P.box_half[1]), P.box_half[1]), fminf(fmaxf(dl.z, -P.box_half[2]), P.box_half[2]));
+            f3 del = dl - q; const float dist2 = dot(del, del);
+            if (dist2 < rad * rad && dist2 > 1e-12f) {
+                const float inv = rsqrtf(dist2);
+                f3 nb = inv * del;
+                f3 n = axpy(nb.x, bx, axpy(nb.y, by, nb.z * bz)), x = axpy(q.x, bx, axpy(q.y, by, q.z * bz));
+                f3 vb = e.b.v + mk(du[0], du[1], du[2]), wb = e.b.w + mk(du[3], du[4], du[5]);
+                f3 vpt = vb + cross(wb, x);
+                const float vrel = dot(n, sv - vpt);
+                if (vrel < 0.f) {
+                    f3 xn = cross(x, n);
+                    float z[6] = {n.x, n.y, n.z, xn.x, xn.y, xn.z};                  // J^T n restricted to the trunk coordinates
+                    fwd6(d.L, z);
+                    float G = 0.f;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) G = fmaf(z[a], z[a], G);
+                    bwd6(d.L, z);                                                     // z = S^-1 J^T n  (trunk part of M^-1 J^T n)
+                    const float er = (-vrel > 0.001f) ? 0.95f : 0.f;                  // steel-steel pair ENV:244
+                    const float lam = -(1.0f + er) * vrel / (G + 1.0f / mass);
+                    sv = axpy(lam / mass, n, sv);
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) du[a] -= lam * z[a];
+                    // joint part of M^-1 J^T n:  -Y^T z  (this lane's leg)
+                    dq.x += lam * (d.Y[0][0] * z[0] + d.Y[1][0] * z[1] + d.Y[2][0] * z[2] + d.Y[3][0] * z[3] + d.Y[4][0] * z[4] + d.Y[5][0] * z[5]);
+                    dq.y += lam * (d.Y[0][1] * z[0] + d.Y[1][1] * z[1] + d.Y[2][1] * z[2] + d.Y[3][1] * z[3] + d.Y[4][1] * z[4] + d.Y[5][1] * z[5]);
+                    dq.z += lam * (d.Y[0][2] * z[0] + d.Y[1][2] * z[1] + d.Y[2][2] * z[2] + d.Y[3][2] * z[3] + d.Y[4][2] * z[4] + d.Y[5][2] * z[5]);
+                }
+            }
+            float hh = 0.f; f3 nn = mk(0.f, 0.f, 1.f);
+            if (P.terrain) terrain_sample(P, sp.x, sp.y, hh, nn);
+            if ((sp.z - hh) * nn.z - rad <= 0.f) {
+                const float vn = dot(nn, sv);
+                if (vn < 0.f) {
+                    sv = axpy(-vn, nn, sv);
+                    const float vt = sqrtf(dot(sv, sv));
+                    if (vt > 1e-9f) { const float dv = fminf(vt, 0.8f * (-vn)) / vt; sv = axpy(-dv, sv, sv); }
+                }
+            }
+            sp = axpy(dt, sv, sp);
+        }
+        e.b.v = e.b.v + mk(du[0], du[1], du[2]); e.b.w = e.b.w + mk(du[3], du[4], du[5]);
+        e.qd = e.qd + dq;
+        if (valid) store_env(S, r, leg, e);
+    }
+    if (valid && leg == 0) { st4(mp, sp.x, sp.y, sp.z, sv.x); st4(mp + 4, sv.y, sv.z, (float)mode, rad); mp[8] = mass; }
+}
+
 // single physics substep with externally supplied joint torques (parity tests of world.integrate())
 __global__ void __launch_bounds__(BLOCK) env_integrate_kernel(EnvParams P, DevState S, const float* tau12, float* contact_out) {
     const int tid = blockIdx.x * BLOCK + threadIdx.x;
@@ -575,6 +654,7 @@ void launch_env_step(const StepArgs& a, cudaStream_t st) {
     if (a.P.N > 6144) env_step_kernel<128, true><<<(a.P.N * 4 + 127) / 128, 128, 0, st>>>(a);
     else env_step_kernel<64, false><<<quad_grid(a.P.N), 64, 0, st>>>(a);
 }
+void launch_env_meteor(const StepArgs& a, int respawn_only, cudaStream_t st) { env_meteor_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a, respawn_only); }
 void launch_env_reset(const StepArgs& a, cudaStream_t st) { env_reset_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a); }
 void launch_env_observe(const EnvParams& P, const DevState& S, float* ob, cudaStream_t st) { env_observe_kernel<<<(P.N + 127) / 128, 128, 0, st>>>(P, S, ob); }
 void launch_env_probe(const EnvParams& P, const DevState& S, float* M, float* Minv, float* h, cudaStream_t st) { env_probe_kernel<<<quad_grid(P.N), BLOCK, 0, st>>>(P, S, M, Minv, h); }

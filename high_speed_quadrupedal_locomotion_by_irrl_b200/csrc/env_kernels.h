@@ -20,6 +20,7 @@ struct StepArgs {
 
 void launch_env_step(const StepArgs& a, cudaStream_t st);
 void launch_env_reset(const StepArgs& a, cudaStream_t st);
+void launch_env_meteor(const StepArgs& a, int respawn_only, cudaStream_t st);   // Crutial: True only; before every env step / after a reset
 void launch_env_observe(const EnvParams& P, const DevState& S, float* ob, cudaStream_t st);
 void launch_env_probe(const EnvParams& P, const DevState& S, float* M, float* Minv, float* h, cudaStream_t st);
 void launch_env_integrate(const EnvParams& P, const DevState& S, const float* tau, float* contact_out, cudaStream_t st);

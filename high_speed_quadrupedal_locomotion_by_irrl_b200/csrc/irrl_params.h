@@ -35,6 +35,7 @@ struct EnvParams {
     float sim_dt, control_dt;
     int loop_count;               // ENV:711
     int disturb_every;            // ENV:746 : control steps between state disturbances = int(period / control_dt * 10)
+    int flag_crucial, num_cube, meteor_every;   // Crutial: True (ENV:717-741, 815-861): meteor sphere re-created every int(5 * period / control_dt) control steps
     int gait_type;
     float phase[4];               // ENV:398-409
     float filter_para;            // ENV:396
@@ -83,6 +84,7 @@ struct DevState {
     int* ep_len;       // [N] steps since last reset (RaisimGymVecEnv.py:42-50 bookkeeping)
     float* ep_ret;     // [N] reward sum since last reset
     int* solver_sweeps;// [N] Gauss-Seidel sweeps used by the last substep (diagnostic)
+    float* meteor;     // [N][12] : sphere p(3) v(3) mode radius mass pad(3)  (Crutial: True only, else null)
 };
 
 }  // namespace irrl

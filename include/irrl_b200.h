@@ -94,6 +94,10 @@ int irrl_get_nonlinear(irrl_env* env, float* out /*[N,18]*/);        /* Environm
 int irrl_get_mass_matrix(irrl_env* env, float* out /*[N,324]*/);     /* RaiSim getMassMatrix (parity probe, north_star) */
 int irrl_set_contact_coefficient(irrl_env* env, const float* coeff /*[N,3] mu, restitution, threshold*/); /* Environment.hpp:1407-1418 */
 int irrl_get_sphere_info(irrl_env* env, float* out /*[N,4]*/);       /* Environment.hpp:1423-1436 (needs Crutial; returns -3 otherwise) */
+/* Crutial: True (meteor sphere, Environment.hpp:717-741, 815-861): test access to its state, host memory [N,9] = position(3),
+ * velocity(3), mode (0 just placed / 1 falling), radius, mass.  -3 when Crutial is False. */
+int irrl_get_meteor(irrl_env* env, float* out /*[N,9]*/);
+int irrl_set_meteor(irrl_env* env, const float* in /*[N,9]*/);
 int irrl_get_model_params(irrl_env* env, float* out /*[N,94]: mu,rest,thr, 13 x (mass, com3, joint offset3)*/);
 
 /* ---- state injection / extraction (the reference only has setState internally, Environment.hpp:618-622).

@@ -335,6 +335,12 @@ template <typename T> struct Env {
     M3<T> bodyFrameMatrix_;
     T phase_[4];
     T t0_ = 0; int frame_idx = 0;  // current_time_ = t0_ + frame_idx*control_dt_  (ENV:557,631,786)
+    // ---- Crutial: True -- meteor spheres (ENV:273-283, 608-611, 717-741, 815-861).  The reference drops CubeNum steel spheres from
+    // 1 m above the trunk every 5 gait periods; cube_place_radius is 0 (ENV:1976), so they coincide and are modelled as ONE
+    // sphere of CubeNum times the mass (identical frictionless bodies hitting the same point).  New specification (RaiSim is
+    // not available): sphere <-> trunk box and sphere <-> ground only, handled once per control step before the physics substeps.
+    int num_cube = 0;
+    T met_p[3] = {0, 0, 0}, met_v[3] = {0, 0, 0}, met_r = 0, met_m = 0; int met_mode = 0;   // mode 0 = static (just placed), 1 = falling
     T jointRef_[NJ], jointRefLast_[NJ], jointDotRef_[NJ], EndEffectorRef_[NJ], EndEffector_[NJ], EndEffectorOffset_[NJ];
     T command[3] = {0, 0, 0}, command_filtered[3] = {0, 0, 0};
     T contact_[4] = {0, 0, 0, 0}, contact_filtered[4] = {0, 0, 0, 0};
@@ -369,7 +375,7 @@ template <typename T> struct Env {
         BodyAttiCoeff = T(c.get("BodyAttitudeRewardCoeff")); JointMimicCoeff = T(c.get("JointRewardCoeff")); VelKeepCoeff = T(c.get("VelRewardCoeff"));
         TorqueCoeff = T(c.get("TorqueCoeff")); ContactCoeff = T(c.get("ContactCoeff"));
         stiffness = T(c.get("Stiffness")); (void)c.get("Stiffness_Low"); abad_ratio = T(c.get("AbadRatio")); damping = T(c.get("Damping"));
-        freq = T(c.get("Freq")); max_time = T(c.get("max_time")); (void)c.get("CubeNum"); (void)c.get("FPS");
+        freq = T(c.get("Freq")); max_time = T(c.get("max_time")); num_cube = int(c.get("CubeNum")); (void)c.get("FPS");
         actionNoise = T(c.get("ActionNoise")); noise_flag = T(c.get("ObsNoise")); gaitType = (int)c.get("GaitType");
         MotorMaxTorque = T(c.get("MotorMaxTorque")); MotorCriticalSpeed = T(c.get("MotorCriticalSpeed")); MotorMaxSpeed = T(c.get("MotorMaxSpeed"));
         simulation_dt_ = T(c.get("simulation_dt")); control_dt_ = T(c.get("control_dt"));   // VEC:151-152
@@ -912,6 +918,68 @@ template <typename T> struct Env {
         contact_obs_update();                                                                  // ENV:627
         command_obs_update(false, P_CMD + P_IN_RESET);                                         // ENV:628
         frame_idx++;                                                                           // ENV:630-631
+        if (flag_crucial) meteor_respawn();                                                    // ENV:608-611
+    }
+
+    // ENV:827-838: spheres re-created above the robot (STATIC), size and mass grow with the episode time
+    void meteor_respawn() {
+        T t = current_time();
+        met_r = (t / T(5.0) + T(1.0)) * T(0.08);                                               // cube_len ENV:1974
+        met_m = T(num_cube) * (t / T(5) + T(0.2));
+        met_p[0] = gc_[0] + T(0.05); met_p[1] = gc_[1]; met_p[2] = gc_[2] + T(1.0);             // circle_place(0, i, n, 1.0) ENV:836-837
+        met_v[0] = met_v[1] = met_v[2] = 0; met_mode = 0;
+    }
+    // ENV:717-741 (schedule) + the sphere's own dynamics over one control step (new specification, see above)
+    void meteor_update() {
+        int every = int(T(5) * period_ / control_dt_);
+        if (every > 0 && frame_idx % every == 0) { meteor_respawn(); return; }                  // ENV:731-735
+        if (met_mode == 0) { met_mode = 1; met_v[0] = gv_[0]; met_v[1] = gv_[1]; met_v[2] = T(-5); }   // ENV:736-740, 849-858
+        const T dt = simulation_dt_;
+        int loopCount = int(control_dt_ / simulation_dt_ + T(1e-10));
+        Kin k; kinematics(gc_, gv_, k);
+        static thread_local T M[NV][NV]; Chol<T, NV> ch; bool have_m = false;
+        T du[NV]; for (int i = 0; i < NV; ++i) du[i] = 0;
+        const M3<T>& R = k.R[0];
+        for (int sub = 0; sub < loopCount; ++sub) {
+            met_v[2] -= model.gravity * dt;
+            // ---- trunk box (centred on the trunk origin, URDF:26): closest point of the box to the sphere centre
+            V3<T> dw(met_p[0] - gc_[0], met_p[1] - gc_[1], met_p[2] - gc_[2]);
+            V3<T> d = transpose(R) * dw;
+            V3<T> q(std::min(std::max(d.x, -model.box_half.x), model.box_half.x), std::min(std::max(d.y, -model.box_half.y), model.box_half.y),
+                    std::min(std::max(d.z, -model.box_half.z), model.box_half.z));
+            V3<T> del = d - q; T dist2 = dot(del, del);
+            if (dist2 < met_r * met_r && dist2 > T(1e-12)) {
+                V3<T> n = R * ((T(1) / std::sqrt(dist2)) * del), x = R * q;
+                V3<T> vb(gv_[0] + du[0], gv_[1] + du[1], gv_[2] + du[2]), wb(gv_[3] + du[3], gv_[4] + du[4], gv_[5] + du[5]);
+                V3<T> vpt = vb + cross(wb, x);
+                T vrel = n.x * (met_v[0] - vpt.x) + n.y * (met_v[1] - vpt.y) + n.z * (met_v[2] - vpt.z);
+                if (vrel < T(0)) {
+                    if (!have_m) { mass_matrix(k, M); if (!ch.factor(M)) throw std::runtime_error("mass matrix not PD"); have_m = true; }
+                    T J[3][NV]; point_jacobian(k, 0, x, J);
+                    T jn[NV], w[NV];
+                    for (int c = 0; c < NV; ++c) jn[c] = J[0][c] * n.x + J[1][c] * n.y + J[2][c] * n.z;
+                    ch.solve(jn, w);
+                    T G = 0; for (int c = 0; c < NV; ++c) G += jn[c] * w[c];
+                    T e = (-vrel > T(0.001)) ? T(0.95) : T(0);                                   // steel-steel pair ENV:244
+                    T lam = -(T(1) + e) * vrel / (G + T(1) / met_m);
+                    met_v[0] += lam / met_m * n.x; met_v[1] += lam / met_m * n.y; met_v[2] += lam / met_m * n.z;
+                    for (int c = 0; c < NV; ++c) du[c] -= lam * w[c];
+                }
+            }
+            // ---- ground: inelastic, Coulomb friction 0.8 on a point mass
+            T hh = 0; V3<T> nn(0, 0, 1);
+            if (terrain.valid()) terrain.sample(met_p[0], met_p[1], hh, nn);
+            if ((met_p[2] - hh) * nn.z - met_r <= T(0)) {
+                T vn = nn.x * met_v[0] + nn.y * met_v[1] + nn.z * met_v[2];
+                if (vn < T(0)) {
+                    met_v[0] -= vn * nn.x; met_v[1] -= vn * nn.y; met_v[2] -= vn * nn.z;
+                    T vt = std::sqrt(met_v[0] * met_v[0] + met_v[1] * met_v[1] + met_v[2] * met_v[2]);
+                    if (vt > T(1e-9)) { T dv = std::min(vt, T(0.8) * (-vn)) / vt; met_v[0] -= dv * met_v[0]; met_v[1] -= dv * met_v[1]; met_v[2] -= dv * met_v[2]; }
+                }
+            }
+            for (int a = 0; a < 3; ++a) met_p[a] += met_v[a] * dt;
+        }
+        for (int i = 0; i < NV; ++i) gv_[i] += du[i];
     }
 
     // ENV:692-809
@@ -925,6 +993,7 @@ template <typename T> struct Env {
             pTarget12_[j] = p; pTarget12Last_[j] = p;                                          // ENV:706-707
         }
         int loopCount = int(control_dt_ / simulation_dt_ + T(1e-10));                          // ENV:711
+        if (flag_crucial) meteor_update();                                                     // ENV:717-741
         // ENV:744-754: ForceDisturbance.  With Manual the base state is perturbed every 10 gait periods (state_disturbance,
         // ENV:912-940, ratio 0.5; the quaternion is re-normalised here, RaiSim's setState is assumed to do the same);
         // without Manual force_attack(random() < 0.0027) never fires: no external force.

@@ -99,6 +99,9 @@ template <typename T> void model_params(Env<T>& e, double* out) {
 #define H(h) (reinterpret_cast<Handle*>(h))
 #define DISPATCH(h, expr_d, expr_f) do { if (H(h)->precision == 0) { auto& V = H(h)->d; (void)V; expr_d; } else { auto& V = H(h)->f; (void)V; expr_f; } } while (0)
 
+// meteor sphere (Crutial: True): [p(3), v(3), mode, radius, mass]
+template <typename T> void get_meteor(const Env<T>& e, double* s) { for (int i = 0; i < 3; ++i) { s[i] = e.met_p[i]; s[3 + i] = e.met_v[i]; } s[6] = e.met_mode; s[7] = e.met_r; s[8] = e.met_m; }
+template <typename T> void set_meteor(Env<T>& e, const double* s) { for (int i = 0; i < 3; ++i) { e.met_p[i] = T(s[i]); e.met_v[i] = T(s[3 + i]); } e.met_mode = int(s[6]); e.met_r = T(s[7]); e.met_m = T(s[8]); }
 extern "C" {
 
 void* bp5o_create(const char* cfg, int precision, int env_offset) {
@@ -123,6 +126,8 @@ int bp5o_step(void* h, const float* action, float* ob, float* reward, uint8_t* d
     catch (const std::exception& e) { fprintf(stderr, "bp5o_step: %s\n", e.what()); return -1; }
     return 0;
 }
+void bp5o_get_meteor(void* h, int env, double* s) { DISPATCH(h, get_meteor(V.envs[env], s), get_meteor(V.envs[env], s)); }
+void bp5o_set_meteor(void* h, int env, const double* s) { DISPATCH(h, set_meteor(V.envs[env], s), set_meteor(V.envs[env], s)); }
 void bp5o_get_state(void* h, int env, double* s) { DISPATCH(h, get_state(V.envs[env], s), get_state(V.envs[env], s)); }
 void bp5o_set_state(void* h, int env, const double* s) { DISPATCH(h, set_state(V.envs[env], s), set_state(V.envs[env], s)); }
 void bp5o_mass_and_h(void* h, int env, double* M, double* hh) { DISPATCH(h, mass_and_h(V.envs[env], M, hh), mass_and_h(V.envs[env], M, hh)); }

@@ -54,6 +54,12 @@ class Cuda:
     def sweeps(self):
         s = np.zeros(self.n, np.int32); self.env.getSolverSweeps(s); return s
 
+    def get_meteor(self):
+        m = np.zeros((self.n, 9), np.float32); self.env.getMeteor(m); return m
+
+    def set_meteor(self, m):
+        self.env.setMeteor(np.ascontiguousarray(m, np.float32))
+
     def model_params(self):
         o = np.zeros((self.n, 94), np.float32); self.env.getModelParams(o); return o
 

@@ -102,6 +102,18 @@ class Oracle:
         assert s.shape == (STATE_DIM,)
         self.L.bp5o_set_state(self.h, C.c_int(env), _p(s))
 
+    def get_meteor(self):
+        """[n,9]: sphere position, velocity, mode (0 static / 1 falling), radius, mass (Crutial: True)"""
+        out = np.zeros((self.n, 9), np.float64)
+        for i in range(self.n):
+            self.L.bp5o_get_meteor(self.h, C.c_int(i), _p(out[i]))
+        return out
+
+    def set_meteor(self, m):
+        m = np.ascontiguousarray(m, np.float64)
+        for i in range(self.n):
+            self.L.bp5o_set_meteor(self.h, C.c_int(i), _p(m[i]))
+
     def mass_and_h(self, env=0):
         M = np.zeros((18, 18)); h = np.zeros(18)
         self.L.bp5o_mass_and_h(self.h, C.c_int(env), _p(M), _p(h))

@@ -107,6 +107,43 @@ def test_state_disturbance_every_ten_periods():   # ENV:744-747, 912-940 (ForceD
     assert rel(sg[ok][:, S["gc"]], so[ok][:, S["gc"]]) < 2e-5 and rel(obg[ok], obo[ok]) < 2e-5 and rel(rg[ok], ro[ok]) < 2e-5
 
 
+def test_meteor_sphere_attack():             # Crutial: True, ENV:717-741, 815-861 (new specification shared with the oracle)
+    cfg = _cfg(Crutial=True, CubeNum=2)
+    o, c = Oracle(cfg), Cuda(cfg)
+    o.set_tick(1); c.env.setTick(1)
+    obo, obg = o.reset(), c.reset()
+    mo, mg = o.get_meteor(), c.get_meteor()
+    assert rel(mg, mo) < 1e-6 and (mo[:, 6] == 0).all() and np.allclose(mo[:, 2], o.get_state()[:, 2] + 1.0)      # placed 1 m above the trunk
+    info = np.zeros((o.n, 4), np.float32); c.env.GetSphereInfo(info)
+    assert np.allclose(info[:, :3], mo[:, :3], atol=1e-6) and np.allclose(info[:, 3], mo[:, 7], atol=1e-7)
+    a = np.zeros((o.n, 12), np.float32)
+    hit = hit_checked = 0
+    for t in range(140):
+        c.set_state(o.get_state().astype(np.float32)); c.set_meteor(o.get_meteor().astype(np.float32))
+        vz0 = o.get_meteor()[:, 5].copy(); gv0 = o.get_state()[:, S["gv"]].copy()
+        obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
+        mo, mg = o.get_meteor(), c.get_meteor()
+        so, sg = o.get_state(), c.get_state()
+        fresh = do | dg                                   # auto-reset: the oracle re-places the sphere at once, the kernel at its next step
+        b_o, b_g = (mo[:, 5] > vz0 + 1.0) & ~fresh, (mg[:, 5] > vz0 + 1.0) & ~fresh      # the sphere's vertical velocity jumped up: it hit
+        hit += int(b_o.sum())
+        ok = ~fresh & (b_o == b_g)
+        assert (b_o != b_g).sum() <= 1, t
+        assert rel(mg[ok], mo[ok]) < 2e-5, (t, rel(mg[ok], mo[ok]))                      # the sphere itself: flight, bounce, ground
+        # the robot: the synchronized touchdown of 128 identical robots is dense with knife-edge contact decisions (see _run), so
+        # the bulk is checked tightly and the tail loosely
+        err = np.maximum(np.abs(obg - obo).max(axis=1) / np.abs(obo).max(), np.abs(sg[:, S["gv"]] - so[:, S["gv"]]).max(axis=1) / np.abs(so[:, S["gv"]]).max())
+        assert np.median(err[ok]) < 1e-5 and np.percentile(err[ok], 90) < 1e-4, (t, np.median(err[ok]), np.percentile(err[ok], 90))
+        # the impulse handed to the robot: where the sphere struck the trunk, the trunk was pushed down by the same amount
+        struck = ok & b_o & (mo[:, 2] > so[:, 2])
+        if struck.any():
+            dvz_o, dvz_g = so[struck][:, S["gv"]][:, 2] - gv0[struck][:, 2], sg[struck][:, S["gv"]][:, 2] - gv0[struck][:, 2]
+            good = np.abs(dvz_g - dvz_o) < 2e-3 * np.abs(dvz_o).max()
+            assert good.sum() >= struck.sum() - 1 and (dvz_o < 0).mean() > 0.9, (t, dvz_o[:4], dvz_g[:4])
+            hit_checked += int(struck.sum())
+    assert hit >= o.n // 2 and hit_checked >= o.n // 2     # most spheres did strike their robot within 0.28 s
+
+
 def test_other_time_steps_loop_count():      # ENV:711
     o, c = _run(_cfg(simulation_dt=0.0005, control_dt=0.004), steps=6)
 

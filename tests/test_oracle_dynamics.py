@@ -220,3 +220,40 @@ def test_state_disturbance_fires_every_ten_periods_only():
     dq = np.abs(q_on - q_off).max(axis=1)
     assert (dq > 1e-4).all() and (dq < 0.12).all()
     assert np.allclose(np.linalg.norm(q_on, axis=1), 1.0, atol=1e-9)
+
+
+def test_meteor_sphere_schedule_flight_and_bounce():
+    """Crutial: True (ENV:717-741, 815-861; new specification in oracle/bp5_oracle.hpp): placed 1 m above the trunk at reset and every
+    5 gait periods, released at (vx, vy, -5) one step later, ballistic until it strikes the trunk, restitution 0.95 against the robot"""
+    n = 4
+    cfg = trot_cfg(num_envs=n, num_threads=2, StochasticDynamics=False, ObsNoise=0.0, Crutial=True, CubeNum=3)
+    o = Oracle(cfg); o.set_tick(1); o.reset()
+    s0, m0 = o.get_state(), o.get_meteor()
+    t1 = s0[:, S["t0"]] + 1 * cfg["control_dt"]                              # current_time right after reset (frame_idx = 1)
+    assert np.allclose(m0[:, 7], (t1 / 5 + 1) * 0.08) and np.allclose(m0[:, 8], 3 * (t1 / 5 + 0.2))      # radius, mass of 3 coincident spheres
+    assert np.allclose(m0[:, 0], s0[:, 0] + 0.05) and np.allclose(m0[:, 1], s0[:, 1]) and np.allclose(m0[:, 2], s0[:, 2] + 1.0) and (m0[:, 6] == 0).all()
+    a = np.zeros((n, 12), np.float32)
+    dt, sub = cfg["simulation_dt"], int(cfg["control_dt"] / cfg["simulation_dt"] + 1e-10)
+    o.step(a); m1 = o.get_meteor()
+    assert (m1[:, 6] == 1).all() and np.allclose(m1[:, 3], s0[:, S["gv"]][:, 0]) and np.allclose(m1[:, 5], -5 - 9.81 * dt * sub)
+    # semi-implicit Euler flight: z_k = z_0 + sum_j (v0 - g dt j) dt
+    z_expect = m0[:, 2] + sum((-5 - 9.81 * dt * j) * dt for j in range(1, sub + 1))
+    assert np.allclose(m1[:, 2], z_expect, atol=1e-12)
+    struck = np.zeros(n, bool); e_seen = []
+    for t in range(2, 140):
+        mb = o.get_meteor(); sb = o.get_state()
+        _, _, done, _ = o.step(a)
+        ma = o.get_meteor()
+        for i in range(n):
+            if not struck[i] and not done[i] and ma[i, 5] > mb[i, 5] + 1.0 and mb[i, 2] > sb[i, 2]:
+                struck[i] = True
+                # normal ~ +z on the flat top of the box: relative vertical velocity reversed with e = 0.95 (trunk moves too, so compare loosely)
+                e_seen.append(-(ma[i, 5] + 9.81 * dt * 0) / (mb[i, 5] - sb[i, S["gv"]][2]))
+    assert struck.all() and all(0.5 < e < 1.2 for e in e_seen), e_seen
+    # periodic re-creation every int(5 * period / control_dt) control steps
+    every = int(5 * cfg["period"] / cfg["control_dt"])
+    s = o.get_state(); s[:, S["frame_idx"]] = every
+    for i in range(n):
+        o.set_state(i, s[i])
+    o.step(a); m = o.get_meteor(); s2 = o.get_state()
+    assert (m[:, 6] == 0).all() and np.allclose(m[:, 3:6], 0)                # static again, just placed above the robot (pose at the start of that step)

@@ -42,8 +42,9 @@ struct PolicyWeights {      // device pointers, fp32, layouts as in the referenc
     const float* bperm[4];  // derived: [192] biases in the same column order
     const unsigned char* tcblob;   // derived: 2 towers x TC_BLOB_BYTES, hi/lo-split UMMA-layout weights (policy_tc_kernels.cu)
 };
-constexpr int TC_BIAS_BYTES = 2048;   // [2][192] gate biases (gate-interleaved), [16] head bias, [16] logstd, zero pad
-constexpr int TC_BLOB_BYTES = (11 + 12) * 12288 + 6 * 1024 + TC_BIAS_BYTES;
+constexpr int TC_BIAS_BYTES = 4096;   // [2][192] gate biases (gate-interleaved), [16] head bias, [16] logstd, [16] sigma = exp(logstd),
+                                      // [48][12] head weights (12 means / 1 value, zero padded), zero pad
+constexpr int TC_BLOB_BYTES = (11 + 12) * 12288 + TC_BIAS_BYTES;
 struct ActArgs {
     PolicyWeights W;
     const float* obs;       // [N,35]

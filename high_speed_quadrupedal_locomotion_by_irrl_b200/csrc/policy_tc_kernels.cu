@@ -25,8 +25,10 @@
 //   * epilogue: 16 warps; warp w reads TMEM lanes 32 (w%4).., gate columns 48 (w/4).. with tcgen05.ld.32x32b.x16 --
 //     columns are gate-interleaved (4 unit + gate), so 16 columns = 4 hidden units x (i,f,o,g): the cell update is done
 //     in registers (5 ex2 + 3 rcp per unit: MUFU-bound), h (hi/lo) goes straight into the A-operand tile of the next GEMM.
-//   * the heads are a third GEMM (N = 16) on h of the top layer (weights: one 6 KB copy over the dead layer-1 tile);
-//     the Gaussian draws, sigma and neglogp are computed while it runs; lanes then write their own environment.
+//   * the heads (48 x 12 means, 48 x 1 value) run on the CUDA cores: every epilogue thread multiplies its 12 top-layer units with the
+//     fp32 head weights (one 3 KB copy over the dead layer-1 tile), the four column blocks of a row meet in shared memory; the
+//     Gaussian draws, sigma and neglogp are computed beforehand; lanes of warps 0-3 then write their own environment.
+//     (A third tcgen05 GEMM with N = 16 was measured first: 4.7 k cycles of hand-offs for 18 tiny MMAs.)
 // Roles: warps 0-15 stage + epilogue, warp 16 lane 0 = bulk-copy producer, warp 17 = MMA issuer (owns TMEM).
 // Measured (B200, L2 flushed): 25 us at 4096 and 8192 environments, 44 us at 16384, 80 us at 32768
 // (fp32 FMA kernel: 40 / 57 / 103 / 174 us).
@@ -39,19 +41,16 @@ namespace tc {
 
 constexpr int TM = 128;                          // environments per CTA = MMA M
 constexpr int NG = 192;                          // gate columns = MMA N
-constexpr int NHEAD = 16;                        // head columns (12 means / 1 value, zero padded) = MMA N of the head GEMM
-constexpr int KS1 = 11, KS2 = 12, KSH = 6;       // k-steps (8 floats) of layer 0 [obs 35 -> 40 ; h 48], layer 1 [h_new 48 ; h 48], head [h 48]
+constexpr int KS1 = 11, KS2 = 12;                // k-steps (8 floats) of layer 0 [obs 35 -> 40 ; h 48] and layer 1 [h_new 48 ; h 48]
 constexpr int A_HALF = 2 * TM * 16;              // bytes of the hi (or lo) part of one A k-step : [chunk 2][row 128][16 B]
 constexpr int A_KSTEP = 2 * A_HALF;              // 8192
 constexpr int B_HALF = 2 * NG * 16;              // 6144
 constexpr int B_KSTEP = 2 * B_HALF;              // 12288
-constexpr int H_HALF = 2 * NHEAD * 16;           // 512
-constexpr int H_KSTEP = 2 * H_HALF;              // 1024
 constexpr int NST = 3;                           // weight ring stages in their own shared memory
 constexpr int NSLOT = 6;                         // + 3 more for layer 1, carved out of the part of the layer-0 A tile that is dead by then
 constexpr int NWORK = 512;                       // staging / epilogue threads (16 warps: TMEM lane quarter w%4, 48-column block w/4)
 constexpr int NTHR = NWORK + 64;
-constexpr int TMEM_COLS = 512;                   // 192 (layer 0) + 192 (layer 1) + 16 (head) -> next power of two
+constexpr int TMEM_COLS = 512;                   // 192 (layer 0) + 192 (layer 1) -> next power of two
 constexpr int STG_PITCH = 400;                   // bytes per row of the state staging tile: [c(48) h(48)] = 384 B + 16 B (odd number of 16-byte groups: no bank conflicts)
 constexpr int OFF_A1 = 0;
 constexpr int OFF_A2 = OFF_A1 + KS1 * A_KSTEP;   // 90112 : h(t-1) of layer 1 (and, before that, the raw observation tile)
@@ -59,9 +58,11 @@ constexpr int OFF_RING = OFF_A2 + 6 * A_KSTEP;   // 139264
 constexpr int OFF_STG = OFF_RING + NST * B_KSTEP;    // 176128 : [row][c | h] of one layer, in (bulk loads) and out (bulk stores)
 constexpr int OFF_BIAS = OFF_STG + TM * STG_PITCH;   // 227328 : TC_BIAS_BYTES = 2 x 192 gate biases, 16 head biases, 16 logstd (+ pad)
 constexpr int OFF_BAR = OFF_BIAS + TC_BIAS_BYTES;
-constexpr int NBAR = 2 * NSLOT + 1 + 3 + 5;      // full, empty, a_ready, d_full[3], in_bar[2], obs_bar, bias_bar, head_full
+constexpr int NBAR = 2 * NSLOT + 1 + 3 + 4;      // full, empty, a_ready, d_full[3], in_bar[2], obs_bar, bias_bar
 constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
-static_assert((KS1 + KS2) * B_KSTEP + KSH * H_KSTEP + TC_BIAS_BYTES == TC_BLOB_BYTES, "blob size");
+static_assert((KS1 + KS2) * B_KSTEP + TC_BIAS_BYTES == TC_BLOB_BYTES, "blob size");
+constexpr int BIAS_HEADW = 2 * NG + 48;          // float offset of the [48][12] head weights inside the bias block
+constexpr int OFF_HEADP = 0;                     // inside the (dead by then) layer-1 A tile: [4 column blocks][128 rows][12] partial head sums
 static_assert(SMEM_BYTES <= 232448, "shared memory");
 static_assert(6 * A_KSTEP + 3 * B_KSTEP <= KS1 * A_KSTEP, "extra ring slots must fit behind the h_new columns of the layer-0 A tile");
 // weight k-step i (0..22) lives in ring slot: layer 0 cycles through the 3 dedicated slots, layer 1 through all 6
@@ -172,8 +173,7 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
     uint64_t* in_bar = d_full + 3;          // [2] : state rows of layer 0 / layer 1 have landed in the staging tile
     uint64_t* obs_bar = in_bar + 2;
     uint64_t* bias_bar = obs_bar + 1;
-    uint64_t* head_full = bias_bar + 1;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(head_full + 1);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bias_bar + 1);
     const int rows = min(TM, A.N - e0);
     // the observation tile is one contiguous block; the bulk engine wants 16-byte granularity on both ends
     const bool obs_bulk = ((reinterpret_cast<uintptr_t>(A.obs) & 15) == 0) && ((rows & 3) == 0);
@@ -183,7 +183,6 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
         for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(a_ready, NWORK);
         for (int i = 0; i < 3; ++i) mbar_init(&d_full[i], 1);
-        mbar_init(head_full, 1);
         mbar_init(&in_bar[0], TM); mbar_init(&in_bar[1], TM);
         mbar_init(obs_bar, 1); mbar_init(bias_bar, 1);
         fence_mbar_init();
@@ -253,6 +252,21 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
             for (int i = t; i < rows * OB_DIM; i += NWORK) A.obs_store[(size_t)e0 * OB_DIM + i] = stage[i];      // fence.proxy.async would wait for them
         }
         if (tower == 0 && A.done_store && t < rows) A.done_store[e0 + t] = A.done ? A.done[e0 + t] : 0;       // mb_dones (ppo2.py:526)
+        // ---- also behind the first GEMM: everything of the Gaussian policy head that does not depend on the network output
+        mbar_wait(bias_bar, 0);
+        const float* hb = sbias + 2 * NG;
+        float sg[3][4];                                               // sigma * z per action: the 12 Gaussian draws, sigma = exp(logstd) and
+        float nlp = 0.5f * 1.8378770664093453f * ACT_DIM;             // neglogp = sum(0.5 z^2 + logstd) + 6 ln(2 pi) (z = the draw itself)
+        if (part == 0 && tower == 0) {
+#pragma unroll
+            for (int g3 = 0; g3 < 3; ++g3) {
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!A.deterministic) gauss4(A.seed, (uint32_t)envc + A.env_offset, A.tick, P_POLICY_EPS + g3, g);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { sg[g3][j] = hb[32 + 4 * g3 + j] * g[j]; nlp += 0.5f * g[j] * g[j] + hb[16 + 4 * g3 + j]; }
+            }
+        }
+
         mbar_wait(&in_bar[1], 0);
         worker_sync();                                                // obs_store has finished reading the buffer that h1 overwrites
         float4 da, db, dc;
@@ -266,11 +280,11 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
         da = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part) * 4);
         db = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part + 4) * 4);
         dc = *reinterpret_cast<const float4*>(sSTG + row * STG_PITCH + (12 * part + 8) * 4);
-        mbar_wait(bias_bar, 0);
         worker_sync();                                                // staging tile free for the epilogue's output rows
 
         // ------------------------------------------------------------ cell updates straight out of tensor memory
         // Rolled loops on purpose: every warp runs this code once per launch, so its size is paid in instruction fetches.
+        float4 ha = make_float4(0.f, 0.f, 0.f, 0.f), hb4 = ha, hc = ha;
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
             mbar_wait(&d_full[l], 0);
@@ -298,14 +312,15 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
                     const float ec = __expf(-2.0f * fabsf(cn[j]));
                     hn[j] = copysignf(__fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec)), cn[j]);                 // sigmoid(zo) * tanh(c)
                 }
-                store_hilo(sA1, op_off(12 * part + 4 * i, row, TM), A_HALF, hn);      // A operand of the next GEMM (k = unit index)
+                if (l == 0) store_hilo(sA1, op_off(12 * part + 4 * i, row, TM), A_HALF, hn);      // A operand of the next GEMM (k = unit index)
                 *reinterpret_cast<float4*>(orow + 16 * i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                 *reinterpret_cast<float4*>(orow + LSTM_H * 4 + 16 * i) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 ca = cb; cb = cc;
+                ha = hb4; hb4 = hc; hc = make_float4(hn[0], hn[1], hn[2], hn[3]);      // after the loop: units 12 part + 0..3 | 4..7 | 8..11
             }
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(a_ready);
+            if (l == 0) mbar_arrive(a_ready);
             if (t == 0) TC_MARK(6 + 4 * l);
             worker_sync();                                            // all output rows of this layer are in the staging tile
             if (t < rows) { bulk_s2g(strow + l * 2 * LSTM_H, smem_u32(sSTG + t * STG_PITCH), 2 * LSTM_H * 4); bulk_commit(); }
@@ -315,35 +330,45 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
                 worker_sync();
             }
         }
-        // ------------------------------------------------------------ heads: lanes of warps 0-3 own one environment each
-        // the 12 Gaussian draws, sigma = exp(logstd) and neglogp = sum(0.5 z^2 + logstd) + 6 ln(2 pi) (z = the draw itself) do not
-        // depend on the head GEMM: they are computed while it runs
-        const float* hb = sbias + 2 * NG;
-        float sg[3][4];                                               // sigma * z per action
-        float nlp = 0.5f * 1.8378770664093453f * ACT_DIM;
-        if (part == 0 && tower == 0) {
+        // ------------------------------------------------------------ heads on the CUDA cores: 48 x 12 (48 x 1) is too small to pay
+        // for another operand hand-off to the tensor core.  Every thread multiplies its 12 hidden units of the top layer with the
+        // head weights (fp32 [48][16], copied over the dead layer-1 A tile), the 4 column blocks of a row are summed through shared memory.
+        {
+            const float4* Wh = reinterpret_cast<const float4*>(sbias + BIAS_HEADW) + (12 * part) * 3;       // row u = 3 float4 (12 outputs)
+            const float hu[12] = {ha.x, ha.y, ha.z, ha.w, hb4.x, hb4.y, hb4.z, hb4.w, hc.x, hc.y, hc.z, hc.w};
+            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0;
 #pragma unroll
-            for (int g3 = 0; g3 < 3; ++g3) {
-                float g[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!A.deterministic) gauss4(A.seed, (uint32_t)envc + A.env_offset, A.tick, P_POLICY_EPS + g3, g);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float ls = hb[16 + 4 * g3 + j]; sg[g3][j] = expf(ls) * g[j]; nlp += 0.5f * g[j] * g[j] + ls; }
+            for (int u = 0; u < 12; ++u) {
+                const float4 w0 = Wh[3 * u], w1 = Wh[3 * u + 1], w2 = Wh[3 * u + 2];
+                p0.x = fmaf(hu[u], w0.x, p0.x); p0.y = fmaf(hu[u], w0.y, p0.y); p0.z = fmaf(hu[u], w0.z, p0.z); p0.w = fmaf(hu[u], w0.w, p0.w);
+                p1.x = fmaf(hu[u], w1.x, p1.x); p1.y = fmaf(hu[u], w1.y, p1.y); p1.z = fmaf(hu[u], w1.z, p1.z); p1.w = fmaf(hu[u], w1.w, p1.w);
+                p2.x = fmaf(hu[u], w2.x, p2.x); p2.y = fmaf(hu[u], w2.y, p2.y); p2.z = fmaf(hu[u], w2.z, p2.z); p2.w = fmaf(hu[u], w2.w, p2.w);
             }
+            float4* P = reinterpret_cast<float4*>(sA2 + OFF_HEADP) + (size_t)(part * TM + row) * 3;
+            P[0] = p0; P[1] = p1; P[2] = p2;
         }
-        mbar_wait(&d_full[2], 0);
-        tc_fence_after();
+        worker_sync();
         if (t == 0) TC_MARK(12);
         if (part == 0) {
-            uint32_t v[16];
-            tmem_ld16(tmem + ((uint32_t)(32 * wq) << 16) + 2 * NG, v);
-            tmem_ld_wait();
+            float v[12];
+            {
+                const float4* P = reinterpret_cast<const float4*>(sA2 + OFF_HEADP) + (size_t)row * 3;
+                float4 s0 = P[0], s1 = P[1], s2 = P[2];
+#pragma unroll
+                for (int pb = 1; pb < 4; ++pb) {
+                    const float4 q0 = P[pb * TM * 3], q1 = P[pb * TM * 3 + 1], q2 = P[pb * TM * 3 + 2];
+                    s0.x += q0.x; s0.y += q0.y; s0.z += q0.z; s0.w += q0.w; s1.x += q1.x; s1.y += q1.y; s1.z += q1.z; s1.w += q1.w;
+                    s2.x += q2.x; s2.y += q2.y; s2.z += q2.z; s2.w += q2.w;
+                }
+                v[0] = s0.x; v[1] = s0.y; v[2] = s0.z; v[3] = s0.w; v[4] = s1.x; v[5] = s1.y; v[6] = s1.z; v[7] = s1.w; v[8] = s2.x; v[9] = s2.y; v[10] = s2.z; v[11] = s2.w;
+            }
             if (tower == 0) {
                 if (valid) {
 #pragma unroll
                     for (int g3 = 0; g3 < 3; ++g3) {
                         float x[4], mean[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) { mean[j] = __uint_as_float(v[4 * g3 + j]) + hb[4 * g3 + j]; x[j] = mean[j] + sg[g3][j]; }
+                        for (int j = 0; j < 4; ++j) { mean[j] = v[4 * g3 + j] + hb[4 * g3 + j]; x[j] = mean[j] + sg[g3][j]; }
                         reinterpret_cast<float4*>(A.action + (size_t)env * ACT_DIM)[g3] = make_float4(x[0], x[1], x[2], x[3]);
                         if (A.clipped)                                                                                   // ppo2.py:529-531
                             reinterpret_cast<float4*>(A.clipped + (size_t)env * ACT_DIM)[g3] =
@@ -353,7 +378,7 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
                     A.neglogp[env] = nlp;
                 }
             } else if (valid) {
-                A.value[env] = __uint_as_float(v[0]) + hb[0];
+                A.value[env] = v[0] + hb[0];
             }
         }
         if (t == 0) TC_MARK(21);
@@ -374,53 +399,43 @@ __global__ void __launch_bounds__(NTHR, 1) lstm_act_tc_kernel(const __grid_const
             src += B_KSTEP;
             if (i == NST - 1) TC_MARK(14);
         }
-        mbar_wait(&d_full[1], 0);                                     // head weights (6 KB, one copy) overlay the layer-1 A tile once its GEMM is done
-        mbar_expect_tx(head_full, KSH * H_KSTEP);
-        bulk_g2s(smem_u32(sA2), src, KSH * H_KSTEP, head_full);
         TC_MARK(15);
     } else if (warp == NWORK / 32 + 1) {
         // ------------------------------------------------------------ MMA issuer: the whole warp walks the loop (warp-uniform control flow keeps
         // descriptors in uniform registers), one elected lane issues
         const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), ring = smem_u32(smem + OFF_RING);
         constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);        // SBO = 128 B, descriptor version 1
-        constexpr uint32_t A_LBO = (uint32_t)(TM * 16 >> 4) << 16, G_LBO = (uint32_t)(NG * 16 >> 4) << 16, H_LBO = (uint32_t)(NHEAD * 16 >> 4) << 16;
+        constexpr uint32_t A_LBO = (uint32_t)(TM * 16 >> 4) << 16, G_LBO = (uint32_t)(NG * 16 >> 4) << 16;
         uint32_t phase = 0;                                           // per-slot parity of the next `full` completion
         int i = 0;
 #pragma unroll 1
-        for (int layer = 0; layer < 3; ++layer) {
+        for (int layer = 0; layer < 2; ++layer) {
             mbar_wait(a_ready, layer & 1);
-            if (layer == 2) mbar_wait(head_full, 0);
             tc_fence_after();
-            if (lane == 0) TC_MARK(layer == 0 ? 2 : layer == 1 ? 7 : 11);
-            const int nks = layer == 0 ? KS1 : layer == 1 ? KS2 : KSH;
+            if (lane == 0) TC_MARK(layer == 0 ? 2 : 7);
+            const int nks = layer == 0 ? KS1 : KS2;
             const uint32_t d = tmem + layer * NG;
-            const uint32_t idesc = layer == 2 ? make_idesc(TM, NHEAD) : make_idesc(TM, NG);
-            const uint32_t bhalf = (layer == 2 ? H_HALF : B_HALF) >> 4, blbo = layer == 2 ? H_LBO : G_LBO;
+            const uint32_t idesc = make_idesc(TM, NG);
 #pragma unroll 1
             for (int ks = 0; ks < nks; ++ks, ++i) {
-                uint32_t bb; int sl = 0;
-                if (layer < 2) {
-                    sl = slot_of(i);
-                    mbar_wait(&full[sl], (phase >> sl) & 1); phase ^= 1u << sl;
-                    tc_fence_after();
-                    bb = slot_addr(ring, a1, sl);
-                } else {
-                    bb = a2 + ks * H_KSTEP;
-                }
+                const int sl = slot_of(i);
+                mbar_wait(&full[sl], (phase >> sl) & 1); phase ^= 1u << sl;
+                tc_fence_after();
+                const uint32_t bb = slot_addr(ring, a1, sl);
                 const uint32_t ab = (layer == 1 && ks >= 6) ? a2 + (ks - 6) * A_KSTEP : a1 + ks * A_KSTEP;
-                const uint32_t alo = (ab >> 4) | A_LBO, blo = (bb >> 4) | blbo;
+                const uint32_t alo = (ab >> 4) | A_LBO, blo = (bb >> 4) | G_LBO;
                 const uint64_t ah = ((uint64_t)DESC_HI << 32) | alo, al = ((uint64_t)DESC_HI << 32) | (alo + (A_HALF >> 4));
-                const uint64_t bh = ((uint64_t)DESC_HI << 32) | blo, bl = ((uint64_t)DESC_HI << 32) | (blo + bhalf);
+                const uint64_t bh = ((uint64_t)DESC_HI << 32) | blo, bl = ((uint64_t)DESC_HI << 32) | (blo + (B_HALF >> 4));
                 if (elect_one()) {
                     mma_tf32(d, al, bh, idesc, ks > 0);
                     mma_tf32(d, ah, bl, idesc, 1);
                     mma_tf32(d, ah, bh, idesc, 1);
-                    if (layer < 2) umma_commit(&empty[sl]);
+                    umma_commit(&empty[sl]);
                     if (ks == nks - 1) umma_commit(&d_full[layer]);
                 }
                 __syncwarp();
             }
-            if (lane == 0) TC_MARK(layer == 0 ? 4 : layer == 1 ? 8 : 13);
+            if (lane == 0) TC_MARK(layer == 0 ? 4 : 8);
         }
     }
     tc_fence_before();
@@ -568,13 +583,12 @@ void pack_tc_blob(const float* wx0, const float* wh0, const float* b0, const flo
         for (int k = 0; k < LSTM_H; ++k) put(l1, tc::op_off(k, n, tc::NG), tc::B_HALF, wx1[(size_t)k * tc::NG + src]);
         for (int k = 0; k < LSTM_H; ++k) put(l1, tc::op_off(48 + k, n, tc::NG), tc::B_HALF, wh1[(size_t)k * tc::NG + src]);
     }
-    unsigned char* hd = out + (tc::KS1 + tc::KS2) * tc::B_KSTEP;
-    for (int n = 0; n < head_cols; ++n)
-        for (int k = 0; k < LSTM_H; ++k) put(hd, tc::op_off(k, n, tc::NHEAD), tc::H_HALF, head_w[(size_t)k * head_cols + n]);
     float* bias = reinterpret_cast<float*>(out + TC_BLOB_BYTES - TC_BIAS_BYTES);      // [2][192] gate biases, [16] head bias, [16] logstd
     for (int n = 0; n < tc::NG; ++n) { const int src = (n & 3) * LSTM_H + (n >> 2); bias[n] = b0[src]; bias[tc::NG + n] = b1[src]; }
     for (int n = 0; n < head_cols; ++n) bias[2 * tc::NG + n] = head_b[n];
-    if (logstd) for (int n = 0; n < ACT_DIM; ++n) bias[2 * tc::NG + 16 + n] = logstd[n];
+    if (logstd) for (int n = 0; n < ACT_DIM; ++n) { bias[2 * tc::NG + 16 + n] = logstd[n]; bias[2 * tc::NG + 32 + n] = expf(logstd[n]); }
+    for (int n = 0; n < head_cols; ++n)                                            // fp32 [48 units][12 outputs], zero padded
+        for (int k = 0; k < LSTM_H; ++k) bias[tc::BIAS_HEADW + k * 12 + n] = head_w[(size_t)k * head_cols + n];
 }
 
 }  // namespace irrl

@@ -71,7 +71,7 @@ struct irrl_env_impl {
     uint32_t tick = 0;
     bool initialised = false;
     std::string resource_dir, ref_path;
-    double max_time_d = 0, control_dt_d = 0, sim_dt_d = 0;
+    double max_time_d = 0, control_dt_d = 0, sim_dt_d = 0, period_d = 0;
     // heightfield (host copy + generator settings from the YAML)
     std::vector<float> terrain_h; std::string terrain_kind = "perlin"; double stair_rise = 0.08, stair_run = 0.3, stair_start = 1.0; int terrain_seed = 0; float* d_terrain = nullptr;   // YAML values in double: integer counts are derived like the reference does
     std::vector<std::string> extra_names;
@@ -161,7 +161,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         E->control_dt_d = ctl_dt; E->sim_dt_d = sim_dt;
         if (!num("seedd", d)) goto bad; P.seed = (uint32_t)(int)d;                                               // VEC:171
         // ENV:1598-1613
-        NUM("abad", P.abad) NUM("period", P.period) P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ P.meteor_every = int(5.0 * d / ctl_dt);   /* ENV:731 */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
+        NUM("abad", P.abad) NUM("period", P.period) E->period_d = d; P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ P.meteor_every = int(5.0 * d / ctl_dt);   /* ENV:731 */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
         IGN("down_height") IGN("gait_step")
         NUM("Vx", P.Vx_max) P.Vx_min = 0.f;                                                                      // ENV:1606-1607, 2054
         NUM("Vy", P.Vy_max) P.Vy_min = -P.Vy_max; NUM("Omega", P.omega_max) P.omega_min = -P.omega_max;
@@ -495,7 +495,11 @@ int irrl_running_episode_stats(irrl_env* env, float* ep_return, int32_t* ep_leng
 int irrl_set_seed(irrl_env* env, int seed) { ENV(env); E->P.seed = (uint32_t)seed; return 0; }
 int irrl_close(irrl_env* env) { ENV(env); if (E->stream) CUDA_OK(cudaStreamSynchronize(E->stream)); return 0; }
 int irrl_set_simulation_time_step(irrl_env* env, double dt) { ENV(env); E->P.sim_dt = (float)dt; E->sim_dt_d = dt; E->P.loop_count = int(E->control_dt_d / dt + 1e-10); return 0; }
-int irrl_set_control_time_step(irrl_env* env, double dt) { ENV(env); E->P.control_dt = (float)dt; E->control_dt_d = dt; E->P.loop_count = int(dt / E->sim_dt_d + 1e-10); return 0; }
+int irrl_set_control_time_step(irrl_env* env, double dt) {
+    ENV(env); E->P.control_dt = (float)dt; E->control_dt_d = dt; E->P.loop_count = int(dt / E->sim_dt_d + 1e-10);
+    E->P.disturb_every = int(E->period_d / dt * 10.0); E->P.meteor_every = int(5.0 * E->period_d / dt);     // ENV:746, 731 evaluate control_dt_ at every step
+    return 0;
+}
 int irrl_curriculum_update(irrl_env* env) { ENV(env); return 0; }
 int irrl_start_recording_video(irrl_env* env, const char*) { ENV(env); return 0; }
 int irrl_stop_recording_video(irrl_env* env) { ENV(env); return 0; }

@@ -270,13 +270,13 @@ def run_b200(args):
     env.reset(h_obs)
     state.zero_()
 
+    act_args = (C.c_void_p(stream.cuda_stream), N, C.c_void_p(h_obs.ctypes.data), C.c_void_p(h_done.view(np.uint8).ctypes.data), C.c_void_p(state.data_ptr()),
+                C.c_void_p(h_act.ctypes.data), C.c_void_p(h_clip.ctypes.data), C.c_void_p(h_val.ctypes.data), C.c_void_p(h_nlp.ctypes.data))
+
     def e2e_step(t):
         # model.step(obs, states, dones): obs/mask host -> device, actions/values/neglogp device -> host; LSTM state stays
         # an opaque device-resident handle (the Runner only threads `states` through, ppo2.py:520)
-        m = h_done.view(np.uint8)
-        _lib.check(L.irrl_policy_act(pol.handle, C.c_void_p(stream.cuda_stream), N, C.c_void_p(h_obs.ctypes.data), C.c_void_p(m.ctypes.data),
-                                     C.c_void_p(state.data_ptr()), C.c_void_p(h_act.ctypes.data), C.c_void_p(h_clip.ctypes.data), C.c_void_p(h_val.ctypes.data),
-                                     C.c_void_p(h_nlp.ctypes.data), 0, 1, rank * N, 100000 + t), "policy_act")
+        _lib.check(L.irrl_policy_act(pol.handle, *act_args, 0, 1, rank * N, 100000 + t), "policy_act")
         env.step(h_clip, h_obs, h_rew, h_done, h_extra)     # RaisimGymVecEnv.step -> wrapper.step (RaisimGymVecEnv.py:31)
 
     for t in range(3):

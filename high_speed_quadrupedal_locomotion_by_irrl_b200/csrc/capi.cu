@@ -95,26 +95,6 @@ struct irrl_policy_impl {
     unsigned char* h_pin = nullptr;
 };
 
-bool is_device_ptr(const void* p) {
-    if (!p) return false;
-    cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-
-// page-locked host memory (cudaHostAlloc / cudaHostRegister): DMA can target it directly, no staging copy needed
-bool is_pinned_host_ptr(const void* p, size_t bytes = 1) {
-    if (!p) return false;
-    // both ends of the range must be page-locked (a stale registration may cover only part of a recycled allocation)
-    const void* ends[2] = {p, static_cast<const char*>(p) + (bytes ? bytes - 1 : 0)};
-    for (const void* q : ends) {
-        cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, q);
-        if (e != cudaSuccess) { cudaGetLastError(); return false; }
-        if (a.type != cudaMemoryTypeHost) return false;
-    }
-    return true;
-}
-
 // Registry of the ranges page-locked through irrl_host_register.  With IRRL_ZERO_COPY=1 (outputs and inputs) or 2 (inputs only)
 // the kernels use those buffers in place (mapped pinned memory) instead of cudaMemcpy staging.  Measured on B200 / PCIe 5:
 // in-place outputs are 35 % SLOWER end to end (the step kernel's scalar observation stores become small PCIe writes) and
@@ -134,6 +114,38 @@ template <typename T> static T* mapped_alias(T* p, size_t bytes) {
     if (a + bytes > it->first + it->second.bytes) return nullptr;
     return reinterpret_cast<T*>(it->second.dev + (a - it->first));
 }
+// [p, p+bytes) lies inside a block this library page-locked itself: no driver query needed to classify it
+static bool in_registry(const void* p, size_t bytes) {
+    if (!p) return false;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    auto it = g_pinned.upper_bound(a);
+    if (it == g_pinned.begin()) return false;
+    --it;
+    return a + bytes <= it->first + it->second.bytes;
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p || in_registry(p, 1)) return false;
+    cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// page-locked host memory (cudaHostAlloc / cudaHostRegister): DMA can target it directly, no staging copy needed
+bool is_pinned_host_ptr(const void* p, size_t bytes = 1) {
+    if (!p) return false;
+    if (in_registry(p, bytes ? bytes : 1)) return true;
+    // both ends of the range must be page-locked (a stale registration may cover only part of a recycled allocation)
+    const void* ends[2] = {p, static_cast<const char*>(p) + (bytes ? bytes - 1 : 0)};
+    for (const void* q : ends) {
+        cudaPointerAttributes a; cudaError_t e = cudaPointerGetAttributes(&a, q);
+        if (e != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
+}
+
 static cudaError_t wait_stream(cudaStream_t st) { return cudaStreamSynchronize(st); }
 
 template <typename T> int dev_alloc(irrl_env_impl* E, T** p, size_t n) {

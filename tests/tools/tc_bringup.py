@@ -1,5 +1,5 @@
 """GPU bring-up of the tcgen05 act kernel: GEMM probe variants, then tc vs FMA vs numpy-oracle act parity, then timing.
-Run each stage in its own process (a trap poisons the CUDA context): python scripts/tc_bringup.py probe|act|time"""
+Run each stage in its own process (a trap poisons the CUDA context): python tests/tools/tc_bringup.py probe|act|time"""
 import ctypes as C
 import os
 import sys
@@ -7,14 +7,14 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 from high_speed_quadrupedal_locomotion_by_irrl_b200 import _lib
 from high_speed_quadrupedal_locomotion_by_irrl_b200.policy import FusedLstmPolicy, PARAM_NAMES
 
 L = _lib.load()
 NOFLUSH = "noflush" in sys.argv
-G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+G = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden")
 
 
 def probe():

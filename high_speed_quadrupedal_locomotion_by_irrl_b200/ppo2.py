@@ -184,8 +184,11 @@ class PPO2:
 
     def __init__(self, env, policy_params: Optional[Sequence[np.ndarray]] = None, gamma=0.99, n_steps=750, ent_coef=0.0, learning_rate=1e-3,
                  vf_coef=0.5, max_grad_norm=0.5, lam=0.998, nminibatches=1, noptepochs=10, cliprange=0.2, verbose=1, device: Optional[int] = None,
-                 seed: int = 0):
+                 seed: int = 0, matmul_tf32: bool = False):
         from .policy import FusedLstmPolicy
+        # opt-in: run the learner's cuBLAS GEMMs (input projections, weight gradients) as single-pass TF32 tensor-core products.
+        # Default False = fp32 like the reference's TF1 graph; rollout kernels are unaffected (they are fp32-accurate either way).
+        self.matmul_tf32 = bool(matmul_tf32)
         self.env = env                                     # RaisimGymVecEnv over FlexibleGymEnv
         self.n_envs = env.num_envs
         self.gamma, self.lam, self.n_steps, self.ent_coef, self.vf_coef = gamma, lam, int(n_steps), ent_coef, vf_coef
@@ -245,6 +248,14 @@ class PPO2:
         return mb_states, ep_infos
 
     def _update(self, mb_states, lr, cliprange):
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.matmul_tf32
+        try:
+            return self._update_impl(mb_states, lr, cliprange)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+    def _update_impl(self, mb_states, lr, cliprange):
         b = self._buf
         N, T = self.n_envs, self.n_steps
         # the rollout buffers are time-major [T,N,...]; an env minibatch is a gather along dim 1 (the reference flattens env-major,

@@ -57,3 +57,16 @@ def test_yaml_missing_key_is_reported_like_read_yaml():
     cfg = trot_cfg(); del cfg["Stiffness"]
     with pytest.raises(RuntimeError, match="Stiffness"):
         FlexibleGymEnv("", dump_yaml(cfg))
+
+
+def test_pinned_block_lays_arrays_out_back_to_back():
+    """_lib.pinned_block carves one block into the arrays of a C-ABI call in the order the native side writes them (one DMA copy per
+    call); without a GPU the block simply stays pageable"""
+    import numpy as np
+    from high_speed_quadrupedal_locomotion_by_irrl_b200 import _lib
+    n = 37
+    ob, rew, extra, done = _lib.pinned_block(((n, 35), np.float32), ((n,), np.float32), ((n, 6), np.float32), ((n,), np.bool_))
+    assert ob.shape == (n, 35) and rew.shape == (n,) and extra.shape == (n, 6) and done.dtype == np.bool_
+    assert rew.ctypes.data == ob.ctypes.data + ob.nbytes and extra.ctypes.data == rew.ctypes.data + rew.nbytes and done.ctypes.data == extra.ctypes.data + extra.nbytes
+    ob[:] = 1; rew[:] = 2; extra[:] = 3; done[:] = True
+    assert ob.sum() == n * 35 and rew.sum() == 2 * n and extra.sum() == 18 * n and done.all()

@@ -40,6 +40,52 @@
 
 namespace bp5o {
 
+// ------------------------------------------------------------------ scalar functions (mth::) and the op-counting scalar
+// The env is templated on its scalar type; Counted<double> counts every floating-point operation it performs ("the
+// oracle carries an op counter"): add/sub, mul, div, sqrt, transcendental, compare.  bp5o_count_flops() reports them per env-step.
+struct OpCount { unsigned long long add = 0, mul = 0, div = 0, sqrt = 0, trans = 0, cmp = 0; };
+inline OpCount& op_count() { static thread_local OpCount c; return c; }
+struct Counted {
+    double v;
+    Counted() : v(0) {}
+    Counted(double x) : v(x) {}
+    explicit operator double() const { return v; }
+    explicit operator float() const { return (float)v; }
+    explicit operator int() const { return (int)v; }
+    friend Counted operator+(const Counted& a, const Counted& b) { op_count().add++; return Counted(a.v + b.v); }
+    friend Counted operator-(const Counted& a, const Counted& b) { op_count().add++; return Counted(a.v - b.v); }
+    friend Counted operator*(const Counted& a, const Counted& b) { op_count().mul++; return Counted(a.v * b.v); }
+    friend Counted operator/(const Counted& a, const Counted& b) { op_count().div++; return Counted(a.v / b.v); }
+    Counted operator-() const { return Counted(-v); }
+    Counted& operator+=(const Counted& b) { op_count().add++; v += b.v; return *this; }
+    Counted& operator-=(const Counted& b) { op_count().add++; v -= b.v; return *this; }
+    Counted& operator*=(const Counted& b) { op_count().mul++; v *= b.v; return *this; }
+    Counted& operator/=(const Counted& b) { op_count().div++; v /= b.v; return *this; }
+    friend bool operator<(const Counted& a, const Counted& b) { op_count().cmp++; return a.v < b.v; }
+    friend bool operator>(const Counted& a, const Counted& b) { op_count().cmp++; return a.v > b.v; }
+    friend bool operator<=(const Counted& a, const Counted& b) { op_count().cmp++; return a.v <= b.v; }
+    friend bool operator>=(const Counted& a, const Counted& b) { op_count().cmp++; return a.v >= b.v; }
+    friend bool operator==(const Counted& a, const Counted& b) { op_count().cmp++; return a.v == b.v; }
+    friend bool operator!=(const Counted& a, const Counted& b) { op_count().cmp++; return a.v != b.v; }
+};
+namespace mth {
+using std::sqrt; using std::fabs; using std::exp; using std::sin; using std::cos; using std::min; using std::max; using std::fmod; using std::fmax;
+using std::fmin; using std::asin; using std::acos; using std::log;
+inline Counted sqrt(const Counted& a) { op_count().sqrt++; return Counted(std::sqrt(a.v)); }
+inline Counted fabs(const Counted& a) { return Counted(std::fabs(a.v)); }
+inline Counted exp(const Counted& a) { op_count().trans++; return Counted(std::exp(a.v)); }
+inline Counted sin(const Counted& a) { op_count().trans++; return Counted(std::sin(a.v)); }
+inline Counted cos(const Counted& a) { op_count().trans++; return Counted(std::cos(a.v)); }
+inline Counted asin(const Counted& a) { op_count().trans++; return Counted(std::asin(a.v)); }
+inline Counted acos(const Counted& a) { op_count().trans++; return Counted(std::acos(a.v)); }
+inline Counted log(const Counted& a) { op_count().trans++; return Counted(std::log(a.v)); }
+inline Counted fmod(const Counted& a, const Counted& b) { op_count().div++; return Counted(std::fmod(a.v, b.v)); }
+inline Counted min(const Counted& a, const Counted& b) { op_count().cmp++; return a.v < b.v ? a : b; }
+inline Counted max(const Counted& a, const Counted& b) { op_count().cmp++; return a.v < b.v ? b : a; }
+inline Counted fmin(const Counted& a, const Counted& b) { op_count().cmp++; return a.v < b.v ? a : b; }
+inline Counted fmax(const Counted& a, const Counted& b) { op_count().cmp++; return a.v < b.v ? b : a; }
+}  // namespace mth
+
 // ------------------------------------------------------------------ Philox4x32-10 (Salmon et al. SC'11)
 // Counter-based RNG shared *by specification* with the CUDA path: key = (seed, 0x1BD11BDA),
 // counter = (global env id, tick, purpose, 0).  Replaces the reference's racy libc rand()/random()
@@ -116,7 +162,7 @@ template <typename T> V3<T> tmul(const M3<T>& a, const V3<T>& v) {  // a^T v
 }
 // Rodrigues rotation about a unit axis
 template <typename T> M3<T> axis_angle(const V3<T>& a, T th) {
-    T c = std::cos(th), s = std::sin(th), v = T(1) - c;
+    T c = mth::cos(th), s = mth::sin(th), v = T(1) - c;
     M3<T> r;
     r.m[0][0] = c + a.x * a.x * v;       r.m[0][1] = a.x * a.y * v - a.z * s; r.m[0][2] = a.x * a.z * v + a.y * s;
     r.m[1][0] = a.y * a.x * v + a.z * s; r.m[1][1] = c + a.y * a.y * v;       r.m[1][2] = a.y * a.z * v - a.x * s;
@@ -227,16 +273,16 @@ template <typename T> inline V3<T> cubicBezier(const V3<T>& p0, const V3<T>& pf,
     T b = bezier_b(ph); return p0 + b * (pf - p0);
 }
 template <typename T> inline T gauss(T x, T width, T height) {                                               // ENV:96-99
-    return height * std::exp(-(x - width / 2) * (x - width / 2) / (2 * (width / 6) * (width / 6)));
+    return height * mth::exp(-(x - width / 2) * (x - width / 2) / (2 * (width / 6) * (width / 6)));
 }
 template <typename T> inline V3<T> Bezier2(const V3<T>& p0, const V3<T>& pf, T ph, T height) {                // ENV:104-113
     T b = bezier_b(ph);
     return {p0.x + b * (pf.x - p0.x), p0.y + b * (pf.y - p0.y), p0.z + gauss(ph, T(1.0), height)};
 }
 template <typename T> inline T smooth_raw(T phase, T slope, T lam) {                                         // ENV:118-129
-    T f = std::fmod(phase, T(1.0));
-    if (f < lam) return (std::sin(f / lam * 2 * T(BP5O_PI)) * slope) + T(0.5);
-    return (-std::sin((f - lam) / (T(1.0) - lam) * 2 * T(BP5O_PI)) * slope) + T(0.5);
+    T f = mth::fmod(phase, T(1.0));
+    if (f < lam) return (mth::sin(f / lam * 2 * T(BP5O_PI)) * slope) + T(0.5);
+    return (-mth::sin((f - lam) / (T(1.0) - lam) * 2 * T(BP5O_PI)) * slope) + T(0.5);
 }
 template <typename T> inline T smooth_function(T phase, T slope, T lam) {                                    // ENV:118-136
     T t = smooth_raw(phase, slope, lam); if (t > T(1)) return T(1); if (t < T(0)) return T(0); return t;
@@ -252,7 +298,7 @@ template <typename T, int N> struct Chol {
         for (int j = 0; j < N; ++j) {
             T d = A[j][j]; for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
             if (!(d > T(0))) return false;
-            L[j][j] = std::sqrt(d);
+            L[j][j] = mth::sqrt(d);
             for (int i = j + 1; i < N; ++i) { T s = A[i][j]; for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k]; L[i][j] = s / L[j][j]; }
             for (int i = 0; i < j; ++i) L[i][j] = T(0);
         }
@@ -291,7 +337,7 @@ struct Terrain {
         T a, b;   // slopes dh/dx, dh/dy of the triangle under (u,v)
         if (u >= v) { a = (h10 - h00) / T(dx); b = (h11 - h10) / T(dy); height = h00 + (h10 - h00) * u + (h11 - h10) * v; }
         else        { a = (h11 - h01) / T(dx); b = (h01 - h00) / T(dy); height = h00 + (h11 - h01) * u + (h01 - h00) * v; }
-        T inv = T(1) / std::sqrt(T(1) + a * a + b * b);
+        T inv = T(1) / mth::sqrt(T(1) + a * a + b * b);
         n = V3<T>(-a * inv, -b * inv, inv);
     }
 };
@@ -407,7 +453,7 @@ template <typename T> struct Env {
         const T vstd[3] = {5, 35, 40};
         for (int i = 0; i < 12; ++i) obStd_[17 + i] = vstd[i % 3];
         for (int i = 0; i < 3; ++i) { obStd_[29 + i] = T(0.7); obStd_[32 + i] = T(3.0); }
-        max_len = std::sqrt(l_hip_ * l_hip_ + (l_calf_ + l_thigh_) * (l_calf_ + l_thigh_));   // ENV:395
+        max_len = mth::sqrt(l_hip_ * l_hip_ + (l_calf_ + l_thigh_) * (l_calf_ + l_thigh_));   // ENV:395
         filter_para = flag_filter ? (1 - freq * control_dt_) : 0;                              // ENV:396
         switch (gaitType) {                                                                    // ENV:398-409
             case 0: phase_[0] = T(0.5); phase_[1] = 0; phase_[2] = 0; phase_[3] = T(0.5); break;
@@ -553,7 +599,7 @@ template <typename T> struct Env {
     // contact frame rows (t1, t2, n): t1 = x-axis projected on the tangent plane, t2 = n x t1 (identity on flat ground)
     static void contact_frame(const V3<T>& n, V3<T> D[3]) {
         V3<T> t1(T(1) - n.x * n.x, -n.x * n.y, -n.x * n.z);
-        T inv = T(1) / std::sqrt(dot(t1, t1)); t1 = inv * t1;
+        T inv = T(1) / mth::sqrt(dot(t1, t1)); t1 = inv * t1;
         D[0] = t1; D[1] = cross(n, t1); D[2] = n;
     }
 
@@ -607,7 +653,7 @@ template <typename T> struct Env {
                     inv3(Gii, Ginv);
                     T lo[3] = {lam[3 * i], lam[3 * i + 1], lam[3 * i + 2]}, ln[3];
                     solve_one_contact(v, Gii, Ginv, lo, vtarget[i], ln);
-                    for (int r = 0; r < 3; ++r) { T d = std::fabs(ln[r] - lo[r]); if (d > maxd) maxd = d; if (std::fabs(ln[r]) > maxl) maxl = std::fabs(ln[r]); lam[3 * i + r] = ln[r]; }
+                    for (int r = 0; r < 3; ++r) { T d = mth::fabs(ln[r] - lo[r]); if (d > maxd) maxd = d; if (mth::fabs(ln[r]) > maxl) maxl = mth::fabs(ln[r]); lam[3 * i + r] = ln[r]; }
                 }
                 last_solver_sweeps = sweep + 1;
                 if (maxd <= solver_tol * maxl) break;
@@ -623,15 +669,15 @@ template <typename T> struct Env {
         for (int a = 0; a < 3; ++a) gc_[a] += dt * gv_[a];
         {   // orientation: rotate by |w| dt about w (world frame): q+ = dq (x) q
             T wx = gv_[3], wy = gv_[4], wz = gv_[5];
-            T wn = std::sqrt(wx * wx + wy * wy + wz * wz), th = wn * dt;
+            T wn = mth::sqrt(wx * wx + wy * wy + wz * wz), th = wn * dt;
             T kk, cw;
-            if (th > T(1e-8)) { kk = std::sin(th / 2) / wn; cw = std::cos(th / 2); } else { kk = dt / 2; cw = T(1); }
+            if (th > T(1e-8)) { kk = mth::sin(th / 2) / wn; cw = mth::cos(th / 2); } else { kk = dt / 2; cw = T(1); }
             T dq[4] = {cw, kk * wx, kk * wy, kk * wz}, q[4] = {gc_[3], gc_[4], gc_[5], gc_[6]}, o[4];
             o[0] = dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2] - dq[3] * q[3];
             o[1] = dq[0] * q[1] + dq[1] * q[0] + dq[2] * q[3] - dq[3] * q[2];
             o[2] = dq[0] * q[2] - dq[1] * q[3] + dq[2] * q[0] + dq[3] * q[1];
             o[3] = dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1] + dq[3] * q[0];
-            T nn = T(1) / std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+            T nn = T(1) / mth::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
             for (int a = 0; a < 4; ++a) gc_[3 + a] = o[a] * nn;
         }
         for (int j = 0; j < NJ; ++j) gc_[7 + j] += dt * gv_[6 + j];
@@ -645,7 +691,7 @@ template <typename T> struct Env {
         T e[3] = {v[0], v[1], v[2] - vtn};
         T ls[3]; for (int r = 0; r < 3; ++r) ls[r] = lo[r] - (Ginv[r][0] * e[0] + Ginv[r][1] * e[1] + Ginv[r][2] * e[2]);
         if (!(ls[2] > T(0))) { ln[0] = ln[1] = ln[2] = 0; return; }
-        T lt = std::sqrt(ls[0] * ls[0] + ls[1] * ls[1]);
+        T lt = mth::sqrt(ls[0] * ls[0] + ls[1] * ls[1]);
         if (lt <= mu * ls[2]) { ln[0] = ls[0]; ln[1] = ls[1]; ln[2] = ls[2]; return; }
         // b = velocity with zero impulse at this contact
         T b[3]; for (int r = 0; r < 3; ++r) b[r] = v[r] - (G[r][0] * lo[0] + G[r][1] * lo[1] + G[r][2] * lo[2]);
@@ -658,7 +704,7 @@ template <typename T> struct Env {
             T l0 = mu * lnz * dx, l1 = mu * lnz * dy;
             T vx = b[0] + G[0][0] * l0 + G[0][1] * l1 + G[0][2] * lnz;
             T vy = b[1] + G[1][0] * l0 + G[1][1] * l1 + G[1][2] * lnz;
-            T vn = std::sqrt(vx * vx + vy * vy);
+            T vn = mth::sqrt(vx * vx + vy * vy);
             if (vn > T(1e-9)) { dx = -vx / vn; dy = -vy / vn; }
         }
         {   // final normal solve with the converged direction
@@ -679,29 +725,29 @@ template <typename T> struct Env {
             up = up * ratio;
             T low = (s < -MotorCriticalSpeed) ? ((-MotorMaxSpeed - s) / (-MotorMaxSpeed + MotorCriticalSpeed) * -MotorMaxTorque) : -MotorMaxTorque;
             low = low * ratio;
-            torque[i] = std::fmax(std::fmin(torque[i], up), low);
+            torque[i] = mth::fmax(mth::fmin(torque[i], up), low);
         }
     }
 
     // ENV:1687-1751
     void inverse_kinematics(T x, T y, T z, T l_hip, T l_thigh, T l_calf, T* theta, bool is_right) const {
-        T ll = std::sqrt(x * x + y * y + z * z);
+        T ll = mth::sqrt(x * x + y * y + z * z);
         if (ll > max_len) { x = x * (max_len - T(1e-5)) / ll; y = y * (max_len - T(1e-5)) / ll; z = z * (max_len - T(1e-5)) / ll; }
         T temp, temp1, temp2 = 0;
-        if (is_right) { temp = (-z * l_hip - std::sqrt(y * y * (z * z + y * y - l_hip * l_hip))) / (z * z + y * y); if (std::fabs(temp) <= 1) theta[0] = std::asin(temp); }
-        else          { temp = ( z * l_hip + std::sqrt(y * y * (z * z + y * y - l_hip * l_hip))) / (z * z + y * y); if (std::fabs(temp) <= 1) theta[0] = std::asin(temp); }
-        T lr = std::sqrt(x * x + y * y + z * z - l_hip * l_hip);
+        if (is_right) { temp = (-z * l_hip - mth::sqrt(y * y * (z * z + y * y - l_hip * l_hip))) / (z * z + y * y); if (mth::fabs(temp) <= 1) theta[0] = mth::asin(temp); }
+        else          { temp = ( z * l_hip + mth::sqrt(y * y * (z * z + y * y - l_hip * l_hip))) / (z * z + y * y); if (mth::fabs(temp) <= 1) theta[0] = mth::asin(temp); }
+        T lr = mth::sqrt(x * x + y * y + z * z - l_hip * l_hip);
         lr = (lr > (l_thigh + l_calf)) ? (l_thigh + l_calf - T(1e-4)) : lr;
         temp = (l_thigh * l_thigh + l_calf * l_calf - lr * lr) / 2 / l_thigh / l_calf + T(1e-5);
-        if (std::fabs(temp) <= 1) theta[2] = -(T(BP5O_PI) - std::acos(temp));
+        if (mth::fabs(temp) <= 1) theta[2] = -(T(BP5O_PI) - mth::acos(temp));
         temp1 = x / lr;
         temp2 = (lr * lr + l_thigh * l_thigh - l_calf * l_calf) / 2 / lr / l_thigh - T(1e-5);
-        if (std::fabs(temp1) <= 1 && std::fabs(temp2) <= 1) theta[1] = std::acos(temp2) - std::asin(temp1);
+        if (mth::fabs(temp1) <= 1 && mth::fabs(temp2) <= 1) theta[1] = mth::acos(temp2) - mth::asin(temp1);
     }
 
     // toe target for leg i at absolute time tt   (body of the loops at ENV:1802-1842 / ENV:1844-1885)
     void leg_reference(int i, T tt, T* joint3, T* toe3) const {
-        T real_phase = std::fmod(tt + phase_[i] * period_, period_) / period_;
+        T real_phase = mth::fmod(tt + phase_[i] * period_, period_) / period_;
         // NB: the reference computes fmod(current_time_ + phase*period [- dt], period); tt already carries the -dt
         T anti_flag = (i < 2) ? T(1.0) : T(-1.0);
         V3<T> p0, pf, toe;
@@ -730,9 +776,9 @@ template <typename T> struct Env {
         side_step_ = command_filtered[1] * lam_ * period_;            // ENV:1775
         rot_step_ = command_filtered[2] * period_ * T(0.4);           // ENV:1777
         if (flag_HeightVariable) {                                    // ENV:1779-1792
-            T ratio = std::fabs(command_filtered[0]) / Vx_max;
-            if (Vy_max > 0) ratio = std::fmax(ratio, std::fabs(command_filtered[1]) / Vy_max);
-            if (omega_max > 0) ratio = std::fmax(ratio, std::fabs(command_filtered[2] / omega_max));
+            T ratio = mth::fabs(command_filtered[0]) / Vx_max;
+            if (Vy_max > 0) ratio = mth::fmax(ratio, mth::fabs(command_filtered[1]) / Vy_max);
+            if (omega_max > 0) ratio = mth::fmax(ratio, mth::fabs(command_filtered[2] / omega_max));
             up_height_ = (ratio > T(0.1)) ? up_height_max_ : ratio * up_height_max_;
         }
         T toe3[3];
@@ -784,7 +830,7 @@ template <typename T> struct Env {
         } else {
             for (int i = 0; i < 4; ++i) {
                 float real_phase = float(current_time() + phase_[i] * period_);             // ENV:1172-1181 (float locals)
-                real_phase = float(std::fmod(T(real_phase), period_) / period_);
+                real_phase = float(mth::fmod(T(real_phase), period_) / period_);
                 contact_filtered[i] = (T(real_phase) < lam_) ? T(1) : T(0); contact_[i] = contact_filtered[i];
             }
         }
@@ -795,20 +841,20 @@ template <typename T> struct Env {
         for (int i = 0; i < 4; ++i) {
             contact_force_norm[i] = 0;
             if (foot_in_contact[i]) {
-                T n = std::sqrt(foot_impulse[i][0] * foot_impulse[i][0] + foot_impulse[i][1] * foot_impulse[i][1] + foot_impulse[i][2] * foot_impulse[i][2]);
+                T n = mth::sqrt(foot_impulse[i][0] * foot_impulse[i][0] + foot_impulse[i][1] * foot_impulse[i][1] + foot_impulse[i][2] * foot_impulse[i][2]);
                 contact_force_norm[i] = n / control_dt_;   // ENV:1208 (divides by control_dt, quirk 4)
             }
         }
         Kin k; kinematics(gc_, gv_, k);
-        for (int i = 0; i < 4; ++i) contact_vel_norm[i] = std::sqrt(dot(k.vtoe[i], k.vtoe[i]));   // ENV:1224-1231
+        for (int i = 0; i < 4; ++i) contact_vel_norm[i] = mth::sqrt(dot(k.vtoe[i], k.vtoe[i]));   // ENV:1224-1231
     }
 
     // ENV:956-1004
     void updateObservation(uint32_t pbase) {
         for (int i = 0; i < 35; ++i) obDouble_[i] = 0;
         if (flag_manual || flag_ManualTraj) {
-            obDouble_[3] = std::sin(2 * T(BP5O_PI) * current_time() / period_);
-            obDouble_[4] = std::cos(2 * T(BP5O_PI) * current_time() / period_);
+            obDouble_[3] = mth::sin(2 * T(BP5O_PI) * current_time() / period_);
+            obDouble_[4] = mth::cos(2 * T(BP5O_PI) * current_time() / period_);
         } else {
             const float* row = ref + (size_t)frame_idx * 30; obDouble_[3] = T(row[25]); obDouble_[4] = T(row[26]);   // ENV:972
         }
@@ -834,8 +880,8 @@ template <typename T> struct Env {
         uint32_t r[4]; Philox::gen(seed, env_id, tick, purpose, r);
         for (int p = 0; p < 2; ++p) {
             float u1 = (float)((r[2 * p] >> 8) + 1u) * (1.0f / 16777216.0f), u2 = u01(r[2 * p + 1]);
-            T rad = std::sqrt(T(-2.0) * std::log(T(u1))), ang = T(6.283185307179586) * T(u2);
-            g[2 * p] = rad * std::cos(ang); g[2 * p + 1] = rad * std::sin(ang);
+            T rad = mth::sqrt(T(-2.0) * mth::log(T(u1))), ang = T(6.283185307179586) * T(u2);
+            g[2 * p] = rad * mth::cos(ang); g[2 * p + 1] = rad * mth::sin(ang);
         }
     }
 
@@ -847,30 +893,30 @@ template <typename T> struct Env {
             V3<T> e = tmul(bodyFrameMatrix_, k.toe[i]);   // R^T (p_toe - p_base)  ENV:1452-1456
             for (int a = 0; a < 3; ++a) { EndEffector_[3 * i + a] = e[a]; T d = e[a] - EndEffectorRef_[3 * i + a]; ee += d * d; }
         }
-        EndEffectorReward = EECoeff * std::exp(-40 * ee);                                              // ENV:1459-1460
+        EndEffectorReward = EECoeff * mth::exp(-40 * ee);                                              // ENV:1459-1460
         T dz = gc_[2] - ground_height() - stand_height_;     // height above the terrain under the trunk (flat ground: z)
-        BodyCenterReward = BodyPosCoeff * std::exp(-80 * (dz * dz));                                   // ENV:1467-1476
-        BodyAttitudeReward = BodyAttiCoeff * std::exp(-80 * (obDouble_[29] * obDouble_[29] + obDouble_[30] * obDouble_[30]));  // ENV:1481-1483
+        BodyCenterReward = BodyPosCoeff * mth::exp(-80 * (dz * dz));                                   // ENV:1467-1476
+        BodyAttitudeReward = BodyAttiCoeff * mth::exp(-80 * (obDouble_[29] * obDouble_[29] + obDouble_[30] * obDouble_[30]));  // ENV:1481-1483
         T jr = 0, jd = 0;
         for (int j = 0; j < NJ; ++j) { T a = jointRef_[j] - gc_[7 + j]; jr += a * a; T b = jointDotRef_[j] - gv_[6 + j]; jd += b * b; }
-        JointReward = JointMimicCoeff * T(0.25) * std::exp(T(-2.0) * jr);                              // ENV:1492-1493
-        JointDotReward = JointMimicCoeff * T(0.75) * std::exp(-control_dt_ * jd);                      // ENV:1494-1495
+        JointReward = JointMimicCoeff * T(0.25) * mth::exp(T(-2.0) * jr);                              // ENV:1492-1493
+        JointDotReward = JointMimicCoeff * T(0.75) * mth::exp(-control_dt_ * jd);                      // ENV:1494-1495
         T lref[3] = {flag_WildCat ? -command_filtered[0] : command_filtered[0], command_filtered[1], 0};   // ENV:1500-1502
         T aref[3] = {0, 0, command_filtered[2]};
         T le = 0, ae = 0; for (int a = 0; a < 3; ++a) { T d = bodyLinearVel_[a] - lref[a]; le += d * d; T e2 = bodyAngularVel_[a] - aref[a]; ae += e2 * e2; }
-        VelocityReward = VelKeepCoeff / 2 * std::exp(-2 * le) + VelKeepCoeff / 2 * std::exp(-2 * ae);  // ENV:1504-1505
+        VelocityReward = VelKeepCoeff / 2 * mth::exp(-2 * le) + VelKeepCoeff / 2 * mth::exp(-2 * ae);  // ENV:1504-1505
         T tn = 0, td = 0;
         for (int j = 0; j < NJ; ++j) { torque[j] = torque[j] / torque_limit[j]; tn += torque[j] * torque[j]; T d = torque[j] - torque_last[j]; td += d * d; }   // ENV:1511
-        TorqueReward = TorqueCoeff / T(2.0) * std::exp(T(-0.1) * tn) + TorqueCoeff / T(2.0) * std::exp(T(-0.1) / control_dt_ * td);   // ENV:1513-1514
+        TorqueReward = TorqueCoeff / T(2.0) * mth::exp(T(-0.1) * tn) + TorqueCoeff / T(2.0) * mth::exp(T(-0.1) / control_dt_ * td);   // ENV:1513-1514
         for (int j = 0; j < NJ; ++j) torque_last[j] = torque[j];                                        // ENV:1515
         T cr = 0;
         for (int i = 0; i < 4; ++i) {                                                                   // ENV:1521-1528
             T real_phase = current_time() + phase_[i] * period_;
-            real_phase = std::fmod(real_phase, period_) / period_;
+            real_phase = mth::fmod(real_phase, period_) / period_;
             cr += 4 * contact_vel_norm[i] * contact_vel_norm[i] * smooth_function(real_phase, T(2), lam_);
             cr += 2 * (contact_force_norm[i] / T(12.5)) * (contact_force_norm[i] / T(12.5)) * smooth_function2(real_phase, T(2), lam_);
         }
-        ContactReward = ContactCoeff * std::exp(-2 * cr);                                               // ENV:1529
+        ContactReward = ContactCoeff * mth::exp(-2 * cr);                                               // ENV:1529
         return (EndEffectorReward + BodyCenterReward + JointReward + JointDotReward + VelocityReward + BodyAttitudeReward + TorqueReward + ContactReward);  // ENV:1546-1547
     }
 
@@ -945,11 +991,11 @@ template <typename T> struct Env {
             // ---- trunk box (centred on the trunk origin, URDF:26): closest point of the box to the sphere centre
             V3<T> dw(met_p[0] - gc_[0], met_p[1] - gc_[1], met_p[2] - gc_[2]);
             V3<T> d = transpose(R) * dw;
-            V3<T> q(std::min(std::max(d.x, -model.box_half.x), model.box_half.x), std::min(std::max(d.y, -model.box_half.y), model.box_half.y),
-                    std::min(std::max(d.z, -model.box_half.z), model.box_half.z));
+            V3<T> q(mth::min(mth::max(d.x, -model.box_half.x), model.box_half.x), mth::min(mth::max(d.y, -model.box_half.y), model.box_half.y),
+                    mth::min(mth::max(d.z, -model.box_half.z), model.box_half.z));
             V3<T> del = d - q; T dist2 = dot(del, del);
             if (dist2 < met_r * met_r && dist2 > T(1e-12)) {
-                V3<T> n = R * ((T(1) / std::sqrt(dist2)) * del), x = R * q;
+                V3<T> n = R * ((T(1) / mth::sqrt(dist2)) * del), x = R * q;
                 V3<T> vb(gv_[0] + du[0], gv_[1] + du[1], gv_[2] + du[2]), wb(gv_[3] + du[3], gv_[4] + du[4], gv_[5] + du[5]);
                 V3<T> vpt = vb + cross(wb, x);
                 T vrel = n.x * (met_v[0] - vpt.x) + n.y * (met_v[1] - vpt.y) + n.z * (met_v[2] - vpt.z);
@@ -973,8 +1019,8 @@ template <typename T> struct Env {
                 T vn = nn.x * met_v[0] + nn.y * met_v[1] + nn.z * met_v[2];
                 if (vn < T(0)) {
                     met_v[0] -= vn * nn.x; met_v[1] -= vn * nn.y; met_v[2] -= vn * nn.z;
-                    T vt = std::sqrt(met_v[0] * met_v[0] + met_v[1] * met_v[1] + met_v[2] * met_v[2]);
-                    if (vt > T(1e-9)) { T dv = std::min(vt, T(0.8) * (-vn)) / vt; met_v[0] -= dv * met_v[0]; met_v[1] -= dv * met_v[1]; met_v[2] -= dv * met_v[2]; }
+                    T vt = mth::sqrt(met_v[0] * met_v[0] + met_v[1] * met_v[1] + met_v[2] * met_v[2]);
+                    if (vt > T(1e-9)) { T dv = mth::min(vt, T(0.8) * (-vn)) / vt; met_v[0] -= dv * met_v[0]; met_v[1] -= dv * met_v[1]; met_v[2] -= dv * met_v[2]; }
                 }
             }
             for (int a = 0; a < 3; ++a) met_p[a] += met_v[a] * dt;
@@ -1005,7 +1051,7 @@ template <typename T> struct Env {
                 gc_[2] += T(0.03) * T(usym(ra[0])) * ratio;
                 gc_[3] += T(0.1) * T(usym(ra[1])) * ratio; gc_[4] += T(0.1) * T(usym(ra[2])) * ratio;
                 gc_[5] += T(0.1) * T(usym(ra[3])) * ratio; gc_[6] += T(0.1) * T(usym(rb[0])) * ratio;
-                T qn = std::sqrt(gc_[3] * gc_[3] + gc_[4] * gc_[4] + gc_[5] * gc_[5] + gc_[6] * gc_[6]);
+                T qn = mth::sqrt(gc_[3] * gc_[3] + gc_[4] * gc_[4] + gc_[5] * gc_[5] + gc_[6] * gc_[6]);
                 for (int i = 3; i < 7; ++i) gc_[i] /= qn;
                 gv_[2] += T(0.1) * T(usym(rb[1])) * ratio; gv_[3] += T(0.3) * T(usym(rb[2])) * ratio; gv_[4] += T(0.3) * T(usym(rb[3])) * ratio;
             }

@@ -164,6 +164,29 @@ void bp5o_philox_raw(const unsigned* ctr, const unsigned* key, unsigned* out) {
 // CPU baseline timing: `steps` control steps over all envs with the same OpenMP
 // structure as VEC:273; actions = clip(N(0, sigma^2), +-1) (sigma = 0 -> zeros).  Returns seconds spent
 // inside step() only (std::chrono::steady_clock), env-steps = steps * num_envs.
+// F_step measured by the oracle's op counter.  Builds the same vec-env on the counting scalar (single thread), runs `warm`
+// control steps, then counts every floating-point operation of `steps` further steps (actions ~ clip(N(0, sigma^2))).
+// out[0..5] = add/sub, mul, div, sqrt, transcendental, compare -- each per env-step; returns add + mul + div + sqrt + transcendental.
+double bp5o_count_flops(const char* cfg, int warm, int steps, double sigma, unsigned seed, double* out6) {
+    try {
+        Cfg c = Cfg::parse(cfg);
+        VecEnv<Counted> V; V.create(c, 0);
+        int n = (int)V.envs.size();
+        std::vector<float> act((size_t)n * 12, 0.f), ob((size_t)n * 35), rew(n), extra((size_t)n * 6);
+        std::vector<uint8_t> done(n);
+        std::mt19937 gen(seed); std::normal_distribution<float> nd(0.f, 1.f);
+        V.reset_all();
+        for (int s = 0; s < warm + steps; ++s) {
+            if (s == warm) op_count() = OpCount();
+            if (sigma > 0) for (auto& a : act) { float v = (float)sigma * nd(gen); a = v > 1.f ? 1.f : (v < -1.f ? -1.f : v); }
+            V.step(act.data(), ob.data(), rew.data(), done.data(), extra.data());
+        }
+        const OpCount& k = op_count(); const double d = (double)n * steps;
+        if (out6) { out6[0] = k.add / d; out6[1] = k.mul / d; out6[2] = k.div / d; out6[3] = k.sqrt / d; out6[4] = k.trans / d; out6[5] = k.cmp / d; }
+        return (k.add + k.mul + k.div + k.sqrt + k.trans) / d;
+    } catch (const std::exception& e) { fprintf(stderr, "bp5o_count_flops: %s\n", e.what()); return -1.0; }
+}
+
 double bp5o_time_steps(void* h, int steps, double sigma, unsigned seed, long* n_done_out) {
     int n = bp5o_num_envs(h);
     std::vector<float> act((size_t)n * 12, 0.f), ob((size_t)n * 35), rew(n), extra((size_t)n * 6);

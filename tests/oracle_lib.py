@@ -45,6 +45,17 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def count_flops(cfg: dict, warm=200, steps=300, sigma=0.1, seed=0):
+    """Floating-point operations per env-step of the oracle itself (Counted scalar): (total, dict of op classes)"""
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import to_kv_string
+    L = lib()
+    L.bp5o_count_flops.restype = C.c_double
+    L.bp5o_count_flops.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_void_p]
+    out = np.zeros(6)
+    total = L.bp5o_count_flops(to_kv_string(dict(cfg, num_threads=1)).encode(), warm, steps, sigma, seed, out.ctypes.data)
+    return total, dict(zip(("add", "mul", "div", "sqrt", "transcendental", "compare"), out))
+
+
 class Oracle:
     """The reference-semantics CPU vec-env: precision 'double' (like the reference) or 'float'."""
 

@@ -257,3 +257,15 @@ def test_meteor_sphere_schedule_flight_and_bounce():
         o.set_state(i, s[i])
     o.step(a); m = o.get_meteor(); s2 = o.get_state()
     assert (m[:, 6] == 0).all() and np.allclose(m[:, 3:6], 0)                # static again, just placed above the robot (pose at the start of that step)
+
+
+def test_oracle_op_counter():
+    """the oracle carries an op counter.  It counts the oracle's own (dense-Jacobian, dense 18x18 Cholesky) arithmetic, which is
+    several times what the block-arrow CUDA formulation executes; bench.py therefore uses the kernel's measured count for the roofline
+    and reports this one beside it (profiles/kernel_counts.json)."""
+    from oracle_lib import count_flops
+    cfg = trot_cfg(num_envs=8, StochasticDynamics=True, ObsNoise=2.0)
+    f1, k1 = count_flops(cfg, warm=60, steps=40)
+    f2, k2 = count_flops(cfg, warm=60, steps=40)
+    assert f1 == f2 and 3e5 < f1 < 2e6                       # deterministic; 8 substeps x O(1e5) operations
+    assert k1["mul"] > k1["div"] > k1["sqrt"] > 0 and k1["transcendental"] > 8 * 12          # 12 joint sin/cos pairs per substep at least

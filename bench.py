@@ -325,6 +325,7 @@ def run_b200(args):
                     "frac": N * B_STEP_BYTES / (step_kernel_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_env_step": B_STEP_BYTES}}
     if flop_per_env_step:
         ach = N * flop_per_env_step / (step_kernel_ms * 1e-3) / 1e12
+        roof["oracle_flop_per_env_step"] = counts.get("oracle", {}).get("flop_per_env_step")   # dense CPU formulation, reported only
         roof.update({"achieved": ach, "frac": ach / roof["peak"], "flop_per_env_step": flop_per_env_step,
                      "flop_source": counts.get("env_step", {}).get("source", "ncu")})
     else:

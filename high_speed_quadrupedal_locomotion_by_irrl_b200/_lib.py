@@ -58,6 +58,7 @@ def load() -> C.CDLL:
     L.irrl_policy_destroy.restype = None
     L.irrl_policy_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     L.irrl_policy_set_act_path.argtypes = [C.c_int]
+    L.irrl_parse_urdf.argtypes = [C.c_char_p, C.c_void_p]
     L.irrl_tc_timeline.argtypes = [C.c_int, C.c_void_p]
     L.irrl_tc_mma_rate.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
     L.irrl_tc_gemm_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]

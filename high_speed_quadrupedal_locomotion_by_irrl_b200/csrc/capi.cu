@@ -17,6 +17,7 @@
 
 #include "../../include/irrl_b200.h"
 #include "env_kernels.h"
+#include "urdf_reader.h"
 
 using namespace irrl;
 
@@ -246,6 +247,26 @@ void model_defaults(EnvParams& P) {
     P.m3 = (float)(ms + mt); P.com3z = (float)zc; P.knee_z = -0.201f;                                           // URDF:106
 }
 
+// robot description found under resourceDir (ENV:231): overrides the built-in bp5 constants
+void apply_urdf(EnvParams& P, const CompactModel& M) {
+    for (int i = 0; i < 3; ++i) { P.I0[i] = (float)M.I0[i]; P.I1[i] = (float)M.I1[i]; P.I3[i] = (float)M.I3[i]; P.rotor[i] = (float)M.rotor[i]; P.box_half[i] = (float)M.box_half[i];
+                                  P.com0[i] = (float)M.com0[i]; P.com1[i] = (float)M.com1[i]; P.com2[i] = (float)M.com2[i]; }
+    for (int i = 0; i < 4; ++i) P.I2[i] = (float)M.I2[i];
+    P.off1x = (float)M.off1x; P.off1y = (float)M.off1y; P.off2y = (float)M.off2y; P.toe_z = (float)M.toe_z; P.toe_r = (float)M.toe_r;
+    P.m0 = (float)M.m0; P.m1 = (float)M.m1; P.m2 = (float)M.m2; P.m3 = (float)M.m3; P.com3z = (float)M.com3z; P.knee_z = (float)M.knee_z;
+    P.joint_damping = (float)M.joint_damping;
+}
+// the model fields of EnvParams in a fixed order (irrl_parse_urdf, tests)
+void model_to_array(const EnvParams& P, float* o) {
+    int k = 0;
+    for (int i = 0; i < 3; ++i) o[k++] = P.I0[i]; for (int i = 0; i < 3; ++i) o[k++] = P.I1[i]; for (int i = 0; i < 4; ++i) o[k++] = P.I2[i]; for (int i = 0; i < 3; ++i) o[k++] = P.I3[i];
+    for (int i = 0; i < 3; ++i) o[k++] = P.rotor[i];
+    o[k++] = P.off1x; o[k++] = P.off1y; o[k++] = P.off2y; o[k++] = P.toe_z; o[k++] = P.toe_r;
+    for (int i = 0; i < 3; ++i) o[k++] = P.box_half[i];
+    o[k++] = P.joint_damping; o[k++] = P.m0; for (int i = 0; i < 3; ++i) o[k++] = P.com0[i]; o[k++] = P.m1; for (int i = 0; i < 3; ++i) o[k++] = P.com1[i];
+    o[k++] = P.m2; for (int i = 0; i < 3; ++i) o[k++] = P.com2[i]; o[k++] = P.m3; o[k++] = P.com3z; o[k++] = P.knee_z;      // 40 values
+}
+
 int load_csv(const std::string& path, std::vector<float>& out, int& rows, int& cols) {
     // readCSV_m  VEC:33-76
     std::ifstream in(path); rows = 0; cols = 0;
@@ -317,6 +338,21 @@ int irrl_create(const char* resource_dir, const char* cfg_yaml, int device, int 
     if (!y.parse(cfg_yaml, err)) { delete E; return fail(-3, err); }
     model_defaults(E->P);
     if (int rc = read_cfg(E, y)) { delete E; return rc; }
+    // ENV:231: the robot description lives in the resource directory.  When it is there it replaces the built-in bp5 constants
+    // (a description the compact model cannot represent is an error); when it is not, the built-in constants of that very file are used.
+    if (!E->resource_dir.empty()) {
+        for (const char* rel : {"/black_panther.urdf", "/urdf/black_panther.urdf"}) {
+            const std::string path = E->resource_dir + rel;
+            std::ifstream probe(path);
+            if (!probe.is_open()) continue;
+            CompactModel M; std::string uerr;
+            if (int rc = read_urdf(path, M, uerr)) { (void)rc; delete E; return fail(-3, path + ": " + uerr); }
+            const float yaml_damping = E->P.joint_damping;
+            apply_urdf(E->P, M);
+            if (y.has("joint_damping")) E->P.joint_damping = yaml_damping;
+            break;
+        }
+    }
     E->P.env_offset = (uint32_t)env_offset;
     E->extra_names = {"EndEffectorReward(0.15)", "Height_Keep_Reward(0.1)", "base height", "Balance_Keep_Reward(0.1)", "JointReward(0.65)", "VelocityReward(0.2)"};   // ENV:944-949
     *out = reinterpret_cast<irrl_env*>(E);
@@ -795,6 +831,13 @@ int irrl_policy_set_params(irrl_policy* pol, const float* params) {
     std::vector<float> hp(IRRL_POLICY_NUM_PARAMS);
     CUDA_OK(cudaMemcpy(hp.data(), Pn->d_params, hp.size() * sizeof(float), cudaMemcpyDeviceToHost));
     return upload_derived(Pn, hp.data());
+}
+// CPU-callable: the compact robot model read from a URDF file as 40 floats (order of model_to_array); path NULL -> the built-in constants
+int irrl_parse_urdf(const char* path, float* out40) {
+    if (!out40) return fail(-1, "null argument");
+    EnvParams P{}; model_defaults(P); P.joint_damping = 0.01f;
+    if (path) { CompactModel M; std::string uerr; if (int rc = read_urdf(path, M, uerr)) return fail(rc, std::string(path) + ": " + uerr); apply_urdf(P, M); }
+    model_to_array(P, out40); return 0;
 }
 int irrl_policy_set_act_path(int mode) {
     if (mode < 0 || mode > 2) return fail(-1, "irrl_policy_set_act_path: mode must be 0 (auto), 1 (fp32 FMA kernel) or 2 (tcgen05 kernel)");

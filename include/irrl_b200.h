@@ -98,6 +98,12 @@ int irrl_get_sphere_info(irrl_env* env, float* out /*[N,4]*/);       /* Environm
  * velocity(3), mode (0 just placed / 1 falling), radius, mass.  -3 when Crutial is False. */
 int irrl_get_meteor(irrl_env* env, float* out /*[N,9]*/);
 int irrl_set_meteor(irrl_env* env, const float* in /*[N,9]*/);
+/* The robot description of the resource directory (Environment.hpp:231 addArticulatedSystem(resourceDir + "/black_panther.urdf")).
+ * irrl_create reads <resource_dir>/black_panther.urdf (or <resource_dir>/urdf/black_panther.urdf) when present and fails if its four
+ * legs are not mirror images (the kernels carry one set of leg constants); without the file the built-in constants of the shipped
+ * description are used.  irrl_parse_urdf needs no GPU: 40 floats = I0(3) I1(3) I2(xx,yy,zz,|yz|) I3(3) rotor(3) off1x off1y off2y
+ * toe_z toe_r box_half(3) joint_damping m0 com0(3) m1 com1(3) m2 com2(3) m3 com3z knee_z; path NULL returns the built-in model. */
+int irrl_parse_urdf(const char* path, float* out40);
 int irrl_get_model_params(irrl_env* env, float* out /*[N,94]: mu,rest,thr, 13 x (mass, com3, joint offset3)*/);
 
 /* ---- state injection / extraction (the reference only has setState internally, Environment.hpp:618-622).

@@ -241,6 +241,25 @@ template <typename T> struct Model {
         gravity = T(9.81);
         joint_damping = T(0.01);
     }
+    // A robot description other than the shipped one, as the compact mirror-symmetric model of include/irrl_b200.h (irrl_parse_urdf):
+    // I0(3) I1(3) I2(xx,yy,zz,|yz|) I3(3) rotor(3) off1x off1y off2y toe_z toe_r box_half(3) joint_damping m0 com0(3) m1 com1(3) m2 com2(3) m3 com3z knee_z
+    void set_compact(const double* m) {
+        const double *I0 = m, *I1 = m + 3, *I2 = m + 6, *I3 = m + 10, *rot = m + 13, *box = m + 21, *c0 = m + 26, *c1 = m + 30, *c2 = m + 34;
+        const double off1x = m[16], off1y = m[17], off2y = m[18], toe_z = m[19], toe_r = m[20], damp = m[24], m0 = m[25], m1 = m[29], m2 = m[33], m3 = m[37], com3z = m[38], knee_z = m[39];
+        b[0].mass = T(m0); b[0].com = {T(c0[0]), T(c0[1]), T(c0[2])};
+        b[0].I = M3<T>(); b[0].I.m[0][0] = T(I0[0]); b[0].I.m[1][1] = T(I0[1]); b[0].I.m[2][2] = T(I0[2]);
+        const int sxs[4] = {+1, +1, -1, -1}, sys[4] = {-1, +1, -1, +1};
+        for (int l = 0; l < 4; ++l) {
+            T sx = T(sxs[l]), sy = T(sys[l]);
+            Body<T>& a = b[1 + 3 * l]; a.off = {T(off1x) * sx, T(off1y) * sy, T(0)}; a.mass = T(m1); a.com = {T(c1[0]) * sx, T(c1[1]) * sy, T(c1[2])};
+            a.I = M3<T>(); a.I.m[0][0] = T(I1[0]); a.I.m[1][1] = T(I1[1]); a.I.m[2][2] = T(I1[2]); a.rotor = T(rot[0]);
+            Body<T>& t = b[2 + 3 * l]; t.off = {T(0), T(off2y) * sy, T(0)}; t.mass = T(m2); t.com = {T(c2[0]) * sx, T(c2[1]) * sy, T(c2[2])};
+            t.I = M3<T>(); t.I.m[0][0] = T(I2[0]); t.I.m[1][1] = T(I2[1]); t.I.m[2][2] = T(I2[2]); t.I.m[1][2] = t.I.m[2][1] = T(-I2[3]) * sy; t.rotor = T(rot[1]);
+            Body<T>& s = b[3 + 3 * l]; s.off = {T(0), T(0), T(knee_z)}; s.mass = T(m3); s.com = {T(0), T(0), T(com3z)};
+            s.I = M3<T>(); s.I.m[0][0] = T(I3[0]); s.I.m[1][1] = T(I3[1]); s.I.m[2][2] = T(I3[2]); s.rotor = T(rot[2]);
+        }
+        toe_off = {T(0), T(0), T(toe_z)}; toe_radius = T(toe_r); box_half = {T(box[0]), T(box[1]), T(box[2])}; joint_damping = T(damp);
+    }
 };
 
 // ------------------------------------------------------------------ configuration (YAML keys of ENV:1594-1659, VEC:146-171)
@@ -426,7 +445,7 @@ template <typename T> struct Env {
         MotorMaxTorque = T(c.get("MotorMaxTorque")); MotorCriticalSpeed = T(c.get("MotorCriticalSpeed")); MotorMaxSpeed = T(c.get("MotorMaxSpeed"));
         simulation_dt_ = T(c.get("simulation_dt")); control_dt_ = T(c.get("control_dt"));   // VEC:151-152
         // solver / model switches (new-spec, optional)
-        model.joint_damping = T(c.get_or("joint_damping", 0.01));
+        model.joint_damping = T(c.get_or("joint_damping", double(model.joint_damping)));
         solver_iters = (int)c.get_or("solver_iters", 10); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 1); solver_jacobi = (int)c.get_or("solver_jacobi", 1);
         mu = T(c.get_or("friction", 0.6)); restitution = T(c.get_or("restitution", 0.2)); rest_threshold = T(c.get_or("restitution_threshold", 0.01));
 
@@ -1101,10 +1120,11 @@ template <typename T> struct VecEnv {
     int num_threads = 1;
     uint32_t tick = 0;
     std::vector<float> ref; int ref_rows = 0;
-    void create(const Cfg& c, int env_offset = 0) {
+    void create(const Cfg& c, int env_offset = 0, const double* compact_model = nullptr) {
         int n = (int)c.get("num_envs"); num_threads = (int)c.get("num_threads");
         uint32_t seed = (uint32_t)(int)c.get("seedd");   // VEC:171 (double truncated to int)
         envs.resize(n);
+        if (compact_model) for (int i = 0; i < n; ++i) envs[i].model.set_compact(compact_model);
         for (int i = 0; i < n; ++i) envs[i].configure(c, (uint32_t)(env_offset + i), seed);
         if ((envs[0].flag_ManualTraj || envs[0].flag_manual) && !envs[0].flag_terrain) reset_all();   // VEC:172-182: init() resets every env once (tick 0); with a terrain the caller sets it first and then calls reset_all()
     }

@@ -112,6 +112,15 @@ void* bp5o_create(const char* cfg, int precision, int env_offset) {
     } catch (const std::exception& e) { fprintf(stderr, "bp5o_create: %s\n", e.what()); delete h; return nullptr; }
     return h;
 }
+// same as bp5o_create with a robot description other than the shipped one (40 numbers, see Model::set_compact)
+void* bp5o_create_with_model(const char* cfg, int precision, int env_offset, const double* model40) {
+    Handle* h = new Handle(); h->precision = precision;
+    try {
+        Cfg c = Cfg::parse(cfg);
+        if (precision == 0) h->d.create(c, env_offset, model40); else h->f.create(c, env_offset, model40);
+    } catch (const std::exception& e) { fprintf(stderr, "bp5o_create_with_model: %s\n", e.what()); delete h; return nullptr; }
+    return h;
+}
 void bp5o_destroy(void* h) { delete H(h); }
 int bp5o_state_dim() { return STATE_DIM; }
 int bp5o_num_envs(void* h) { return H(h)->precision == 0 ? (int)H(h)->d.envs.size() : (int)H(h)->f.envs.size(); }

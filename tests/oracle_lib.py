@@ -59,10 +59,15 @@ def count_flops(cfg: dict, warm=200, steps=300, sigma=0.1, seed=0):
 class Oracle:
     """The reference-semantics CPU vec-env: precision 'double' (like the reference) or 'float'."""
 
-    def __init__(self, cfg: dict, precision="double", env_offset=0):
+    def __init__(self, cfg: dict, precision="double", env_offset=0, model40=None):
         from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import to_kv_string
         self.L = lib()
-        self.h = C.c_void_p(self.L.bp5o_create(to_kv_string(cfg).encode(), 0 if precision == "double" else 1, env_offset))
+        if model40 is None:
+            self.h = C.c_void_p(self.L.bp5o_create(to_kv_string(cfg).encode(), 0 if precision == "double" else 1, env_offset))
+        else:   # a robot description other than the shipped one: the 40 numbers of irrl_parse_urdf (include/irrl_b200.h)
+            m = np.ascontiguousarray(model40, np.float64); assert m.shape == (40,)
+            self.L.bp5o_create_with_model.restype = C.c_void_p
+            self.h = C.c_void_p(self.L.bp5o_create_with_model(to_kv_string(cfg).encode(), 0 if precision == "double" else 1, env_offset, _p(m)))
         if not self.h:
             raise RuntimeError("oracle creation failed (missing cfg key?)")
         self.n = self.L.bp5o_num_envs(self.h)

@@ -61,3 +61,22 @@ def test_the_shipped_description_gives_the_builtin_constants():
     rc, got, err = _parse(L, REF)
     assert rc == 0, err
     assert np.array_equal(got, builtin)
+
+
+def test_oracle_accepts_the_same_compact_model():
+    """the CPU oracle can be built on the 40 numbers of a description (parity tests under a modified robot, tests/test_gpu_urdf.py)"""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from oracle_lib import Oracle
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg
+    L = _lib()
+    _, builtin, _ = _parse(L, None)
+    cfg = trot_cfg(num_envs=2, num_threads=1, StochasticDynamics=False, ObsNoise=0.0)
+    base, same = Oracle(cfg), Oracle(cfg, model40=builtin.astype(np.float64))
+    m = builtin.astype(np.float64).copy(); m[25] = 5.25          # trunk mass
+    heavy = Oracle(cfg, model40=m)
+    for o in (base, same, heavy):
+        o.set_tick(1); o.reset()
+    M0, Ms, Mh = base.mass_and_h(0)[0], same.mass_and_h(0)[0], heavy.mass_and_h(0)[0]
+    assert abs(M0[0, 0] - (3.72 + 4 * (0.54 + 0.636 + 0.114))) < 1e-9 and np.abs(Ms - M0).max() < 1e-6        # float32 rounding of the 40 numbers
+    assert abs(Mh[0, 0] - M0[0, 0] - (5.25 - 3.72)) < 1e-6

@@ -201,7 +201,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         // optional solver / model switches of this implementation
         auto opt = [&](const char* k, double dflt) { double v; return y.has(k) && num(k, v) ? v : dflt; };
         P.joint_damping = (float)opt("joint_damping", 0.01);                                                     // URDF:56
-        P.solver_iters = (int)opt("solver_iters", 10); P.slide_iters = (int)opt("slide_iters", 1); P.solver_tol = (float)opt("solver_tol", 1e-5);
+        P.solver_iters = (int)opt("solver_iters", 30); P.jacobi_sweeps = (int)opt("jacobi_sweeps", 6); P.slide_iters = (int)opt("slide_iters", 1); P.solver_tol = (float)opt("solver_tol", 1e-5);
         E->stair_rise = opt("stair_rise", 0.08); E->stair_run = opt("stair_run", 0.3); E->stair_start = opt("stair_start", 1.0); E->terrain_seed = (int)opt("terrain_seed", 0);
         P.mu = (float)opt("friction", 0.6); P.restitution = (float)opt("restitution", 0.2); P.rest_threshold = (float)opt("restitution_threshold", 0.01);   // ENV:433
     }
@@ -546,6 +546,11 @@ int irrl_set_simulation_time_step(irrl_env* env, double dt) { ENV(env); E->P.sim
 int irrl_set_control_time_step(irrl_env* env, double dt) {
     ENV(env); E->P.control_dt = (float)dt; E->control_dt_d = dt; E->P.loop_count = int(dt / E->sim_dt_d + 1e-10);
     E->P.disturb_every = int(E->period_d / dt * 10.0); E->P.meteor_every = int(5.0 * E->period_d / dt);     // ENV:746, 731 evaluate control_dt_ at every step
+    if (E->d_ref) {   // frame_len = int(max_time / control_dt_) (ENV:539) follows the control step; the table must still be long enough
+        const int frame_len = int(E->max_time_d / dt);
+        if (E->P.ref_rows / 2 <= frame_len + 10) return fail(-3, "setControlTimeStep: the reference table is too short for this control step (ENV:538-539, 571)");
+        E->P.frame_len = frame_len;
+    }
     return 0;
 }
 int irrl_curriculum_update(irrl_env* env) { ENV(env); return 0; }
@@ -740,6 +745,10 @@ int irrl_get_heightfield(irrl_env* env, float* heights, int* nx, int* ny, double
 int irrl_set_ref_traj(irrl_env* env, const float* table, int rows) {
     ENV(env);
     if (!table || rows <= 0) return fail(-1, "empty reference table");
+    {   // reset() draws its start row from [0, rows/2 - frame_len - 10) (ENV:571): a shorter table would index before row 0
+        const int frame_len = int(E->max_time_d / E->control_dt_d);
+        if (rows / 2 <= frame_len + 10) return fail(-3, "reference table too short: rows/2 = " + std::to_string(rows / 2) + " must exceed max_time/control_dt + 10 = " + std::to_string(frame_len + 10) + " (ENV:538-539, 571)");
+    }
     float* d = nullptr; CUDA_OK(cudaMalloc((void**)&d, (size_t)rows * 30 * sizeof(float))); E->allocs.push_back(d);
     CUDA_OK(cudaMemcpy(d, table, (size_t)rows * 30 * sizeof(float), is_device_ptr(table) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     E->d_ref = d; E->P.ref = d; E->P.ref_rows = rows; E->P.frame_max = rows / 2; E->P.frame_len = int(E->max_time_d / E->control_dt_d);   // ENV:538-539 (double, like the reference)

@@ -69,6 +69,9 @@ __device__ __forceinline__ void store_env(const DevState& S, int r, int leg, con
 }
 
 __device__ __forceinline__ float cur_time(const EnvParams& P, const EnvRegs& e) { return fmaf((float)e.frame_idx, P.control_dt, e.t0); }
+// table row of frame_idx: the reference indexes its Eigen table unchecked (ENV:1670); here a run past the last row (long episodes,
+// step() without the forced reset) holds the last row instead of reading out of bounds
+__device__ __forceinline__ int ref_row(const EnvParams& P, int frame_idx) { return min(max(frame_idx, 0), P.ref_rows - 1); }
 __device__ __forceinline__ f3 nominal_q(const EnvParams& P, int leg) { return mk((leg & 1) ? P.abad : -P.abad, -0.78f, 1.57f); }   // ENV:317-322
 
 // ------------------------------------------------------------------ observation (ENV:956-1004); writes obDouble_ to HBM
@@ -106,7 +109,7 @@ __device__ __forceinline__ void update_observation(const EnvParams& P, const Dev
         if (P.flag_manual || P.flag_manual_traj) {                 // ENV:964-968
             float t = cur_time(P, e);
             ph3 = sinf(2.f * IRRL_PI_REF * t / P.period); ph4 = cosf(2.f * IRRL_PI_REF * t / P.period);
-        } else { const float* row = P.ref + (size_t)e.frame_idx * 30; ph3 = row[25]; ph4 = row[26]; }   // ENV:972
+        } else { const float* row = P.ref + (size_t)ref_row(P, e.frame_idx) * 30; ph3 = row[25]; ph4 = row[26]; }   // ENV:972
         obd[0] = 0.f; obd[1] = 0.f; obd[2] = 0.f;                  // obDouble_.setZero  ENV:960
         obd[3] = ph3; obd[4] = ph4;
         obd[29] = o.ob29; obd[30] = o.ob30; obd[31] = o.ob31;
@@ -148,7 +151,7 @@ __device__ __forceinline__ void command_obs_update(const EnvParams& P, const Dev
         e.jref = ref;
         e.eeref = mk(toe.x + 0.19f * e.lm.sx, toe.y + 0.058f * e.lm.sy, toe.z);   // ENV:331-334, 1882-1889
     } else {
-        const float* row = P.ref + (size_t)e.frame_idx * 30;       // ENV:1102-1106, 1670-1671
+        const float* row = P.ref + (size_t)ref_row(P, e.frame_idx) * 30;       // ENV:1102-1106, 1670-1671
         e.cmdf[0] = row[27]; e.cmdf[1] = row[28]; e.cmdf[2] = row[29];
         if (leg == 0) { obd[0] = e.cmdf[0]; obd[1] = e.cmdf[1]; obd[2] = e.cmdf[2]; }
         e.jref = mk(row[3 * leg], row[3 * leg + 1], row[3 * leg + 2]);
@@ -174,6 +177,9 @@ static __device__ __noinline__ void reset_env(const EnvParams& P, const DevState
         double ratio = u01(rr.z);
         double rs = (ratio < 0.5 && ratio > 0) ? ratio * 4.0 / 3.0 : (2.0 * ratio + 1.0) / 3.0;
         e.frame_idx = int((P.frame_max - P.frame_len - 10) * rs);
+        // the episode clock and the table row are separate counters in the reference (current_time_ ENV:557,631,786 vs frame_idx):
+        // cur_time() = t0 + frame_idx * dt, so the random start row is taken out of t0 here
+        e.t0 = (float)((double)e.t0 - (double)e.frame_idx * (double)P.control_dt);
     }
     e.cmdf[0] = e.cmdf[1] = e.cmdf[2] = 0.f;                                       // ENV:559-562
     e.torque_last = mk(0.f, 0.f, 0.f);                                             // ENV:575

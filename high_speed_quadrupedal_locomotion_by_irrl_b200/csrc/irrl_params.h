@@ -57,7 +57,7 @@ struct EnvParams {
     float m0, com0[3], m1, com1[3], m2, com2[3], m3, com3z, knee_z;
     float mu, restitution, rest_threshold;   // default material ENV:433
     // ---- contact solver (new specification)
-    int solver_iters, slide_iters;
+    int solver_iters, slide_iters, jacobi_sweeps;
     float solver_tol;
     // ---- bookkeeping
     uint32_t seed, env_offset;

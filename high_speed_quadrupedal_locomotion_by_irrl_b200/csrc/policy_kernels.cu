@@ -193,8 +193,10 @@ void launch_lstm_act(const ActArgs& a, cudaStream_t st) {
     if (tc) launch_lstm_act_tc(a, st); else launch_lstm_act_fma(a, st);
 }
 void launch_lstm_act_fma(const ActArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(lstm_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ActSmem)); configured = true; }
+    {   // the attribute is per device (a process may hold envs / policies on several GPUs through the C ABI)
+        static unsigned long long configured_devices = 0ull; int dev = 0; cudaGetDevice(&dev);
+        if (dev >= 64 || !((configured_devices >> dev) & 1ull)) { cudaFuncSetAttribute(lstm_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ActSmem)); if (dev < 64) configured_devices |= 1ull << dev; }
+    }
     int grid = (a.N + TM - 1) / TM;
     lstm_act_kernel<<<grid, NTHR, sizeof(ActSmem), st>>>(a);
 }
@@ -429,8 +431,10 @@ void launch_lstm_seq_bwd(int T, int K, int N, const float* dH, const float* wh, 
                          float* dz, cudaStream_t st) {
     dim3 grid((N + SEQ_TM - 1) / SEQ_TM, K);
     constexpr int smem = sizeof(float) * (G4 * H + G4 * SEQ_TM);
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+    {   // the attribute is per device (a process may hold envs / policies on several GPUs through the C ABI)
+        static unsigned long long configured_devices = 0ull; int dev = 0; cudaGetDevice(&dev);
+        if (dev >= 64 || !((configured_devices >> dev) & 1ull)) { cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (dev < 64) configured_devices |= 1ull << dev; }
+    }
     lstm_seq_bwd_kernel<<<grid, SEQ_THR, smem, st>>>(T, K, N, dH, wh, c0, keep, gates, Cs, dz);
 }
 

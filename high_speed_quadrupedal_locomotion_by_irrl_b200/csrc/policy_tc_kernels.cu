@@ -539,8 +539,10 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int N, int reps, ui
 }  // namespace tc
 
 void launch_lstm_act_tc(const ActArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(tc::lstm_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES); configured = true; }
+    {   // the attribute is per device (a process may hold envs / policies on several GPUs through the C ABI)
+        static unsigned long long configured_devices = 0ull; int dev = 0; cudaGetDevice(&dev);
+        if (dev >= 64 || !((configured_devices >> dev) & 1ull)) { cudaFuncSetAttribute(tc::lstm_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES); if (dev < 64) configured_devices |= 1ull << dev; }
+    }
     dim3 grid((a.N + tc::TM - 1) / tc::TM, 2);
     tc::lstm_act_tc_kernel<<<grid, tc::NTHR, tc::SMEM_BYTES, st>>>(a);
 }

@@ -200,6 +200,11 @@ class PPO2:
         self.optim = TF1Adam(self.model.param_list())
         _, rank, world = dist_info()
         self.rank, self.world = rank, world
+        if world > 1:   # equal shards only: gradients are averaged as sum / world of per-rank means and n_batch = n_envs * n_steps * world
+            import torch.distributed as _d
+            sizes = [None] * world; _d.all_gather_object(sizes, int(self.n_envs))
+            if len(set(sizes)) != 1:
+                raise ValueError(f"PPO2 needs the same number of environments on every rank, got {sizes}")
         self.act_model = FusedLstmPolicy(self.model.export_params(), n_env=self.n_envs, device=self.device_index, seed=seed, env_offset=rank * self.n_envs)
         self.num_timesteps = 0
         # Runner state (AbstractEnvRunner.__init__): obs = env.reset(), states = zeros, dones = False

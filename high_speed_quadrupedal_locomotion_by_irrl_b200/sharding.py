@@ -22,6 +22,9 @@ def make_sharded_env(cfg: dict, total_envs: int, resource_dir: str = ""):
     from ._flexible_robot import FlexibleGymEnv
     from .cfg import dump_yaml
     rank, local, world = env_from_torchrun()
+    if total_envs % world != 0:
+        # PPO2 averages per-rank mean gradients with equal weights and keys the act model with rank * n_envs: shards must be equal
+        raise ValueError(f"total_envs = {total_envs} is not a multiple of the world size {world}: environment shards must be equal")
     lo, hi = shard_range(total_envs, world, rank)
     c = dict(cfg, num_envs=hi - lo)
     return FlexibleGymEnv(resource_dir, dump_yaml(c), device=local, env_offset=lo)

@@ -70,7 +70,7 @@ struct Counted {
 };
 namespace mth {
 using std::sqrt; using std::fabs; using std::exp; using std::sin; using std::cos; using std::min; using std::max; using std::fmod; using std::fmax;
-using std::fmin; using std::asin; using std::acos; using std::log;
+using std::fmin; using std::asin; using std::acos; using std::log; using std::atan2;
 inline Counted sqrt(const Counted& a) { op_count().sqrt++; return Counted(std::sqrt(a.v)); }
 inline Counted fabs(const Counted& a) { return Counted(std::fabs(a.v)); }
 inline Counted exp(const Counted& a) { op_count().trans++; return Counted(std::exp(a.v)); }
@@ -79,6 +79,7 @@ inline Counted cos(const Counted& a) { op_count().trans++; return Counted(std::c
 inline Counted asin(const Counted& a) { op_count().trans++; return Counted(std::asin(a.v)); }
 inline Counted acos(const Counted& a) { op_count().trans++; return Counted(std::acos(a.v)); }
 inline Counted log(const Counted& a) { op_count().trans++; return Counted(std::log(a.v)); }
+inline Counted atan2(const Counted& a, const Counted& b) { op_count().trans++; return Counted(std::atan2(a.v, b.v)); }
 inline Counted fmod(const Counted& a, const Counted& b) { op_count().div++; return Counted(std::fmod(a.v, b.v)); }
 inline Counted min(const Counted& a, const Counted& b) { op_count().cmp++; return a.v < b.v ? a : b; }
 inline Counted max(const Counted& a, const Counted& b) { op_count().cmp++; return a.v < b.v ? b : a; }
@@ -287,6 +288,7 @@ struct Cfg {
 
 // ------------------------------------------------------------------ helper shape functions
 #define BP5O_PI 3.1415926  /* ENV:45 (sic) */
+inline double sampling_reshape(double ratio) { return (ratio < 0.5 && ratio > 0) ? ratio * 4.0 / 3.0 : (2.0 * ratio + 1.0) / 3.0; }   // ENV:71-81
 template <typename T> inline T bezier_b(T ph) { return ph * ph * ph + T(3.0) * (ph * ph * (T(1.0) - ph)); }  // ENV:89
 template <typename T> inline V3<T> cubicBezier(const V3<T>& p0, const V3<T>& pf, T ph) {                      // ENV:86-91
     T b = bezier_b(ph); return p0 + b * (pf - p0);
@@ -382,10 +384,13 @@ template <typename T> struct Env {
     T mass_distrubance_ratio = T(0.15), com_distrubance = T(0.02), calf_distrubance = T(0.01);  // ENV:2069-2071
     // contact material: default (0.6, 0.2, 0.01) ENV:433
     T mu = T(0.6), restitution = T(0.2), rest_threshold = T(0.01);
-    int solver_iters = 10;        // per-contact Gauss-Seidel sweeps cap (new spec)
+    int solver_iters = 30;        // per-contact Gauss-Seidel sweeps cap (new spec)
     T solver_tol = T(1e-5);       // relative impulse change for early exit
     int slide_iters = 1;          // fixed-point iterations for the sliding direction
     int solver_jacobi = 1;        // 1: feet updated simultaneously per sweep (see integrate())
+    int jacobi_sweeps = 6;        // sweeps after which the feet are visited one after the other too (block Jacobi need not converge when 3-4 feet couple strongly)
+    int slide_exact = 0;          // 1: exact maximal-dissipation sliding solve by bisection on the cone boundary (RaiSim's rule, Hwangbo et al. 2018);
+                                  // CPU-only yardstick for the one-step direction update the product uses (tests/test_oracle_contact_solver.py)
 
     // ---- state
     Model<T> model;
@@ -399,7 +404,8 @@ template <typename T> struct Env {
     T bodyLinearVel_[3], bodyAngularVel_[3];
     M3<T> bodyFrameMatrix_;
     T phase_[4];
-    T t0_ = 0; int frame_idx = 0;  // current_time_ = t0_ + frame_idx*control_dt_  (ENV:557,631,786)
+    T t0_ = 0; int frame_idx = 0;  // current_time_ = t0_ + frame_idx*control_dt_  (ENV:557,631,786); table mode: reset() takes the random start row out of t0_
+    int ref_row() const { int r = frame_idx < 0 ? 0 : frame_idx; return r > ref_rows - 1 ? ref_rows - 1 : r; }   // clamped like the CUDA path (the reference reads unchecked)
     // ---- Crutial: True -- meteor spheres (ENV:273-283, 608-611, 717-741, 815-861).  The reference drops CubeNum steel spheres from
     // 1 m above the trunk every 5 gait periods; cube_place_radius is 0 (ENV:1976), so they coincide and are modelled as ONE
     // sphere of CubeNum times the mass (identical frictionless bodies hitting the same point).  New specification (RaiSim is
@@ -418,6 +424,10 @@ template <typename T> struct Env {
     int n_contacts = 0; int contact_kind[MAXC]; T contact_impulse[MAXC][3];
     int foot_in_contact[4] = {0, 0, 0, 0}; T foot_impulse[4][3];
     int last_solver_sweeps = 0;
+    // distance of this control step's discrete decisions from their thresholds (test infrastructure: fp32 and fp64 can only agree on
+    // a decision whose margin exceeds fp32 resolution).  geo: min |signed gap| of any toe / trunk corner over the substeps [m];
+    // rest: min |v_n + threshold| over new contacts [m/s]; term: min distance of the termination tests (ENV:1560) from their bounds
+    mutable T margin_geo = T(1e30), margin_rest = T(1e30), margin_term = T(1e30);
     // optional reference table (ManualTraj False; ENV:17-21, VEC:158-182)
     const float* ref = nullptr; int ref_rows = 0, frame_max = 0, frame_len = 0;
     Terrain terrain;               // valid() only when Terrain: True
@@ -446,7 +456,7 @@ template <typename T> struct Env {
         simulation_dt_ = T(c.get("simulation_dt")); control_dt_ = T(c.get("control_dt"));   // VEC:151-152
         // solver / model switches (new-spec, optional)
         model.joint_damping = T(c.get_or("joint_damping", double(model.joint_damping)));
-        solver_iters = (int)c.get_or("solver_iters", 10); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 1); solver_jacobi = (int)c.get_or("solver_jacobi", 1);
+        solver_iters = (int)c.get_or("solver_iters", 30); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 1); solver_jacobi = (int)c.get_or("solver_jacobi", 1); jacobi_sweeps = (int)c.get_or("jacobi_sweeps", 6); slide_exact = (int)c.get_or("slide_exact", 0);
         mu = T(c.get_or("friction", 0.6)); restitution = T(c.get_or("restitution", 0.2)); rest_threshold = T(c.get_or("restitution_threshold", 0.01));
 
         // gc_init_ ENV:317-322
@@ -600,6 +610,7 @@ template <typename T> struct Env {
             T hh = 0; V3<T> nn(0, 0, 1);
             if (terrain.valid()) terrain.sample(gc[0] + k.toe[l].x, gc[1] + k.toe[l].y, hh, nn);
             T gap = (gc[2] + k.toe[l].z - hh) * nn.z - model.toe_radius;
+            if (mth::fabs(gap) < margin_geo) margin_geo = mth::fabs(gap);
             if (gap <= T(0)) {
                 cs[n].kind = l; cs[n].body = 3 + 3 * l; cs[n].n = nn;
                 cs[n].point = k.toe[l] - model.toe_radius * nn; ++n;
@@ -611,6 +622,7 @@ template <typename T> struct Env {
             V3<T> w = k.R[0] * loc;
             T hh = 0; V3<T> nn(0, 0, 1);
             if (terrain.valid()) terrain.sample(gc[0] + w.x, gc[1] + w.y, hh, nn);
+            if (mth::fabs((gc[2] + w.z - hh) * nn.z) < margin_geo) margin_geo = mth::fabs((gc[2] + w.z - hh) * nn.z);
             if ((gc[2] + w.z - hh) * nn.z <= T(0)) { cs[n].kind = 4 + c; cs[n].body = 0; cs[n].n = nn; cs[n].point = w; ++n; ++nbox; }
         }
         return n;
@@ -655,6 +667,7 @@ template <typename T> struct Env {
                 for (int j = 0; j < nc; ++j) for (int s = 0; s < 3; ++s) { T acc = 0; for (int a = 0; a < NV; ++a) acc += J[i][r][a] * W[j][s][a]; G[3 * i + r][3 * j + s] = acc; }
                 T acc = 0, pre = 0; for (int a = 0; a < NV; ++a) { acc += J[i][r][a] * ufree[a]; pre += J[i][r][a] * gv_[a]; }
                 c[3 * i + r] = acc; lam[3 * i + r] = 0;
+                if (r == 2 && mth::fabs(pre + rest_threshold) < margin_rest) margin_rest = mth::fabs(pre + rest_threshold);
                 if (r == 2) vtarget[i] = (pre < -rest_threshold) ? -restitution * pre : T(0);   // Newton restitution above the threshold speed
             }
             // per-contact Gauss-Seidel (normal = +z on the plane, so contact frame == world frame)
@@ -666,7 +679,7 @@ template <typename T> struct Env {
                 // plain Gauss-Seidel over all contacts.
                 T lam_prev[3 * MAXC]; for (int q = 0; q < 3 * nc; ++q) lam_prev[q] = lam[q];
                 for (int i = 0; i < nc; ++i) {
-                    const T* lsrc = (solver_jacobi && cs[i].kind < 4) ? lam_prev : lam;
+                    const T* lsrc = (solver_jacobi && sweep < jacobi_sweeps && cs[i].kind < 4) ? lam_prev : lam;
                     T v[3]; for (int r = 0; r < 3; ++r) { T acc = c[3 * i + r]; for (int q = 0; q < 3 * nc; ++q) acc += G[3 * i + r][q] * lsrc[q]; v[r] = acc; }
                     T Gii[3][3], Ginv[3][3]; for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) Gii[r][s] = G[3 * i + r][3 * i + s];
                     inv3(Gii, Ginv);
@@ -715,6 +728,40 @@ template <typename T> struct Env {
         // b = velocity with zero impulse at this contact
         T b[3]; for (int r = 0; r < 3; ++r) b[r] = v[r] - (G[r][0] * lo[0] + G[r][1] * lo[1] + G[r][2] * lo[2]);
         T dx = ls[0] / lt, dy = ls[1] / lt;
+        if (slide_exact) {
+            // impulse on the cone boundary lambda = ln (mu d, 1), d = (cos th, sin th): v_n(lambda) = vtn fixes ln(th); the sliding
+            // velocity v_t(th) must be anti-parallel to d (maximal dissipation).  f(th) = d x v_t changes sign at the solution;
+            // scan the circle from the stick direction, bisect the dissipative root closest to it.
+            auto eval = [&](T th, T& lnz_, T& f, T& dotp) {
+                T cx = mth::cos(th), sy = mth::sin(th);
+                T den = G[2][2] + mu * (G[2][0] * cx + G[2][1] * sy);
+                lnz_ = (den > T(1e-12)) ? (vtn - b[2]) / den : T(0); if (lnz_ < T(0)) lnz_ = 0;
+                T l0 = mu * lnz_ * cx, l1 = mu * lnz_ * sy;
+                T vx = b[0] + G[0][0] * l0 + G[0][1] * l1 + G[0][2] * lnz_, vy = b[1] + G[1][0] * l0 + G[1][1] * l1 + G[1][2] * lnz_;
+                f = cx * vy - sy * vx; dotp = cx * vx + sy * vy;
+            };
+            const T th0 = mth::atan2(dy, dx); const int NS = 64; const T step = T(2 * BP5O_PI) / NS;
+            T best_lo = 0, best_hi = 0; bool found = false; T best_dist = T(1e30);
+            T fp, lp, dp; eval(th0, lp, fp, dp);
+            for (int s2 = 1; s2 <= NS; ++s2) {
+                // alternate +/- around th0 so the closest bracket is found first
+                for (int sgn = -1; sgn <= 1; sgn += 2) {
+                    T a = th0 + T(sgn) * step * T(s2 - 1), bnd = th0 + T(sgn) * step * T(s2);
+                    T fa, la, da, fb, lb, db; eval(a, la, fa, da); eval(bnd, lb, fb, db);
+                    if ((fa <= T(0)) != (fb <= T(0)) && (da < T(0) || db < T(0))) {
+                        T dist = step * T(s2 - 1);
+                        if (dist < best_dist) { best_dist = dist; best_lo = a; best_hi = bnd; found = true; }
+                    }
+                }
+                if (found) break;
+            }
+            if (found) {
+                T a = best_lo, bnd = best_hi, fa, la, da; eval(a, la, fa, da);
+                for (int it = 0; it < 60; ++it) { T m = (a + bnd) / 2, fm, lm, dm; eval(m, lm, fm, dm); if ((fm <= T(0)) == (fa <= T(0))) { a = m; fa = fm; } else bnd = m; }
+                T th = (a + bnd) / 2, lz, f, dp2; eval(th, lz, f, dp2);
+                ln[0] = mu * lz * mth::cos(th); ln[1] = mu * lz * mth::sin(th); ln[2] = lz; return;
+            }
+        }
         T lnz = 0;
         for (int it = 0; it < slide_iters; ++it) {
             T den = G[2][2] + mu * (G[2][0] * dx + G[2][1] * dy);
@@ -810,7 +857,7 @@ template <typename T> struct Env {
     }
     // ENV:1664-1682 (table mode)
     void gait_generator_table() {
-        const float* row = ref + (size_t)frame_idx * 30;
+        const float* row = ref + (size_t)ref_row() * 30;
         for (int j = 0; j < NJ; ++j) { jointRef_[j] = T(row[j]); jointDotRef_[j] = T(row[12 + j]); }
     }
 
@@ -836,7 +883,7 @@ template <typename T> struct Env {
             for (int i = 0; i < 3; ++i) obDouble_[i] = command_filtered[i];                                         // ENV:1095-1097
             gait_generator_manual(flag_reset);                                                                      // ENV:1098
         } else {
-            const float* row = ref + (size_t)frame_idx * 30;                                                        // ENV:1102-1106
+            const float* row = ref + (size_t)ref_row() * 30;                                                        // ENV:1102-1106
             for (int i = 0; i < 3; ++i) { obDouble_[i] = T(row[27 + i]); command_filtered[i] = obDouble_[i]; }
             gait_generator_table();
         }
@@ -875,7 +922,7 @@ template <typename T> struct Env {
             obDouble_[3] = mth::sin(2 * T(BP5O_PI) * current_time() / period_);
             obDouble_[4] = mth::cos(2 * T(BP5O_PI) * current_time() / period_);
         } else {
-            const float* row = ref + (size_t)frame_idx * 30; obDouble_[3] = T(row[25]); obDouble_[4] = T(row[26]);   // ENV:972
+            const float* row = ref + (size_t)ref_row() * 30; obDouble_[3] = T(row[25]); obDouble_[4] = T(row[26]);   // ENV:972
         }
         uint32_t r[4];
         for (int blk = 0; blk < 3; ++blk) {
@@ -947,8 +994,9 @@ template <typename T> struct Env {
         t0_ = flag_manual ? T(0) : T(u01(r[3])); frame_idx = 0;                               // ENV:557, 565-573 (ManualTraj)
         if (!flag_ManualTraj && !flag_manual) {                                               // ENV:571
             double ratio = u01(r[2]);
-            double rs = (ratio < 0.5 && ratio > 0) ? ratio * 4.0 / 3.0 : (2.0 * ratio + 1.0) / 3.0;   // ENV:71-81 sampling_reshape
+            double rs = sampling_reshape(ratio);
             frame_idx = int((frame_max - frame_len - 10) * rs);
+            t0_ = T(double(t0_) - double(frame_idx) * double(control_dt_));   // current_time_ (ENV:557,631,786) does not include the start row: current_time() adds frame_idx * dt back
         }
         for (int i = 0; i < 3; ++i) command_filtered[i] = 0;                                   // ENV:559-562
         for (int j = 0; j < NJ; ++j) torque_last[j] = 0;                                       // ENV:575
@@ -1049,6 +1097,7 @@ template <typename T> struct Env {
 
     // ENV:692-809
     T step(const float* action) {
+        margin_geo = margin_rest = margin_term = T(1e30);
         uint32_t r[4]; Philox::gen(seed, env_id, tick, P_ACT, r);
         T an = T(usym(r[0]));
         for (int j = 0; j < NJ; ++j) {
@@ -1096,6 +1145,7 @@ template <typename T> struct Env {
     bool isTerminalState(float& terminalReward) const {
         terminalReward = float(terminalRewardCoeff_);
         T zrel = gc_[2] - ground_height();
+        margin_term = mth::fmin(mth::fmin(mth::fabs(zrel - T(0.15)), mth::fabs(zrel - T(0.65))), mth::fabs(obDouble_[31] - T(0.5)));
         if (zrel < T(0.15) || zrel > T(0.65) || obDouble_[31] < T(0.5)) return true;
         terminalReward = 0.f; return false;
     }

@@ -153,10 +153,27 @@ int bp5o_integrate(void* h, int env, const double* tau12) {
     return 0;
 }
 void bp5o_contact_info(void* h, int env, double* out) { DISPATCH(h, contact_info(V.envs[env], out), contact_info(V.envs[env], out)); }
+// [geo, rest, term] decision margins of the last control step (see Env::margin_*)
+void bp5o_margins(void* h, int env, double* out) { DISPATCH(h, { out[0] = V.envs[env].margin_geo; out[1] = V.envs[env].margin_rest; out[2] = V.envs[env].margin_term; }, { out[0] = V.envs[env].margin_geo; out[1] = V.envs[env].margin_rest; out[2] = V.envs[env].margin_term; }); }
 void bp5o_reward_terms(void* h, int env, double* out) { DISPATCH(h, reward_terms(V.envs[env], out), reward_terms(V.envs[env], out)); }
 void bp5o_model_params(void* h, int env, double* out) { DISPATCH(h, model_params(V.envs[env], out), model_params(V.envs[env], out)); }
 int bp5o_is_terminal(void* h, int env) {
     float tr; return H(h)->precision == 0 ? (int)H(h)->d.envs[env].isTerminalState(tr) : (int)H(h)->f.envs[env].isTerminalState(tr);
+}
+// the pure helper functions, for the comparison with the compiled slices of the reference (oracle/_ref, tests/test_oracle_ref_slices.py)
+// which: 0 sampling_reshape(a)  1 gauss(a,b,c)  2 smooth_function(a,b,c)  3 smooth_function2(a,b,c)
+double bp5o_helper(int which, double a, double b, double c) {
+    switch (which) { case 0: return sampling_reshape(a); case 1: return gauss<double>(a, b, c); case 2: return smooth_function<double>(a, b, c); default: return smooth_function2<double>(a, b, c); }
+}
+// ENV:1687-1751 on env 0's leg lengths / max_len; theta[3] in/out
+void bp5o_ik(void* h, double x, double y, double z, int is_right, double* theta) {
+    if (H(h)->precision == 0) { auto& e = H(h)->d.envs[0]; e.inverse_kinematics(x, y, z, e.l_hip_, e.l_thigh_, e.l_calf_, theta, is_right != 0); }
+    else { auto& e = H(h)->f.envs[0]; float th[3] = {(float)theta[0], (float)theta[1], (float)theta[2]}; e.inverse_kinematics((float)x, (float)y, (float)z, e.l_hip_, e.l_thigh_, e.l_calf_, th, is_right != 0); for (int i = 0; i < 3; ++i) theta[i] = th[i]; }
+}
+// ENV:1273-1305 on env 0's motor constants: torque[12] in/out, gv[18]
+void bp5o_torque_clamp(void* h, double* torque, const double* gv) {
+    if (H(h)->precision == 0) { auto& e = H(h)->d.envs[0]; for (int i = 0; i < 12; ++i) e.torque[i] = torque[i]; e.torque_clamp(gv); for (int i = 0; i < 12; ++i) torque[i] = e.torque[i]; }
+    else { auto& e = H(h)->f.envs[0]; float g[18]; for (int i = 0; i < 18; ++i) g[i] = (float)gv[i]; for (int i = 0; i < 12; ++i) e.torque[i] = (float)torque[i]; e.torque_clamp(g); for (int i = 0; i < 12; ++i) torque[i] = e.torque[i]; }
 }
 // Philox block exposed so tests can pin the RNG against the published Random123 known-answer vectors
 void bp5o_philox(unsigned seed, unsigned env, unsigned tick, unsigned purpose, unsigned* out) { Philox::gen(seed, env, tick, purpose, out); }

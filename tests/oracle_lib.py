@@ -35,7 +35,7 @@ def lib():
         L.bp5o_time_steps.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint, C.POINTER(C.c_long)]
         L.bp5o_gait.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p, C.c_int] + [C.c_void_p] * 3
         for name in ("destroy", "reset", "observe", "step", "get_state", "set_state", "mass_and_h", "body_kin", "toe_kin",
-                     "integrate", "contact_info", "reward_terms", "model_params", "set_ref", "set_tick"):
+                     "integrate", "contact_info", "reward_terms", "margins", "model_params", "set_ref", "set_tick"):
             getattr(L, "bp5o_" + name).argtypes = None
         _lib = L
     return _lib
@@ -167,6 +167,14 @@ class Oracle:
         o = np.zeros(8)
         self.L.bp5o_reward_terms(self.h, C.c_int(env), _p(o))
         return o
+
+    def margins(self):
+        """[n,3]: how far the last control step's discrete decisions were from their thresholds (geometric gap [m], restitution
+        threshold [m/s], termination bounds).  Captured by step() BEFORE the auto-reset."""
+        out = np.zeros((self.n, 3))
+        for i in range(self.n):
+            self.L.bp5o_margins(self.h, C.c_int(i), _p(out[i]))
+        return out
 
     def model_params(self, env=0):
         o = np.zeros(3 + 13 * 7)

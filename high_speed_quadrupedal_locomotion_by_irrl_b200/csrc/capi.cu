@@ -171,10 +171,10 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         IGN("num_threads");
         double sim_dt, ctl_dt; if (!num("simulation_dt", sim_dt)) goto bad; if (!num("control_dt", ctl_dt)) goto bad;
         P.sim_dt = (float)sim_dt; P.control_dt = (float)ctl_dt; P.loop_count = int(ctl_dt / sim_dt + 1e-10);   // ENV:711
-        E->control_dt_d = ctl_dt; E->sim_dt_d = sim_dt;
+        E->control_dt_d = ctl_dt; E->sim_dt_d = sim_dt; P.control_dt_d = ctl_dt;
         if (!num("seedd", d)) goto bad; P.seed = (uint32_t)(int)d;                                               // VEC:171
         // ENV:1598-1613
-        NUM("abad", P.abad) NUM("period", P.period) E->period_d = d; P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ P.meteor_every = int(5.0 * d / ctl_dt);   /* ENV:731 */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
+        NUM("abad", P.abad) NUM("period", P.period) E->period_d = d; P.period_d = d; P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ P.meteor_every = int(5.0 * d / ctl_dt);   /* ENV:731 */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
         IGN("down_height") IGN("gait_step")
         NUM("Vx", P.Vx_max) P.Vx_min = 0.f;                                                                      // ENV:1606-1607, 2054
         NUM("Vy", P.Vy_max) P.Vy_min = -P.Vy_max; NUM("Omega", P.omega_max) P.omega_min = -P.omega_max;
@@ -544,7 +544,7 @@ int irrl_set_seed(irrl_env* env, int seed) { ENV(env); E->P.seed = (uint32_t)see
 int irrl_close(irrl_env* env) { ENV(env); if (E->stream) CUDA_OK(cudaStreamSynchronize(E->stream)); return 0; }
 int irrl_set_simulation_time_step(irrl_env* env, double dt) { ENV(env); E->P.sim_dt = (float)dt; E->sim_dt_d = dt; E->P.loop_count = int(E->control_dt_d / dt + 1e-10); return 0; }
 int irrl_set_control_time_step(irrl_env* env, double dt) {
-    ENV(env); E->P.control_dt = (float)dt; E->control_dt_d = dt; E->P.loop_count = int(dt / E->sim_dt_d + 1e-10);
+    ENV(env); E->P.control_dt = (float)dt; E->control_dt_d = dt; E->P.control_dt_d = dt; E->P.loop_count = int(dt / E->sim_dt_d + 1e-10);
     E->P.disturb_every = int(E->period_d / dt * 10.0); E->P.meteor_every = int(5.0 * E->period_d / dt);     // ENV:746, 731 evaluate control_dt_ at every step
     if (E->d_ref) {   // frame_len = int(max_time / control_dt_) (ENV:539) follows the control step; the table must still be long enough
         const int frame_len = int(E->max_time_d / dt);

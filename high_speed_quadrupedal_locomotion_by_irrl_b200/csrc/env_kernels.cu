@@ -72,6 +72,13 @@ __device__ __forceinline__ float cur_time(const EnvParams& P, const EnvRegs& e) 
 // table row of frame_idx: the reference indexes its Eigen table unchecked (ENV:1670); here a run past the last row (long episodes,
 // step() without the forced reset) holds the last row instead of reading out of bounds
 __device__ __forceinline__ int ref_row(const EnvParams& P, int frame_idx) { return min(max(frame_idx, 0), P.ref_rows - 1); }
+// phase of leg `leg` in its gait cycle, fmod(t + phase * T, T) / T (ENV:1172-1181, 1523-1527), reduced in double: in fp32 the clock
+// t ~ 1.5 s carries 1e-7 s, which the contact-reward shaping (slope 2 * 2 pi / lam) turns into 1e-5 of the reward exponent
+__device__ __forceinline__ float gait_phase(const EnvParams& P, const EnvRegs& e, int leg) {
+    const double t = (double)e.t0 + (double)e.frame_idx * P.control_dt_d;
+    const double x = t / P.period_d + (double)P.phase[leg];
+    return (float)(x - floor(x));
+}
 __device__ __forceinline__ f3 nominal_q(const EnvParams& P, int leg) { return mk((leg & 1) ? P.abad : -P.abad, -0.78f, 1.57f); }   // ENV:317-322
 
 // ------------------------------------------------------------------ observation (ENV:956-1004); writes obDouble_ to HBM
@@ -162,9 +169,7 @@ __device__ __forceinline__ void command_obs_update(const EnvParams& P, const Dev
 // time-based contact flag (ENV:1169-1188) or the detected one
 __device__ __forceinline__ float contact_flag(const EnvParams& P, const EnvRegs& e, int leg, int detected) {
     if (!P.flag_time_contact) return detected ? 1.f : 0.f;
-    float rp = cur_time(P, e) + P.phase[leg] * P.period;
-    rp = fmodf(rp, P.period) / P.period;
-    return (rp < P.lam) ? 1.f : 0.f;
+    return (gait_phase(P, e, leg) < P.lam) ? 1.f : 0.f;
 }
 
 // ------------------------------------------------------------------ reset (ENV:547-635)
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
     const float kp0 = P.stiffness * P.abad_ratio, kd0 = P.damping * P.abad_ratio;
     const float rr_ = P.motor_max_torque / (P.motor_max_speed - P.motor_crit_speed);
     const float ilow_ = 1.0f / (-P.motor_max_speed + P.motor_crit_speed);      // hoisted out of the substep loop
-    f3 tau = mk(0.f, 0.f, 0.f);
+    f3 tau = e.torque_last;      // a step with zero substeps (simulation_dt > control_dt, int() ENV:711) sees the stale member `torque`, which equals torque_last between steps (ENV:1511-1515)
     ContactOut co; co.foot_active = 0; co.foot_impulse = mk(0, 0, 0); co.sweeps = 0;
     for (int it = 0; it < P.loop_count; ++it) {
         float t0 = (pt.x - e.q.x) * kp0 - e.qd.x * kd0;
@@ -347,8 +352,7 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
         float tns = qsum(dot(tn, tn)), tds = qsum(dot(dtq, dtq));
         float r_tq = P.torque_coeff / 2.0f * expf(-0.1f * tns) + P.torque_coeff / 2.0f * expf(-0.1f / P.control_dt * tds);
         e.torque_last = tn;                                               // ENV:1515
-        float rp = cur_time(P, e) + P.phase[leg] * P.period;              // ENV:1523-1527
-        rp = fmodf(rp, P.period) / P.period;
+        const float rp = gait_phase(P, e, leg);                           // ENV:1523-1527
         float cr = 4.f * vel_norm * vel_norm * smooth_function(rp, 2.f, P.lam) +
                    2.f * (force_norm / 12.5f) * (force_norm / 12.5f) * smooth_function2(rp, 2.f, P.lam);
         cr = qsum(cr);

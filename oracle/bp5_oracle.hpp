@@ -427,7 +427,9 @@ template <typename T> struct Env {
     // distance of this control step's discrete decisions from their thresholds (test infrastructure: fp32 and fp64 can only agree on
     // a decision whose margin exceeds fp32 resolution).  geo: min |signed gap| of any toe / trunk corner over the substeps [m];
     // rest: min |v_n + threshold| over new contacts [m/s]; term: min distance of the termination tests (ENV:1560) from their bounds
-    mutable T margin_geo = T(1e30), margin_rest = T(1e30), margin_term = T(1e30);
+    // cone: min relative distance |lambda_t| vs mu lambda_n of any single-contact visit from the stick / slide boundary (the one-step
+    // sliding rule is not continuous across it: the stick impulse points along d, the sliding one along G_tt d)
+    mutable T margin_geo = T(1e30), margin_rest = T(1e30), margin_term = T(1e30), margin_cone = T(1e30);
     // optional reference table (ManualTraj False; ENV:17-21, VEC:158-182)
     const float* ref = nullptr; int ref_rows = 0, frame_max = 0, frame_len = 0;
     Terrain terrain;               // valid() only when Terrain: True
@@ -724,6 +726,7 @@ template <typename T> struct Env {
         T ls[3]; for (int r = 0; r < 3; ++r) ls[r] = lo[r] - (Ginv[r][0] * e[0] + Ginv[r][1] * e[1] + Ginv[r][2] * e[2]);
         if (!(ls[2] > T(0))) { ln[0] = ln[1] = ln[2] = 0; return; }
         T lt = mth::sqrt(ls[0] * ls[0] + ls[1] * ls[1]);
+        { T mc = mth::fabs(lt - mu * ls[2]) / (mu * ls[2]); if (mc < margin_cone) margin_cone = mc; }
         if (lt <= mu * ls[2]) { ln[0] = ls[0]; ln[1] = ls[1]; ln[2] = ls[2]; return; }
         // b = velocity with zero impulse at this contact
         T b[3]; for (int r = 0; r < 3; ++r) b[r] = v[r] - (G[r][0] * lo[0] + G[r][1] * lo[1] + G[r][2] * lo[2]);
@@ -1097,7 +1100,7 @@ template <typename T> struct Env {
 
     // ENV:692-809
     T step(const float* action) {
-        margin_geo = margin_rest = margin_term = T(1e30);
+        margin_geo = margin_rest = margin_term = margin_cone = T(1e30);
         uint32_t r[4]; Philox::gen(seed, env_id, tick, P_ACT, r);
         T an = T(usym(r[0]));
         for (int j = 0; j < NJ; ++j) {

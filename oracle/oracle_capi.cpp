@@ -39,7 +39,7 @@ template <typename T> void set_state(Env<T>& e, const double* s) {
     for (int i = 0; i < NQ; ++i) e.gc_[i] = T(s[o++]);
     for (int i = 0; i < NV; ++i) e.gv_[i] = T(s[o++]);
     for (int i = 0; i < NJ; ++i) e.pTarget12Last_[i] = T(s[o++]);
-    for (int i = 0; i < NJ; ++i) e.torque_last[i] = T(s[o++]);
+    for (int i = 0; i < NJ; ++i) { e.torque_last[i] = T(s[o++]); e.torque[i] = e.torque_last[i]; }   // between steps torque == torque_last (ENV:1511-1515); matters only when a step runs zero substeps
     for (int i = 0; i < 3; ++i) e.command[i] = T(s[o++]);
     for (int i = 0; i < 3; ++i) e.command_filtered[i] = T(s[o++]);
     for (int i = 0; i < NJ; ++i) { e.jointRef_[i] = T(s[o++]); e.jointRefLast_[i] = e.jointRef_[i]; }
@@ -153,8 +153,8 @@ int bp5o_integrate(void* h, int env, const double* tau12) {
     return 0;
 }
 void bp5o_contact_info(void* h, int env, double* out) { DISPATCH(h, contact_info(V.envs[env], out), contact_info(V.envs[env], out)); }
-// [geo, rest, term] decision margins of the last control step (see Env::margin_*)
-void bp5o_margins(void* h, int env, double* out) { DISPATCH(h, { out[0] = V.envs[env].margin_geo; out[1] = V.envs[env].margin_rest; out[2] = V.envs[env].margin_term; }, { out[0] = V.envs[env].margin_geo; out[1] = V.envs[env].margin_rest; out[2] = V.envs[env].margin_term; }); }
+// [geo, rest, term, cone] decision margins of the last control step (see Env::margin_*)
+void bp5o_margins(void* h, int env, double* out) { DISPATCH(h, { out[0] = V.envs[env].margin_geo; out[1] = V.envs[env].margin_rest; out[2] = V.envs[env].margin_term; out[3] = V.envs[env].margin_cone; }, { out[0] = V.envs[env].margin_geo; out[1] = V.envs[env].margin_rest; out[2] = V.envs[env].margin_term; out[3] = V.envs[env].margin_cone; }); }
 void bp5o_reward_terms(void* h, int env, double* out) { DISPATCH(h, reward_terms(V.envs[env], out), reward_terms(V.envs[env], out)); }
 void bp5o_model_params(void* h, int env, double* out) { DISPATCH(h, model_params(V.envs[env], out), model_params(V.envs[env], out)); }
 int bp5o_is_terminal(void* h, int env) {

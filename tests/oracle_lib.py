@@ -169,9 +169,9 @@ class Oracle:
         return o
 
     def margins(self):
-        """[n,3]: how far the last control step's discrete decisions were from their thresholds (geometric gap [m], restitution
-        threshold [m/s], termination bounds).  Captured by step() BEFORE the auto-reset."""
-        out = np.zeros((self.n, 3))
+        """[n,4]: how far the last control step's discrete decisions were from their thresholds (geometric gap [m], restitution
+        threshold [m/s], termination bounds, stick/slide boundary [relative]).  Captured by step() BEFORE the auto-reset."""
+        out = np.zeros((self.n, 4))
         for i in range(self.n):
             self.L.bp5o_margins(self.h, C.c_int(i), _p(out[i]))
         return out

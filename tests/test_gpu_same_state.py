@@ -1,0 +1,227 @@
+"""-m gpu: observation, the eight reward terms and the torque clamp of the CUDA step kernel against the oracle "computed on the same
+state" (BASELINE.json north_star: within 1e-5 relative), plus probe values, the relaxation configuration and a flag comparison
+with zero tolerated exceptions away from fp32 resolution.
+
+How "the same state" is obtained through the public surface only: `simulation_dt = 2 * control_dt` makes
+`loopCount = int(control_dt / simulation_dt)` zero (ENV:711), so `step()` runs no physics substep and evaluates
+updateObservation (ENV:956-1004), contact_information_update (ENV:1199-1231), DeepMimicRewardUpdate (ENV:1444-1548),
+command_obs_update, isTerminalState and observe on exactly the injected state; `simulation_dt = control_dt` runs one substep, whose
+joint torques (PD ENV:761-764 + torque_clamp ENV:1273-1305) are a function of the injected state alone.
+
+Error measure here is ELEMENT-wise: |a - b| <= tol * max(|b|, floor) with the floor stated per quantity (an fp32 result cannot be
+1e-5 relative to a reference value that is itself ~0)."""
+import numpy as np
+import pytest
+
+from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import trot_cfg, relaxation_cfg, test_cfg as manual_test_cfg
+from oracle_lib import Oracle, S
+from gpu_lib import Cuda, random_states, stance_states
+
+pytestmark = pytest.mark.gpu
+N = 512
+GEO = 1e-7      # metres: fp32 resolution of a toe height (z ~ 0.3 m carries 3e-8, the leg chain sums a few such terms); every observed flip sat below 6e-8
+CONE = 2e-3     # relative distance of |lambda_t| from mu lambda_n: the one-step sliding rule jumps across the stick / slide boundary (observed up to 4e-4)
+COEFFS = ("EndEffectorRewardCoeff", "BodyPosRewardCoeff", "BodyAttitudeRewardCoeff", "JointRewardCoeff", "VelRewardCoeff", "TorqueCoeff", "ContactCoeff")
+
+
+def _elem(a, b, floor):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max())
+
+
+def _states(o, rng):
+    """injected states: the command / reference / clock fields of a fresh reset, the mechanical state replaced by (a) random
+    free-flight states with moderate tilt, (b) stance poses, (c) the reset states themselves"""
+    s = o.get_state()
+    n = len(s); k = n // 3
+    r = random_states(rng, k, z=(0.2, 0.6), vel=1.0, jitter=0.4)
+    tilt = rng.normal(size=(k, 3)) * 0.25                                 # mostly upright (|R22| > 0.5), some beyond the termination bound
+    r[:, 3] = 1.0; r[:, 4:7] = tilt / 2; r[:, 3:7] /= np.linalg.norm(r[:, 3:7], axis=1, keepdims=True)
+    s[:k, 0:37] = r[:, 0:37]
+    s[k:2 * k, 0:37] = stance_states(rng, k)[:, 0:37]
+    s[:, S["torque_last"]] = rng.uniform(-0.8, 0.8, size=(n, 12))
+    return s
+
+
+def _zero_substep_pair(noise, **kw):
+    cfg = trot_cfg(num_envs=N, num_threads=8, StochasticDynamics=True, ObsNoise=noise, simulation_dt=0.004, control_dt=0.002)
+    cfg.update(kw)
+    o, c = Oracle(cfg), Cuda(cfg)
+    o.set_tick(7); c.env.setTick(7)
+    o.reset(); c.reset()
+    return o, c
+
+
+@pytest.mark.parametrize("noise", [0.0, 2.0])
+def test_observation_on_the_injected_state_1e5(noise):
+    o, c = _zero_substep_pair(noise)
+    rng = np.random.default_rng(0)
+    s = _states(o, rng)
+    for i in range(N):
+        o.set_state(i, s[i])
+    c.set_state(s.astype(np.float32))
+    s32 = c.get_state().astype(np.float64)                                 # the fp32-rounded state is the common input
+    for i in range(N):
+        o.set_state(i, s32[i])
+    a = np.clip(rng.normal(0, 0.3, size=(N, 12)), -1, 1).astype(np.float32)
+    obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
+    m = o.margins()
+    safe = m[:, 2] > 1e-5                                                  # termination decision away from its bound
+    assert safe.mean() > 0.99
+    assert (do[safe] == dg[safe]).all()
+    keep = safe & ~do                                                      # terminated envs were reset: their row is the reset observation (tested elsewhere)
+    assert keep.sum() > N // 2
+    err = _elem(obg[keep], obo[keep], 1.0)                                 # scaled observations are O(1): floor 1
+    assert err <= 1e-5, err
+    # and the unscaled obDouble_ (ENV:956-1004) kept in the state
+    so, sg = o.get_state(), c.get_state()
+    assert _elem(sg[keep][:, S["ob"]], so[keep][:, S["ob"]], 1.0) <= 1e-5
+    assert (sg[keep][:, S["frame_idx"]] == so[keep][:, S["frame_idx"]]).all()
+
+
+def _one_term_cfg(which):
+    kw = {k: 0.0 for k in COEFFS}
+    kw[which] = {"EndEffectorRewardCoeff": 0.15, "BodyPosRewardCoeff": 0.2, "BodyAttitudeRewardCoeff": 0.2, "JointRewardCoeff": 0.4,
+                 "VelRewardCoeff": 0.2, "TorqueCoeff": 0.1, "ContactCoeff": 0.1}[which]
+    kw["terminalRewardCoeff"] = 0.0
+    return kw
+
+
+@pytest.mark.parametrize("which", COEFFS)
+def test_each_reward_term_on_the_injected_state_1e5(which):
+    """one coefficient non-zero at a time: the step reward IS that term (JointRewardCoeff carries two: JointReward is also reported in
+    extraInfo, JointDotReward is the remainder).  Compared with the oracle's individual terms (bp5o_reward_terms)."""
+    kw = _one_term_cfg(which)
+    o, c = _zero_substep_pair(0.0, **kw)
+    rng = np.random.default_rng(1)
+    s = _states(o, rng)
+    if which == "JointRewardCoeff":      # keep the joint-rate error small enough that exp(-dt * sum) is not flushed to a subnormal
+        s[:, 25:37] = s[:, S["joint_dot_ref"]] + rng.normal(size=(N, 12)) * 6
+    c.set_state(s.astype(np.float32))
+    s32 = c.get_state().astype(np.float64)
+    for i in range(N):
+        o.set_state(i, s32[i])
+    a = np.zeros((N, 12), np.float32)
+    obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
+    terms = np.stack([o.reward_terms(i) for i in range(N)])               # EE, BodyCenter, BodyAttitude, Joint, JointDot, Velocity, Torque, Contact
+    assert np.abs(ro - terms.sum(axis=1)).max() < 1e-6                    # the oracle's total is the sum of its terms (terminal coefficient 0)
+    coeff = kw[which]
+    floor = 1e-3 * coeff                                                  # a term below 0.1 % of its coefficient is compared absolutely
+    idx = {"EndEffectorRewardCoeff": [0], "BodyPosRewardCoeff": [1], "BodyAttitudeRewardCoeff": [2], "JointRewardCoeff": [3, 4],
+           "VelRewardCoeff": [5], "TorqueCoeff": [6], "ContactCoeff": [7]}[which]
+    want = terms[:, idx].sum(axis=1)
+    assert want.max() > 0.05 * coeff                                      # the fixture exercises the term
+    assert _elem(rg, want, floor) <= 1e-5, (which, _elem(rg, want, floor))
+    if which == "JointRewardCoeff":
+        assert _elem(eg[:, 4], terms[:, 3], floor) <= 1e-5
+        assert _elem(rg - eg[:, 4], terms[:, 4], floor) <= 2e-5           # difference of two fp32 numbers
+    extra_col = {"EndEffectorRewardCoeff": 0, "BodyPosRewardCoeff": 1, "BodyAttitudeRewardCoeff": 3, "VelRewardCoeff": 5}.get(which)
+    if extra_col is not None:
+        assert _elem(eg[:, extra_col], want, floor) <= 1e-5
+    assert _elem(eg[:, 2], s32[:, 2], 1.0) == 0.0                         # "base height" is the state itself
+
+
+@pytest.mark.parametrize("motor", [(18.0, 100.0, 200.0), (18.0, 14.2, 40.0)])
+def test_pd_torque_filter_and_clamp_on_the_injected_state_1e5(motor):
+    """one substep per control step: the applied joint torques depend on the injected state only (ENV:761-767, 1273-1305)"""
+    cfg = trot_cfg(num_envs=N, num_threads=8, StochasticDynamics=False, ObsNoise=0.0, simulation_dt=0.002, control_dt=0.002,
+                   MotorMaxTorque=motor[0], MotorCriticalSpeed=motor[1], MotorMaxSpeed=motor[2])
+    o, c = Oracle(cfg), Cuda(cfg)
+    o.set_tick(3); c.env.setTick(3)
+    o.reset(); c.reset()
+    rng = np.random.default_rng(2)
+    s = o.get_state()
+    s[:, 0:37] = random_states(rng, N, z=(1.0, 2.0))[:, 0:37]
+    s[:, 25:37] = rng.uniform(-1.3, 1.3, size=(N, 12)) * motor[2]         # joint speeds on both sides of the critical / maximal speed
+    s[: N // 2, 25:37] = rng.uniform(-12, 12, size=(N // 2, 12))           # and slow joints, where the PD torque itself is inside the limits
+    s[:, S["torque_last"]] = rng.uniform(-1, 1, size=(N, 12))
+    c.set_state(s.astype(np.float32))
+    s32 = c.get_state().astype(np.float64)
+    for i in range(N):
+        o.set_state(i, s32[i])
+    a = np.clip(rng.normal(0, 0.6, size=(N, 12)), -1, 1).astype(np.float32)
+    o.step(a); c.step(a)
+    want = o.get_state()[:, S["torque"]]
+    got = np.zeros((N, 12), np.float32); c.env.GetJointEffort(got)
+    lim = np.tile([motor[0], motor[0], motor[0] * 1.55], 4)
+    assert (np.abs(want) >= lim - 1e-9).mean() > 0.05 and (np.abs(want) < lim - 1e-3).mean() > 0.2    # clamped and unclamped entries
+    assert _elem(got, want, 1.0) <= 1e-5, _elem(got, want, 1.0)           # torques are O(10) N m: floor 1
+    gf = np.zeros((N, 18), np.float32); c.env.GetGeneralizedForce(gf)
+    assert (gf[:, :6] == 0).all() and np.array_equal(gf[:, 6:], got)      # ENV:1363-1370
+
+
+def test_probe_values_after_ordinary_steps():
+    """OriginState / ReferenceState / GetJointEffort / GetGeneralizedForce (ENV:1317-1370) by value, teacher-forced"""
+    cfg = trot_cfg(num_envs=N, num_threads=8, StochasticDynamics=True, ObsNoise=0.0)
+    o, c = Oracle(cfg), Cuda(cfg)
+    o.set_tick(1); c.env.setTick(1)
+    o.reset(); c.reset()
+    rng = np.random.default_rng(3)
+    for t in range(45):                                                   # 40 steps of the oracle alone (robots land), then 5 teacher-forced steps
+        a = np.clip(rng.normal(0, 0.2, size=(N, 12)), -1, 1).astype(np.float32)
+        if t >= 40:
+            c.env.setTick(o.get_tick()); c.set_state(o.get_state().astype(np.float32)); c.step(a)
+        o.step(a)
+    so = o.get_state(); m = o.margins()
+    safe = (m[:, 0] > GEO) & (m[:, 1] > 1e-4) & (m[:, 2] > 1e-5) & (m[:, 3] > CONE)
+    assert safe.mean() > 0.95
+    origin = np.zeros((N, 41), np.float32); c.env.OriginState(origin)
+    refer = np.zeros((N, 24), np.float32); c.env.ReferenceState(refer)
+    effort = np.zeros((N, 12), np.float32); c.env.GetJointEffort(effort)
+    gf = np.zeros((N, 18), np.float32); c.env.GetGeneralizedForce(gf)
+    assert c.env.GetOriginStateDim() == 41
+    assert (origin[safe][:, 37:41] == so[safe][:, S["contact"]]).all()                        # contact flags bit-exact
+    assert so[safe][:, S["contact"]].sum() > N // 4                                           # robots have landed
+    assert _elem(origin[safe][:, 0:19], so[safe][:, S["gc"]], 1.0) <= 1e-5                    # gc
+    assert _elem(origin[safe][:, 19:37], so[safe][:, S["gv"]], 1.0) <= 2e-4                   # gv after 8 contact substeps (joint rates O(10))
+    assert _elem(refer[:, :12], so[:, S["joint_ref"]], 1.0) <= 1e-5 and _elem(refer[:, 12:], so[:, S["joint_dot_ref"]], 1.0) <= 5e-4   # (ref - last) / 0.002: one fp32 ulp of a 2 rad angle is 1.2e-4 rad/s
+    assert _elem(effort[safe], so[safe][:, S["torque"]], 1.0) <= 2e-4
+    assert (gf[:, :6] == 0).all() and np.array_equal(gf[:, 6:], effort)
+
+
+def _teacher_forced(cfg, steps, sigma, seed, tol=2e-5):
+    """single-step comparisons from the oracle's own rollout states.  Env-steps whose discrete decisions sit within fp32
+    resolution of a threshold (oracle margins: any toe / trunk-corner gap within 1e-7 m of zero during the substeps, a touch-down
+    speed within 1e-4 m/s of the restitution threshold, a contact impulse within 0.2 % of the friction-cone boundary, termination test
+    within 1e-5 of its bound) are set aside and counted; on
+    every other env-step ALL flags must be equal and the values within `tol` -- no tolerated exceptions.  `tol` = 2e-5 element-wise (observed worst 1.3e-5, p99.9 5e-6): a
+    control step is 8 contact substeps whose impulse iteration stops at a relative change of 1e-5."""
+    o, c = Oracle(cfg), Cuda(cfg)
+    rng = np.random.default_rng(seed)
+    o.set_tick(1); c.env.setTick(1)
+    o.reset(); c.reset()
+    n = o.n; aside = 0; total = 0; worst = 0.0; contacts = 0; dones = 0
+    for t in range(steps):
+        c.set_state(o.get_state().astype(np.float32))
+        a = np.clip(rng.normal(0, sigma, size=(n, 12)), -1, 1).astype(np.float32)
+        obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
+        so, sg = o.get_state(), c.get_state(); m = o.margins()
+        safe = (m[:, 0] > GEO) & (m[:, 1] > 1e-4) & (m[:, 2] > 1e-5) & (m[:, 3] > CONE)
+        aside += int((~safe).sum()); total += n
+        assert (do[safe] == dg[safe]).all(), t                                                # done flags
+        assert (sg[safe][:, S["contact"]] == so[safe][:, S["contact"]]).all(), t              # contact masks
+        assert (sg[safe][:, S["frame_idx"]] == so[safe][:, S["frame_idx"]]).all() and (sg[safe][:, S["itera"]] == so[safe][:, S["itera"]]).all(), t   # episode counters
+        e_ob = _elem(obg[safe], obo[safe], 1.0); e_r = _elem(rg[safe], ro[safe], 1.0); e_x = _elem(eg[safe], eo[safe], 1.0)
+        worst = max(worst, e_ob, e_r, e_x)
+        assert max(e_ob, e_r, e_x) <= tol, (t, e_ob, e_r, e_x)
+        contacts += int(so[:, S["contact"]].sum()); dones += int(do.sum())
+    return aside / total, worst, contacts, dones
+
+
+def test_flags_bit_exact_with_zero_exceptions_away_from_fp32_resolution():
+    cfg = trot_cfg(num_envs=N, num_threads=8, StochasticDynamics=True, ObsNoise=2.0)
+    frac, worst, contacts, dones = _teacher_forced(cfg, steps=70, sigma=0.3, seed=4)
+    print(f"set aside {frac:.4%} of the env-steps, worst value error {worst:.1e}, contact flags seen {contacts}, terminations {dones}")
+    assert frac < 0.025 and contacts > 1000
+
+
+def test_relaxation_configuration_parity():
+    """BASELINE.json configs[2]: mimic reward removed (JointRewardCoeff = EndEffectorRewardCoeff = 0), the bench workload"""
+    cfg = relaxation_cfg(num_envs=N, num_threads=8, StochasticDynamics=True, ObsNoise=2.0)
+    frac, worst, contacts, dones = _teacher_forced(cfg, steps=60, sigma=0.3, seed=5)
+    assert frac < 0.025 and contacts > 1000
+    # the reward really lacks the mimic terms: extraInfo reports them as zero
+    o, c = Oracle(cfg), Cuda(cfg)
+    o.reset(); c.reset()
+    ob, r, d, e = c.step(np.zeros((N, 12), np.float32))
+    assert (e[:, 0] == 0).all() and (e[:, 4] == 0).all() and (r > 0).all()

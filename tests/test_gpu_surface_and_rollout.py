@@ -211,9 +211,11 @@ def test_bp5_155_policy_reproduces_the_references_robot_level_results():
     import importlib.util, os as _os
     spec = importlib.util.spec_from_file_location("eval_bp5_155", _os.path.join(_os.path.dirname(_os.path.dirname(__file__)), "scripts", "eval_bp5_155.py"))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
-    r = mod.run(vx_cmd=5.0, mu=0.8, n=4, seconds=6.0)
+    r = mod.run(vx_cmd=5.0, mu=0.8, n=4, seconds=10.0)
     assert r["falls"] == 0
     assert abs(r["z_mean"] - 0.2732) < 0.02 * 0.2732                   # within 2 % of the RaiSim rollout
-    assert abs(r["vx_mean"] - r["cmd_mean_second_half"]) < 0.35        # tracks the command like the reference (err ~ -0.07 +- 0.07)
+    # tracks the ramped command within 2 % of the 5 m/s command (north_star bar); the reference's RaiSim rollout: error -0.036 / -0.066 +- 0.067 m/s.
+    # (Round 1 compared the 8 s mean 4.71 m/s with the final command 5.0; the command itself averages 4.71 over that window.)
+    assert abs(r["vx_mean"] - r["cmd_mean_second_half"]) < 0.02 * 5.0, r
     assert abs(r["stride_hz"] - 5.0) < 0.26 and abs(r["bounce_hz"] - 10.0) < 0.51
     assert abs(r["roll_mean"]) < 0.02 and abs(r["pitch_mean"]) < 0.02

@@ -165,13 +165,20 @@ def global_mean_std(x: torch.Tensor):
     return mean.to(x.dtype), torch.sqrt(var).to(x.dtype)
 
 
+ALLREDUCE_EVENTS = None   # set to a list to collect (start, end) CUDA events of every gradient all-reduce
+
+
 def allreduce_grads(grads: Sequence[torch.Tensor]):
     """one flat buffer (70 741 floats = 283 KB), sum over ranks / world."""
     dist, _, world = dist_info()
     if world == 1:
         return list(grads)
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat)
+    if ALLREDUCE_EVENTS is not None:      # bench.py: device time of the one collective of the workload (CUDA events around the NCCL call)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); dist.all_reduce(flat); e1.record(); ALLREDUCE_EVENTS.append((e0, e1))
+    else:
+        dist.all_reduce(flat)
     flat /= world
     out, o = [], 0
     for g in grads:

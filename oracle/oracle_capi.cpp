@@ -2,6 +2,7 @@
 // loaded by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
 #include "bp5_oracle.hpp"
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <random>
 
@@ -175,6 +176,47 @@ void bp5o_torque_clamp(void* h, double* torque, const double* gv) {
     if (H(h)->precision == 0) { auto& e = H(h)->d.envs[0]; for (int i = 0; i < 12; ++i) e.torque[i] = torque[i]; e.torque_clamp(gv); for (int i = 0; i < 12; ++i) torque[i] = e.torque[i]; }
     else { auto& e = H(h)->f.envs[0]; float g[18]; for (int i = 0; i < 18; ++i) g[i] = (float)gv[i]; for (int i = 0; i < 12; ++i) e.torque[i] = (float)torque[i]; e.torque_clamp(g); for (int i = 0; i < 12; ++i) torque[i] = e.torque[i]; }
 }
+// CPU arm of bench.py: the two-tower 2x48 LSTM act (CustomerLstmNN.py:112-156 + run_bp_v5.py:117-185; float32 like the
+// reference's TF graph) over all envs with OpenMP, one env per iteration.  params = the 19 arrays of the checkpoint flattened in
+// their order (70 741 floats); state [n,384] updated in place; eps [n,12] standard normal draws (NULL: deterministic).
+static inline float sigm(float x) { return 1.0f / (1.0f + std::exp(-x)); }
+static void lstm_cell_f(const float* x, int nin, float* c, float* h, const float* wx, const float* wh, const float* b) {
+    float g[192];
+    for (int j = 0; j < 192; ++j) g[j] = b[j];
+    for (int k = 0; k < nin; ++k) { const float xv = x[k]; const float* w = wx + (size_t)k * 192; for (int j = 0; j < 192; ++j) g[j] += xv * w[j]; }
+    for (int k = 0; k < 48; ++k) { const float hv = h[k]; const float* w = wh + (size_t)k * 192; for (int j = 0; j < 192; ++j) g[j] += hv * w[j]; }
+    for (int u = 0; u < 48; ++u) {          // gate order i, f, o, g (CustomerLstmNN.py:119-122)
+        const float i = sigm(g[u]), f = sigm(g[48 + u]), o = sigm(g[96 + u]), gg = std::tanh(g[144 + u]);
+        c[u] = f * c[u] + i * gg; h[u] = o * std::tanh(c[u]);
+    }
+}
+void bp5o_lstm_act(const float* params, int n, const float* obs, float* state, const uint8_t* done, const float* eps, float* action, float* value, float* neglogp, int threads) {
+    const float* p = params; const int in[4] = {35, 48, 35, 48};
+    const float *wx[4], *wh[4], *bb[4];
+    for (int i = 0; i < 4; ++i) { wx[i] = p; p += in[i] * 192; wh[i] = p; p += 48 * 192; bb[i] = p; p += 192; }
+    const float* vf_w = p; p += 48; const float* vf_b = p; p += 1; const float* pi_w = p; p += 48 * 12; const float* pi_b = p; p += 12; const float* logstd = p;
+    #pragma omp parallel for schedule(static) num_threads(threads)
+    for (int e = 0; e < n; ++e) {
+        float* s = state + (size_t)e * 384; const float* ob = obs + (size_t)e * 35;
+        if (done && done[e]) for (int k = 0; k < 384; ++k) s[k] = 0.f;                     // SB lstm(): c *= 1 - m, h *= 1 - m
+        for (int tower = 0; tower < 2; ++tower) {                                          // state = [c0,h0,c1,h1]_pi || [c0,h0,c1,h1]_V
+            float* t = s + 192 * tower;
+            lstm_cell_f(ob, 35, t, t + 48, wx[2 * tower], wh[2 * tower], bb[2 * tower]);
+            lstm_cell_f(t + 48, 48, t + 96, t + 144, wx[2 * tower + 1], wh[2 * tower + 1], bb[2 * tower + 1]);
+        }
+        const float* hp = s + 144; const float* hv = s + 192 + 144;
+        float v = vf_b[0]; for (int k = 0; k < 48; ++k) v += hv[k] * vf_w[k];
+        value[e] = v;
+        float nl = 0.5f * 12.f * std::log(2.0f * 3.14159265358979f);
+        for (int j = 0; j < 12; ++j) {
+            float m = pi_b[j]; for (int k = 0; k < 48; ++k) m += hp[k] * pi_w[k * 12 + j];
+            const float sd = std::exp(logstd[j]); const float a = eps ? m + sd * eps[(size_t)e * 12 + j] : m;
+            action[(size_t)e * 12 + j] = a; const float zz = (a - m) / sd; nl += 0.5f * zz * zz + logstd[j];
+        }
+        neglogp[e] = nl;
+    }
+}
+
 // Philox block exposed so tests can pin the RNG against the published Random123 known-answer vectors
 void bp5o_philox(unsigned seed, unsigned env, unsigned tick, unsigned purpose, unsigned* out) { Philox::gen(seed, env, tick, purpose, out); }
 // raw Philox4x32-10 with arbitrary counter/key, for the Random123 KAT

@@ -18,17 +18,31 @@ S = dict(gc=slice(0, 19), gv=slice(19, 37), ptarget_last=slice(37, 49), torque_l
 
 def build():
     src = [os.path.join(ROOT, "oracle", f) for f in ("oracle_capi.cpp", "bp5_oracle.hpp")]
-    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src if os.path.exists(s)):
+    if os.path.exists(_SO) and os.path.exists(_SO_FAST) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src if os.path.exists(s)):
         return _SO
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     return _SO
 
 
-def lib():
-    global _lib
+_SO_FAST = os.path.join(ROOT, "oracle", "libbp5_oracle_fast.so")   # same source, the reference's build flags (-O3 -mtune=native, CMakeLists.txt:28): timed CPU baseline only
+_lib_fast = None
+
+
+def lib(fast=False):
+    global _lib, _lib_fast
+    if fast:
+        if _lib_fast is None:
+            build()
+            _lib_fast = _declare(C.CDLL(_SO_FAST))
+        return _lib_fast
     if _lib is None:
         build()
-        L = C.CDLL(_SO)
+        _lib = _declare(C.CDLL(_SO))
+    return _lib
+
+
+def _declare(L):
+    if True:
         L.bp5o_create.restype = C.c_void_p
         L.bp5o_create.argtypes = [C.c_char_p, C.c_int, C.c_int]
         L.bp5o_time_steps.restype = C.c_double
@@ -37,8 +51,7 @@ def lib():
         for name in ("destroy", "reset", "observe", "step", "get_state", "set_state", "mass_and_h", "body_kin", "toe_kin",
                      "integrate", "contact_info", "reward_terms", "margins", "model_params", "set_ref", "set_tick"):
             getattr(L, "bp5o_" + name).argtypes = None
-        _lib = L
-    return _lib
+    return L
 
 
 def _p(a):
@@ -59,9 +72,9 @@ def count_flops(cfg: dict, warm=200, steps=300, sigma=0.1, seed=0):
 class Oracle:
     """The reference-semantics CPU vec-env: precision 'double' (like the reference) or 'float'."""
 
-    def __init__(self, cfg: dict, precision="double", env_offset=0, model40=None):
+    def __init__(self, cfg: dict, precision="double", env_offset=0, model40=None, fast=False):
         from high_speed_quadrupedal_locomotion_by_irrl_b200.cfg import to_kv_string
-        self.L = lib()
+        self.L = lib(fast)
         if model40 is None:
             self.h = C.c_void_p(self.L.bp5o_create(to_kv_string(cfg).encode(), 0 if precision == "double" else 1, env_offset))
         else:   # a robot description other than the shipped one: the 40 numbers of irrl_parse_urdf (include/irrl_b200.h)

@@ -17,6 +17,8 @@ if os.environ.get("IRRL_FASTDIV"):
     NVCC_FLAGS += ["-DIRRL_FASTDIV=" + os.environ["IRRL_FASTDIV"]]
 if os.environ.get("IRRL_SINCOS"):               # 0 libdevice sincosf, 1 MUFU, 2 (default) Cody-Waite polynomial
     NVCC_FLAGS += ["-DIRRL_SINCOS=" + os.environ["IRRL_SINCOS"]]
+if os.environ.get("IRRL_EXP"):                  # experiment switches: space-separated -D macros
+    NVCC_FLAGS += ["-D" + m for m in os.environ["IRRL_EXP"].split()]
 if os.environ.get("IRRL_STEP_MINWARPS"):       # tuning knob: register cap of the step kernel = 65536 / (32 * resident warps per SM)
     NVCC_FLAGS += ["-DSTEP_MINWARPS=" + os.environ["IRRL_STEP_MINWARPS"]]
 

@@ -174,7 +174,7 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         E->control_dt_d = ctl_dt; E->sim_dt_d = sim_dt; P.control_dt_d = ctl_dt;
         if (!num("seedd", d)) goto bad; P.seed = (uint32_t)(int)d;                                               // VEC:171
         // ENV:1598-1613
-        NUM("abad", P.abad) NUM("period", P.period) E->period_d = d; P.period_d = d; P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ P.meteor_every = int(5.0 * d / ctl_dt);   /* ENV:731 */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
+        NUM("abad", P.abad) NUM("period", P.period) E->period_d = d; P.period_d = d; P.inv_period_d = 1.0 / d; P.disturb_every = int(d / ctl_dt * 10.0);   /* ENV:746, double like the reference */ P.meteor_every = int(5.0 * d / ctl_dt);   /* ENV:731 */ NUM("lam", P.lam) NUM("stand_height", P.stand_height) NUM("up_height", P.up_height_max)
         IGN("down_height") IGN("gait_step")
         NUM("Vx", P.Vx_max) P.Vx_min = 0.f;                                                                      // ENV:1606-1607, 2054
         NUM("Vy", P.Vy_max) P.Vy_min = -P.Vy_max; NUM("Omega", P.omega_max) P.omega_min = -P.omega_max;
@@ -201,11 +201,12 @@ int read_cfg(irrl_env_impl* E, const YamlMap& y) {
         // optional solver / model switches of this implementation
         auto opt = [&](const char* k, double dflt) { double v; return y.has(k) && num(k, v) ? v : dflt; };
         P.joint_damping = (float)opt("joint_damping", 0.01);                                                     // URDF:56
-        P.solver_iters = (int)opt("solver_iters", 30); P.jacobi_sweeps = (int)opt("jacobi_sweeps", 6); P.slide_iters = (int)opt("slide_iters", 1); P.solver_tol = (float)opt("solver_tol", 1e-5);
+        P.solver_iters = (int)opt("solver_iters", 30); P.jacobi_sweeps = (int)opt("jacobi_sweeps", 10); P.slide_iters = (int)opt("slide_iters", 1); P.solver_tol = (float)opt("solver_tol", 1e-5);
         E->stair_rise = opt("stair_rise", 0.08); E->stair_run = opt("stair_run", 0.3); E->stair_start = opt("stair_start", 1.0); E->terrain_seed = (int)opt("terrain_seed", 0);
         P.mu = (float)opt("friction", 0.6); P.restitution = (float)opt("restitution", 0.2); P.rest_threshold = (float)opt("restitution_threshold", 0.01);   // ENV:433
     }
     if (P.N <= 0) return fail(-3, "num_envs must be positive");
+    if (P.slide_iters != 1) return fail(-3, "slide_iters: the CUDA contact solve takes exactly one fixed-point step on the sliding direction (other values exist in the CPU oracle only)");
     // ForceDisturbance: with Manual the step kernel perturbs the base state every 10 gait periods (state_disturbance, ENV:912-940);
     // without Manual force_attack(random() < 0.0027) never fires -> zero external force.
     switch (P.gait_type) {                                                                                       // ENV:398-409

@@ -371,7 +371,9 @@ __device__ __forceinline__ void solve_full(const Dyn& d, const float* rb, f3 rl,
 // Same rule as the oracle's solve_one_contact (separation / stick / slide with a fixed point on the
 // sliding direction).
 __device__ __forceinline__ float rsqrt_nr(float x) { float r = rsqrtf(x); return r * (1.5f - 0.5f * x * r * r); }   // ~1 ulp
-__device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Ginv, f3 lo, float vtn, float mu, int slide_iters) {
+// The sliding direction takes ONE fixed-point step from the stick direction (slide_iters = 1 of the oracle).  Branches, not selects:
+// measured 8 us faster at 4096 robots than a select-only version (separating / sticking contacts skip the sliding arithmetic).
+__device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Ginv, f3 lo, float vtn, float mu) {
     f3 e = mk(v.x, v.y, v.z - vtn);
     f3 ls = lo - mul(Ginv, e);
     if (!(ls.z > 0.f)) return mk(0.f, 0.f, 0.f);
@@ -381,20 +383,18 @@ __device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Gin
     f3 b = v - mul(G, lo);
     float il = rsqrt_nr(lt2);
     float dx = ls.x * il, dy = ls.y * il, lnz = 0.f;
-    for (int it = 0; it < slide_iters; ++it) {
-        float den = G.zz + mu * (G.xz * dx + G.yz * dy);
-        if (!(den > 1e-12f)) break;
-        lnz = fmaxf((IRRL_FASTDIV & 2) ? __fdividef(vtn - b.z, den) : (vtn - b.z) / den, 0.f);
+    const float rhs = vtn - b.z;
+    float den = G.zz + mu * (G.xz * dx + G.yz * dy);
+    if (den > 1e-12f) {
+        lnz = fmaxf((IRRL_FASTDIV & 2) ? __fdividef(rhs, den) : rhs / den, 0.f);
         float l0 = mu * lnz * dx, l1 = mu * lnz * dy;
         float vx = b.x + G.xx * l0 + G.xy * l1 + G.xz * lnz;
         float vy = b.y + G.xy * l0 + G.yy * l1 + G.yz * lnz;
         float vn2 = vx * vx + vy * vy;
         if (vn2 > 1e-18f) { float iv = rsqrt_nr(vn2); dx = -vx * iv; dy = -vy * iv; }
     }
-    {
-        float den = G.zz + mu * (G.xz * dx + G.yz * dy);
-        if (den > 1e-12f) lnz = fmaxf((IRRL_FASTDIV & 2) ? __fdividef(vtn - b.z, den) : (vtn - b.z) / den, 0.f);
-    }
+    den = G.zz + mu * (G.xz * dx + G.yz * dy);
+    if (den > 1e-12f) lnz = fmaxf((IRRL_FASTDIV & 2) ? __fdividef(rhs, den) : rhs / den, 0.f);
     return mk(mu * lnz * dx, mu * lnz * dy, lnz);
 }
 
@@ -481,7 +481,7 @@ __device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1
 
 // One Gauss-Seidel visit of the contact slot owned by lane `owner`: every lane evaluates its own slot, only the
 // owner's result is committed and its trunk-space increment is broadcast to the quad.
-__device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int owner, bool frozen, float mu, int slide_iters,
+__device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int owner, bool frozen, float mu,
                                          float& maxd, float& maxl) {
     // only the owner of an active, unconverged contact evaluates the solve: idle lanes (swinging feet) would otherwise
     // drag the whole warp through the sliding branch with meaningless velocities
@@ -491,7 +491,7 @@ __device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int own
         f3 v = ct.c + mul(ct.T, ct.lam);
 #pragma unroll
         for (int a = 0; a < 6; ++a) { v.x = fmaf(ct.Q[a][0], y[a], v.x); v.y = fmaf(ct.Q[a][1], y[a], v.y); v.z = fmaf(ct.Q[a][2], y[a], v.z); }
-        f3 ln = solve_one_contact(v, ct.G, ct.Ginv, ct.lam, ct.vtn, mu, slide_iters);
+        f3 ln = solve_one_contact(v, ct.G, ct.Ginv, ct.lam, ct.vtn, mu);
         dl = ln - ct.lam;
         ct.lam = ln;
         maxd = fmaxf(maxd, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
@@ -610,23 +610,28 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
         float y[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         bool frozen = !(qsum((float)(cf.active + cb.active)) > 0.f);    // robots without contacts never iterate
         int sweeps = 0;
-        for (int sweep = 0; sweep < P.solver_iters; ++sweep) {
-            if (__all_sync(FULLMASK, frozen)) break;
-            float maxd = 0.f, maxl = 0.f;
-            if (sweep >= P.jacobi_sweeps) {   // block Jacobi need not converge when 3-4 feet couple strongly (rare: 0.03 % of bounding
-                                               // contact substeps): from sweep jacobi_sweeps on the feet are visited one after the other too
+        // One loop over visits: iteration `it` is sweep `it` while it < jacobi_sweeps (all feet at once, block Jacobi); after that four
+        // iterations form one sweep, each with one leg enabled (the feet one after the other, Gauss-Seidel: block Jacobi need not
+        // converge when 3-4 feet couple strongly, 0.03 % of bounding contact substeps).  The trunk-box corners and the convergence test
+        // run at the end of every sweep.  One copy of the foot code, no inner loop.
+        const int J = min(P.jacobi_sweeps, P.solver_iters), it_end = J + 4 * (P.solver_iters - J);
+        float maxd = 0.f, maxl = 0.f;
 #pragma unroll 1
-                for (int o = 0; o < 4; ++o) {
-                    if (!__any_sync(FULLMASK, leg == o && cf.active && !frozen)) continue;
-                    gs_visit(cf, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
-                }
-            } else {   // feet: block Jacobi -- every lane updates its own foot contact from the same trunk-space vector y
+        for (int it = 0; it < it_end; ++it) {
+            if (__all_sync(FULLMASK, frozen)) break;
+#ifdef EXP_NO_SEQ
+            const bool seq = false;
+#else
+            const bool seq = it >= J;
+#endif
+            const int vi = (it - J) & 3;
+            {
                 f3 dl = mk(0.f, 0.f, 0.f);
-                if (cf.active && !frozen) {
+                if (cf.active && !frozen && (!seq || leg == vi)) {
                     f3 v = cf.c + mul(cf.T, cf.lam);
 #pragma unroll
                     for (int a = 0; a < 6; ++a) { v.x = fmaf(cf.Q[a][0], y[a], v.x); v.y = fmaf(cf.Q[a][1], y[a], v.y); v.z = fmaf(cf.Q[a][2], y[a], v.z); }
-                    f3 ln = solve_one_contact(v, cf.G, cf.Ginv, cf.lam, cf.vtn, bm.mu, P.slide_iters);
+                    f3 ln = solve_one_contact(v, cf.G, cf.Ginv, cf.lam, cf.vtn, bm.mu);
                     dl = ln - cf.lam; cf.lam = ln;
                     maxd = fmaxf(maxd, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
                     maxl = fmaxf(maxl, fmaxf(fabsf(ln.x), fmaxf(fabsf(ln.y), fabsf(ln.z))));
@@ -634,15 +639,17 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
 #pragma unroll
                 for (int a = 0; a < 6; ++a) y[a] += qsum(cf.Q[a][0] * dl.x + cf.Q[a][1] * dl.y + cf.Q[a][2] * dl.z);
             }
+            if (seq && vi != 3) continue;                                   // sweep not finished yet
             if (any_box) {
 #pragma unroll 1
                 for (int o = 0; o < 4; ++o) {
                     if (!__any_sync(FULLMASK, leg == o && cb.active && !frozen)) continue;
-                    gs_visit(cb, y, leg, o, frozen, bm.mu, P.slide_iters, maxd, maxl);
+                    gs_visit(cb, y, leg, o, frozen, bm.mu, maxd, maxl);
                 }
             }
             maxd = qmax(maxd); maxl = qmax(maxl);
-            if (!frozen) { sweeps = sweep + 1; if (maxd <= P.solver_tol * maxl) frozen = true; }
+            if (!frozen) { sweeps += 1; if (maxd <= P.solver_tol * maxl) frozen = true; }
+            maxd = 0.f; maxl = 0.f;
         }
         out.sweeps = sweeps;
 #pragma unroll

@@ -75,9 +75,13 @@ __device__ __forceinline__ int ref_row(const EnvParams& P, int frame_idx) { retu
 // phase of leg `leg` in its gait cycle, fmod(t + phase * T, T) / T (ENV:1172-1181, 1523-1527), reduced in double: in fp32 the clock
 // t ~ 1.5 s carries 1e-7 s, which the contact-reward shaping (slope 2 * 2 pi / lam) turns into 1e-5 of the reward exponent
 __device__ __forceinline__ float gait_phase(const EnvParams& P, const EnvRegs& e, int leg) {
+#ifdef EXP_F32_PHASE
+    float rp = fmaf((float)e.frame_idx, P.control_dt, e.t0) + P.phase[leg] * P.period; return fmodf(rp, P.period) / P.period;
+#else
     const double t = (double)e.t0 + (double)e.frame_idx * P.control_dt_d;
-    const double x = t / P.period_d + (double)P.phase[leg];
+    const double x = t * P.inv_period_d + (double)P.phase[leg];       // reciprocal precomputed on the host: no fp64 division subroutine
     return (float)(x - floor(x));
+#endif
 }
 __device__ __forceinline__ f3 nominal_q(const EnvParams& P, int leg) { return mk((leg & 1) ? P.abad : -P.abad, -0.78f, 1.57f); }   // ENV:317-322
 
@@ -663,7 +667,9 @@ __global__ void env_init_kernel(EnvParams P, DevState S) {
 static inline int quad_grid(int N) { return (N * 4 + BLOCK - 1) / BLOCK; }
 void launch_env_step(const StepArgs& a, cudaStream_t st) {
     static const int sync_min = [] { const char* e = getenv("IRRL_STEP_SYNC_MIN"); return e ? atoi(e) : 5120; }();   // tuning knob: robots above which the barrier variant runs (measured: 4096 -> 67.8 vs 73.6 us without / with barriers, 6144 -> 79.4 vs 77.5)
-    if (a.P.N > sync_min) env_step_kernel<128, true><<<(a.P.N * 4 + 127) / 128, 128, 0, st>>>(a);
+    static const int blk = [] { const char* e = getenv("IRRL_STEP_BLK"); return e ? atoi(e) : 0; }();   // experiment: force the CTA size (256 = one lock-stepped CTA per SM)
+    if (blk == 256) env_step_kernel<256, true><<<(a.P.N * 4 + 255) / 256, 256, 0, st>>>(a);
+    else if (blk == 128 || (blk == 0 && a.P.N > sync_min)) env_step_kernel<128, true><<<(a.P.N * 4 + 127) / 128, 128, 0, st>>>(a);
     else env_step_kernel<64, false><<<quad_grid(a.P.N), 64, 0, st>>>(a);
 }
 void launch_env_meteor(const StepArgs& a, int respawn_only, cudaStream_t st) { env_meteor_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a, respawn_only); }

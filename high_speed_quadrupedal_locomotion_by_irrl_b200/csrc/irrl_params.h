@@ -33,7 +33,7 @@ struct EnvParams {
     float stiffness, abad_ratio, damping, max_time, action_noise, noise_flag;
     float motor_max_torque, motor_crit_speed, motor_max_speed;
     float sim_dt, control_dt;
-    double control_dt_d, period_d; // the YAML doubles: the gait phase of the contact reward / time-based contact flags is reduced in double (a handful of fp64 operations per control step)
+    double control_dt_d, period_d, inv_period_d; // the YAML doubles: the gait phase of the contact reward / time-based contact flags is reduced in double (a handful of fp64 operations per control step)
     int loop_count;               // ENV:711
     int disturb_every;            // ENV:746 : control steps between state disturbances = int(period / control_dt * 10)
     int flag_crucial, num_cube, meteor_every;   // Crutial: True (ENV:717-741, 815-861): meteor sphere re-created every int(5 * period / control_dt) control steps

@@ -388,7 +388,7 @@ template <typename T> struct Env {
     T solver_tol = T(1e-5);       // relative impulse change for early exit
     int slide_iters = 1;          // fixed-point iterations for the sliding direction
     int solver_jacobi = 1;        // 1: feet updated simultaneously per sweep (see integrate())
-    int jacobi_sweeps = 6;        // sweeps after which the feet are visited one after the other too (block Jacobi need not converge when 3-4 feet couple strongly)
+    int jacobi_sweeps = 10;       // sweeps after which the feet are visited one after the other too (block Jacobi need not converge when 3-4 feet couple strongly)
     int slide_exact = 0;          // 1: exact maximal-dissipation sliding solve by bisection on the cone boundary (RaiSim's rule, Hwangbo et al. 2018);
                                   // CPU-only yardstick for the one-step direction update the product uses (tests/test_oracle_contact_solver.py)
 
@@ -458,7 +458,7 @@ template <typename T> struct Env {
         simulation_dt_ = T(c.get("simulation_dt")); control_dt_ = T(c.get("control_dt"));   // VEC:151-152
         // solver / model switches (new-spec, optional)
         model.joint_damping = T(c.get_or("joint_damping", double(model.joint_damping)));
-        solver_iters = (int)c.get_or("solver_iters", 30); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 1); solver_jacobi = (int)c.get_or("solver_jacobi", 1); jacobi_sweeps = (int)c.get_or("jacobi_sweeps", 6); slide_exact = (int)c.get_or("slide_exact", 0);
+        solver_iters = (int)c.get_or("solver_iters", 30); solver_tol = T(c.get_or("solver_tol", 1e-5)); slide_iters = (int)c.get_or("slide_iters", 1); solver_jacobi = (int)c.get_or("solver_jacobi", 1); jacobi_sweeps = (int)c.get_or("jacobi_sweeps", 10); slide_exact = (int)c.get_or("slide_exact", 0);
         mu = T(c.get_or("friction", 0.6)); restitution = T(c.get_or("restitution", 0.2)); rest_threshold = T(c.get_or("restitution_threshold", 0.01));
 
         // gc_init_ ENV:317-322

@@ -4,7 +4,7 @@ The RaiSim boundary is unpinned (closed source), so this file pins the solver ag
 (Hwangbo, Lee, Hutter, RA-L 2018; call site ENV:768, material ENV:433, ERP 0 ENV:246): per-contact Gauss-Seidel sweeps to
 convergence, each visit solving the single-contact problem exactly on the friction cone (bisection on the cone boundary).
 
-* schedule: the product runs the foot contacts of a sweep simultaneously (block Jacobi) for the first 6 sweeps because that maps
+* schedule: the product runs the foot contacts of a sweep simultaneously (block Jacobi) for the first 10 sweeps because that maps
   onto one lane per leg, then one after the other like the trunk-box corners; <= 30 sweeps, relative tolerance 1e-5.
   `solver_jacobi=0, solver_iters=500, solver_tol=1e-12` is plain per-contact Gauss-Seidel to convergence.  On > 10^4
   contact-rich substeps the two give the same post-impact velocity to <= 1e-5 (belly-down poses with 6-8 contacts: 1e-4) and

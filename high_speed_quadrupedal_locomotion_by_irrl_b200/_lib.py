@@ -17,6 +17,10 @@ class RolloutBuffers(C.Structure):
                                            "state", "ep_return", "ep_length")]
 
 
+class ActStepIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "done", "state", "action", "clipped", "value", "neglogp", "next_obs", "reward", "next_done", "extra")]
+
+
 def load() -> C.CDLL:
     global _lib
     if _lib is not None:
@@ -63,6 +67,7 @@ def load() -> C.CDLL:
     L.irrl_tc_mma_rate.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
     L.irrl_tc_gemm_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.irrl_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(RolloutBuffers), C.c_int]
+    L.irrl_act_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ActStepIO), C.c_int, C.c_uint32, C.c_int]
     L.irrl_gae.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     L.irrl_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.irrl_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -82,6 +82,8 @@ struct irrl_env_impl {
     float* d_ref = nullptr;
     unsigned char* h_pin = nullptr; size_t h_pin_bytes = 0; size_t scratch_floats = 0;
     std::vector<void*> allocs;
+    // irrl_act_step: device copies of the act outputs [action | clipped | value | neglogp], chunk streams and their join events
+    float* d_fused_act = nullptr; cudaStream_t chunk_stream[8] = {}; cudaEvent_t chunk_done[8] = {}; cudaEvent_t fork_ev = nullptr; int n_chunk_streams = 0;
     // optional per-kernel timing of irrl_rollout (CUDA events on the env's stream)
     bool profiling = false; std::vector<cudaEvent_t> prof_events; size_t prof_cursor = 0; double prof_act_ms = 0, prof_step_ms = 0; long prof_count = 0;
 };
@@ -310,7 +312,7 @@ int deliver(irrl_env_impl* E, void* user, const void* dev, size_t bytes) {
 
 StepArgs make_args(irrl_env_impl* E, const float* action, float* ob, float* reward, uint8_t* done, float* extra) {
     StepArgs a; a.P = E->P; a.S = E->S; a.action = action; a.ob = ob; a.reward = reward; a.done = done; a.extra = extra;
-    a.ep_ret_out = E->d_ep_ret; a.ep_len_out = E->d_ep_len; a.tick = E->tick; return a;
+    a.ep_ret_out = E->d_ep_ret; a.ep_len_out = E->d_ep_len; a.tick = E->tick; a.r_begin = 0; a.r_end = E->P.N; return a;
 }
 
 // generic probe helper: run `fn` into a device buffer of `per_env` floats and deliver
@@ -366,6 +368,8 @@ void irrl_destroy(irrl_env* env) {
     if (E->stream) cudaStreamSynchronize(E->stream);
     for (void* p : E->allocs) cudaFree(p);
     if (E->h_pin) cudaFreeHost(E->h_pin);
+    for (int i = 0; i < E->n_chunk_streams; ++i) { cudaStreamDestroy(E->chunk_stream[i]); cudaEventDestroy(E->chunk_done[i]); }
+    if (E->fork_ev) cudaEventDestroy(E->fork_ev);
     if (E->own_stream && E->stream) cudaStreamDestroy(E->stream);
     delete E;
 }
@@ -968,6 +972,104 @@ int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buff
         E->tick++;
     }
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- one host entry per control step: model.step (run_bp_v5.py:178-185) -> np.clip (ppo2.py:529-531) -> env.step (RaisimGymVecEnv.py:26-52)
+// The environments are cut into chunks that travel through separate streams: the host->device copy of chunk k+1 and the
+// device->host copy of chunk k-1 overlap the two kernels of chunk k, so the PCIe time of a step hides behind its compute.
+static int batch_copy(void** dst, void** src, size_t* bytes, int n, cudaMemcpyKind kind, cudaStream_t st) {
+    static bool use_batch = [] { const char* e = getenv("IRRL_BATCH_COPY"); return !e || atoi(e) != 0; }();
+    if (use_batch && n > 1) {
+        cudaMemcpyAttributes attr{}; attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream; attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+        size_t idx = 0, fail = 0;
+        cudaError_t e = cudaMemcpyBatchAsync(dst, src, bytes, (size_t)n, &attr, &idx, 1, &fail, st);
+        if (e == cudaSuccess) return 0;
+        cudaGetLastError(); use_batch = false;                      // not supported by this driver / stream: plain copies from now on
+    }
+    for (int i = 0; i < n; ++i) CUDA_OK(cudaMemcpyAsync(dst[i], src[i], bytes[i], kind, st));
+    return 0;
+}
+int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, int deterministic, uint32_t act_tick, int chunks) {
+    ENV(env); NEED_INIT();
+    irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn || !io) return fail(-1, "null argument");
+    if (E->P.flag_obs_filter) return fail(-3, "irrl_act_step does not support ObsFilter: True (use irrl_policy_act + irrl_step)");
+    if (!io->obs || !io->state || !io->action || !io->value || !io->neglogp || !io->next_obs || !io->reward || !io->next_done) return fail(-1, "irrl_act_step: null buffer");
+    if (!is_device_ptr(io->state)) return fail(-1, "irrl_act_step: the LSTM state must be device memory (it stays resident between steps)");
+    const size_t N = (size_t)E->P.N;
+    const bool host = !is_device_ptr(io->obs);
+    const void* all[] = {io->obs, io->done, io->action, io->clipped, io->value, io->neglogp, io->next_obs, io->reward, io->next_done, io->extra};
+    const size_t all_bytes[] = {N * 140, N, N * 48, N * 48, N * 4, N * 4, N * 140, N * 4, N, N * 24};
+    for (int i = 0; i < 10; ++i) {
+        if (!all[i]) continue;
+        if (host ? !is_pinned_host_ptr(all[i], all_bytes[i]) : !is_device_ptr(all[i]))
+            return fail(-1, host ? "irrl_act_step: host buffers must be page-locked (irrl_host_register / cudaHostAlloc): the copies run asynchronously on several streams"
+                                 : "irrl_act_step: obs is device memory, so every buffer must be device memory");
+    }
+    // device images of the host buffers: [action | clipped | value | neglogp] next to the env's own [ob | reward | extra | done] block
+    if (host && !E->d_fused_act) { void* q = nullptr; CUDA_OK(cudaMalloc(&q, N * 26 * sizeof(float))); E->allocs.push_back(q); E->d_fused_act = (float*)q; }
+    // measured (scripts/r2_e2e.py): the kernels are latency-bound below ~8k environments (a half-size launch takes as long as a full
+    // one) and every extra stream hop costs ~5 us, so the batch is cut only from 12k environments on (2 chunks)
+    int K = chunks > 0 ? chunks : (N >= 12288 ? 2 : 1);
+    if (!host || E->P.flag_crucial) K = 1;
+    K = std::min(K, 8);
+    size_t per = ((N + K - 1) / K + 127) / 128 * 128;      // chunk boundaries on multiples of 128 environments (the tile of the tensor-core act kernel)
+    while (E->n_chunk_streams < K) {
+        CUDA_OK(cudaStreamCreateWithFlags(&E->chunk_stream[E->n_chunk_streams], cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&E->chunk_done[E->n_chunk_streams], cudaEventDisableTiming)); E->n_chunk_streams++;
+    }
+    if (!E->fork_ev) CUDA_OK(cudaEventCreateWithFlags(&E->fork_ev, cudaEventDisableTiming));
+    float *d_act = host ? E->d_fused_act : io->action, *d_clip = host ? E->d_fused_act + N * 12 : (io->clipped ? io->clipped : E->d_action),
+          *d_val = host ? E->d_fused_act + N * 24 : io->value, *d_nlp = host ? E->d_fused_act + N * 25 : io->neglogp;
+    float *d_ob = host ? E->d_ob : io->next_obs, *d_rew = host ? E->d_reward : io->reward, *d_ext = host ? E->d_extra : io->extra; uint8_t* d_done = host ? E->d_done : io->next_done;
+    const float* d_obs_in = host ? E->d_ob : io->obs; const uint8_t* d_done_in = host ? (io->done ? E->d_done : nullptr) : io->done;
+    // host buffers laid out like the device images (fused_host_step in vec_env.py does that): one copy per block instead of one per array
+    const bool in_place = io->obs == io->next_obs && (!io->done || io->done == io->next_done);
+    const bool env_block = host && io->extra && io->reward == io->next_obs + N * 35 && io->extra == io->reward + N && io->next_done == reinterpret_cast<uint8_t*>(io->extra + N * 6);
+    const bool act_block = host && io->clipped && io->clipped == io->action + N * 12 && io->value == io->clipped + N * 12 && io->neglogp == io->value + N;
+    if (E->P.flag_crucial) { StepArgs m = make_args(E, nullptr, nullptr, nullptr, nullptr, nullptr); launch_env_meteor(m, 0, E->stream); }
+    if (K > 1) CUDA_OK(cudaEventRecord(E->fork_ev, E->stream));
+    int used = 0;
+    for (size_t lo = 0; lo < N; lo += per, ++used) {
+        const size_t hi = std::min(N, lo + per), n = hi - lo;
+        cudaStream_t st = K == 1 ? E->stream : E->chunk_stream[used];
+        if (K > 1) CUDA_OK(cudaStreamWaitEvent(st, E->fork_ev, 0));
+        if (host) {
+            if (K == 1 && env_block && in_place && io->done) {     // [ob | reward | extra | done] in one copy (reward / extra ride along: 28 of 169 bytes per env)
+                CUDA_OK(cudaMemcpyAsync(E->d_ob, io->obs, N * 168 + N, cudaMemcpyHostToDevice, st));
+            } else {
+                void* dst[2] = {(void*)(E->d_ob + lo * 35), (void*)(E->d_done + lo)}; void* src[2] = {(void*)(io->obs + lo * 35), (void*)(io->done ? io->done + lo : nullptr)};
+                size_t by[2] = {n * 140, n};
+                if (int rc = batch_copy(dst, src, by, io->done ? 2 : 1, cudaMemcpyHostToDevice, st)) return rc;
+            }
+        }
+        ActArgs a; a.W = Pn->W; a.N = (int)n; a.deterministic = deterministic; a.seed = E->P.seed; a.env_offset = E->P.env_offset + (uint32_t)lo; a.tick = act_tick; a.n_total = (int)N;
+        a.mean = nullptr; a.obs_store = nullptr; a.done_store = nullptr;
+        a.obs = d_obs_in + lo * 35; a.done = d_done_in ? d_done_in + lo : nullptr; a.state = io->state + lo * 384;
+        a.action = d_act + lo * 12; a.clipped = d_clip + lo * 12; a.value = d_val + lo; a.neglogp = d_nlp + lo;
+        launch_lstm_act(a, st);
+        StepArgs s = make_args(E, d_clip, d_ob, d_rew, d_done, d_ext ? d_ext : E->d_extra);
+        s.r_begin = (int)lo; s.r_end = (int)hi;
+        launch_env_step(s, st);
+        if (host) {
+            if (K == 1 && env_block && act_block) {
+                CUDA_OK(cudaMemcpyAsync(io->action, E->d_fused_act, N * 26 * sizeof(float), cudaMemcpyDeviceToHost, st));
+                CUDA_OK(cudaMemcpyAsync(io->next_obs, E->d_ob, N * 168 + N, cudaMemcpyDeviceToHost, st));
+            } else {
+                void* dst[8]; void* src[8]; size_t by[8]; int c = 0;
+                auto add = [&](void* h, void* d, size_t b) { if (h) { dst[c] = h; src[c] = d; by[c] = b; ++c; } };
+                add(io->action + lo * 12, d_act + lo * 12, n * 48); if (io->clipped) add(io->clipped + lo * 12, d_clip + lo * 12, n * 48);
+                add(io->value + lo, d_val + lo, n * 4); add(io->neglogp + lo, d_nlp + lo, n * 4);
+                add(io->next_obs + lo * 35, d_ob + lo * 35, n * 140); add(io->reward + lo, d_rew + lo, n * 4);
+                if (io->extra) add(io->extra + lo * 6, E->d_extra + lo * 6, n * 24); add(io->next_done + lo, d_done + lo, n);
+                if (int rc = batch_copy(dst, src, by, c, cudaMemcpyDeviceToHost, st)) return rc;
+            }
+        }
+        if (K > 1) { CUDA_OK(cudaEventRecord(E->chunk_done[used], st)); CUDA_OK(cudaStreamWaitEvent(E->stream, E->chunk_done[used], 0)); }
+    }
+    CUDA_OK(cudaGetLastError());
+    E->tick++;
+    if (host) CUDA_OK(cudaStreamSynchronize(E->stream));
     return 0;
 }
 

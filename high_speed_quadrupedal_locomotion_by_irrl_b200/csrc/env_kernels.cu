@@ -256,9 +256,9 @@ template <int BLK, bool SYNC>
 __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env_step_kernel(const __grid_constant__ StepArgs A) {
     const EnvParams& P = A.P; const DevState& S = A.S;
     const int tid = blockIdx.x * BLK + threadIdx.x;
-    int r = tid >> 2; const int leg = tid & 3;
-    const bool valid = r < P.N;
-    if (!valid) r = P.N - 1;                      // tail lanes shadow the last robot (no stores) so quads stay convergent
+    int r = A.r_begin + (tid >> 2); const int leg = tid & 3;
+    const bool valid = r < A.r_end;
+    if (!valid) r = A.r_end - 1;                  // tail lanes shadow the last robot (no stores) so quads stay convergent
     const int gid = r + (int)P.env_offset;
     EnvRegs e; load_env(S, r, leg, e);
 
@@ -668,9 +668,10 @@ static inline int quad_grid(int N) { return (N * 4 + BLOCK - 1) / BLOCK; }
 void launch_env_step(const StepArgs& a, cudaStream_t st) {
     static const int sync_min = [] { const char* e = getenv("IRRL_STEP_SYNC_MIN"); return e ? atoi(e) : 5120; }();   // tuning knob: robots above which the barrier variant runs (measured: 4096 -> 67.8 vs 73.6 us without / with barriers, 6144 -> 79.4 vs 77.5)
     static const int blk = [] { const char* e = getenv("IRRL_STEP_BLK"); return e ? atoi(e) : 0; }();   // experiment: force the CTA size (256 = one lock-stepped CTA per SM)
-    if (blk == 256) env_step_kernel<256, true><<<(a.P.N * 4 + 255) / 256, 256, 0, st>>>(a);
-    else if (blk == 128 || (blk == 0 && a.P.N > sync_min)) env_step_kernel<128, true><<<(a.P.N * 4 + 127) / 128, 128, 0, st>>>(a);
-    else env_step_kernel<64, false><<<quad_grid(a.P.N), 64, 0, st>>>(a);
+    const int n = a.r_end - a.r_begin; if (n <= 0) return;
+    if (blk == 256) env_step_kernel<256, true><<<(n * 4 + 255) / 256, 256, 0, st>>>(a);
+    else if (blk == 128 || (blk == 0 && n > sync_min)) env_step_kernel<128, true><<<(n * 4 + 127) / 128, 128, 0, st>>>(a);
+    else env_step_kernel<64, false><<<quad_grid(n), 64, 0, st>>>(a);
 }
 void launch_env_meteor(const StepArgs& a, int respawn_only, cudaStream_t st) { env_meteor_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a, respawn_only); }
 void launch_env_reset(const StepArgs& a, cudaStream_t st) { env_reset_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a); }

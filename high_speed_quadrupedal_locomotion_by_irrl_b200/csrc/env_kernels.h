@@ -16,6 +16,7 @@ struct StepArgs {
     float* ep_ret_out;     // [N] episode return of the envs that finished this step (may be null)
     int* ep_len_out;       // [N]
     uint32_t tick;
+    int r_begin, r_end;    // env range of this launch of the step kernel (irrl_act_step pipelines chunks of envs over several streams); whole shard = [0, N)
 };
 
 void launch_env_step(const StepArgs& a, cudaStream_t st);
@@ -59,6 +60,7 @@ struct ActArgs {
     uint8_t* done_store;    // [N] copy of the mask (Runner's mb_dones), may be null
     int N; int deterministic;
     uint32_t seed, env_offset, tick;
+    int n_total = 0;        // when this launch covers a chunk of a larger batch: size of the whole batch (selects the same kernel for every chunk); 0 = N
 };
 void launch_lstm_act(const ActArgs& a, cudaStream_t st);          // dispatches on N and g_act_path
 void launch_lstm_act_fma(const ActArgs& a, cudaStream_t st);      // fp32 FMA kernel (policy_kernels.cu)

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NTHR, 2) lstm_act_kernel(const __grid_constant
 int g_act_path = 0;
 void launch_lstm_act(const ActArgs& a, cudaStream_t st) {
     // the tensor-core kernel moves state rows with the bulk-copy engine: 16-byte aligned rows required (always true for [N,384] allocations)
-    const bool tc = (g_act_path == 2 || (g_act_path == 0 && a.N >= 256)) && (reinterpret_cast<uintptr_t>(a.state) & 15) == 0;
+    const bool tc = (g_act_path == 2 || (g_act_path == 0 && (a.n_total > a.N ? a.n_total : a.N) >= 256)) && (reinterpret_cast<uintptr_t>(a.state) & 15) == 0;
     if (tc) launch_lstm_act_tc(a, st); else launch_lstm_act_fma(a, st);
 }
 void launch_lstm_act_fma(const ActArgs& a, cudaStream_t st) {

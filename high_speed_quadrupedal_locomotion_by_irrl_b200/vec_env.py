@@ -6,8 +6,9 @@ flex_gym/env/RaisimGymVecEnv.py (attributes `wrapper, num_obs, num_acts, _observ
   * `info` is a lazy sequence.  The reference materialises 6N one-key dicts per step (entry k holds extra-info j = k // N of env
     i = k % N, and entry i also gets env i's `episode`), of which only `info[i]['episode']` is ever read (ppo2.py:534-537).
     `LazyInfo` builds an entry only when it is indexed, with the same content.
-  * episode return / length bookkeeping happens in the step kernel; `self.rewards` keeps the reference's list-of-lists view only
-    with `track_rewards=True`.
+  * episode return / length bookkeeping happens in the step kernel; `self.rewards` is the reference's list of per-env reward lists
+    (RaisimGymVecEnv.py:21, 42-50) up to `TRACK_REWARDS_MAX_ENVS` environments (the reference's own scale: 200 envs) and an O(1)
+    stand-in above it unless `track_rewards=True` is passed: N Python list appends per step are what dominates at N >= 16k.
   * numpy >= 1.24 spellings (`bool`, `np.inf`).
 """
 from __future__ import annotations
@@ -50,7 +51,7 @@ class LazyInfo(Sequence):
         return entry
 
     def copy(self):
-        return self
+        return LazyInfo(self._names, self._extra.copy(), dict(self._episodes))
 
     def episodes(self):
         """the `episode` records only, by env index"""
@@ -71,8 +72,28 @@ _PASSTHROUGH = {"close": "close", "start_recording_video": "startRecordingVideo"
                 "curriculum_callback": "curriculumUpdate", "show_window": "showWindow", "hide_window": "hideWindow"}
 
 
+TRACK_REWARDS_MAX_ENVS = 1024
+
+
+class _UntrackedRewards(Sequence):
+    """`rewards` above TRACK_REWARDS_MAX_ENVS: indexable like the reference's list of lists, every per-env history empty"""
+
+    def __init__(self, n):
+        self._n = n
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [[] for _ in range(*i.indices(self._n))]
+        if not -self._n <= i < self._n:
+            raise IndexError(i)
+        return []
+
+
 class RaisimGymVecEnv:
-    def __init__(self, impl, track_rewards: bool = False):
+    def __init__(self, impl, track_rewards=None):
         self.wrapper = impl
         impl.init()
         n = impl.getNumOfEnvs()
@@ -90,8 +111,8 @@ class RaisimGymVecEnv:
             self._reward = np.zeros(n, np.float32)
             self._done = np.zeros(n, bool)
             self._extraInfo = np.zeros((n, len(self._extraInfoNames)), np.float32)
-        self._track = track_rewards
-        self.rewards = [[] for _ in range(n)] if track_rewards else None
+        self._track = (n <= TRACK_REWARDS_MAX_ENVS) if track_rewards is None else bool(track_rewards)
+        self.rewards = [[] for _ in range(n)] if self._track else _UntrackedRewards(n)
 
     # ------------------------------------------------------------------ hot path
     def step(self, action, visualize=False):
@@ -156,3 +177,35 @@ class RaisimGymVecEnv:
     observation_space = property(lambda self: self._observation_space)
     action_space = property(lambda self: self._action_space)
     extra_info_names = property(lambda self: self._extraInfoNames)
+
+
+class fused_host_step:
+    """One native call per control step of a host-side rollout loop (include/irrl_b200.h irrl_act_step): model.step -> clip ->
+    env.step with page-locked host buffers owned here.  `obs` / `done` are inputs and outputs (Runner.run threads them through,
+    ppo2.py:519-538); `action, clipped, value, neglogp, reward, extra` are the step's results.  `state` is a device tensor / pointer.
+
+        fs = fused_host_step(env.wrapper, policy, state, stream_ptr)
+        env.wrapper.reset(fs.obs)
+        for t in range(T): fs(tick0 + t); mb_obs.append(fs.obs.copy()) ...
+    """
+
+    def __init__(self, wrapper, policy, state, stream_ptr=None, seed=None, env_offset=None, chunks=0, deterministic=False):
+        import ctypes as C
+        from . import _lib
+        self._L, self._C = _lib.load(), C
+        n = wrapper.getNumOfEnvs()
+        self.action, self.clipped, self.value, self.neglogp, self.obs, self.reward, self.extra, self.done = _lib.pinned_block(
+            ((n, 12), np.float32), ((n, 12), np.float32), ((n,), np.float32), ((n,), np.float32),
+            ((n, 35), np.float32), ((n,), np.float32), ((n, 6), np.float32), ((n,), np.bool_))
+        self._wrapper, self._policy, self._state = wrapper, policy, state          # keep the owners alive
+        sp = state.data_ptr() if hasattr(state, "data_ptr") else int(state)
+        p = lambda a: a.ctypes.data
+        self._io = _lib.ActStepIO(obs=p(self.obs), done=p(self.done), state=sp, action=p(self.action), clipped=p(self.clipped), value=p(self.value),
+                                  neglogp=p(self.neglogp), next_obs=p(self.obs), reward=p(self.reward), next_done=p(self.done), extra=p(self.extra))
+        self._chunks, self._det = int(chunks), int(bool(deterministic))
+        self.h2d_bytes = n * (35 * 4 + 1) if (chunks > 1 or (chunks == 0 and n >= 12288)) else n * (42 * 4 + 1)   # the un-chunked path moves the whole [obs | reward | extra | done] block
+        self.d2h_bytes = n * (12 * 4 * 2 + 4 + 4 + 35 * 4 + 4 + 6 * 4 + 1)
+
+    def __call__(self, tick):
+        from . import _lib
+        _lib.check(self._L.irrl_act_step(self._wrapper.handle, self._policy.handle, self._C.byref(self._io), self._det, int(tick) & 0xFFFFFFFF, self._chunks), "act_step")

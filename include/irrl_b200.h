@@ -172,6 +172,27 @@ typedef struct irrl_rollout_buffers {
     int32_t* ep_length;/* [T,N] (may be NULL) */
 } irrl_rollout_buffers;
 int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* buf, int deterministic);
+/* One host entry per control step of a rollout: model.step (run_bp_v5.py:178-185) -> np.clip (ppo2.py:529-531) -> env.step
+ * (RaisimGymVecEnv.py:26-52 -> VectorizedEnvironment.hpp:268-278), i.e. what Runner.run does between two iterations of its loop
+ * (ppo2.py:519-538) with ONE call instead of two.  Buffers are either all device memory (no copies, asynchronous on the env's stream)
+ * or all PAGE-LOCKED host memory (irrl_host_register): then the environments are cut into `chunks` pieces (0 = automatic) that
+ * travel through separate streams, so that the copies of one chunk overlap the kernels of another, and the call returns when
+ * everything has landed.  obs / done may alias next_obs / next_done (the outputs of one call are the inputs of the next).  The LSTM
+ * state is device memory (the Runner only threads `states` through, ppo2.py:520).  act_tick keys the Gaussian draws. */
+typedef struct irrl_act_step_io {
+    const float* obs;        /* [N,35] in  */
+    const uint8_t* done;     /* [N]    in: done flag of the previous step = LSTM mask (may be NULL) */
+    float* state;            /* [N,384] in/out, DEVICE */
+    float* action;           /* [N,12] out: sampled, unclipped (mb_actions) */
+    float* clipped;          /* [N,12] out: what the env received (may be NULL) */
+    float* value;            /* [N]    out */
+    float* neglogp;          /* [N]    out */
+    float* next_obs;         /* [N,35] out */
+    float* reward;           /* [N]    out */
+    uint8_t* next_done;      /* [N]    out */
+    float* extra;            /* [N,6]  out (may be NULL) */
+} irrl_act_step_io;
+int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, int deterministic, uint32_t act_tick, int chunks);
 /* sequence-persistent BPTT through one LSTM layer of K towers (the PPO learner's recurrence, ppo2.py:136-197 over run_bp_v5.py:143-166):
  * one launch per direction, a CTA owns 32 envs for all T steps.  Time-major device tensors: xw / gates / dz [T,K,N,192] (gate order
  * i,f,o,g), Cs / Hs / dH [T,K,N,48], keep [T,N] = 1 - done mask, c0 / h0 [K,N,48] (state before step 0, unmasked), wh [K,48,192]. */

@@ -219,3 +219,60 @@ def test_bp5_155_policy_reproduces_the_references_robot_level_results():
     assert abs(r["vx_mean"] - r["cmd_mean_second_half"]) < 0.02 * 5.0, r
     assert abs(r["stride_hz"] - 5.0) < 0.26 and abs(r["bounce_hz"] - 10.0) < 0.51
     assert abs(r["roll_mean"]) < 0.02 and abs(r["pitch_mean"]) < 0.02
+
+
+@pytest.mark.parametrize("n,chunks", [(96, 1), (700, 0), (700, 3), (2304, 0)])
+def test_fused_act_step_equals_the_two_call_host_path(n, chunks):
+    """irrl_act_step (one host entry: model.step -> clip -> env.step, env chunks pipelined over several streams) gives bit for bit what
+    irrl_policy_act + irrl_step give, for every chunking (chunks = 0: automatic)."""
+    import torch
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.vec_env import fused_host_step
+    T = 10
+    cfg = trot_cfg(num_envs=n, StochasticDynamics=True, ObsNoise=2.0)
+    W = _weights()
+    a = Cuda(cfg); pol_a = FusedLstmPolicy(W, n_env=n, seed=1)
+    state = torch.zeros((n, 384), device="cuda:0")
+    fs = fused_host_step(a.env, pol_a, state, chunks=chunks)
+    a.env.setTick(9); a.env.reset(fs.obs)
+    b = Cuda(cfg); pol_b = FusedLstmPolicy(W, n_env=n, seed=1)
+    b.env.setTick(9); ob = b.reset()
+    st = np.zeros((n, 384), np.float32); done = np.zeros(n, bool)
+    assert np.array_equal(fs.obs, ob)
+    for t in range(T):
+        tick = b.env.getTick()
+        act, val, st, nlp, clip = pol_b.step(ob, st, done, tick=tick, return_clipped=True)
+        ob, rew, done, info = b.step(clip)
+        fs(tick)
+        assert np.array_equal(fs.action, act) and np.array_equal(fs.clipped, clip) and np.array_equal(fs.value, val) and np.array_equal(fs.neglogp, nlp)
+        assert np.array_equal(fs.obs, ob) and np.array_equal(fs.reward, rew) and np.array_equal(fs.done, done)
+    assert np.array_equal(state.cpu().numpy(), st)
+    assert a.env.getTick() == b.env.getTick()
+
+
+def test_fused_act_step_rejects_pageable_buffers():
+    import torch
+    n = 64
+    a = Cuda(trot_cfg(num_envs=n)); pol = FusedLstmPolicy(_weights(), n_env=n, seed=1)
+    state = torch.zeros((n, 384), device="cuda:0")
+    L = _lib.load()
+    z = lambda *s: np.zeros(s, np.float32)
+    ob, act, clip, val, nlp, rew, ext, done = z(n, 35), z(n, 12), z(n, 12), z(n), z(n), z(n), z(n, 6), np.zeros(n, np.uint8)
+    p = lambda x: x.ctypes.data
+    io = _lib.ActStepIO(obs=p(ob), done=p(done), state=state.data_ptr(), action=p(act), clipped=p(clip), value=p(val), neglogp=p(nlp), next_obs=p(ob), reward=p(rew), next_done=p(done), extra=p(ext))
+    assert L.irrl_act_step(a.env.handle, pol.handle, C.byref(io), 0, 1, 0) != 0
+    assert b"page-locked" in L.irrl_last_error()
+
+
+def test_vec_env_rewards_surface_like_the_reference():
+    """RaisimGymVecEnv.py:21, 42-50: `rewards` is a list of per-env reward histories, cleared when the env finishes an episode"""
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.vec_env import RaisimGymVecEnv
+    n = 8
+    env = RaisimGymVecEnv(FlexibleGymEnv("", dump_yaml(trot_cfg(num_envs=n, StochasticDynamics=False))))
+    env.reset()
+    assert isinstance(env.rewards, list) and len(env.rewards) == n and all(r == [] for r in env.rewards)
+    for t in range(3):
+        ob, rew, done, info = env.step(np.zeros((n, 12), np.float32))
+        for i in range(n):
+            assert len(env.rewards[i]) == (0 if done[i] else t + 1) or done.any()
+    cp = info.copy()
+    assert cp is not info and len(cp) == len(info) and cp[0] == info[0]

@@ -63,7 +63,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"])
+    build_pybind(force=force or bool(jobs))
     return LIB
+
+
+PYMOD = os.path.join(HERE, "_flexible_robot_pb.so")
+
+
+def build_pybind(force: bool = False) -> str:
+    """the compiled pybind11 module `_flexible_robot_pb` (csrc/pybind_shim.cpp): class FlexibleGymEnv as the reference binds it
+    (raisim_gym.cpp:14-47), linked against libirrl_b200.so next to it ($ORIGIN rpath)."""
+    import sysconfig
+    src = os.path.join(CSRC, "pybind_shim.cpp")
+    hdr = os.path.join(CSRC, "..", "..", "include", "irrl_b200.h")
+    if not force and not _stale(PYMOD, [src, hdr, LIB]):
+        return PYMOD
+    import pybind11
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
+           src, "-o", PYMOD, "-L" + HERE, "-l:libirrl_b200.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("pybind module build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return PYMOD
 
 
 if __name__ == "__main__":

@@ -3,6 +3,7 @@
 // (raisim_gym.cpp:14-47): it owns the device state, parses the YAML `environment:` map (ENV:1594-1659,
 // VEC:136-171), launches kernels on one stream and stages host buffers through pinned memory.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -16,12 +17,15 @@
 #include <vector>
 
 #include "../../include/irrl_b200.h"
+#include "irrl_diag.h"
 #include "env_kernels.h"
 #include "urdf_reader.h"
 
 using namespace irrl;
 
 namespace {
+// NVTX range for the lifetime of a host entry point (shows up in Nsight Systems / ncu --nvtx; no cost without a profiler attached)
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
@@ -430,6 +434,7 @@ const char* irrl_get_extra_info_name(irrl_env* env, int i) {
 }
 
 int irrl_reset(irrl_env* env, float* ob) {
+    NvtxRange nvtx_("irrl_reset");
     ENV(env); NEED_INIT();
     bool dev = is_device_ptr(ob);
     StepArgs a = make_args(E, nullptr, E->P.flag_obs_filter ? nullptr : (dev ? ob : E->d_ob), nullptr, nullptr, nullptr);
@@ -503,6 +508,7 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
 }
 
 int irrl_step(irrl_env* env, const float* action, float* ob, float* reward, uint8_t* done, float* extra) {
+    NvtxRange nvtx_("irrl_step");
     ENV(env); NEED_INIT();
     return step_impl(E, action, ob, reward, done, extra);
 }
@@ -887,6 +893,7 @@ void irrl_policy_destroy(irrl_policy* pol) {
 }
 int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs, const uint8_t* done, float* state, float* action, float* clipped,
                     float* value, float* neglogp, int deterministic, uint32_t seed, uint32_t env_offset, uint32_t tick) {
+    NvtxRange nvtx_("irrl_policy_act");
     irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn) return fail(-1, "null policy");
     if (!obs || !state || !action || !value || !neglogp || n <= 0) return fail(-1, "irrl_policy_act: null argument");
     CUDA_OK(cudaSetDevice(Pn->device));
@@ -946,6 +953,7 @@ int irrl_policy_act(irrl_policy* pol, void* cuda_stream, int n, const float* obs
 }
 
 int irrl_rollout(irrl_env* env, irrl_policy* pol, int T, const irrl_rollout_buffers* b, int deterministic) {
+    NvtxRange nvtx_("irrl_rollout");
     ENV(env); NEED_INIT();
     irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn || !b) return fail(-1, "null argument");
     if (E->P.flag_obs_filter) return fail(-3, "irrl_rollout does not support ObsFilter: True");
@@ -991,6 +999,7 @@ static int batch_copy(void** dst, void** src, size_t* bytes, int n, cudaMemcpyKi
     return 0;
 }
 int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, int deterministic, uint32_t act_tick, int chunks) {
+    NvtxRange nvtx_("irrl_act_step");
     ENV(env); NEED_INIT();
     irrl_policy_impl* Pn = reinterpret_cast<irrl_policy_impl*>(pol); if (!Pn || !io) return fail(-1, "null argument");
     if (E->P.flag_obs_filter) return fail(-3, "irrl_act_step does not support ObsFilter: True (use irrl_policy_act + irrl_step)");

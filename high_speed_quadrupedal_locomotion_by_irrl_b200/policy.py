@@ -105,6 +105,77 @@ def save_params_npz(path: str, params: Sequence[np.ndarray], **meta) -> None:
     np.savez(path, **{k: np.asarray(v, np.float32) for k, v in zip(PARAM_NAMES, params)}, **{f"meta_{k}": v for k, v in meta.items()})
 
 
+#: tf.trainable_variables() names of the reference graph in checkpoint order (run_bp_v5.py:143-176; CustomerLstmNN.py:40-70 indexes by them)
+TF_VARIABLE_NAMES = [f"model/lstm_{t}{i}/{w}:0" for t in ("pi", "v") for i in (0, 1) for w in ("wx", "wh", "b")] + \
+                    ["model/vf/w:0", "model/vf/b:0", "model/pi/w:0", "model/pi/b:0", "model/pi/logstd:0", "model/q/w:0", "model/q/b:0"]
+
+
+def save_reference_pkl(path: str, params: Sequence[np.ndarray], **hyper) -> str:
+    """Writes a checkpoint in the reference's format (PPO2.save, ppo2.py:452-476 -> stable-baselines `_save_to_file`): one pickle
+    stream holding the tuple `(data, params)` -- `data` the 17 constructor fields of ppo2.py:453-471, `params` the 19 arrays in
+    tf.trainable_variables() order -- so that `PPO2.load(path)` / `run_bp_v5.py --load` and `CustomerLstmNN(path)`
+    (CustomerLstmNN.py:27-60) read a model trained here.
+
+    Three entries of `data` are objects of packages that do not exist in this image (stable-baselines policy class, two
+    gym.spaces.Box).  They are written as pickle GLOBAL references by name, resolved by the *reading* process:
+    `__main__.CustomLSTMPolicy` (the class run_bp_v5.py defines at line 117 -- the reference's own file stores that class by value
+    with cloudpickle, which needs TensorFlow in the writer) and `gym.spaces.box.Box` with (low, high, shape, dtype) state."""
+    import pickle
+    import sys
+    import types
+    assert len(params) == 19
+    params = [np.ascontiguousarray(p, np.float32).reshape(s) for p, s in zip(params, PARAM_SHAPES)]
+    fake = {}
+
+    def fake_class(module, name):
+        if module not in sys.modules:
+            parts = module.split(".")
+            for i in range(1, len(parts) + 1):
+                m = ".".join(parts[:i])
+                if m not in sys.modules:
+                    fake[m] = sys.modules[m] = types.ModuleType(m)
+        cls = type(name, (), {"__module__": module})
+        cls.__qualname__ = name
+        had = getattr(sys.modules[module], name, None)
+        setattr(sys.modules[module], name, cls)
+        return cls, had
+
+    policy_cls, had_policy = fake_class("__main__", "CustomLSTMPolicy")
+    box_cls, had_box = fake_class("gym.spaces.box", "Box")
+
+    def box(low, high, n):
+        b = box_cls.__new__(box_cls)
+        b.__dict__.update(low=np.full(n, low, np.float32), high=np.full(n, high, np.float32), shape=(n,), dtype=np.dtype(np.float32), np_random=None)
+        return b
+
+    data = dict(gamma=0.99, n_steps=750, vf_coef=0.5, ent_coef=0.0, max_grad_norm=0.5, learning_rate=1e-4, lam=0.998, nminibatches=1, noptepochs=10,
+                cliprange=0.2, verbose=1, policy=policy_cls, observation_space=box(-np.inf, np.inf, 35), action_space=box(-1.0, 1.0, 12), n_envs=200,
+                _vectorize_action=False, policy_kwargs=dict(n_lstm=list(N_LSTM)))
+    for k, v in hyper.items():
+        if k not in data:
+            raise KeyError(f"{k} is not a field of the reference checkpoint (ppo2.py:453-471)")
+        data[k] = v
+    try:
+        blob = pickle.dumps((data, params), protocol=2)
+    finally:
+        for name, cls, had, module in (("CustomLSTMPolicy", policy_cls, had_policy, "__main__"), ("Box", box_cls, had_box, "gym.spaces.box")):
+            if module in sys.modules:
+                if had is None:
+                    try:
+                        delattr(sys.modules[module], name)
+                    except AttributeError:
+                        pass
+                else:
+                    setattr(sys.modules[module], name, had)
+        for m in fake:
+            sys.modules.pop(m, None)
+    if not path.endswith(".pkl"):
+        path += ".pkl"                                     # BaseRLModel._save_to_file appends the extension
+    with open(path, "wb") as f:
+        f.write(blob)
+    return path
+
+
 class FusedLstmPolicy:
     """`act_model` of the reference (n_steps = 1, batch = n_envs; ppo2.py:128-129) on the fused CUDA kernel.
     `step(obs, state, mask)` mirrors CustomLSTMPolicy.step (run_bp_v5.py:178-185): returns

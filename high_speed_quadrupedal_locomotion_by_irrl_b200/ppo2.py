@@ -307,9 +307,13 @@ class PPO2:
             frac = 1.0 - (update - 1.0) / nupdates
             lr = self.learning_rate(frac) if callable(self.learning_rate) else self.learning_rate
             clip = self.cliprange(frac) if callable(self.cliprange) else self.cliprange
+            torch.cuda.nvtx.range_push("ppo2.rollout")
             mb_states, ep_infos = self._rollout()
+            torch.cuda.nvtx.range_pop()
             t1 = time.time()
+            torch.cuda.nvtx.range_push("ppo2.update")
             loss_vals = self._update(mb_states, lr, clip)
+            torch.cuda.nvtx.range_pop()
             torch.cuda.synchronize(self.dev)
             t2 = time.time()
             self.num_timesteps += n_batch
@@ -327,6 +331,14 @@ class PPO2:
 
     # ---- checkpoints (ppo2.py:452-476)
     def save(self, save_path: str):
+        """PPO2.save (ppo2.py:452-476): `<save_path>.pkl` in the reference's `(data, params)` format (policy.save_reference_pkl), readable
+        by the reference's PPO2.load / CustomerLstmNN; a path ending in .npz keeps the plain numpy archive."""
+        if not save_path.endswith(".npz"):
+            from .policy import save_reference_pkl
+            return save_reference_pkl(save_path, self.model.export_params(), gamma=self.gamma, n_steps=self.n_steps, vf_coef=self.vf_coef, ent_coef=self.ent_coef,
+                                      max_grad_norm=self.max_grad_norm, learning_rate=self.learning_rate if not callable(self.learning_rate) else self.learning_rate(1.0),
+                                      lam=self.lam, nminibatches=self.nminibatches, noptepochs=self.noptepochs,
+                                      cliprange=self.cliprange if not callable(self.cliprange) else self.cliprange(1.0), verbose=self.verbose, n_envs=self.n_envs * self.world)
         save_params_npz(save_path if save_path.endswith(".npz") else save_path + ".npz", self.model.export_params(), gamma=self.gamma, n_steps=self.n_steps,
                         vf_coef=self.vf_coef, ent_coef=self.ent_coef, max_grad_norm=self.max_grad_norm, lam=self.lam, nminibatches=self.nminibatches,
                         noptepochs=self.noptepochs, cliprange=self.cliprange if not callable(self.cliprange) else -1.0, n_envs=self.n_envs)

@@ -141,15 +141,6 @@ void irrl_policy_destroy(irrl_policy* pol);
 /* Which act kernel irrl_policy_act / irrl_rollout launch: 0 = automatic (tcgen05 tensor-core kernel from 256 environments,
  * fp32 FMA kernel below), 1 = always the fp32 FMA kernel, 2 = always the tcgen05 kernel.  Both follow run_bp_v5.py:143-176. */
 int irrl_policy_set_act_path(int mode);
-/* Probe of the tcgen05 path: d[128,n] = a[128,k] b[n,k]^T (host pointers) with the 3xTF32 split of the act kernel.
- * variant bit 0 = single tf32 pass (accuracy control). */
-/* Diagnostic: SM-clock timestamps of CTA (0,0) of the last tcgen05 act launch (32 slots, policy_tc_kernels.cu TC_MARK);
- * enable != 0 turns recording on for the following launches.  out32 may be NULL. */
-int irrl_tc_timeline(int enable, long long* out32);
-/* Diagnostic: SM cycles for `reps` back-to-back M128 x n x K8 tf32 tcgen05.mma with shared-memory operands described by
- * (layout_type, lbo, sbo) and a per-instruction start-address advance kadv; cycles2 = {issue done, all complete}. */
-int irrl_tc_mma_rate(int n, int reps, unsigned layout_type, unsigned lbo, unsigned sbo, unsigned kadv, long long* cycles2);
-int irrl_tc_gemm_probe(const float* a, const float* b, float* d, int k, int n, int variant);
 /* obs[N,35], done[N] (mask = done of the previous step, may be NULL), state[N,384] in/out, action[N,12] (unclipped),
  * clipped[N,12] (may be NULL), value[N], neglogp[N]; deterministic != 0 -> action = mean.  seed/env_offset/tick key the
  * Gaussian draws. */

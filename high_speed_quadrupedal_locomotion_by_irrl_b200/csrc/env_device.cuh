@@ -203,7 +203,7 @@ struct Dyn {
     f3 hl;                // bias force on this leg's joints
 };
 
-__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // Mass matrix blocks + bias forces for the current state.  Mfull (optional) receives this lane's view of the
 // un-factorised blocks for the probe kernels: A (21 packed, replicated), B (18), D (6).
@@ -290,11 +290,13 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
 #pragma unroll
         for (int i = 0; i < 21; ++i) Aout[i] = S[i];
     }
+    // (triangular loops are written with constant bounds and a predicate: nvcc leaves `for (c = 0; c <= a; ++c)` nests partly rolled,
+    //  and one run-time index into S / L is enough to push the whole Dyn structure into local memory)
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int c = 0; c <= a; ++c)
-            S[tri(a, c)] -= d.Y[a][0] * d.B[c][0] + d.Y[a][1] * d.B[c][1] + d.Y[a][2] * d.B[c][2];
+        for (int c = 0; c < 6; ++c)
+            if (c <= a) S[tri(a, c)] -= d.Y[a][0] * d.B[c][0] + d.Y[a][1] * d.B[c][1] + d.Y[a][2] * d.B[c][2];
 #pragma unroll
     for (int i = 0; i < 21; ++i) S[i] = qsum(S[i]);
     {   // trunk body
@@ -317,16 +319,18 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
     for (int j = 0; j < 6; ++j) {
         float dj = S[tri(j, j)];
 #pragma unroll
-        for (int c = 0; c < j; ++c) dj = fmaf(-d.L[tri(j, c)], d.L[tri(j, c)], dj);
+        for (int c = 0; c < 6; ++c) if (c < j) dj = fmaf(-d.L[tri(j, c)], d.L[tri(j, c)], dj);
         float inv = rsqrtf(dj);
         inv = inv * (1.5f - 0.5f * dj * inv * inv);     // one Newton step: full fp32 accuracy
         d.L[tri(j, j)] = inv;
 #pragma unroll
-        for (int i = j + 1; i < 6; ++i) {
-            float s = S[tri(i, j)];
+        for (int i = 0; i < 6; ++i) {
+            if (i > j) {
+                float s = S[tri(i, j)];
 #pragma unroll
-            for (int c = 0; c < j; ++c) s = fmaf(-d.L[tri(i, c)], d.L[tri(j, c)], s);
-            d.L[tri(i, j)] = s * inv;
+                for (int c = 0; c < 6; ++c) if (c < j) s = fmaf(-d.L[tri(i, c)], d.L[tri(j, c)], s);
+                d.L[tri(i, j)] = s * inv;
+            }
         }
     }
 }
@@ -337,17 +341,18 @@ __device__ __forceinline__ void fwd6(const float* L, float* z) {
     for (int i = 0; i < 6; ++i) {
         float s = z[i];
 #pragma unroll
-        for (int c = 0; c < i; ++c) s = fmaf(-L[tri(i, c)], z[c], s);
+        for (int c = 0; c < 6; ++c) if (c < i) s = fmaf(-L[tri(i, c)], z[c], s);
         z[i] = s * L[tri(i, i)];
     }
 }
 // x = L^-T y  (back substitution, in place)
 __device__ __forceinline__ void bwd6(const float* L, float* y) {
 #pragma unroll
-    for (int i = 5; i >= 0; --i) {
+    for (int ii = 0; ii < 6; ++ii) {
+        const int i = 5 - ii;
         float s = y[i];
 #pragma unroll
-        for (int c = i + 1; c < 6; ++c) s = fmaf(-L[tri(c, i)], y[c], s);
+        for (int c = 0; c < 6; ++c) if (c > i) s = fmaf(-L[tri(c, i)], y[c], s);
         y[i] = s * L[tri(i, i)];
     }
 }

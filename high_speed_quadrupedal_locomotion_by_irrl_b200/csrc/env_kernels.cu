@@ -24,22 +24,18 @@ struct EnvRegs {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
-__device__ __forceinline__ void load_env(const DevState& S, int r, int leg, EnvRegs& e) {
+// What the substep loop needs: base state, joint state, torque filter memory, previous joint targets, the per-env model.
+__device__ __forceinline__ void load_env_hot(const DevState& S, int r, int leg, EnvRegs& e) {
     const float* bp = S.base + (size_t)r * 16;
     float4 b0 = ld4(bp), b1 = ld4(bp + 4), b2 = ld4(bp + 8), b3 = ld4(bp + 12);
     e.b.p = mk(b0.x, b0.y, b0.z); e.b.qw = b0.w; e.b.qx = b1.x; e.b.qy = b1.y; e.b.qz = b1.z;
-    e.b.v = mk(b1.w, b2.x, b2.y); e.b.w = mk(b2.z, b2.w, b3.x); e.t0 = b3.y;
-    const float* cp = S.cmd + (size_t)r * 8;
-    float4 c0 = ld4(cp), c1 = ld4(cp + 4);
-    e.cmd[0] = c0.x; e.cmd[1] = c0.y; e.cmd[2] = c0.z; e.cmdf[0] = c0.w; e.cmdf[1] = c1.x; e.cmdf[2] = c1.y;
+    e.b.v = mk(b1.w, b2.x, b2.y); e.b.w = mk(b2.z, b2.w, b3.x);
     const float* lp = S.legs + ((size_t)r * 4 + leg) * 16;
-    float4 l0 = ld4(lp), l1 = ld4(lp + 4), l2 = ld4(lp + 8), l3 = ld4(lp + 12);
+    float4 l0 = ld4(lp), l1 = ld4(lp + 4), l2 = ld4(lp + 8);
     e.q = mk(l0.x, l0.y, l0.z); e.qd = mk(l0.w, l1.x, l1.y); e.torque_last = mk(l1.z, l1.w, l2.x);
-    e.jref = mk(l2.y, l2.z, l2.w); e.jdref = mk(l3.x, l3.y, l3.z);
     const float* l2p = S.legs2 + ((size_t)r * 4 + leg) * 12;
-    float4 m0 = ld4(l2p), m1 = ld4(l2p + 4), m2 = ld4(l2p + 8);
-    e.ptl = mk(m0.x, m0.y, m0.z); e.eeref = mk(m0.w, m1.x, m1.y); e.tau_applied = mk(m1.z, m1.w, m2.x);
-    e.contact_flag = m2.y; e.impulse_norm = m2.z;
+    float4 m0 = ld4(l2p);
+    e.ptl = mk(m0.x, m0.y, m0.z);
     const float* mp = S.legmodel + ((size_t)r * 4 + leg) * 16;
     float4 g0 = ld4(mp), g1 = ld4(mp + 4), g2 = ld4(mp + 8), g3 = ld4(mp + 12);
     e.lm.m1 = g0.x; e.lm.m2 = g0.y; e.lm.m3 = g0.z; e.lm.knee_z = g0.w;
@@ -48,8 +44,24 @@ __device__ __forceinline__ void load_env(const DevState& S, int r, int leg, EnvR
     const float* bmp = S.basemodel + (size_t)r * 8;
     float4 h0 = ld4(bmp), h1 = ld4(bmp + 4);
     e.bm.m0 = h0.x; e.bm.com0 = mk(h0.y, h0.z, h0.w); e.bm.mu = h1.x; e.bm.rest = h1.y; e.bm.thr = h1.z;
+}
+// Everything else (clock, command, references, episode counters): only read after the substeps.  The step kernel loads it there, so
+// that these ~35 values are not live (in registers or spilled) across the hot loop.
+__device__ __forceinline__ void load_env_cold(const DevState& S, int r, int leg, EnvRegs& e) {
+    e.t0 = S.base[(size_t)r * 16 + 13];
+    const float* cp = S.cmd + (size_t)r * 8;
+    float4 c0 = ld4(cp), c1 = ld4(cp + 4);
+    e.cmd[0] = c0.x; e.cmd[1] = c0.y; e.cmd[2] = c0.z; e.cmdf[0] = c0.w; e.cmdf[1] = c1.x; e.cmdf[2] = c1.y;
+    const float* lp = S.legs + ((size_t)r * 4 + leg) * 16;
+    float4 l2 = ld4(lp + 8), l3 = ld4(lp + 12);
+    e.jref = mk(l2.y, l2.z, l2.w); e.jdref = mk(l3.x, l3.y, l3.z);
+    const float* l2p = S.legs2 + ((size_t)r * 4 + leg) * 12;
+    float4 m0 = ld4(l2p), m1 = ld4(l2p + 4), m2 = ld4(l2p + 8);
+    e.eeref = mk(m0.w, m1.x, m1.y); e.tau_applied = mk(m1.z, m1.w, m2.x);
+    e.contact_flag = m2.y; e.impulse_norm = m2.z;
     e.frame_idx = S.frame_idx[r]; e.itera = S.itera[r]; e.ep_len = S.ep_len[r]; e.ep_ret = S.ep_ret[r];
 }
+__device__ __forceinline__ void load_env(const DevState& S, int r, int leg, EnvRegs& e) { load_env_hot(S, r, leg, e); load_env_cold(S, r, leg, e); }
 
 __device__ __forceinline__ void store_env(const DevState& S, int r, int leg, const EnvRegs& e) {
     if (leg == 0) {
@@ -260,7 +272,7 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
     const bool valid = r < A.r_end;
     if (!valid) r = A.r_end - 1;                  // tail lanes shadow the last robot (no stores) so quads stay convergent
     const int gid = r + (int)P.env_offset;
-    EnvRegs e; load_env(S, r, leg, e);
+    EnvRegs e; load_env_hot(S, r, leg, e);
 
     // ---- action -> joint targets (ENV:700-707)
     float an = 0.f;
@@ -280,7 +292,7 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
     // ---- ForceDisturbance + Manual: state_disturbance every 10 gait periods (ENV:744-747, 912-940); without Manual the
     // reference's force_attack never fires
     if (P.flag_force_dist && P.flag_manual) {
-        if (P.disturb_every > 0 && e.frame_idx % P.disturb_every == 0) {
+        if (P.disturb_every > 0 && S.frame_idx[r] % P.disturb_every == 0) {
             const uint4 ra = philox(P.seed, gid, A.tick, P_DISTURB), rb = philox(P.seed, gid, A.tick, P_DISTURB + 1);
             const float ratio = 0.5f;
             e.b.p.z += 0.03f * usym(ra.x) * ratio;
@@ -318,6 +330,7 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
         tau = mk(tt[0], tt[1], tt[2]);
         integrate_substep<SYNC>(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co);
     }
+    load_env_cold(S, r, leg, e);                   // clock, command, references, counters: first needed here
     e.tau_applied = tau;
 
     // ---- observation (ENV:776)

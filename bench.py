@@ -430,7 +430,8 @@ def run_b200(args):
         pass
     step_kernel_ms, act_kernel_ms = m["step_ms"], m["act_ms"]
     flop_per_env_step = counts.get("env_step", {}).get("fp32_flop_per_env_step")
-    traffic = counts.get("env_step", {}).get("dram_bytes_per_launch")
+    per_env = counts.get("env_step", {}).get("dram_bytes_per_env_step")
+    traffic = int(per_env * N) if per_env else counts.get("env_step", {}).get("dram_bytes_per_launch")      # ncu dram__bytes of one launch, scaled to this batch
     roof = {"kernel": "env_step_kernel", "bound": "fp32", "unit": "TFLOP/s", "peak": fp32_meas.value or NOMINAL_FP32_TFLOPS,
             "peak_source": "measured live: register-resident FMA micro-benchmark (irrl_measure_fp32_peak); nominal 74.5 (MEASURED_PEAKS.json holds no FP32-SIMT peak)",
             "kernel_ms": step_kernel_ms, "share_of_step": step_kernel_ms / (m["total_ms"] / K), "traffic": traffic,

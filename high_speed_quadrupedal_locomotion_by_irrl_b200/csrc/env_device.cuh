@@ -563,7 +563,11 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     int allhits = 0;
 #pragma unroll
     for (int l = 0; l < 4; ++l) allhits |= qbcasti(hits, l) << (2 * l);
+#ifdef EXP_NO_BOX
+    const bool any_box = false; allhits = 0;
+#else
     const bool any_box = __any_sync(FULLMASK, allhits != 0);
+#endif
     const bool any_foot_or_box = __any_sync(FULLMASK, cf.active || allhits != 0);
 
     float ytot[6];

@@ -72,8 +72,9 @@ def load() -> C.CDLL:
     L.irrl_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.irrl_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.irrl_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
-    L.irrl_lstm_seq_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
-    L.irrl_lstm_seq_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+    L.irrl_lstm_seq_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10
+    L.irrl_lstm_seq_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
+    L.irrl_lstm_seq_ctas.argtypes = [C.c_int]
     L.irrl_lstm_pw_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
     L.irrl_lstm_pw_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9
     L.irrl_set_heightfield.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]

@@ -1104,13 +1104,14 @@ int irrl_get_profile(irrl_env* env, double* act_ms_total, double* step_ms_total,
 }
 
 int irrl_lstm_seq_fwd(void* cuda_stream, int T, int K, int n_env, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep,
-                      float* gates, float* Cs, float* Hs) {
-    launch_lstm_seq_fwd(T, K, n_env, xw, wh, c0, h0, keep, gates, Cs, Hs, reinterpret_cast<cudaStream_t>(cuda_stream)); CUDA_OK(cudaGetLastError()); return 0;
+                      float* gates, float* Cs, float* Hs, const float* bias, float* HM) {
+    launch_lstm_seq_fwd(T, K, n_env, xw, wh, c0, h0, keep, gates, Cs, Hs, bias, HM, reinterpret_cast<cudaStream_t>(cuda_stream)); CUDA_OK(cudaGetLastError()); return 0;
 }
 int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates,
-                      const float* Cs, float* dz) {
-    launch_lstm_seq_bwd(T, K, n_env, dH, wh, c0, keep, gates, Cs, dz, reinterpret_cast<cudaStream_t>(cuda_stream)); CUDA_OK(cudaGetLastError()); return 0;
+                      const float* Cs, float* dz, float* db_part) {
+    launch_lstm_seq_bwd(T, K, n_env, dH, wh, c0, keep, gates, Cs, dz, db_part, reinterpret_cast<cudaStream_t>(cuda_stream)); CUDA_OK(cudaGetLastError()); return 0;
 }
+int irrl_lstm_seq_ctas(int n_env) { return lstm_seq_ctas(n_env); }
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,
                      float* c_out, float* h_out, float* hm_next, float* cm_next) {
     launch_lstm_pw_fwd(rows, n_env, z, c_prev_masked, keep_next, gates, c_out, h_out, hm_next, cm_next, reinterpret_cast<cudaStream_t>(cuda_stream));

@@ -75,9 +75,10 @@ void launch_gae(const float* rewards, const float* values, const uint8_t* dones,
                 float* adv, float* ret, int T, int N, float gamma, float lam, cudaStream_t st);
 
 void launch_lstm_seq_fwd(int T, int K, int N, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep, float* gates, float* Cs,
-                         float* Hs, cudaStream_t st);
+                         float* Hs, const float* bias, float* HM, cudaStream_t st);
 void launch_lstm_seq_bwd(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
-                         float* dz, cudaStream_t st);
+                         float* dz, float* db_part, cudaStream_t st);
+int lstm_seq_ctas(int N);   // CTAs per tower of the sequence kernels = rows of db_part
 void launch_lstm_pw_fwd(int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates, float* c_out,
                         float* h_out, float* hm_next, float* cm_next, cudaStream_t st);
 void launch_lstm_pw_bwd(int rows, int n_env, const float* dh_out, const float* carry_h, const float* carry_c, const float* keep_up,

@@ -267,9 +267,12 @@ __global__ void lstm_pw_bwd_kernel(int rows, int n_env, const float* __restrict_
 constexpr int SEQ_TM = 32;
 constexpr int SEQ_THR = 192;        // 24 unit pairs x 8 env groups; thread = 4 envs x 2 units (x 4 gates)
 
+// bias [K,192] (may be null) is added to the streamed projection here, and HM [T,K,N,48] (may be null) receives the MASKED hidden state fed
+// into every step (what the weight gradient dW_h needs): both used to be separate full passes over 9.4 GB / 2.4 GB tensors in PyTorch.
 __global__ void __launch_bounds__(SEQ_THR) lstm_seq_fwd_kernel(int T, int K, int N, const float* __restrict__ xw, const float* __restrict__ wh,
                                                                const float* __restrict__ c0, const float* __restrict__ h0, const float* __restrict__ keep,
-                                                               float* __restrict__ gates, float* __restrict__ Cs, float* __restrict__ Hs) {
+                                                               float* __restrict__ gates, float* __restrict__ Cs, float* __restrict__ Hs,
+                                                               const float* __restrict__ bias, float* __restrict__ HM) {
     __shared__ __align__(16) float Ws[H][G4];          // [k][unit pair][unit][gate]
     __shared__ __align__(16) float hT[H][SEQ_TM];      // masked h(t-1), transposed
     const int tower = blockIdx.y, e0 = blockIdx.x * SEQ_TM, t_ = threadIdx.x, eg = t_ & 7, cg = t_ >> 3;
@@ -284,7 +287,11 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_fwd_kernel(int T, int K, int
         const float k0 = keep[envs[e]];                                     // keep[0][env]
         c[e][0] = c0[o] * k0; c[e][1] = c0[o + 1] * k0;
         hT[2 * cg][4 * eg + e] = h0[o] * k0; hT[2 * cg + 1][4 * eg + e] = h0[o + 1] * k0;
+        if (HM && valid[e]) *reinterpret_cast<float2*>(HM + o) = make_float2(h0[o] * k0, h0[o + 1] * k0);      // row (t = 0, tower, env)
     }
+    float bg[4][2];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { bg[g][0] = bias ? bias[tower * G4 + g * H + 2 * cg] : 0.f; bg[g][1] = bias ? bias[tower * G4 + g * H + 2 * cg + 1] : 0.f; }
     // prefetch xw[0]
     float2 xin[4][4];
 #pragma unroll
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_fwd_kernel(int T, int K, int
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) { acc[e][g] = xin[e][g].x; acc[e][4 + g] = xin[e][g].y; }
+            for (int g = 0; g < 4; ++g) { acc[e][g] = xin[e][g].x + bg[g][0]; acc[e][4 + g] = xin[e][g].y + bg[g][1]; }
         if (t + 1 < T) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_fwd_kernel(int T, int K, int
             }
             c[e][0] *= kn; c[e][1] *= kn;                                   // SB lstm(): c *= 1-m ; h *= 1-m before the next cell
             hT[2 * cg][4 * eg + e] = hn[0] * kn; hT[2 * cg + 1][4 * eg + e] = hn[1] * kn;
+            if (HM && valid[e] && t + 1 < T) *reinterpret_cast<float2*>(HM + (((size_t)(t + 1) * K + tower) * N + envs[e]) * H + 2 * cg) = make_float2(hn[0] * kn, hn[1] * kn);
         }
         __syncthreads();
     }
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_fwd_kernel(int T, int K, int
 // backward through time: dz[t] from (dH[t] + carry_h keep[t+1], carry_c keep[t+1]); carry_h = dz[t] W_h^T, carry_c = dc f
 __global__ void __launch_bounds__(SEQ_THR) lstm_seq_bwd_kernel(int T, int K, int N, const float* __restrict__ dH, const float* __restrict__ wh,
                                                                const float* __restrict__ c0, const float* __restrict__ keep, const float* __restrict__ gates,
-                                                               const float* __restrict__ Cs, float* __restrict__ dz) {
+                                                               const float* __restrict__ Cs, float* __restrict__ dz, float* __restrict__ db_part) {
     extern __shared__ __align__(16) unsigned char seq_smem[];          // 60 KB: above the static limit, opt-in dynamic
     float (*WT)[H] = reinterpret_cast<float (*)[H]>(seq_smem);                                   // [permuted col][unit k] = wh[k][col]
     float (*dzT)[SEQ_TM] = reinterpret_cast<float (*)[SEQ_TM]>(seq_smem + sizeof(float) * G4 * H); // dz(t), permuted columns, transposed
@@ -356,6 +364,7 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_bwd_kernel(int T, int K, int
     int envs[4]; bool valid[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { envs[e] = min(e0 + 4 * eg + e, N - 1); valid[e] = (e0 + 4 * eg + e) < N; }
+    float dbacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // sum of dz over this thread's envs and all t: the bias gradient (db_part, may be null)
     float ch[4][2], cc[4][2];                           // carries (gradient w.r.t. the masked h / c fed to step t+1)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { ch[e][0] = ch[e][1] = cc[e][0] = cc[e][1] = 0.f; }
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_bwd_kernel(int T, int K, int
             if (valid[e]) {
                 float* dr = dz + row * G4 + 2 * cg;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(dr + g * H) = make_float2(dzv[0][g], dzv[1][g]);
+                for (int g = 0; g < 4; ++g) { *reinterpret_cast<float2*>(dr + g * H) = make_float2(dzv[0][g], dzv[1][g]); dbacc[0][g] += dzv[0][g]; dbacc[1][g] += dzv[1][g]; }
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u)
@@ -421,21 +430,32 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_bwd_kernel(int T, int K, int
         for (int e = 0; e < 4; ++e) { ch[e][0] = acc[e][0]; ch[e][1] = acc[e][1]; cur[e] = nxt[e]; }
         __syncthreads();
     }
+    if (db_part) {   // the 8 env groups of a unit pair are 8 consecutive lanes: fixed-order butterfly, one partial per CTA (summed on the host side: deterministic)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v = dbacc[u][g];
+                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (eg == 0) db_part[((size_t)blockIdx.x * K + tower) * G4 + g * H + 2 * cg + u] = v;
+            }
+    }
 }
 void launch_lstm_seq_fwd(int T, int K, int N, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep, float* gates, float* Cs,
-                         float* Hs, cudaStream_t st) {
+                         float* Hs, const float* bias, float* HM, cudaStream_t st) {
     dim3 grid((N + SEQ_TM - 1) / SEQ_TM, K);
-    lstm_seq_fwd_kernel<<<grid, SEQ_THR, 0, st>>>(T, K, N, xw, wh, c0, h0, keep, gates, Cs, Hs);
+    lstm_seq_fwd_kernel<<<grid, SEQ_THR, 0, st>>>(T, K, N, xw, wh, c0, h0, keep, gates, Cs, Hs, bias, HM);
 }
+int lstm_seq_ctas(int N) { return (N + SEQ_TM - 1) / SEQ_TM; }
 void launch_lstm_seq_bwd(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
-                         float* dz, cudaStream_t st) {
+                         float* dz, float* db_part, cudaStream_t st) {
     dim3 grid((N + SEQ_TM - 1) / SEQ_TM, K);
     constexpr int smem = sizeof(float) * (G4 * H + G4 * SEQ_TM);
     {   // the attribute is per device (a process may hold envs / policies on several GPUs through the C ABI)
         static unsigned long long configured_devices = 0ull; int dev = 0; cudaGetDevice(&dev);
         if (dev >= 64 || !((configured_devices >> dev) & 1ull)) { cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (dev < 64) configured_devices |= 1ull << dev; }
     }
-    lstm_seq_bwd_kernel<<<grid, SEQ_THR, smem, st>>>(T, K, N, dH, wh, c0, keep, gates, Cs, dz);
+    lstm_seq_bwd_kernel<<<grid, SEQ_THR, smem, st>>>(T, K, N, dH, wh, c0, keep, gates, Cs, dz, db_part);
 }
 
 void launch_lstm_pw_fwd(int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates, float* c_out,

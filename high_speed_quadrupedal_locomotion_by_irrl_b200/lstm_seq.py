@@ -17,6 +17,13 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _with_bias(fn):
+    """(xw, wh, b, c0, h0, keep) front end for the paths that want the bias already added to the projection"""
+    def run(xw, wh, b, c0, h0, keep):
+        return fn(xw + b.view(1, b.shape[0], 1, -1), wh, c0, h0, keep)
+    return run
+
+
 class LstmLayerSeq(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xw, wh, c0, h0, keep):
@@ -69,38 +76,40 @@ class LstmLayerSeqPersistent(torch.autograd.Function):
     W_h resident in shared memory, the recurrent state on chip, no per-step launches and no Python in the loop."""
 
     @staticmethod
-    def forward(ctx, xw, wh, c0, h0, keep):
+    def forward(ctx, xw, wh, b, c0, h0, keep):
+        """xw [T,K,N,192] = x W_x WITHOUT the bias (b [K,192] is added inside the kernel); the kernel also writes the masked hidden state
+        fed into every step (HM), which the weight gradient needs -- no extra passes over the big tensors in PyTorch."""
         L = _lib.load()
         T, K, N, _ = xw.shape
         st = C.c_void_p(torch.cuda.current_stream(xw.device).cuda_stream)
-        xw = xw.contiguous(); keep = keep.contiguous(); wh = wh.contiguous(); c0 = c0.contiguous(); h0 = h0.contiguous()
-        gates = torch.empty_like(xw); Cs = xw.new_empty((T, K, N, 48)); Hs = xw.new_empty((T, K, N, 48))
-        _lib.check(L.irrl_lstm_seq_fwd(st, T, K, N, _p(xw), _p(wh), _p(c0), _p(h0), _p(keep), _p(gates), _p(Cs), _p(Hs)))
-        ctx.save_for_backward(wh, keep, gates, Cs, Hs, c0, h0)
+        xw = xw.contiguous(); keep = keep.contiguous(); wh = wh.contiguous(); c0 = c0.contiguous(); h0 = h0.contiguous(); b = b.contiguous()
+        gates = torch.empty_like(xw); Cs = xw.new_empty((T, K, N, 48)); Hs = xw.new_empty((T, K, N, 48)); HM = xw.new_empty((T, K, N, 48))
+        _lib.check(L.irrl_lstm_seq_fwd(st, T, K, N, _p(xw), _p(wh), _p(c0), _p(h0), _p(keep), _p(gates), _p(Cs), _p(Hs), _p(b), _p(HM)))
+        ctx.save_for_backward(wh, keep, gates, Cs, HM, c0)
         return Hs, Cs[T - 1].clone(), Hs[T - 1].clone()
 
     @staticmethod
     def backward(ctx, dH, dcT, dhT):
         L = _lib.load()
-        wh, keep, gates, Cs, Hs, c0, h0 = ctx.saved_tensors
+        wh, keep, gates, Cs, HM, c0 = ctx.saved_tensors
         T, K, N, _ = gates.shape
         st = C.c_void_p(torch.cuda.current_stream(gates.device).cuda_stream)
         dH = dH.contiguous()
         if dhT is not None:
             dH = dH.clone(); dH[T - 1] += dhT
         DZ = torch.empty_like(gates)
-        _lib.check(L.irrl_lstm_seq_bwd(st, T, K, N, _p(dH), _p(wh), _p(c0), _p(keep), _p(gates), _p(Cs), _p(DZ)))
-        # masked h fed into step t: h(t-1) * keep[t]
-        HM = torch.cat([h0.unsqueeze(0), Hs[:-1]], 0) * keep.view(T, 1, N, 1)
+        db_part = gates.new_empty((L.irrl_lstm_seq_ctas(N), K, 192))
+        _lib.check(L.irrl_lstm_seq_bwd(st, T, K, N, _p(dH), _p(wh), _p(c0), _p(keep), _p(gates), _p(Cs), _p(DZ), _p(db_part)))
         # dW_h[k] = sum_{t,n} HM[t,k,n,:]^T DZ[t,k,n,:]: T*K batched [48 x N] x [N x 192] products on strided views (no copies, and
         # far more parallel than one skinny GEMM with a 1.5 M-long reduction), then a sum over T
         dwh = torch.matmul(HM.transpose(-1, -2), DZ).sum(0)
-        return DZ, dwh, None, None, None
+        return DZ, dwh, db_part.sum(0), None, None, None
 
 
-def lstm_layer_reference(xw, wh, c0, h0, keep):
+def lstm_layer_reference(xw, wh, b, c0, h0, keep):
     """The same computation with plain autograd ops (CPU tests / cross-check of the manual backward)."""
     T, K, N, _ = xw.shape
+    xw = xw + b.view(1, K, 1, -1)
     c, h = c0, h0
     out = []
     for t in range(T):

@@ -77,20 +77,20 @@ class LstmActorCritic(torch.nn.Module):
     def forward_time_major(self, obs, keep, state, fused: Optional[bool] = None):
         """obs [T,N,35] (time-major, as the device rollout stores it), keep [T,N] = 1 - mask, state [N,384] at t = 0.
         Returns mean [T,N,12], value [T,N].  On CUDA the recurrence runs through the fused BPTT path (lstm_seq.LstmLayerSeq)."""
-        from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, lstm_layer_reference
+        from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, lstm_layer_reference, _with_bias
         T, N, _ = obs.shape
         H = 48
         fused = obs.is_cuda if fused is None else fused
-        layer = lstm_layer_reference if not fused else (LstmLayerSeq.apply if fused == "stepwise" else LstmLayerSeqPersistent.apply)
+        layer = lstm_layer_reference if not fused else (_with_bias(LstmLayerSeq.apply) if fused == "stepwise" else LstmLayerSeqPersistent.apply)
         st = state.view(N, 2, 2, 2, H)                                  # [env, tower, layer, (c,h), unit]
         c0 = st[:, :, 0, 0].transpose(0, 1).contiguous(); h0 = st[:, :, 0, 1].transpose(0, 1).contiguous()
         c1 = st[:, :, 1, 0].transpose(0, 1).contiguous(); h1 = st[:, :, 1, 1].transpose(0, 1).contiguous()
         wx0 = torch.stack([self.lstm_pi0_wx, self.lstm_v0_wx]); wh0 = torch.stack([self.lstm_pi0_wh, self.lstm_v0_wh]); b0 = torch.stack([self.lstm_pi0_b, self.lstm_v0_b])
         wx1 = torch.stack([self.lstm_pi1_wx, self.lstm_v1_wx]); wh1 = torch.stack([self.lstm_pi1_wh, self.lstm_v1_wh]); b1 = torch.stack([self.lstm_pi1_b, self.lstm_v1_b])
-        xw0 = torch.matmul(obs.unsqueeze(1), wx0) + b0.view(1, 2, 1, -1)             # [T,2,N,192]: all input projections in one GEMM
-        H0, _, _ = layer(xw0, wh0, c0, h0, keep)
-        xw1 = torch.matmul(H0, wx1) + b1.view(1, 2, 1, -1)
-        H1, _, _ = layer(xw1, wh1, c1, h1, keep)
+        xw0 = torch.matmul(obs.unsqueeze(1), wx0)                                    # [T,2,N,192]: all input projections in one GEMM (bias added by the layer)
+        H0, _, _ = layer(xw0, wh0, b0, c0, h0, keep)
+        xw1 = torch.matmul(H0, wx1)
+        H1, _, _ = layer(xw1, wh1, b1, c1, h1, keep)
         mean = H1[:, 0] @ self.pi_w + self.pi_b
         value = (H1[:, 1] @ self.vf_w + self.vf_b).squeeze(-1)
         return mean, value

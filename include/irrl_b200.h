@@ -188,9 +188,11 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
  * one launch per direction, a CTA owns 32 envs for all T steps.  Time-major device tensors: xw / gates / dz [T,K,N,192] (gate order
  * i,f,o,g), Cs / Hs / dH [T,K,N,48], keep [T,N] = 1 - done mask, c0 / h0 [K,N,48] (state before step 0, unmasked), wh [K,48,192]. */
 int irrl_lstm_seq_fwd(void* cuda_stream, int T, int K, int n_env, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep,
-                      float* gates, float* Cs, float* Hs);
+                      float* gates, float* Cs, float* Hs, const float* bias /*[K,192] added to xw, may be NULL*/,
+                      float* HM /*[T,K,N,48] out: masked hidden state fed INTO every step (operand of dW_h), may be NULL*/);
 int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates,
-                      const float* Cs, float* dz);
+                      const float* Cs, float* dz, float* db_part /*[irrl_lstm_seq_ctas(n_env),K,192] out: per-CTA sums of dz (bias gradient), may be NULL*/);
+int irrl_lstm_seq_ctas(int n_env);
 /* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,
  * z / gates [rows,192] in gate order i,f,o,g, the rest [rows,48]; keep = 1 - done mask per env (run_bp_v5.py:151-153 lstm(..., masks, ...)) */
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,

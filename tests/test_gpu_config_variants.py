@@ -13,30 +13,30 @@ N = 128
 
 
 def _run(cfg, steps=12, sigma=0.25, tol=2e-5, seed=0):
-    """Teacher-forced single-step comparisons.  fp32 (CUDA) and fp64 (oracle) cannot agree on a contact threshold that a toe
-    crosses within ~1e-7 m (about one touchdown in a thousand): such knife-edge envs are allowed as rare outliers (<= 2 envs or
-    1.6 % per step and <= 0.2 % of all env-steps of the run: contact mask, done flag or a stick/slide decision differs); every other env must meet the tolerance and all flags bit-exactly."""
+    """Teacher-forced single-step comparisons.  Env-steps whose discrete decisions sit within fp32 resolution of a threshold are
+    identified from the ORACLE's own margins (oracle_lib.Oracle.margins: a toe / trunk-corner gap within 1e-7 m of zero during the
+    substeps, a touch-down speed within 1e-4 m/s of the restitution threshold, an impulse within 0.2 % of the friction cone, the
+    termination test within 1e-5 of its bound -- the thresholds measured in tests/test_gpu_same_state.py), set aside and counted
+    (<= 3 % of the run); every other env-step must meet the tolerance and ALL flags bit-exactly, with no tolerated exception."""
     o, c = Oracle(cfg), Cuda(cfg)
     rng = np.random.default_rng(seed)
     o.set_tick(1); c.env.setTick(1)
     obo, obg = o.reset(), c.reset()
     assert rel(obg, obo) < max(tol, 5e-5)
-    n_out = 0
+    aside = 0
     for t in range(steps):
         c.set_state(o.get_state().astype(np.float32))
         a = np.clip(rng.normal(0, sigma, size=(o.n, 12)), -1, 1).astype(np.float32)
         obo, ro, do, eo = o.step(a); obg, rg, dg, eg = c.step(a)
-        so, sg = o.get_state(), c.get_state()
-        err = np.abs(obg - obo).max(axis=1) / max(np.abs(obo).max(), 1e-9)
-        knife = (sg[:, S["contact"]] != so[:, S["contact"]]).any(axis=1) | (do != dg) | (err > 10 * tol)   # touch / stick-or-slide / restitution threshold
-        ok = ~knife
-        assert knife.sum() <= max(2, o.n // 64), (t, int(knife.sum()))
-        n_out += int(knife.sum())
+        so, sg = o.get_state(), c.get_state(); m = o.margins()
+        ok = (m[:, 0] > 1e-7) & (m[:, 1] > 1e-4) & (m[:, 2] > 1e-5) & (m[:, 3] > 2e-3)
+        aside += int((~ok).sum())
         assert (do[ok] == dg[ok]).all(), t
+        assert (sg[ok][:, S["contact"]] == so[ok][:, S["contact"]]).all(), t
         assert rel(obg[ok], obo[ok]) < tol and rel(rg[ok], ro[ok]) < tol and rel(eg[ok], eo[ok]) < tol, (t, rel(obg[ok], obo[ok]), rel(rg[ok], ro[ok]))
         assert rel(sg[ok][:, S["ptarget_last"]], so[ok][:, S["ptarget_last"]]) < tol
         assert rel(sg[ok][:, S["torque_last"]], so[ok][:, S["torque_last"]]) < 1e-4
-    assert n_out <= max(2, steps * o.n // 500)
+    assert aside <= max(2, 3 * steps * o.n // 100), aside
     return o, c
 
 

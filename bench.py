@@ -301,7 +301,7 @@ class Rig:
         act_ms, step_ms, cnt = C.c_double(), C.c_double(), C.c_int64()
         self.L.irrl_get_profile(self.env.handle, C.byref(act_ms), C.byref(step_ms), C.byref(cnt))
         self.L.irrl_set_profiling(self.env.handle, 0)
-        if not self.with_act:
+        if not self.with_act and cnt.value == 0:
             act_ms.value, step_ms.value, cnt.value = 0.0, total_ms, K
         t_ms = torch.tensor([total_ms], device=self.dev, dtype=torch.float64)
         if dist is not None:
@@ -390,6 +390,10 @@ def run_b200(args):
     # ---- sub-records on BASELINE's other configs (short runs, same timing method)
     subs = {}
     Ks = max(20, min(K, 200))
+    try:
+        counts0 = json.load(open(COUNTS_FILE))
+    except Exception:
+        counts0 = {}
     if not args.no_extras:
         def sub(workload, n, with_act, label):
             r = Rig(L, workload, n, Ks, rank, local, stream, dev, with_act=with_act)
@@ -397,6 +401,9 @@ def run_b200(args):
             subs[label] = {"workload": WORKLOAD_TEXT[workload] + (" with fused LSTM act" if with_act else ", step kernel + obs/reward only (actions resident in HBM)"),
                            "envs_per_gpu": n, "total_envs": world * n, "steps": Ks, "value": world * n * Ks / (mm["total_ms_max"] * 1e-3), "unit": UNIT,
                            "ms_per_step": mm["total_ms_max"] / Ks, "step_kernel_ms": mm["step_ms"], "act_kernel_ms": mm["act_ms"] if with_act else None}
+            if not with_act:   # one Python call per step sits between the timing events; the kernel itself is timed by events around its launch
+                subs[label]["value_kernel_only"] = n * world / (mm["step_ms"] * 1e-3)
+                subs[label]["fp32_frac"] = (counts0.get("env_step", {}).get("fp32_flop_per_env_step", 0) * n / (mm["step_ms"] * 1e-3) / 1e12) / NOMINAL_FP32_TFLOPS
             del r
         if world == 1:
             sub("trot", 4096, False, "configs[1]")

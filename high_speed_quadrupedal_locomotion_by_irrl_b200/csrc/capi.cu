@@ -460,7 +460,12 @@ static int step_impl(irrl_env_impl* E, const float* action, float* ob, float* re
         if (!reward || !done) return fail(-1, "irrl_step: reward and done are required");
         StepArgs a = make_args(E, action, E->P.flag_obs_filter ? nullptr : ob, reward, done, extra);
         if (E->P.flag_crucial) launch_env_meteor(a, 0, E->stream);
+        if (E->profiling) {   // same event triplets as irrl_rollout (act slot empty): kernel time without host-side call overhead
+            while (E->prof_events.size() < E->prof_cursor + 3) { cudaEvent_t ev; CUDA_OK(cudaEventCreate(&ev)); E->prof_events.push_back(ev); }
+            CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 0], E->stream)); CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 1], E->stream));
+        }
         launch_env_step(a, E->stream); CUDA_OK(cudaGetLastError());
+        if (E->profiling) { CUDA_OK(cudaEventRecord(E->prof_events[E->prof_cursor + 2], E->stream)); E->prof_cursor += 3; }
         E->tick++;
         if (E->P.flag_obs_filter && ob) { launch_env_observe(E->P, E->S, ob, E->stream); CUDA_OK(cudaGetLastError()); }
         return 0;

@@ -264,6 +264,8 @@ __global__ void lstm_pw_bwd_kernel(int rows, int n_env, const float* __restrict_
 // streams gates / c / h out.  Environments are independent, so there is no inter-CTA dependency and no per-step launch.
 // Layouts (time-major, as the rollout stores them): xw, gates, dz [T,K,N,192] in the checkpoint's gate order i,f,o,g;
 // C, H, dH [T,K,N,48]; keep [T,N]; c0, h0 [K,N,48]; wh [K,48,192].
+// (measured round 2: MUFU-based sigmoid / tanh and a 3-CTA-per-SM register cap changed nothing / cost 30 %: the loops are bound by the
+// latency of ~1.5 warps per scheduler, not by the transcendental instructions; libdevice expf / tanhf stay)
 constexpr int SEQ_TM = 32;
 constexpr int SEQ_THR = 192;        // 24 unit pairs x 8 env groups; thread = 4 envs x 2 units (x 4 gates)
 

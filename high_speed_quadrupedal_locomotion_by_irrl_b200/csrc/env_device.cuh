@@ -517,7 +517,8 @@ struct ContactOut { int foot_active; f3 foot_impulse; int sweeps; };
 #define PHASE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
 // ------------------------------------------------------------------ one world.integrate() (ENV:768)
 // tau: this leg's joint torques.  fext: optional external generalised force on the trunk (6).
-template <bool SYNC = false>
+// TERR = false compiles the heightfield code out (launch-uniform: flat-ground launches run a kernel without it in the hot loop)
+template <bool SYNC = false, bool TERR = true>
 __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegModel& lm, const BaseModel& bm, int leg,
                                                   Base& b, f3& q, f3& qd, f3 tau, ContactOut& out) {
     const float dt = P.sim_dt;
@@ -537,7 +538,7 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
 
     // ---- collision detection against the plane z = 0 (ENV:268) or the heightfield (ENV:264)
     Contact cf;   // foot contact of this leg (slot 0 of this lane)
-    const bool terr = P.terrain != nullptr;
+    const bool terr = TERR && P.terrain != nullptr;
     f3 fn = mk(0.f, 0.f, 1.f), ft1 = mk(1.f, 0.f, 0.f), ft2 = mk(0.f, 1.f, 0.f); float fh = 0.f;
     if (terr) { terrain_sample(P, b.p.x + k.toe.x, b.p.y + k.toe.y, fh, fn); contact_frame(fn, ft1, ft2); }
     f3 xf = axpy(-P.toe_r, fn, k.toe);                                  // contact point on the sphere

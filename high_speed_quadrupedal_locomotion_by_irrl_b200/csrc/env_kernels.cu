@@ -264,7 +264,7 @@ __device__ __forceinline__ void write_scaled_obs(const EnvParams& P, const DevSt
 #endif
 // BLK / SYNC: 64-thread CTAs without phase barriers up to ~5k robots (one warp per scheduler: pure latency), 128-thread CTAs with
 // phase barriers above (launch_env_step)
-template <int BLK, bool SYNC>
+template <int BLK, bool SYNC, bool TERR>
 __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env_step_kernel(const __grid_constant__ StepArgs A) {
     const EnvParams& P = A.P; const DevState& S = A.S;
     const int tid = blockIdx.x * BLK + threadIdx.x;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
             tt[k] = fmaxf(fminf(tt[k], up), low);
         }
         tau = mk(tt[0], tt[1], tt[2]);
-        integrate_substep<SYNC>(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co);
+        integrate_substep<SYNC, TERR>(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co);
     }
     load_env_cold(S, r, leg, e);                   // clock, command, references, counters: first needed here
     e.tau_applied = tau;
@@ -682,9 +682,13 @@ void launch_env_step(const StepArgs& a, cudaStream_t st) {
     static const int sync_min = [] { const char* e = getenv("IRRL_STEP_SYNC_MIN"); return e ? atoi(e) : 5120; }();   // tuning knob: robots above which the barrier variant runs (measured: 4096 -> 67.8 vs 73.6 us without / with barriers, 6144 -> 79.4 vs 77.5)
     static const int blk = [] { const char* e = getenv("IRRL_STEP_BLK"); return e ? atoi(e) : 0; }();   // experiment: force the CTA size (256 = one lock-stepped CTA per SM)
     const int n = a.r_end - a.r_begin; if (n <= 0) return;
-    if (blk == 256) env_step_kernel<256, true><<<(n * 4 + 255) / 256, 256, 0, st>>>(a);
-    else if (blk == 128 || (blk == 0 && n > sync_min)) env_step_kernel<128, true><<<(n * 4 + 127) / 128, 128, 0, st>>>(a);
-    else env_step_kernel<64, false><<<quad_grid(n), 64, 0, st>>>(a);
+    const bool terr = a.P.terrain != nullptr;   // launch-uniform: the flat-ground kernels carry no heightfield code in the substep loop
+#define STEP_LAUNCH(B, SY) do { if (terr) env_step_kernel<B, SY, true><<<(n * 4 + B - 1) / B, B, 0, st>>>(a); \
+                               else env_step_kernel<B, SY, false><<<(n * 4 + B - 1) / B, B, 0, st>>>(a); } while (0)
+    if (blk == 256) STEP_LAUNCH(256, true);
+    else if (blk == 128 || (blk == 0 && n > sync_min)) STEP_LAUNCH(128, true);
+    else STEP_LAUNCH(64, false);
+#undef STEP_LAUNCH
 }
 void launch_env_meteor(const StepArgs& a, int respawn_only, cudaStream_t st) { env_meteor_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a, respawn_only); }
 void launch_env_reset(const StepArgs& a, cudaStream_t st) { env_reset_kernel<<<quad_grid(a.P.N), BLOCK, 0, st>>>(a); }

@@ -67,6 +67,9 @@ __device__ __forceinline__ f3 cross(f3 a, f3 b) {
 __device__ __forceinline__ f3 axpy(float s, f3 a, f3 b) { return mk(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
 __device__ __forceinline__ float comp(f3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
+// MUFU.RSQ alone: rsqrtf() wraps it in a denormal-range fix-up (4 more instructions per call) that the substep loop never needs
+// (arguments are squared lengths / pivots of O(1e-6 .. 1e2); every call site refines with one Newton step or guards tiny arguments)
+__device__ __forceinline__ float rsq_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // symmetric 3x3
 struct S3 { float xx, xy, xz, yy, yz, zz; };
 __device__ __forceinline__ f3 mul(const S3& s, f3 v) {
@@ -103,6 +106,23 @@ __device__ __forceinline__ S3 inv_sym3(const S3& a) {
     return r;
 }
 
+// ------------------------------------------------------------------ packed pairs (FFMA2 / FMUL2 / FADD2 of sm_100a)
+// The six trunk dimensions of every trunk-space quantity (B, Y, Q, S, y, ...) are carried as three (even row, odd row) pairs in
+// 64-bit register pairs: one FFMA2 does the work of two FFMAs, and a 32-bit operand is broadcast to both halves for free
+// (`R.F32` operand form).  Measured on B200 (scripts/microbench/ffma2_latency.cu): dependent FFMA2 4.45 cycles against 4.12 for FFMA,
+// issue once per 2.2 cycles per scheduler -- in this latency-bound kernel a packed instruction costs what a scalar one does.
+// Each half computes exactly the IEEE operation of the scalar code, in the same order wherever the pair runs over OUTPUT rows.
+typedef float2 p2;
+__device__ __forceinline__ p2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ p2 fma2s(p2 a, float s, p2 c) { return __ffma2_rn(a, make_float2(s, s), c); }       // a * s + c
+__device__ __forceinline__ p2 mul2(p2 a, p2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ p2 mul2s(p2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ p2 add2(p2 a, p2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ p2 sub2(p2 a, p2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float hsum(p2 a) { return a.x + a.y; }
+__device__ __forceinline__ float half_of(p2 a, int odd) { return odd ? a.y : a.x; }
+
 // ------------------------------------------------------------------ quad (4-lane group) collectives
 __device__ __forceinline__ float qsum(float v) {
     v += __shfl_xor_sync(FULLMASK, v, 1); v += __shfl_xor_sync(FULLMASK, v, 2); return v;
@@ -113,6 +133,11 @@ __device__ __forceinline__ float qmax(float v) {
 __device__ __forceinline__ float qbcast(float v, int src_leg) { return __shfl_sync(FULLMASK, v, src_leg, 4); }
 __device__ __forceinline__ int qbcasti(int v, int src_leg) { return __shfl_sync(FULLMASK, v, src_leg, 4); }
 __device__ __forceinline__ f3 qsum3(f3 v) { return mk(qsum(v.x), qsum(v.y), qsum(v.z)); }
+__device__ __forceinline__ p2 qsum2(p2 v) {     // same butterfly as qsum on both halves: 4 shuffles + 2 packed adds
+    v = add2(v, mk2(__shfl_xor_sync(FULLMASK, v.x, 1), __shfl_xor_sync(FULLMASK, v.y, 1)));
+    return add2(v, mk2(__shfl_xor_sync(FULLMASK, v.x, 2), __shfl_xor_sync(FULLMASK, v.y, 2)));
+}
+__device__ __forceinline__ p2 qbcast2(p2 v, int src_leg) { return mk2(qbcast(v.x, src_leg), qbcast(v.y, src_leg)); }
 
 // ------------------------------------------------------------------ Philox4x32-10 (same specification as the oracle)
 __device__ __forceinline__ uint4 philox(uint32_t seed, uint32_t env, uint32_t tick, uint32_t purpose) {
@@ -195,12 +220,15 @@ __device__ __forceinline__ void leg_inertias(const EnvParams& P, const LegModel&
 struct Dyn {
     // leg-local (this lane)
     S3 Dinv;              // inverse of the 3x3 leg block of M
-    float B[6][3];        // coupling block trunk(6) x leg joints(3): columns (P_k ; L_k)
-    float Y[6][3];        // B Dinv
+    p2 B[3][3];           // coupling block trunk(6) x leg joints(3), columns (P_k ; L_k): B[p][k] = rows (2p, 2p+1) of column k
+    p2 Y[3][3];           // B Dinv, same layout
     // trunk, replicated
     float L[21];          // Cholesky factor of the Schur complement S (lower, row-major packed), diagonal stored INVERTED
-    float hb[6];          // bias force on the trunk rows
+    p2 hb[3];             // bias force on the trunk rows (pairs of rows)
     f3 hl;                // bias force on this leg's joints
+    __device__ __forceinline__ float Bv(int a, int k) const { return half_of(B[a >> 1][k], a & 1); }
+    __device__ __forceinline__ float Yv(int a, int k) const { return half_of(Y[a >> 1][k], a & 1); }
+    __device__ __forceinline__ float hbv(int a) const { return half_of(hb[a >> 1], a & 1); }
 };
 
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -244,7 +272,7 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
     // with whatever else they sum over the quad (integrate_substep: one 6-value reduction instead of two)
     if (reduce_hb) { fb = qsum3(fb) + F0; nb = qsum3(nb) + N0; }
     else if (leg == 0) { fb = fb + F0; nb = nb + N0; }
-    d.hb[0] = fb.x; d.hb[1] = fb.y; d.hb[2] = fb.z; d.hb[3] = nb.x; d.hb[4] = nb.y; d.hb[5] = nb.z;
+    d.hb[0] = mk2(fb.x, fb.y); d.hb[1] = mk2(fb.z, nb.x); d.hb[2] = mk2(nb.y, nb.z);
 
     // ---- composite inertias about the trunk origin: (mass, first moment, second moment)
     f3 c3 = k.j3 + k.r3, c2 = k.j2 + k.r2, c1 = k.j1 + k.r1;
@@ -258,9 +286,9 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
     mC += lm.m1; hC = axpy(lm.m1, c1, hC); IC = IC + I1; add_point_mass(IC, lm.m1, c1);
     f3 s1l = cross(k.j1, k.a1);
     f3 P1 = axpy(mC, s1l, cross(k.a1, hC)), L1 = cross(hC, s1l) + mul(IC, k.a1);
-    d.B[0][0] = P1.x; d.B[1][0] = P1.y; d.B[2][0] = P1.z; d.B[3][0] = L1.x; d.B[4][0] = L1.y; d.B[5][0] = L1.z;
-    d.B[0][1] = P2.x; d.B[1][1] = P2.y; d.B[2][1] = P2.z; d.B[3][1] = L2.x; d.B[4][1] = L2.y; d.B[5][1] = L2.z;
-    d.B[0][2] = P3.x; d.B[1][2] = P3.y; d.B[2][2] = P3.z; d.B[3][2] = L3.x; d.B[4][2] = L3.y; d.B[5][2] = L3.z;
+    d.B[0][0] = mk2(P1.x, P1.y); d.B[1][0] = mk2(P1.z, L1.x); d.B[2][0] = mk2(L1.y, L1.z);
+    d.B[0][1] = mk2(P2.x, P2.y); d.B[1][1] = mk2(P2.z, L2.x); d.B[2][1] = mk2(L2.y, L2.z);
+    d.B[0][2] = mk2(P3.x, P3.y); d.B[1][2] = mk2(P3.z, L3.x); d.B[2][2] = mk2(L3.y, L3.z);
     S3 D;   // leg block of M (+ rotor inertias on the diagonal, URDF rotor_inertia)
     D.xx = dot(s1l, P1) + dot(k.a1, L1) + P.rotor[0];
     D.xy = dot(s1l, P2) + dot(k.a1, L2);
@@ -271,68 +299,80 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
     if (Dout) *Dout = D;
     d.Dinv = inv_sym3(D);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        d.Y[a][0] = d.B[a][0] * d.Dinv.xx + d.B[a][1] * d.Dinv.xy + d.B[a][2] * d.Dinv.xz;
-        d.Y[a][1] = d.B[a][0] * d.Dinv.xy + d.B[a][1] * d.Dinv.yy + d.B[a][2] * d.Dinv.yz;
-        d.Y[a][2] = d.B[a][0] * d.Dinv.xz + d.B[a][1] * d.Dinv.yz + d.B[a][2] * d.Dinv.zz;
+    for (int p = 0; p < 3; ++p) {
+        d.Y[p][0] = fma2s(d.B[p][2], d.Dinv.xz, fma2s(d.B[p][1], d.Dinv.xy, mul2s(d.B[p][0], d.Dinv.xx)));
+        d.Y[p][1] = fma2s(d.B[p][2], d.Dinv.yz, fma2s(d.B[p][1], d.Dinv.yy, mul2s(d.B[p][0], d.Dinv.xy)));
+        d.Y[p][2] = fma2s(d.B[p][2], d.Dinv.zz, fma2s(d.B[p][1], d.Dinv.yz, mul2s(d.B[p][0], d.Dinv.xz)));
     }
-    // ---- trunk block A (whole-robot composite) and Schur complement S = A - sum_l Y_l B_l^T, reduced over the quad
-    float S[21];
+    // ---- trunk block A (whole-robot composite) and Schur complement S = A - sum_l Y_l B_l^T, reduced over the quad.
+    // S2[p][c] = rows (2p, 2p+1) of column c, c <= 2p+1 (the upper half of the diagonal pair c = 2p+1 is carried along unused).
+    p2 S2[3][6];
     {
         // this leg's composite contribution to A, in (lin, ang) ordering: [[m 1, -[h]x],[[h]x, Io]]
-        S[tri(0, 0)] = mC; S[tri(1, 0)] = 0.f; S[tri(1, 1)] = mC; S[tri(2, 0)] = 0.f; S[tri(2, 1)] = 0.f; S[tri(2, 2)] = mC;
-        S[tri(3, 0)] = 0.f;   S[tri(3, 1)] = -hC.z; S[tri(3, 2)] = hC.y;
-        S[tri(4, 0)] = hC.z;  S[tri(4, 1)] = 0.f;   S[tri(4, 2)] = -hC.x;
-        S[tri(5, 0)] = -hC.y; S[tri(5, 1)] = hC.x;  S[tri(5, 2)] = 0.f;
-        S[tri(3, 3)] = IC.xx; S[tri(4, 3)] = IC.xy; S[tri(4, 4)] = IC.yy; S[tri(5, 3)] = IC.xz; S[tri(5, 4)] = IC.yz; S[tri(5, 5)] = IC.zz;
+        S2[0][0] = mk2(mC, 0.f);     S2[0][1] = mk2(0.f, mC);
+        S2[1][0] = mk2(0.f, 0.f);    S2[1][1] = mk2(0.f, -hC.z);  S2[1][2] = mk2(mC, hC.y);     S2[1][3] = mk2(0.f, IC.xx);
+        S2[2][0] = mk2(hC.z, -hC.y); S2[2][1] = mk2(0.f, hC.x);   S2[2][2] = mk2(-hC.x, 0.f);   S2[2][3] = mk2(IC.xy, IC.xz);
+        S2[2][4] = mk2(IC.yy, IC.yz); S2[2][5] = mk2(0.f, IC.zz);
     }
+#define SV(i, j) half_of(S2[(i) >> 1][j], (i) & 1)
     if (Aout) {   // un-reduced A for the probes
 #pragma unroll
-        for (int i = 0; i < 21; ++i) Aout[i] = S[i];
-    }
-    // (triangular loops are written with constant bounds and a predicate: nvcc leaves `for (c = 0; c <= a; ++c)` nests partly rolled,
-    //  and one run-time index into S / L is enough to push the whole Dyn structure into local memory)
+        for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int a = 0; a < 6; ++a)
+            for (int j = 0; j < 6; ++j) if (j <= i) Aout[tri(i, j)] = SV(i, j);
+    }
+    // (all loops over the triangle are written with constant bounds and a predicate: nvcc leaves `for (c = 0; c <= a; ++c)` nests partly
+    //  rolled, and one run-time index into S / L is enough to push the whole Dyn structure into local memory)
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int c = 0; c < 6; ++c)
-            if (c <= a) S[tri(a, c)] -= d.Y[a][0] * d.B[c][0] + d.Y[a][1] * d.B[c][1] + d.Y[a][2] * d.B[c][2];
+            if (c <= 2 * p + 1) S2[p][c] = sub2(S2[p][c], fma2s(d.Y[p][2], d.Bv(c, 2), fma2s(d.Y[p][1], d.Bv(c, 1), mul2s(d.Y[p][0], d.Bv(c, 0)))));
 #pragma unroll
-    for (int i = 0; i < 21; ++i) S[i] = qsum(S[i]);
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            if (c < 2 * p + 1) S2[p][c] = qsum2(S2[p][c]);
+            else if (c == 2 * p + 1) S2[p][c].y = qsum(S2[p][c].y);
+        }
     {   // trunk body
         f3 h0 = bm.m0 * r0; S3 Io = I0; add_point_mass(Io, bm.m0, r0);
-        float A0[21];
-        A0[tri(0, 0)] = bm.m0; A0[tri(1, 0)] = 0.f; A0[tri(1, 1)] = bm.m0; A0[tri(2, 0)] = 0.f; A0[tri(2, 1)] = 0.f; A0[tri(2, 2)] = bm.m0;
-        A0[tri(3, 0)] = 0.f;   A0[tri(3, 1)] = -h0.z; A0[tri(3, 2)] = h0.y;
-        A0[tri(4, 0)] = h0.z;  A0[tri(4, 1)] = 0.f;   A0[tri(4, 2)] = -h0.x;
-        A0[tri(5, 0)] = -h0.y; A0[tri(5, 1)] = h0.x;  A0[tri(5, 2)] = 0.f;
-        A0[tri(3, 3)] = Io.xx; A0[tri(4, 3)] = Io.xy; A0[tri(4, 4)] = Io.yy; A0[tri(5, 3)] = Io.xz; A0[tri(5, 4)] = Io.yz; A0[tri(5, 5)] = Io.zz;
+        p2 A0[3][6];
+        A0[0][0] = mk2(bm.m0, 0.f);   A0[0][1] = mk2(0.f, bm.m0);
+        A0[1][0] = mk2(0.f, 0.f);     A0[1][1] = mk2(0.f, -h0.z);  A0[1][2] = mk2(bm.m0, h0.y);  A0[1][3] = mk2(0.f, Io.xx);
+        A0[2][0] = mk2(h0.z, -h0.y);  A0[2][1] = mk2(0.f, h0.x);   A0[2][2] = mk2(-h0.x, 0.f);   A0[2][3] = mk2(Io.xy, Io.xz);
+        A0[2][4] = mk2(Io.yy, Io.yz); A0[2][5] = mk2(0.f, Io.zz);
 #pragma unroll
-        for (int i = 0; i < 21; ++i) S[i] += A0[i];
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) if (c <= 2 * p + 1) S2[p][c] = add2(S2[p][c], A0[p][c]);
         if (Aout) {
 #pragma unroll
-            for (int i = 0; i < 21; ++i) Aout[i] = qsum(Aout[i]) + A0[i];
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) if (j <= i) Aout[tri(i, j)] = qsum(Aout[tri(i, j)]) + half_of(A0[i >> 1][j], i & 1);
         }
     }
     // ---- Cholesky of S (6x6), diagonal stored as its reciprocal
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        float dj = S[tri(j, j)];
+        float dj = SV(j, j);
 #pragma unroll
         for (int c = 0; c < 6; ++c) if (c < j) dj = fmaf(-d.L[tri(j, c)], d.L[tri(j, c)], dj);
-        float inv = rsqrtf(dj);
+        float inv = rsq_approx(dj);
         inv = inv * (1.5f - 0.5f * dj * inv * inv);     // one Newton step: full fp32 accuracy
         d.L[tri(j, j)] = inv;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             if (i > j) {
-                float s = S[tri(i, j)];
+                float s = SV(i, j);
 #pragma unroll
                 for (int c = 0; c < 6; ++c) if (c < j) s = fmaf(-d.L[tri(i, c)], d.L[tri(j, c)], s);
                 d.L[tri(i, j)] = s * inv;
             }
         }
     }
+#undef SV
 }
 
 // y = L^-1 z  (forward substitution, in place)
@@ -375,7 +415,7 @@ __device__ __forceinline__ void solve_full(const Dyn& d, const float* rb, f3 rl,
 // v: contact velocity with the current impulse lo applied, G: 3x3 Delassus block (symmetric), n = +z.
 // Same rule as the oracle's solve_one_contact (separation / stick / slide with a fixed point on the
 // sliding direction).
-__device__ __forceinline__ float rsqrt_nr(float x) { float r = rsqrtf(x); return r * (1.5f - 0.5f * x * r * r); }   // ~1 ulp
+__device__ __forceinline__ float rsqrt_nr(float x) { x = fmaxf(x, 1e-30f); float r = rsq_approx(x); return r * (1.5f - 0.5f * x * r * r); }   // ~1 ulp
 // The sliding direction takes ONE fixed-point step from the stick direction (slide_iters = 1 of the oracle).  Branches, not selects:
 // measured 8 us faster at 4096 robots than a select-only version (separating / sticking contacts skip the sliding arithmetic).
 __device__ __forceinline__ f3 solve_one_contact(f3 v, const S3& G, const S3& Ginv, f3 lo, float vtn, float mu) {
@@ -510,6 +550,8 @@ __device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int own
 }
 
 struct ContactOut { int foot_active; f3 foot_impulse; int sweeps; };
+// radius of the trunk box about the trunk origin: below this height a corner can touch flat ground (launch-uniform, computed once per kernel)
+__device__ __forceinline__ float trunk_box_reach(const EnvParams& P) { return sqrtf(P.box_half[0] * P.box_half[0] + P.box_half[1] * P.box_half[1] + P.box_half[2] * P.box_half[2]); }
 
 // PHASE_SYNC (template flag SYNC): block-wide barriers that keep the warps of a CTA in the same stretch of the substep code
 // (39 KB of straight-line SASS, more than the 32 KB instruction cache), so that one instruction fetch serves all of them.
@@ -517,10 +559,13 @@ struct ContactOut { int foot_active; f3 foot_impulse; int sweeps; };
 #define PHASE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
 // ------------------------------------------------------------------ one world.integrate() (ENV:768)
 // tau: this leg's joint torques.  fext: optional external generalised force on the trunk (6).
-// TERR = false compiles the heightfield code out (launch-uniform: flat-ground launches run a kernel without it in the hot loop)
-template <bool SYNC = false, bool TERR = true>
-__device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegModel& lm, const BaseModel& bm, int leg,
-                                                  Base& b, f3& q, f3& qd, f3 tau, ContactOut& out) {
+// TERR = false compiles the heightfield code out (launch-uniform: flat-ground launches run a kernel without it in the hot loop).
+// BOX = false compiles the trunk-box contact path out: when a box corner touches in any robot of the warp (of the CTA with SYNC) the
+// call returns false BEFORE touching the state, and the caller repeats the substep with BOX = true (the step kernel keeps a second,
+// rarely entered copy of its substep loop for that: 7 KB less code in the hot loop, which is instruction-fetch bound).
+template <bool SYNC = false, bool TERR = true, bool BOX = true>
+__device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegModel& lm, const BaseModel& bm, int leg,
+                                                  Base& b, f3& q, f3& qd, f3 tau, ContactOut& out, float box_reach) {
     const float dt = P.sim_dt;
     PHASE_SYNC();
     f3 bx, by, bz; quat_cols(b.qw, b.qx, b.qy, b.qz, bx, by, bz);
@@ -549,7 +594,6 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     }
     // trunk box corners: lane l tests corners 2l and 2l+1, the quad then ranks the hits in corner order
     int hit0 = 0, hit1 = 0; f3 xc0 = mk(0.f, 0.f, 0.f), xc1 = xc0;
-    const float box_reach = sqrtf(P.box_half[0] * P.box_half[0] + P.box_half[1] * P.box_half[1] + P.box_half[2] * P.box_half[2]);
     if (terr || __any_sync(FULLMASK, b.p.z <= box_reach)) {
         int c0 = 2 * leg, c1 = 2 * leg + 1;
         f3 l0 = mk((c0 & 1) ? P.box_half[0] : -P.box_half[0], (c0 & 2) ? P.box_half[1] : -P.box_half[1], (c0 & 4) ? P.box_half[2] : -P.box_half[2]);
@@ -564,11 +608,7 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     int allhits = 0;
 #pragma unroll
     for (int l = 0; l < 4; ++l) allhits |= qbcasti(hits, l) << (2 * l);
-#ifdef EXP_NO_BOX
-    const bool any_box = false; allhits = 0;
-#else
     const bool any_box = __any_sync(FULLMASK, allhits != 0);
-#endif
     const bool any_foot_or_box = __any_sync(FULLMASK, cf.active || allhits != 0);
 
     float ytot[6];
@@ -577,7 +617,9 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     f3 lam_leg = mk(0.f, 0.f, 0.f);
     out.sweeps = 0;
     cf.lam = mk(0.f, 0.f, 0.f);
-    PHASE_SYNC();
+    if (!BOX) {   // hand the substep over to the full version (state untouched so far); the decision is uniform over whatever shares barriers
+        if (SYNC ? (__syncthreads_or(any_box ? 1 : 0) != 0) : any_box) return false;
+    } else PHASE_SYNC();
     if (any_foot_or_box) {
         // ---- foot contact setup (every lane builds its own slot)
         contact_setup(d, xf, Jl0, Jl1, Jl2, true, cf, terr, ft1, ft2, fn);
@@ -594,7 +636,7 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
         }
         // ---- trunk box contact slot (k-th penetrating corner in corner order belongs to lane k, at most 4)
         Contact cb; cb.active = 0; cb.lam = mk(0.f, 0.f, 0.f);
-        if (any_box) {
+        if (BOX && any_box) {
             int rank = -1, cnt = 0; f3 xb = mk(0.f, 0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -650,7 +692,7 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
                 for (int a = 0; a < 6; ++a) y[a] += qsum(cf.Q[a][0] * dl.x + cf.Q[a][1] * dl.y + cf.Q[a][2] * dl.z);
             }
             if (seq && vi != 3) continue;                                   // sweep not finished yet
-            if (any_box) {
+            if (BOX && any_box) {
 #pragma unroll 1
                 for (int o = 0; o < 4; ++o) {
                     if (!__any_sync(FULLMASK, leg == o && cb.active && !frozen)) continue;
@@ -682,18 +724,19 @@ __device__ __forceinline__ void integrate_substep(const EnvParams& P, const LegM
     // ---- semi-implicit Euler on the configuration
     b.p = axpy(dt, b.v, b.p);
     {
-        float wn = sqrtf(dot(b.w, b.w)), th = wn * dt, kk, cw;
-        if (th > 1e-8f) { float sh; SINCOS(0.5f * th, &sh, &cw); kk = (IRRL_FASTDIV & 4) ? __fdividef(sh, wn) : sh / wn; } else { kk = 0.5f * dt; cw = 1.f; }
+        // |w| and 1/|w| from one MUFU.RSQ + a Newton step (~1 ulp): no IEEE sqrt / division slow paths in the loop
+        const float w2 = dot(b.w, b.w), iw = rsqrt_nr(w2), wn = w2 * iw, th = wn * dt; float kk, cw;
+        if (th > 1e-8f) { float sh; SINCOS(0.5f * th, &sh, &cw); kk = sh * iw; } else { kk = 0.5f * dt; cw = 1.f; }
         float dx = kk * b.w.x, dy = kk * b.w.y, dz = kk * b.w.z;
         float ow = cw * b.qw - dx * b.qx - dy * b.qy - dz * b.qz;
         float ox = cw * b.qx + dx * b.qw + dy * b.qz - dz * b.qy;
         float oy = cw * b.qy - dx * b.qz + dy * b.qw + dz * b.qx;
         float oz = cw * b.qz + dx * b.qy - dy * b.qx + dz * b.qw;
-        float nn = rsqrtf(ow * ow + ox * ox + oy * oy + oz * oz);
-        nn = nn * (1.5f - 0.5f * (ow * ow + ox * ox + oy * oy + oz * oz) * nn * nn);
+        float nn = rsqrt_nr(ow * ow + ox * ox + oy * oy + oz * oz);
         b.qw = ow * nn; b.qx = ox * nn; b.qy = oy * nn; b.qz = oz * nn;
     }
     q = axpy(dt, qd, q);
+    return true;
 }
 
 // ------------------------------------------------------------------ gait generator + IK (ENV:1687-1890), one leg per lane

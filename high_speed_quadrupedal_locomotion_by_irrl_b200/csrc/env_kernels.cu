@@ -308,14 +308,15 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
     const float ilow_ = 1.0f / (-P.motor_max_speed + P.motor_crit_speed);      // hoisted out of the substep loop
     f3 tau = e.torque_last;      // a step with zero substeps (simulation_dt > control_dt, int() ENV:711) sees the stale member `torque`, which equals torque_last between steps (ENV:1511-1515)
     ContactOut co; co.foot_active = 0; co.foot_impulse = mk(0, 0, 0); co.sweeps = 0;
-    for (int it = 0; it < P.loop_count; ++it) {
+    const float box_reach = trunk_box_reach(P);
+    // PD + torque filter + torque_clamp (ENV:761-767, 1273-1305) on the current joint state
+    auto pd_torque = [&]() {
         float t0 = (pt.x - e.q.x) * kp0 - e.qd.x * kd0;
         float t1 = (pt.y - e.q.y) * P.stiffness - e.qd.y * P.damping;
         float t2 = (pt.z - e.q.z) * P.stiffness - e.qd.z * P.damping;
         t0 = 0.99f * t0 + (1.0f - 0.99f) * e.torque_last.x;
         t1 = 0.99f * t1 + (1.0f - 0.99f) * e.torque_last.y;
         t2 = 0.99f * t2 + (1.0f - 0.99f) * e.torque_last.z;
-        // torque_clamp ENV:1273-1305
         float tt[3] = {t0, t1, t2}, qv[3] = {e.qd.x, e.qd.y, e.qd.z};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -328,7 +329,20 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
             tt[k] = fmaxf(fminf(tt[k], up), low);
         }
         tau = mk(tt[0], tt[1], tt[2]);
-        integrate_substep<SYNC, TERR>(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co);
+    };
+    // hot loop: substeps without the trunk-box contact code; it hands over (state untouched) at the first substep in which a box corner
+    // touches the ground in this warp / CTA -- a fallen robot, at most the last control step of an episode -- and the complete version
+    // finishes the control step
+    int it = 0;
+#pragma unroll 1
+    for (; it < P.loop_count; ++it) {
+        pd_torque();
+        if (!integrate_substep<SYNC, TERR, false>(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co, box_reach)) break;
+    }
+#pragma unroll 1
+    for (; it < P.loop_count; ++it) {
+        pd_torque();
+        integrate_substep<SYNC, TERR, true>(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co, box_reach);
     }
     load_env_cold(S, r, leg, e);                   // clock, command, references, counters: first needed here
     e.tau_applied = tau;
@@ -572,7 +586,7 @@ __global__ void __launch_bounds__(BLOCK) env_integrate_kernel(EnvParams P, DevSt
     EnvRegs e; load_env(S, r, leg, e);
     const float* t = tau12 + (size_t)r * 12 + 3 * leg;
     f3 tau = mk(t[0], t[1], t[2]);
-    ContactOut co; integrate_substep(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co);
+    ContactOut co; integrate_substep(P, e.lm, e.bm, leg, e.b, e.q, e.qd, tau, co, trunk_box_reach(P));
     e.tau_applied = tau; e.contact_flag = co.foot_active ? 1.f : 0.f;
     e.impulse_norm = co.foot_active ? sqrtf(dot(co.foot_impulse, co.foot_impulse)) : 0.f;
     if (valid) {

@@ -385,6 +385,23 @@ __device__ __forceinline__ void fwd6(const float* L, float* z) {
         z[i] = s * L[tri(i, i)];
     }
 }
+// the same forward substitution on row pairs, column by column: every row sees the same products in the same order as in fwd6
+// (bit-identical), 6 packed + 3 scalar multiply-adds instead of 15
+__device__ __forceinline__ void fwd6p(const float* L, p2* z) {
+    z[0].x *= L[tri(0, 0)];
+    z[0].y = fmaf(-L[tri(1, 0)], z[0].x, z[0].y);
+    z[1] = fma2s(mk2(L[tri(2, 0)], L[tri(3, 0)]), -z[0].x, z[1]); z[2] = fma2s(mk2(L[tri(4, 0)], L[tri(5, 0)]), -z[0].x, z[2]);
+    z[0].y *= L[tri(1, 1)];
+    z[1] = fma2s(mk2(L[tri(2, 1)], L[tri(3, 1)]), -z[0].y, z[1]); z[2] = fma2s(mk2(L[tri(4, 1)], L[tri(5, 1)]), -z[0].y, z[2]);
+    z[1].x *= L[tri(2, 2)];
+    z[1].y = fmaf(-L[tri(3, 2)], z[1].x, z[1].y);
+    z[2] = fma2s(mk2(L[tri(4, 2)], L[tri(5, 2)]), -z[1].x, z[2]);
+    z[1].y *= L[tri(3, 3)];
+    z[2] = fma2s(mk2(L[tri(4, 3)], L[tri(5, 3)]), -z[1].y, z[2]);
+    z[2].x *= L[tri(4, 4)];
+    z[2].y = fmaf(-L[tri(5, 4)], z[2].x, z[2].y);
+    z[2].y *= L[tri(5, 5)];
+}
 // x = L^-T y  (back substitution, in place)
 __device__ __forceinline__ void bwd6(const float* L, float* y) {
 #pragma unroll
@@ -402,13 +419,13 @@ __device__ __forceinline__ void solve_full(const Dyn& d, const float* rb, f3 rl,
     f3 t = mul(d.Dinv, rl);
     float z[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) z[a] = qsum(d.B[a][0] * t.x + d.B[a][1] * t.y + d.B[a][2] * t.z);
+    for (int a = 0; a < 6; ++a) z[a] = qsum(d.Bv(a, 0) * t.x + d.Bv(a, 1) * t.y + d.Bv(a, 2) * t.z);
 #pragma unroll
     for (int a = 0; a < 6; ++a) xb[a] = rb[a] - z[a];
     fwd6(d.L, xb); bwd6(d.L, xb);
-    xl = mk(t.x - (d.Y[0][0] * xb[0] + d.Y[1][0] * xb[1] + d.Y[2][0] * xb[2] + d.Y[3][0] * xb[3] + d.Y[4][0] * xb[4] + d.Y[5][0] * xb[5]),
-            t.y - (d.Y[0][1] * xb[0] + d.Y[1][1] * xb[1] + d.Y[2][1] * xb[2] + d.Y[3][1] * xb[3] + d.Y[4][1] * xb[4] + d.Y[5][1] * xb[5]),
-            t.z - (d.Y[0][2] * xb[0] + d.Y[1][2] * xb[1] + d.Y[2][2] * xb[2] + d.Y[3][2] * xb[3] + d.Y[4][2] * xb[4] + d.Y[5][2] * xb[5]));
+    xl = mk(t.x - (d.Yv(0, 0) * xb[0] + d.Yv(1, 0) * xb[1] + d.Yv(2, 0) * xb[2] + d.Yv(3, 0) * xb[3] + d.Yv(4, 0) * xb[4] + d.Yv(5, 0) * xb[5]),
+            t.y - (d.Yv(0, 1) * xb[0] + d.Yv(1, 1) * xb[1] + d.Yv(2, 1) * xb[2] + d.Yv(3, 1) * xb[3] + d.Yv(4, 1) * xb[4] + d.Yv(5, 1) * xb[5]),
+            t.z - (d.Yv(0, 2) * xb[0] + d.Yv(1, 2) * xb[1] + d.Yv(2, 2) * xb[2] + d.Yv(3, 2) * xb[3] + d.Yv(4, 2) * xb[4] + d.Yv(5, 2) * xb[5]));
 }
 
 // ------------------------------------------------------------------ hard-contact single-contact solve
@@ -466,7 +483,7 @@ __device__ __forceinline__ void contact_frame(f3 n, f3& t1, f3& t2) {
 
 // Per-contact data in the reduced trunk space: v_i = c_i + Q_i^T y + T_i lambda_i,  y = sum_j Q_j lambda_j
 struct Contact {
-    float Q[6][3];   // L^-1 E_i^T
+    p2 Q[3][3];      // L^-1 E_i^T, Q[p][r] = trunk rows (2p, 2p+1) of contact-frame column r
     S3 T, G, Ginv;   // leg-local Delassus term, full diagonal block and its inverse
     f3 c, lam;
     float vtn;
@@ -478,34 +495,33 @@ struct Contact {
 // Jl* must already be rotated by the caller in that case.
 __device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1, f3 Jl2, bool on_leg, Contact& ct,
                                               bool framed = false, f3 t1 = f3{1, 0, 0}, f3 t2 = f3{0, 1, 0}, f3 nn = f3{0, 0, 1}) {
-    // E = J_b - J_l Y^T : 3x6.  J_b = [1, -[x]x]
-    float E[3][6];
-    E[0][0] = 1.f; E[0][1] = 0.f; E[0][2] = 0.f; E[0][3] = 0.f;  E[0][4] = x.z;  E[0][5] = -x.y;
-    E[1][0] = 0.f; E[1][1] = 1.f; E[1][2] = 0.f; E[1][3] = -x.z; E[1][4] = 0.f;  E[1][5] = x.x;
-    E[2][0] = 0.f; E[2][1] = 0.f; E[2][2] = 1.f; E[2][3] = x.y;  E[2][4] = -x.x; E[2][5] = 0.f;
+    // E = J_b - J_l Y^T : 3x6, rows as pairs of trunk dimensions.  J_b = [1, -[x]x]
+    p2 E[3][3];
+    E[0][0] = mk2(1.f, 0.f); E[0][1] = mk2(0.f, 0.f);   E[0][2] = mk2(x.z, -x.y);
+    E[1][0] = mk2(0.f, 1.f); E[1][1] = mk2(0.f, -x.z);  E[1][2] = mk2(0.f, x.x);
+    E[2][0] = mk2(0.f, 0.f); E[2][1] = mk2(1.f, x.y);   E[2][2] = mk2(-x.x, 0.f);
     if (framed) {   // E <- D E with D rows (t1, t2, n)
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            f3 col = mk(E[0][a], E[1][a], E[2][a]);
-            E[0][a] = dot(t1, col); E[1][a] = dot(t2, col); E[2][a] = dot(nn, col);
+        for (int p = 0; p < 3; ++p) {
+            const p2 c0 = E[0][p], c1 = E[1][p], c2 = E[2][p];
+            E[0][p] = fma2s(c0, t1.x, fma2s(c1, t1.y, mul2s(c2, t1.z)));
+            E[1][p] = fma2s(c0, t2.x, fma2s(c1, t2.y, mul2s(c2, t2.z)));
+            E[2][p] = fma2s(c0, nn.x, fma2s(c1, nn.y, mul2s(c2, nn.z)));
         }
     }
     if (on_leg) {
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            E[0][a] -= Jl0.x * d.Y[a][0] + Jl1.x * d.Y[a][1] + Jl2.x * d.Y[a][2];
-            E[1][a] -= Jl0.y * d.Y[a][0] + Jl1.y * d.Y[a][1] + Jl2.y * d.Y[a][2];
-            E[2][a] -= Jl0.z * d.Y[a][0] + Jl1.z * d.Y[a][1] + Jl2.z * d.Y[a][2];
+        for (int p = 0; p < 3; ++p) {
+            E[0][p] = sub2(E[0][p], fma2s(d.Y[p][2], Jl2.x, fma2s(d.Y[p][1], Jl1.x, mul2s(d.Y[p][0], Jl0.x))));
+            E[1][p] = sub2(E[1][p], fma2s(d.Y[p][2], Jl2.y, fma2s(d.Y[p][1], Jl1.y, mul2s(d.Y[p][0], Jl0.y))));
+            E[2][p] = sub2(E[2][p], fma2s(d.Y[p][2], Jl2.z, fma2s(d.Y[p][1], Jl1.z, mul2s(d.Y[p][0], Jl0.z))));
         }
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        float z[6];
+        fwd6p(d.L, E[r]);
 #pragma unroll
-        for (int a = 0; a < 6; ++a) z[a] = E[r][a];
-        fwd6(d.L, z);
-#pragma unroll
-        for (int a = 0; a < 6; ++a) ct.Q[a][r] = z[a];
+        for (int p = 0; p < 3; ++p) ct.Q[p][r] = E[r][p];
     }
     // T = J_l Dinv J_l^T
     ct.T = S3{0, 0, 0, 0, 0, 0};
@@ -515,38 +531,47 @@ __device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1
         f3 dx = mul(d.Dinv, rx), dy = mul(d.Dinv, ry), dz = mul(d.Dinv, rz);
         ct.T.xx = dot(rx, dx); ct.T.xy = dot(rx, dy); ct.T.xz = dot(rx, dz); ct.T.yy = dot(ry, dy); ct.T.yz = dot(ry, dz); ct.T.zz = dot(rz, dz);
     }
+    // G = T + Q^T Q: the three row pairs accumulate in packed form, the two halves are added at the end
     S3 G = ct.T;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        G.xx = fmaf(ct.Q[a][0], ct.Q[a][0], G.xx); G.xy = fmaf(ct.Q[a][0], ct.Q[a][1], G.xy); G.xz = fmaf(ct.Q[a][0], ct.Q[a][2], G.xz);
-        G.yy = fmaf(ct.Q[a][1], ct.Q[a][1], G.yy); G.yz = fmaf(ct.Q[a][1], ct.Q[a][2], G.yz); G.zz = fmaf(ct.Q[a][2], ct.Q[a][2], G.zz);
-    }
+    G.xx += hsum(fma2(ct.Q[2][0], ct.Q[2][0], fma2(ct.Q[1][0], ct.Q[1][0], mul2(ct.Q[0][0], ct.Q[0][0]))));
+    G.xy += hsum(fma2(ct.Q[2][0], ct.Q[2][1], fma2(ct.Q[1][0], ct.Q[1][1], mul2(ct.Q[0][0], ct.Q[0][1]))));
+    G.xz += hsum(fma2(ct.Q[2][0], ct.Q[2][2], fma2(ct.Q[1][0], ct.Q[1][2], mul2(ct.Q[0][0], ct.Q[0][2]))));
+    G.yy += hsum(fma2(ct.Q[2][1], ct.Q[2][1], fma2(ct.Q[1][1], ct.Q[1][1], mul2(ct.Q[0][1], ct.Q[0][1]))));
+    G.yz += hsum(fma2(ct.Q[2][1], ct.Q[2][2], fma2(ct.Q[1][1], ct.Q[1][2], mul2(ct.Q[0][1], ct.Q[0][2]))));
+    G.zz += hsum(fma2(ct.Q[2][2], ct.Q[2][2], fma2(ct.Q[1][2], ct.Q[1][2], mul2(ct.Q[0][2], ct.Q[0][2]))));
     ct.G = G; ct.Ginv = inv_sym3(G);
 }
 
+// Q^T z for a trunk-space vector z (three row pairs): packed partial sums, halves added at the end
+__device__ __forceinline__ f3 qt_mul(const Contact& ct, const p2* z) {
+    return mk(hsum(fma2(ct.Q[2][0], z[2], fma2(ct.Q[1][0], z[1], mul2(ct.Q[0][0], z[0])))),
+              hsum(fma2(ct.Q[2][1], z[2], fma2(ct.Q[1][1], z[1], mul2(ct.Q[0][1], z[0])))),
+              hsum(fma2(ct.Q[2][2], z[2], fma2(ct.Q[1][2], z[1], mul2(ct.Q[0][2], z[0])))));
+}
+// Q dl (trunk-space increment of an impulse change), three row pairs
+__device__ __forceinline__ void q_mul(const Contact& ct, f3 dl, p2* out) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) out[p] = fma2s(ct.Q[p][2], dl.z, fma2s(ct.Q[p][1], dl.y, mul2s(ct.Q[p][0], dl.x)));
+}
 // One Gauss-Seidel visit of the contact slot owned by lane `owner`: every lane evaluates its own slot, only the
 // owner's result is committed and its trunk-space increment is broadcast to the quad.
-__device__ __forceinline__ void gs_visit(Contact& ct, float* y, int leg, int owner, bool frozen, float mu,
+__device__ __forceinline__ void gs_visit(Contact& ct, p2* y, int leg, int owner, bool frozen, float mu,
                                          float& maxd, float& maxl) {
     // only the owner of an active, unconverged contact evaluates the solve: idle lanes (swinging feet) would otherwise
     // drag the whole warp through the sliding branch with meaningless velocities
     const bool commit = (leg == owner) && ct.active && !frozen;
     f3 dl = mk(0.f, 0.f, 0.f);
     if (commit) {
-        f3 v = ct.c + mul(ct.T, ct.lam);
-#pragma unroll
-        for (int a = 0; a < 6; ++a) { v.x = fmaf(ct.Q[a][0], y[a], v.x); v.y = fmaf(ct.Q[a][1], y[a], v.y); v.z = fmaf(ct.Q[a][2], y[a], v.z); }
+        f3 v = ct.c + mul(ct.T, ct.lam) + qt_mul(ct, y);
         f3 ln = solve_one_contact(v, ct.G, ct.Ginv, ct.lam, ct.vtn, mu);
         dl = ln - ct.lam;
         ct.lam = ln;
         maxd = fmaxf(maxd, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
         maxl = fmaxf(maxl, fmaxf(fabsf(ln.x), fmaxf(fabsf(ln.y), fabsf(ln.z))));
     }
+    p2 dy[3]; q_mul(ct, dl, dy);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        float dy = ct.Q[a][0] * dl.x + ct.Q[a][1] * dl.y + ct.Q[a][2] * dl.z;
-        y[a] += qbcast(dy, owner);
-    }
+    for (int p = 0; p < 3; ++p) y[p] = add2(y[p], qbcast2(dy[p], owner));
 }
 
 struct ContactOut { int foot_active; f3 foot_impulse; int sweeps; };
@@ -576,10 +601,10 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
     // ---- free acceleration in the factorised form:  t = Dinv r_l,  w = L^-1 (r_b - sum B t)
     f3 rl = mk(tau.x - P.joint_damping * qd.x - d.hl.x, tau.y - P.joint_damping * qd.y - d.hl.y, tau.z - P.joint_damping * qd.z - d.hl.z);
     f3 t = mul(d.Dinv, rl);
-    float wv[6];
+    p2 wv[3];      // L^-1 (r_b - sum_l B_l t_l), three row pairs
 #pragma unroll
-    for (int a = 0; a < 6; ++a) wv[a] = -qsum(d.hb[a] + d.B[a][0] * t.x + d.B[a][1] * t.y + d.B[a][2] * t.z);
-    fwd6(d.L, wv);
+    for (int p = 0; p < 3; ++p) { const p2 v = qsum2(fma2s(d.B[p][2], t.z, fma2s(d.B[p][1], t.y, fma2s(d.B[p][0], t.x, d.hb[p])))); wv[p] = mk2(-v.x, -v.y); }
+    fwd6p(d.L, wv);
 
     // ---- collision detection against the plane z = 0 (ENV:268) or the heightfield (ENV:264)
     Contact cf;   // foot contact of this leg (slot 0 of this lane)
@@ -611,9 +636,9 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
     const bool any_box = __any_sync(FULLMASK, allhits != 0);
     const bool any_foot_or_box = __any_sync(FULLMASK, cf.active || allhits != 0);
 
-    float ytot[6];
+    p2 ytot2[3];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) ytot[a] = dt * wv[a];
+    for (int p = 0; p < 3; ++p) ytot2[p] = mul2s(wv[p], dt);
     f3 lam_leg = mk(0.f, 0.f, 0.f);
     out.sweeps = 0;
     cf.lam = mk(0.f, 0.f, 0.f);
@@ -628,9 +653,7 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
             if (terr) vb_ = mk(dot(ft1, vb_), dot(ft2, vb_), dot(fn, vb_));
             f3 vpre = vb_ + qd.x * Jl0 + qd.y * Jl1 + qd.z * Jl2;                         // J u (pre-step)
             f3 jt = t.x * Jl0 + t.y * Jl1 + t.z * Jl2;                                    // J_l Dinv r_l
-            f3 qw_ = mk(0.f, 0.f, 0.f);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) { qw_.x = fmaf(cf.Q[a][0], wv[a], qw_.x); qw_.y = fmaf(cf.Q[a][1], wv[a], qw_.y); qw_.z = fmaf(cf.Q[a][2], wv[a], qw_.z); }
+            const f3 qw_ = qt_mul(cf, wv);
             cf.c = vpre + dt * (qw_ + jt);
             cf.vtn = (vpre.z < -bm.thr) ? -bm.rest * vpre.z : 0.f;
         }
@@ -651,15 +674,13 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
             contact_setup(d, xb, mk(0, 0, 0), mk(0, 0, 0), mk(0, 0, 0), false, cb, terr, bt1, bt2, bn);
             f3 vpre = b.v + cross(b.w, xb);
             if (terr) vpre = mk(dot(bt1, vpre), dot(bt2, vpre), dot(bn, vpre));
-            f3 qw_ = mk(0.f, 0.f, 0.f);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) { qw_.x = fmaf(cb.Q[a][0], wv[a], qw_.x); qw_.y = fmaf(cb.Q[a][1], wv[a], qw_.y); qw_.z = fmaf(cb.Q[a][2], wv[a], qw_.z); }
+            const f3 qw_ = qt_mul(cb, wv);
             cb.c = vpre + dt * qw_;
             cb.vtn = (vpre.z < -bm.thr) ? -bm.rest * vpre.z : 0.f;
         }
         // ---- per-contact iteration in the 6-dimensional trunk space: feet simultaneously (block Jacobi, they couple only
         //      weakly through the trunk), trunk-box corners one after the other (Gauss-Seidel), same schedule as the oracle
-        float y[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        p2 y[3] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};     // sum_j Q_j lambda_j (replicated in the quad)
         bool frozen = !(qsum((float)(cf.active + cb.active)) > 0.f);    // robots without contacts never iterate
         int sweeps = 0;
         // One loop over visits: iteration `it` is sweep `it` while it < jacobi_sweeps (all feet at once, block Jacobi); after that four
@@ -680,16 +701,15 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
             {
                 f3 dl = mk(0.f, 0.f, 0.f);
                 if (cf.active && !frozen && (!seq || leg == vi)) {
-                    f3 v = cf.c + mul(cf.T, cf.lam);
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) { v.x = fmaf(cf.Q[a][0], y[a], v.x); v.y = fmaf(cf.Q[a][1], y[a], v.y); v.z = fmaf(cf.Q[a][2], y[a], v.z); }
+                    f3 v = cf.c + mul(cf.T, cf.lam) + qt_mul(cf, y);
                     f3 ln = solve_one_contact(v, cf.G, cf.Ginv, cf.lam, cf.vtn, bm.mu);
                     dl = ln - cf.lam; cf.lam = ln;
                     maxd = fmaxf(maxd, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
                     maxl = fmaxf(maxl, fmaxf(fabsf(ln.x), fmaxf(fabsf(ln.y), fabsf(ln.z))));
                 }
+                p2 dy[3]; q_mul(cf, dl, dy);
 #pragma unroll
-                for (int a = 0; a < 6; ++a) y[a] += qsum(cf.Q[a][0] * dl.x + cf.Q[a][1] * dl.y + cf.Q[a][2] * dl.z);
+                for (int p = 0; p < 3; ++p) y[p] = add2(y[p], qsum2(dy[p]));
             }
             if (seq && vi != 3) continue;                                   // sweep not finished yet
             if (BOX && any_box) {
@@ -705,19 +725,21 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
         }
         out.sweeps = sweeps;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) ytot[a] += y[a];
+        for (int p = 0; p < 3; ++p) ytot2[p] = add2(ytot2[p], y[p]);
         lam_leg = cf.lam;
     }
     out.foot_active = cf.active; out.foot_impulse = cf.lam;
     PHASE_SYNC();
 
     // ---- new velocity: u+ = u + M^-1 (dt r + J^T lambda)
+    float ytot[6] = {ytot2[0].x, ytot2[0].y, ytot2[1].x, ytot2[1].y, ytot2[2].x, ytot2[2].y};
     bwd6(d.L, ytot);                                                    // trunk increment
     f3 jl = mk(dot(Jl0, lam_leg), dot(Jl1, lam_leg), dot(Jl2, lam_leg));   // J_l^T lambda
     f3 tl = axpy(dt, t, mul(d.Dinv, jl));
-    f3 dq = mk(tl.x - (d.Y[0][0] * ytot[0] + d.Y[1][0] * ytot[1] + d.Y[2][0] * ytot[2] + d.Y[3][0] * ytot[3] + d.Y[4][0] * ytot[4] + d.Y[5][0] * ytot[5]),
-               tl.y - (d.Y[0][1] * ytot[0] + d.Y[1][1] * ytot[1] + d.Y[2][1] * ytot[2] + d.Y[3][1] * ytot[3] + d.Y[4][1] * ytot[4] + d.Y[5][1] * ytot[5]),
-               tl.z - (d.Y[0][2] * ytot[0] + d.Y[1][2] * ytot[1] + d.Y[2][2] * ytot[2] + d.Y[3][2] * ytot[3] + d.Y[4][2] * ytot[4] + d.Y[5][2] * ytot[5]));
+    const p2 yt0 = mk2(ytot[0], ytot[1]), yt1 = mk2(ytot[2], ytot[3]), yt2 = mk2(ytot[4], ytot[5]);
+    f3 dq = mk(tl.x - hsum(fma2(d.Y[2][0], yt2, fma2(d.Y[1][0], yt1, mul2(d.Y[0][0], yt0)))),
+               tl.y - hsum(fma2(d.Y[2][1], yt2, fma2(d.Y[1][1], yt1, mul2(d.Y[0][1], yt0)))),
+               tl.z - hsum(fma2(d.Y[2][2], yt2, fma2(d.Y[1][2], yt1, mul2(d.Y[0][2], yt0)))));
     b.v = b.v + mk(ytot[0], ytot[1], ytot[2]);
     b.w = b.w + mk(ytot[3], ytot[4], ytot[5]);
     qd = qd + dq;

@@ -471,14 +471,14 @@ __global__ void __launch_bounds__(BLOCK) env_probe_kernel(EnvParams P, DevState 
     dynamics(P, e.lm, e.bm, e.b, bx, by, bz, k, e.qd, d, A, &D);
     if (valid && hout) {
         float* h = hout + (size_t)r * 18;
-        if (leg == 0) for (int a = 0; a < 6; ++a) h[a] = d.hb[a];
+        if (leg == 0) for (int a = 0; a < 6; ++a) h[a] = d.hbv(a);
         h[6 + 3 * leg] = d.hl.x; h[7 + 3 * leg] = d.hl.y; h[8 + 3 * leg] = d.hl.z;
     }
     if (valid && Mout) {
         float* M = Mout + (size_t)r * 324;
         if (leg == 0) for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) M[i * 18 + j] = A[i >= j ? tri(i, j) : tri(j, i)];
         int c0 = 6 + 3 * leg;
-        for (int a = 0; a < 6; ++a) for (int c = 0; c < 3; ++c) { M[a * 18 + c0 + c] = d.B[a][c]; M[(c0 + c) * 18 + a] = d.B[a][c]; }
+        for (int a = 0; a < 6; ++a) for (int c = 0; c < 3; ++c) { M[a * 18 + c0 + c] = d.Bv(a, c); M[(c0 + c) * 18 + a] = d.Bv(a, c); }
         for (int i = 0; i < 12; ++i) for (int c = 0; c < 3; ++c) if (i / 3 != leg) M[(c0 + c) * 18 + 6 + i] = 0.f;
         M[(c0 + 0) * 18 + c0 + 0] = D.xx; M[(c0 + 0) * 18 + c0 + 1] = D.xy; M[(c0 + 0) * 18 + c0 + 2] = D.xz;
         M[(c0 + 1) * 18 + c0 + 0] = D.xy; M[(c0 + 1) * 18 + c0 + 1] = D.yy; M[(c0 + 1) * 18 + c0 + 2] = D.yz;
@@ -554,9 +554,9 @@ __global__ void __launch_bounds__(BLOCK) env_meteor_kernel(const __grid_constant
 #pragma unroll
                     for (int a = 0; a < 6; ++a) du[a] -= lam * z[a];
                     // joint part of M^-1 J^T n:  -Y^T z  (this lane's leg)
-                    dq.x += lam * (d.Y[0][0] * z[0] + d.Y[1][0] * z[1] + d.Y[2][0] * z[2] + d.Y[3][0] * z[3] + d.Y[4][0] * z[4] + d.Y[5][0] * z[5]);
-                    dq.y += lam * (d.Y[0][1] * z[0] + d.Y[1][1] * z[1] + d.Y[2][1] * z[2] + d.Y[3][1] * z[3] + d.Y[4][1] * z[4] + d.Y[5][1] * z[5]);
-                    dq.z += lam * (d.Y[0][2] * z[0] + d.Y[1][2] * z[1] + d.Y[2][2] * z[2] + d.Y[3][2] * z[3] + d.Y[4][2] * z[4] + d.Y[5][2] * z[5]);
+                    dq.x += lam * (d.Yv(0, 0) * z[0] + d.Yv(1, 0) * z[1] + d.Yv(2, 0) * z[2] + d.Yv(3, 0) * z[3] + d.Yv(4, 0) * z[4] + d.Yv(5, 0) * z[5]);
+                    dq.y += lam * (d.Yv(0, 1) * z[0] + d.Yv(1, 1) * z[1] + d.Yv(2, 1) * z[2] + d.Yv(3, 1) * z[3] + d.Yv(4, 1) * z[4] + d.Yv(5, 1) * z[5]);
+                    dq.z += lam * (d.Yv(0, 2) * z[0] + d.Yv(1, 2) * z[1] + d.Yv(2, 2) * z[2] + d.Yv(3, 2) * z[3] + d.Yv(4, 2) * z[4] + d.Yv(5, 2) * z[5]);
                 }
             }
             float hh = 0.f; f3 nn = mk(0.f, 0.f, 1.f);

@@ -223,12 +223,13 @@ struct Dyn {
     p2 B[3][3];           // coupling block trunk(6) x leg joints(3), columns (P_k ; L_k): B[p][k] = rows (2p, 2p+1) of column k
     p2 Y[3][3];           // B Dinv, same layout
     // trunk, replicated
-    float L[21];          // Cholesky factor of the Schur complement S (lower, row-major packed), diagonal stored INVERTED
+    p2 LP[3][6];          // Cholesky factor of the Schur complement S: LP[p][c] = rows (2p, 2p+1) of column c (c <= 2p+1), diagonal stored INVERTED
     p2 hb[3];             // bias force on the trunk rows (pairs of rows)
     f3 hl;                // bias force on this leg's joints
     __device__ __forceinline__ float Bv(int a, int k) const { return half_of(B[a >> 1][k], a & 1); }
     __device__ __forceinline__ float Yv(int a, int k) const { return half_of(Y[a >> 1][k], a & 1); }
     __device__ __forceinline__ float hbv(int a) const { return half_of(hb[a >> 1], a & 1); }
+    __device__ __forceinline__ float Lv(int i, int j) const { return half_of(LP[i >> 1][j], i & 1); }       // L[i][j], j <= i
 };
 
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -353,22 +354,29 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
                 for (int j = 0; j < 6; ++j) if (j <= i) Aout[tri(i, j)] = qsum(Aout[tri(i, j)]) + half_of(A0[i >> 1][j], i & 1);
         }
     }
-    // ---- Cholesky of S (6x6), diagonal stored as its reciprocal
+    // ---- Cholesky of S (6x6), diagonal stored as its reciprocal.  Column by column; the rows below the pivot are updated as row
+    // pairs (packed), every entry with the same products in the same order as the scalar recurrence.
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         float dj = SV(j, j);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) if (c < j) dj = fmaf(-d.L[tri(j, c)], d.L[tri(j, c)], dj);
+        for (int c = 0; c < 6; ++c) if (c < j) dj = fmaf(-d.Lv(j, c), d.Lv(j, c), dj);
         float inv = rsq_approx(dj);
         inv = inv * (1.5f - 0.5f * dj * inv * inv);     // one Newton step: full fp32 accuracy
-        d.L[tri(j, j)] = inv;
+        if (j & 1) d.LP[j >> 1][j].y = inv; else d.LP[j >> 1][j].x = inv;
+        if (!(j & 1)) {                                  // the odd row of the pivot's own pair
+            float s = SV(j + 1, j);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            if (i > j) {
-                float s = SV(i, j);
+            for (int c = 0; c < 6; ++c) if (c < j) s = fmaf(-d.Lv(j + 1, c), d.Lv(j, c), s);
+            d.LP[j >> 1][j].y = s * inv;
+        }
 #pragma unroll
-                for (int c = 0; c < 6; ++c) if (c < j) s = fmaf(-d.L[tri(i, c)], d.L[tri(j, c)], s);
-                d.L[tri(i, j)] = s * inv;
+        for (int p = 0; p < 3; ++p) {
+            if (2 * p > j) {
+                p2 s2 = S2[p][j];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) if (c < j) s2 = fma2s(d.LP[p][c], -d.Lv(j, c), s2);
+                d.LP[p][j] = mul2s(s2, inv);
             }
         }
     }
@@ -376,41 +384,41 @@ __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm,
 }
 
 // y = L^-1 z  (forward substitution, in place)
-__device__ __forceinline__ void fwd6(const float* L, float* z) {
+__device__ __forceinline__ void fwd6(const Dyn& d, float* z) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         float s = z[i];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) if (c < i) s = fmaf(-L[tri(i, c)], z[c], s);
-        z[i] = s * L[tri(i, i)];
+        for (int c = 0; c < 6; ++c) if (c < i) s = fmaf(-d.Lv(i, c), z[c], s);
+        z[i] = s * d.Lv(i, i);
     }
 }
 // the same forward substitution on row pairs, column by column: every row sees the same products in the same order as in fwd6
 // (bit-identical), 6 packed + 3 scalar multiply-adds instead of 15
-__device__ __forceinline__ void fwd6p(const float* L, p2* z) {
-    z[0].x *= L[tri(0, 0)];
-    z[0].y = fmaf(-L[tri(1, 0)], z[0].x, z[0].y);
-    z[1] = fma2s(mk2(L[tri(2, 0)], L[tri(3, 0)]), -z[0].x, z[1]); z[2] = fma2s(mk2(L[tri(4, 0)], L[tri(5, 0)]), -z[0].x, z[2]);
-    z[0].y *= L[tri(1, 1)];
-    z[1] = fma2s(mk2(L[tri(2, 1)], L[tri(3, 1)]), -z[0].y, z[1]); z[2] = fma2s(mk2(L[tri(4, 1)], L[tri(5, 1)]), -z[0].y, z[2]);
-    z[1].x *= L[tri(2, 2)];
-    z[1].y = fmaf(-L[tri(3, 2)], z[1].x, z[1].y);
-    z[2] = fma2s(mk2(L[tri(4, 2)], L[tri(5, 2)]), -z[1].x, z[2]);
-    z[1].y *= L[tri(3, 3)];
-    z[2] = fma2s(mk2(L[tri(4, 3)], L[tri(5, 3)]), -z[1].y, z[2]);
-    z[2].x *= L[tri(4, 4)];
-    z[2].y = fmaf(-L[tri(5, 4)], z[2].x, z[2].y);
-    z[2].y *= L[tri(5, 5)];
+__device__ __forceinline__ void fwd6p(const Dyn& d, p2* z) {
+    z[0].x *= d.Lv(0, 0);
+    z[0].y = fmaf(-d.Lv(1, 0), z[0].x, z[0].y);
+    z[1] = fma2s(d.LP[1][0], -z[0].x, z[1]); z[2] = fma2s(d.LP[2][0], -z[0].x, z[2]);
+    z[0].y *= d.Lv(1, 1);
+    z[1] = fma2s(d.LP[1][1], -z[0].y, z[1]); z[2] = fma2s(d.LP[2][1], -z[0].y, z[2]);
+    z[1].x *= d.Lv(2, 2);
+    z[1].y = fmaf(-d.Lv(3, 2), z[1].x, z[1].y);
+    z[2] = fma2s(d.LP[2][2], -z[1].x, z[2]);
+    z[1].y *= d.Lv(3, 3);
+    z[2] = fma2s(d.LP[2][3], -z[1].y, z[2]);
+    z[2].x *= d.Lv(4, 4);
+    z[2].y = fmaf(-d.Lv(5, 4), z[2].x, z[2].y);
+    z[2].y *= d.Lv(5, 5);
 }
 // x = L^-T y  (back substitution, in place)
-__device__ __forceinline__ void bwd6(const float* L, float* y) {
+__device__ __forceinline__ void bwd6(const Dyn& d, float* y) {
 #pragma unroll
     for (int ii = 0; ii < 6; ++ii) {
         const int i = 5 - ii;
         float s = y[i];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) if (c > i) s = fmaf(-L[tri(c, i)], y[c], s);
-        y[i] = s * L[tri(i, i)];
+        for (int c = 0; c < 6; ++c) if (c > i) s = fmaf(-d.Lv(c, i), y[c], s);
+        y[i] = s * d.Lv(i, i);
     }
 }
 
@@ -422,7 +430,7 @@ __device__ __forceinline__ void solve_full(const Dyn& d, const float* rb, f3 rl,
     for (int a = 0; a < 6; ++a) z[a] = qsum(d.Bv(a, 0) * t.x + d.Bv(a, 1) * t.y + d.Bv(a, 2) * t.z);
 #pragma unroll
     for (int a = 0; a < 6; ++a) xb[a] = rb[a] - z[a];
-    fwd6(d.L, xb); bwd6(d.L, xb);
+    fwd6(d, xb); bwd6(d, xb);
     xl = mk(t.x - (d.Yv(0, 0) * xb[0] + d.Yv(1, 0) * xb[1] + d.Yv(2, 0) * xb[2] + d.Yv(3, 0) * xb[3] + d.Yv(4, 0) * xb[4] + d.Yv(5, 0) * xb[5]),
             t.y - (d.Yv(0, 1) * xb[0] + d.Yv(1, 1) * xb[1] + d.Yv(2, 1) * xb[2] + d.Yv(3, 1) * xb[3] + d.Yv(4, 1) * xb[4] + d.Yv(5, 1) * xb[5]),
             t.z - (d.Yv(0, 2) * xb[0] + d.Yv(1, 2) * xb[1] + d.Yv(2, 2) * xb[2] + d.Yv(3, 2) * xb[3] + d.Yv(4, 2) * xb[4] + d.Yv(5, 2) * xb[5]));
@@ -519,7 +527,7 @@ __device__ __forceinline__ void contact_setup(const Dyn& d, f3 x, f3 Jl0, f3 Jl1
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        fwd6p(d.L, E[r]);
+        fwd6p(d, E[r]);
 #pragma unroll
         for (int p = 0; p < 3; ++p) ct.Q[p][r] = E[r][p];
     }
@@ -604,7 +612,7 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
     p2 wv[3];      // L^-1 (r_b - sum_l B_l t_l), three row pairs
 #pragma unroll
     for (int p = 0; p < 3; ++p) { const p2 v = qsum2(fma2s(d.B[p][2], t.z, fma2s(d.B[p][1], t.y, fma2s(d.B[p][0], t.x, d.hb[p])))); wv[p] = mk2(-v.x, -v.y); }
-    fwd6p(d.L, wv);
+    fwd6p(d, wv);
 
     // ---- collision detection against the plane z = 0 (ENV:268) or the heightfield (ENV:264)
     Contact cf;   // foot contact of this leg (slot 0 of this lane)
@@ -733,7 +741,7 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
 
     // ---- new velocity: u+ = u + M^-1 (dt r + J^T lambda)
     float ytot[6] = {ytot2[0].x, ytot2[0].y, ytot2[1].x, ytot2[1].y, ytot2[2].x, ytot2[2].y};
-    bwd6(d.L, ytot);                                                    // trunk increment
+    bwd6(d, ytot);                                                      // trunk increment
     f3 jl = mk(dot(Jl0, lam_leg), dot(Jl1, lam_leg), dot(Jl2, lam_leg));   // J_l^T lambda
     f3 tl = axpy(dt, t, mul(d.Dinv, jl));
     const p2 yt0 = mk2(ytot[0], ytot[1]), yt1 = mk2(ytot[2], ytot[3]), yt2 = mk2(ytot[4], ytot[5]);

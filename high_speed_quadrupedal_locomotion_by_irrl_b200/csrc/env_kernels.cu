@@ -543,11 +543,11 @@ __global__ void __launch_bounds__(BLOCK) env_meteor_kernel(const __grid_constant
                 if (vrel < 0.f) {
                     f3 xn = cross(x, n);
                     float z[6] = {n.x, n.y, n.z, xn.x, xn.y, xn.z};                  // J^T n restricted to the trunk coordinates
-                    fwd6(d.L, z);
+                    fwd6(d, z);
                     float G = 0.f;
 #pragma unroll
                     for (int a = 0; a < 6; ++a) G = fmaf(z[a], z[a], G);
-                    bwd6(d.L, z);                                                     // z = S^-1 J^T n  (trunk part of M^-1 J^T n)
+                    bwd6(d, z);                                                       // z = S^-1 J^T n  (trunk part of M^-1 J^T n)
                     const float er = (-vrel > 0.001f) ? 0.95f : 0.f;                  // steel-steel pair ENV:244
                     const float lam = -(1.0f + er) * vrel / (G + 1.0f / mass);
                     sv = axpy(lam / mass, n, sv);

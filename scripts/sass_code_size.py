@@ -50,10 +50,13 @@ loops.sort(key=lambda x: x[1])
 print("loops > 16 KB:", ", ".join("0x%x..0x%x (%d B)" % (t, a, sp) for sp, t, a in loops))
 span, lo, hi = loops[int(os.environ.get("LOOP", "0"))]      # LOOP=1: the second (complete) copy of the substep loop
 print("kernel %s: %d instructions; substep loop 0x%x..0x%x = %d B (%d instructions)" % (name, len(ins), lo, hi, span, span // 16))
+_src = open(os.path.join(ROOT, "high_speed_quadrupedal_locomotion_by_irrl_b200", "csrc", "env_device.cuh")).read().split("\n")
+IS_LO = next(i for i, l in enumerate(_src) if "void integrate_substep(" in l or "bool integrate_substep(" in l) + 1
+IS_HI = next(i for i in range(IS_LO, len(_src)) if _src[i].startswith("}")) + 1
 def phase(fr):
     # outermost frame inside env_device.cuh functions of interest, else the kernel line
     for f, ln in reversed(fr):
-        if f == "env_device.cuh" and 521 <= ln <= 700: return "integrate_substep:%d" % ln
+        if f == "env_device.cuh" and IS_LO <= ln <= IS_HI: return "integrate_substep:%d" % ln
     for f, ln in reversed(fr):
         if f == "env_kernels.cu": return "kernel:%d" % ln
     return ("%s:%d" % fr[-1]) if fr else "?:0"
@@ -61,7 +64,7 @@ def mid(fr):
     # second-level attribution: the frame just inside integrate_substep (dynamics / contact_setup / leg_fk line)
     idx = None
     for i, (f, ln) in enumerate(fr):
-        if f == "env_device.cuh" and 521 <= ln <= 700: idx = i
+        if f == "env_device.cuh" and IS_LO <= ln <= IS_HI: idx = i
     if idx is None or idx == 0: return None
     f, ln = fr[idx - 1]
     return "%s:%d" % (f, ln)

@@ -586,10 +586,16 @@ struct ContactOut { int foot_active; f3 foot_impulse; int sweeps; };
 // radius of the trunk box about the trunk origin: below this height a corner can touch flat ground (launch-uniform, computed once per kernel)
 __device__ __forceinline__ float trunk_box_reach(const EnvParams& P) { return sqrtf(P.box_half[0] * P.box_half[0] + P.box_half[1] * P.box_half[1] + P.box_half[2] * P.box_half[2]); }
 
-// PHASE_SYNC (template flag SYNC): block-wide barriers that keep the warps of a CTA in the same stretch of the substep code
-// (39 KB of straight-line SASS, more than the 32 KB instruction cache), so that one instruction fetch serves all of them.
-// Measured: -7 % kernel time from 8192 robots per GPU with 128-thread CTAs, neutral to slightly negative at 4096.
-#define PHASE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
+// PHASE_SYNC (template flag SYNC): block-wide barriers that keep the warps of a CTA in the same stretch of the substep code (33 KB of
+// straight-line SASS against a 32 KB instruction cache), so that one instruction fetch serves all of them.  Four candidate sites per
+// substep (start, after the dynamics, before the contact phase, before the state update); IRRL_SYNC_MASK selects them.  Measured with
+// 128-thread CTAs: round 1's kernel (55 KB loop) gained 7 % from all four from 8192 robots per GPU; with the round-2 loop (33 KB) one
+// barrier per substep -- the one before the contact phase, which also carries the box-contact hand-over vote -- is best (mask 4:
+// 82.0 / 141.1 / 237.6 us at 8192 / 16384 / 32768 robots against 83.4 / 143.1 / 239.4 with all four); 4096 robots run without barriers.
+#ifndef IRRL_SYNC_MASK
+#define IRRL_SYNC_MASK 4
+#endif
+#define PHASE_SYNC(bit) do { if (SYNC && ((IRRL_SYNC_MASK >> (bit)) & 1)) __syncthreads(); } while (0)
 // ------------------------------------------------------------------ one world.integrate() (ENV:768)
 // tau: this leg's joint torques.  fext: optional external generalised force on the trunk (6).
 // TERR = false compiles the heightfield code out (launch-uniform: flat-ground launches run a kernel without it in the hot loop).
@@ -600,11 +606,11 @@ template <bool SYNC = false, bool TERR = true, bool BOX = true>
 __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegModel& lm, const BaseModel& bm, int leg,
                                                   Base& b, f3& q, f3& qd, f3 tau, ContactOut& out, float box_reach) {
     const float dt = P.sim_dt;
-    PHASE_SYNC();
+    PHASE_SYNC(0);
     f3 bx, by, bz; quat_cols(b.qw, b.qx, b.qy, b.qz, bx, by, bz);
     LegKin k; leg_fk(P, lm, bx, by, bz, q, k);
     Dyn d; dynamics(P, lm, bm, b, bx, by, bz, k, qd, d, nullptr, nullptr, false, leg);
-    PHASE_SYNC();
+    PHASE_SYNC(1);
 
     // ---- free acceleration in the factorised form:  t = Dinv r_l,  w = L^-1 (r_b - sum B t)
     f3 rl = mk(tau.x - P.joint_damping * qd.x - d.hl.x, tau.y - P.joint_damping * qd.y - d.hl.y, tau.z - P.joint_damping * qd.z - d.hl.z);
@@ -652,7 +658,7 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
     cf.lam = mk(0.f, 0.f, 0.f);
     if (!BOX) {   // hand the substep over to the full version (state untouched so far); the decision is uniform over whatever shares barriers
         if (SYNC ? (__syncthreads_or(any_box ? 1 : 0) != 0) : any_box) return false;
-    } else PHASE_SYNC();
+    } else PHASE_SYNC(2);
     if (any_foot_or_box) {
         // ---- foot contact setup (every lane builds its own slot)
         contact_setup(d, xf, Jl0, Jl1, Jl2, true, cf, terr, ft1, ft2, fn);
@@ -737,7 +743,7 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
         lam_leg = cf.lam;
     }
     out.foot_active = cf.active; out.foot_impulse = cf.lam;
-    PHASE_SYNC();
+    PHASE_SYNC(3);
 
     // ---- new velocity: u+ = u + M^-1 (dt r + J^T lambda)
     float ytot[6] = {ytot2[0].x, ytot2[0].y, ytot2[1].x, ytot2[1].y, ytot2[2].x, ytot2[2].y};

@@ -19,8 +19,9 @@ for r in data:
 print("opcode      warp-inst  share   stall-samples  thread-inst")
 for o, c in op.most_common(30):
     print(f"{o:10s} {c:9d} {100 * c / tot_e:5.1f}%   {100 * ops[o] / max(tot_s, 1):5.1f}%   {opt[o]}")
-fl = 2 * opt["FFMA"] + opt["FADD"] + opt["FMUL"] + opt["MUFU"] + opt["FMNMX"] + opt["FSETP"] * 0
-print("FP32 flop (2*FFMA + FADD + FMUL + MUFU + FMNMX), thread level:", fl)
+# packed instructions (sm_100a FFMA2 / FMUL2 / FADD2) do two lanes' worth of work per thread instruction
+fl = 2 * opt["FFMA"] + opt["FADD"] + opt["FMUL"] + opt["MUFU"] + opt["FMNMX"] + 4 * opt["FFMA2"] + 2 * opt["FMUL2"] + 2 * opt["FADD2"]
+print("FP32 flop (2*FFMA + FADD + FMUL + MUFU + FMNMX + 4*FFMA2 + 2*FMUL2 + 2*FADD2), thread level:", fl)
 stall_cols = [h for h in hdr if h.startswith("stall_")]
 if stall_cols:
     tot = {h: sum(int(r[hdr.index(h)] or 0) for r in data) for h in stall_cols}

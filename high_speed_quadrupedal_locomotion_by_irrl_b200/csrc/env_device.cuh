@@ -841,11 +841,9 @@ __device__ __forceinline__ float smooth_raw(float phase, float slope, float lam)
     if (f < lam) return (sinf(f / lam * 2.f * IRRL_PI_REF) * slope) + 0.5f;
     return (-sinf((f - lam) / (1.0f - lam) * 2.f * IRRL_PI_REF) * slope) + 0.5f;
 }
-__device__ __forceinline__ float smooth_function(float phase, float slope, float lam) {
-    float t = smooth_raw(phase, slope, lam); return t > 1.f ? 1.f : (t < 0.f ? 0.f : t);
-}
-__device__ __forceinline__ float smooth_function2(float phase, float slope, float lam) {
-    float t = smooth_raw(phase, slope, lam); return t > 1.f ? 0.f : (t < 0.f ? 1.f : 1.f - t);
-}
+__device__ __forceinline__ float smooth_clamp(float t) { return t > 1.f ? 1.f : (t < 0.f ? 0.f : t); }
+__device__ __forceinline__ float smooth_clamp2(float t) { return t > 1.f ? 0.f : (t < 0.f ? 1.f : 1.f - t); }
+__device__ __forceinline__ float smooth_function(float phase, float slope, float lam) { return smooth_clamp(smooth_raw(phase, slope, lam)); }
+__device__ __forceinline__ float smooth_function2(float phase, float slope, float lam) { return smooth_clamp2(smooth_raw(phase, slope, lam)); }
 
 }  // namespace irrl

@@ -99,46 +99,57 @@ __device__ __forceinline__ f3 nominal_q(const EnvParams& P, int leg) { return mk
 
 // ------------------------------------------------------------------ observation (ENV:956-1004); writes obDouble_ to HBM
 // ob29_31 / bodyvel outputs are replicated in the quad.
-struct ObsOut { float ob29, ob30, ob31; f3 blin, bang; };
+struct ObsOut { float ob29, ob30, ob31; f3 blin, bang; float oq[3], oqd[3], ph3, ph4, om[3]; };   // o* / ph* / om: the obDouble_ entries this lane wrote
+// Quad exchanges of update_observation name only the four lanes of the robot in their mask: the function also runs inside reset_env,
+// i.e. under a branch that is uniform per quad but divergent per warp.
+__device__ __forceinline__ unsigned quad_mask() { return 0xFu << (threadIdx.x & 28); }
+__device__ __forceinline__ float quad_get(unsigned qm, float v, int src) { return __shfl_sync(qm, v, src, 4); }
+// word `w` of the Philox block that lane `src` of the quad holds (w, src differ per destination lane: one shuffle per word, then a pick)
+__device__ __forceinline__ uint32_t quad_word(unsigned qm, uint4 blk, int src, int w) {
+    const uint32_t a = __shfl_sync(qm, blk.x, src, 4), b = __shfl_sync(qm, blk.y, src, 4), c = __shfl_sync(qm, blk.z, src, 4), d = __shfl_sync(qm, blk.w, src, 4);
+    return w == 0 ? a : (w == 1 ? b : (w == 2 ? c : d));
+}
 __device__ __forceinline__ void update_observation(const EnvParams& P, const DevState& S, int r, int gid, int leg, uint32_t tick,
                                                    uint32_t pbase, const EnvRegs& e, ObsOut& o) {
     float* obd = S.obd + (size_t)r * 36;
     float nq[3] = {0.f, 0.f, 0.f}, nqd[3] = {0.f, 0.f, 0.f};
-    float gp[4] = {0.f, 0.f, 0.f, 0.f}, go[4] = {0.f, 0.f, 0.f, 0.f};
+    float gp[3] = {0.f, 0.f, 0.f}, go[3] = {0.f, 0.f, 0.f};
     if (P.noise_flag != 0.f) {
-        // joint j = 3 leg + k lives in Philox block j/4, word j%4 (same draws as the oracle)
-        int j0 = 3 * leg, ba = j0 >> 2, bb = (j0 + 2) >> 2;
-        uint4 qa = philox(P.seed, gid, tick, pbase + P_OBS_Q0 + ba), qb = (bb == ba) ? qa : philox(P.seed, gid, tick, pbase + P_OBS_Q0 + bb);
-        uint4 da = philox(P.seed, gid, tick, pbase + P_OBS_QD0 + ba), db = (bb == ba) ? da : philox(P.seed, gid, tick, pbase + P_OBS_QD0 + bb);
+        // joint j = 3 leg + k lives in Philox block j/4, word j%4 (same draws as the oracle).  The quad computes every block ONCE:
+        // lane l holds block min(l, 2) of the joint-angle and of the joint-rate noise and one Gaussian block (even lanes posture,
+        // odd lanes angular rate); the words are handed to the lanes that need them by shuffles (was: up to 6 blocks per lane).
+        const int blk = min(leg, 2); const unsigned qm = quad_mask();
+        const uint4 qa = philox(P.seed, gid, tick, pbase + P_OBS_Q0 + blk), da = philox(P.seed, gid, tick, pbase + P_OBS_QD0 + blk);
+        float g4[4]; gauss4(P.seed, gid, tick, pbase + ((leg & 1) ? P_OBS_OMEGA : P_OBS_POSTURE), g4);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            int j = j0 + k; bool ina = (j >> 2) == ba;
-            nq[k] = usym(pick(ina ? qa : qb, j & 3)) * P.joint_noise * P.noise_flag;        // ENV:979
-            nqd[k] = usym(pick(ina ? da : db, j & 3)) * P.joint_vel_noise * P.noise_flag;   // ENV:983
+            const int j = 3 * leg + k;
+            nq[k] = usym(quad_word(qm, qa, j >> 2, j & 3)) * P.joint_noise * P.noise_flag;          // ENV:979
+            nqd[k] = usym(quad_word(qm, da, j >> 2, j & 3)) * P.joint_vel_noise * P.noise_flag;     // ENV:983
+            gp[k] = quad_get(qm, g4[k], 0); go[k] = quad_get(qm, g4[k], 1);
         }
-        gauss4(P.seed, gid, tick, pbase + P_OBS_POSTURE, gp);
-        gauss4(P.seed, gid, tick, pbase + P_OBS_OMEGA, go);
     }
-    obd[5 + 3 * leg + 0] = nq[0] + e.q.x; obd[5 + 3 * leg + 1] = nq[1] + e.q.y; obd[5 + 3 * leg + 2] = nq[2] + e.q.z;
-    obd[17 + 3 * leg + 0] = nqd[0] + e.qd.x; obd[17 + 3 * leg + 1] = nqd[1] + e.qd.y; obd[17 + 3 * leg + 2] = nqd[2] + e.qd.z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.oq[k] = nq[k] + comp(e.q, k); o.oqd[k] = nqd[k] + comp(e.qd, k); obd[5 + 3 * leg + k] = o.oq[k]; obd[17 + 3 * leg + k] = o.oqd[k]; }
     f3 bx, by, bz; quat_cols(e.b.qw, e.b.qx, e.b.qy, e.b.qz, bx, by, bz);
     o.ob29 = bx.z + (gp[0] * P.posture_sigma) * P.noise_flag;      // third row of R  ENV:994-996
     o.ob30 = by.z + (gp[1] * P.posture_sigma) * P.noise_flag;
     o.ob31 = bz.z + (gp[2] * P.posture_sigma) * P.noise_flag;
     o.blin = mk(dot(bx, e.b.v), dot(by, e.b.v), dot(bz, e.b.v));   // R^T v   ENV:999
     o.bang = mk(dot(bx, e.b.w), dot(by, e.b.w), dot(bz, e.b.w));   // R^T w   ENV:1000
+    o.om[0] = o.bang.x + P.noise_flag * (go[0] * P.omega_sigma);   // ENV:1001-1003
+    o.om[1] = o.bang.y + P.noise_flag * (go[1] * P.omega_sigma);
+    o.om[2] = o.bang.z + P.noise_flag * (go[2] * P.omega_sigma);
+    o.ph3 = 0.f; o.ph4 = 0.f;
     if (leg == 0) {
-        float ph3, ph4;
         if (P.flag_manual || P.flag_manual_traj) {                 // ENV:964-968
             float t = cur_time(P, e);
-            ph3 = sinf(2.f * IRRL_PI_REF * t / P.period); ph4 = cosf(2.f * IRRL_PI_REF * t / P.period);
-        } else { const float* row = P.ref + (size_t)ref_row(P, e.frame_idx) * 30; ph3 = row[25]; ph4 = row[26]; }   // ENV:972
+            o.ph3 = sinf(2.f * IRRL_PI_REF * t / P.period); o.ph4 = cosf(2.f * IRRL_PI_REF * t / P.period);
+        } else { const float* row = P.ref + (size_t)ref_row(P, e.frame_idx) * 30; o.ph3 = row[25]; o.ph4 = row[26]; }   // ENV:972
         obd[0] = 0.f; obd[1] = 0.f; obd[2] = 0.f;                  // obDouble_.setZero  ENV:960
-        obd[3] = ph3; obd[4] = ph4;
+        obd[3] = o.ph3; obd[4] = o.ph4;
         obd[29] = o.ob29; obd[30] = o.ob30; obd[31] = o.ob31;
-        obd[32] = o.bang.x + P.noise_flag * (go[0] * P.omega_sigma);   // ENV:1001-1003
-        obd[33] = o.bang.y + P.noise_flag * (go[1] * P.omega_sigma);
-        obd[34] = o.bang.z + P.noise_flag * (go[2] * P.omega_sigma);
+        obd[32] = o.om[0]; obd[33] = o.om[1]; obd[34] = o.om[2];
     }
 }
 
@@ -254,6 +265,26 @@ __device__ __forceinline__ void write_scaled_obs(const EnvParams& P, const DevSt
         ob_row[3] = obd[3]; ob_row[4] = obd[4];
         ob_row[29] = obd[29] / 0.7f; ob_row[30] = obd[30] / 0.7f; ob_row[31] = (obd[31] - 1.0f) / 0.7f;
         ob_row[32] = obd[32] / 3.0f; ob_row[33] = obd[33] / 3.0f; ob_row[34] = obd[34] / 3.0f;
+    }
+}
+
+// the same row from the values the step kernel still holds in registers (no read-back of obDouble_ through global memory); cmd = the
+// obDouble_[0..2] entries command_obs_update wrote
+__device__ __forceinline__ void write_scaled_obs_regs(const EnvParams& P, int leg, const ObsOut& o, const float* cmd, float* ob_row) {
+    f3 qn = nominal_q(P, leg);
+    const float vstd[3] = {5.f, 35.f, 40.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ob_row[5 + 3 * leg + k] = (o.oq[k] - comp(qn, k)) / 1.0f;
+        ob_row[17 + 3 * leg + k] = (o.oqd[k] - 0.f) / vstd[k];
+    }
+    if (leg == 0) {
+        ob_row[0] = (cmd[0] - (P.Vx_max + P.Vx_min) / 2.f) / 1.0f;
+        ob_row[1] = (cmd[1] - (P.Vy_max + P.Vy_min) / 2.f) / 1.0f;
+        ob_row[2] = (cmd[2] - (P.omega_max + P.omega_min) / 2.f) / 1.0f;
+        ob_row[3] = o.ph3; ob_row[4] = o.ph4;
+        ob_row[29] = o.ob29 / 0.7f; ob_row[30] = o.ob30 / 0.7f; ob_row[31] = (o.ob31 - 1.0f) / 0.7f;
+        ob_row[32] = o.om[0] / 3.0f; ob_row[33] = o.om[1] / 3.0f; ob_row[34] = o.om[2] / 3.0f;
     }
 }
 
@@ -384,8 +415,9 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
         float r_tq = P.torque_coeff / 2.0f * expf(-0.1f * tns) + P.torque_coeff / 2.0f * expf(-0.1f / P.control_dt * tds);
         e.torque_last = tn;                                               // ENV:1515
         const float rp = gait_phase(P, e, leg);                           // ENV:1523-1527
-        float cr = 4.f * vel_norm * vel_norm * smooth_function(rp, 2.f, P.lam) +
-                   2.f * (force_norm / 12.5f) * (force_norm / 12.5f) * smooth_function2(rp, 2.f, P.lam);
+        const float sraw = smooth_raw(rp, 2.f, P.lam);                    // both shaping functions clamp the same raw value (ENV:118-156)
+        float cr = 4.f * vel_norm * vel_norm * smooth_clamp(sraw) +
+                   2.f * (force_norm / 12.5f) * (force_norm / 12.5f) * smooth_clamp2(sraw);
         cr = qsum(cr);
         float r_ct = P.contact_coeff * expf(-2.f * cr);
         rew = (r_ee + r_pos + r_joint + r_jd + r_vel + r_att + r_tq + r_ct);   // ENV:1546-1547
@@ -422,8 +454,12 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
             S.solver_sweeps[r] = co.sweeps;
         }
     }
-    // every lane scales exactly the obDouble_ entries it wrote itself (no cross-lane dependency)
-    if (!P.flag_obs_filter && A.ob && valid) write_scaled_obs(P, S, r, leg, A.ob + (size_t)r * OB_DIM);
+    // every lane scales exactly the obDouble_ entries it wrote itself (no cross-lane dependency): from registers, except after a reset
+    // (reset_env rewrote obDouble_) and in Manual mode (the command entries are written by SetCommand), where they are read back
+    if (!P.flag_obs_filter && A.ob && valid) {
+        if (done || P.flag_manual) write_scaled_obs(P, S, r, leg, A.ob + (size_t)r * OB_DIM);
+        else write_scaled_obs_regs(P, leg, o, e.cmdf, A.ob + (size_t)r * OB_DIM);
+    }
 }
 
 __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const __grid_constant__ StepArgs A) {

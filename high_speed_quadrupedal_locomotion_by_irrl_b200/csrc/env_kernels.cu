@@ -144,7 +144,7 @@ __device__ __forceinline__ void update_observation(const EnvParams& P, const Dev
     if (leg == 0) {
         if (P.flag_manual || P.flag_manual_traj) {                 // ENV:964-968
             float t = cur_time(P, e);
-            o.ph3 = sinf(2.f * IRRL_PI_REF * t / P.period); o.ph4 = cosf(2.f * IRRL_PI_REF * t / P.period);
+            sincosf(2.f * IRRL_PI_REF * t / P.period, &o.ph3, &o.ph4);      // one range reduction for both (same values as sinf / cosf)
         } else { const float* row = P.ref + (size_t)ref_row(P, e.frame_idx) * 30; o.ph3 = row[25]; o.ph4 = row[26]; }   // ENV:972
         obd[0] = 0.f; obd[1] = 0.f; obd[2] = 0.f;                  // obDouble_.setZero  ENV:960
         obd[3] = o.ph3; obd[4] = o.ph4;
@@ -181,7 +181,8 @@ __device__ __forceinline__ void command_obs_update(const EnvParams& P, const Dev
         f3 last = e.jref;                                          // jointRefLast_ == previous jointRef_ (ENV:1887)
         if (flag_reset) last = leg_reference(P, g, leg, t - P.control_dt, toe);   // ENV:1799-1843
         f3 ref = leg_reference(P, g, leg, t, toe);
-        e.jdref = mk((ref.x - last.x) / P.control_dt, (ref.y - last.y) / P.control_dt, (ref.z - last.z) / P.control_dt);   // ENV:1886
+        const float inv_dt = 1.0f / P.control_dt;              // one (launch-uniform) division instead of three per lane
+        e.jdref = mk((ref.x - last.x) * inv_dt, (ref.y - last.y) * inv_dt, (ref.z - last.z) * inv_dt);   // ENV:1886
         e.jref = ref;
         e.eeref = mk(toe.x + 0.19f * e.lm.sx, toe.y + 0.058f * e.lm.sy, toe.z);   // ENV:331-334, 1882-1889
     } else {
@@ -252,19 +253,19 @@ static __device__ __noinline__ void reset_env(const EnvParams& P, const DevState
 __device__ __forceinline__ void write_scaled_obs(const EnvParams& P, const DevState& S, int r, int leg, float* ob_row) {
     const float* obd = S.obd + (size_t)r * 36;
     f3 qn = nominal_q(P, leg);
-    const float vstd[3] = {5.f, 35.f, 40.f};
+    const float ivstd[3] = {1.0f / 5.f, 1.0f / 35.f, 1.0f / 40.f};   // reciprocal std: constant multiplies instead of IEEE divisions (<= 1 ulp)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         ob_row[5 + 3 * leg + k] = (obd[5 + 3 * leg + k] - comp(qn, k)) / 1.0f;
-        ob_row[17 + 3 * leg + k] = (obd[17 + 3 * leg + k] - 0.f) / vstd[k];
+        ob_row[17 + 3 * leg + k] = (obd[17 + 3 * leg + k] - 0.f) * ivstd[k];
     }
     if (leg == 0) {
         ob_row[0] = (obd[0] - (P.Vx_max + P.Vx_min) / 2.f) / 1.0f;                  // ENV:375, 383
         ob_row[1] = (obd[1] - (P.Vy_max + P.Vy_min) / 2.f) / 1.0f;
         ob_row[2] = (obd[2] - (P.omega_max + P.omega_min) / 2.f) / 1.0f;
         ob_row[3] = obd[3]; ob_row[4] = obd[4];
-        ob_row[29] = obd[29] / 0.7f; ob_row[30] = obd[30] / 0.7f; ob_row[31] = (obd[31] - 1.0f) / 0.7f;
-        ob_row[32] = obd[32] / 3.0f; ob_row[33] = obd[33] / 3.0f; ob_row[34] = obd[34] / 3.0f;
+        ob_row[29] = obd[29] * (1.0f / 0.7f); ob_row[30] = obd[30] * (1.0f / 0.7f); ob_row[31] = (obd[31] - 1.0f) * (1.0f / 0.7f);
+        ob_row[32] = obd[32] * (1.0f / 3.0f); ob_row[33] = obd[33] * (1.0f / 3.0f); ob_row[34] = obd[34] * (1.0f / 3.0f);
     }
 }
 
@@ -272,19 +273,19 @@ __device__ __forceinline__ void write_scaled_obs(const EnvParams& P, const DevSt
 // obDouble_[0..2] entries command_obs_update wrote
 __device__ __forceinline__ void write_scaled_obs_regs(const EnvParams& P, int leg, const ObsOut& o, const float* cmd, float* ob_row) {
     f3 qn = nominal_q(P, leg);
-    const float vstd[3] = {5.f, 35.f, 40.f};
+    const float ivstd[3] = {1.0f / 5.f, 1.0f / 35.f, 1.0f / 40.f};   // reciprocal std: constant multiplies instead of IEEE divisions (<= 1 ulp)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         ob_row[5 + 3 * leg + k] = (o.oq[k] - comp(qn, k)) / 1.0f;
-        ob_row[17 + 3 * leg + k] = (o.oqd[k] - 0.f) / vstd[k];
+        ob_row[17 + 3 * leg + k] = (o.oqd[k] - 0.f) * ivstd[k];
     }
     if (leg == 0) {
         ob_row[0] = (cmd[0] - (P.Vx_max + P.Vx_min) / 2.f) / 1.0f;
         ob_row[1] = (cmd[1] - (P.Vy_max + P.Vy_min) / 2.f) / 1.0f;
         ob_row[2] = (cmd[2] - (P.omega_max + P.omega_min) / 2.f) / 1.0f;
         ob_row[3] = o.ph3; ob_row[4] = o.ph4;
-        ob_row[29] = o.ob29 / 0.7f; ob_row[30] = o.ob30 / 0.7f; ob_row[31] = (o.ob31 - 1.0f) / 0.7f;
-        ob_row[32] = o.om[0] / 3.0f; ob_row[33] = o.om[1] / 3.0f; ob_row[34] = o.om[2] / 3.0f;
+        ob_row[29] = o.ob29 * (1.0f / 0.7f); ob_row[30] = o.ob30 * (1.0f / 0.7f); ob_row[31] = (o.ob31 - 1.0f) * (1.0f / 0.7f);
+        ob_row[32] = o.om[0] * (1.0f / 3.0f); ob_row[33] = o.om[1] * (1.0f / 3.0f); ob_row[34] = o.om[2] * (1.0f / 3.0f);
     }
 }
 
@@ -387,7 +388,8 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
     f3 vtoe = e.b.v + cross(e.b.w, k.j1) + cross(w1, k.j2 - k.j1) + cross(w2, k.j3 - k.j2) + cross(w3, k.toe - k.j3);
     float vel_norm = sqrtf(dot(vtoe, vtoe));
     float imp = co.foot_active ? sqrtf(dot(co.foot_impulse, co.foot_impulse)) : 0.f;
-    float force_norm = imp / P.control_dt;        // ENV:1208 (control_dt, quirk 4)
+    const float inv_dt = 1.0f / P.control_dt;
+    float force_norm = imp * inv_dt;              // ENV:1208 (control_dt, quirk 4)
     e.impulse_norm = imp;
 
     float ground_z = 0.f;
@@ -409,15 +411,15 @@ __global__ void __launch_bounds__(BLK, (STEP_MINWARPS * 32 + BLK - 1) / BLK) env
         f3 lref = mk(P.flag_wildcat ? -e.cmdf[0] : e.cmdf[0], e.cmdf[1], 0.f), aref = mk(0.f, 0.f, e.cmdf[2]);
         f3 le = o.blin - lref, ae = o.bang - aref;
         r_vel = P.vel_coeff / 2.f * expf(-2.f * dot(le, le)) + P.vel_coeff / 2.f * expf(-2.f * dot(ae, ae));
-        f3 tn = mk(tau.x / 18.f, tau.y / 18.f, tau.z / 27.f);            // ENV:354, 1511
+        f3 tn = mk(tau.x * (1.0f / 18.f), tau.y * (1.0f / 18.f), tau.z * (1.0f / 27.f));            // ENV:354, 1511
         f3 dtq = tn - e.torque_last;
         float tns = qsum(dot(tn, tn)), tds = qsum(dot(dtq, dtq));
-        float r_tq = P.torque_coeff / 2.0f * expf(-0.1f * tns) + P.torque_coeff / 2.0f * expf(-0.1f / P.control_dt * tds);
+        float r_tq = P.torque_coeff / 2.0f * expf(-0.1f * tns) + P.torque_coeff / 2.0f * expf(-0.1f * inv_dt * tds);
         e.torque_last = tn;                                               // ENV:1515
         const float rp = gait_phase(P, e, leg);                           // ENV:1523-1527
         const float sraw = smooth_raw(rp, 2.f, P.lam);                    // both shaping functions clamp the same raw value (ENV:118-156)
         float cr = 4.f * vel_norm * vel_norm * smooth_clamp(sraw) +
-                   2.f * (force_norm / 12.5f) * (force_norm / 12.5f) * smooth_clamp2(sraw);
+                   2.f * (force_norm * (1.0f / 12.5f)) * (force_norm * (1.0f / 12.5f)) * smooth_clamp2(sraw);
         cr = qsum(cr);
         float r_ct = P.contact_coeff * expf(-2.f * cr);
         rew = (r_ee + r_pos + r_joint + r_jd + r_vel + r_att + r_tq + r_ct);   // ENV:1546-1547
@@ -484,15 +486,15 @@ __global__ void env_observe_kernel(EnvParams P, DevState S, float* ob) {
         for (int i = 0; i < 35; ++i) last[i] = obd[i];
     }
     float* o = ob + (size_t)r * OB_DIM;
-    const float vstd[3] = {5.f, 35.f, 40.f};
+    const float ivstd[3] = {1.0f / 5.f, 1.0f / 35.f, 1.0f / 40.f};   // reciprocal std: constant multiplies instead of IEEE divisions (<= 1 ulp)
     o[0] = (obd[0] - (P.Vx_max + P.Vx_min) / 2.f) / 1.0f; o[1] = (obd[1] - (P.Vy_max + P.Vy_min) / 2.f) / 1.0f;
     o[2] = (obd[2] - (P.omega_max + P.omega_min) / 2.f) / 1.0f; o[3] = obd[3]; o[4] = obd[4];
     for (int j = 0; j < 12; ++j) {
         float qn = (j % 3 == 0) ? (((j / 3) & 1) ? P.abad : -P.abad) : ((j % 3 == 1) ? -0.78f : 1.57f);
-        o[5 + j] = (obd[5 + j] - qn) / 1.0f; o[17 + j] = obd[17 + j] / vstd[j % 3];
+        o[5 + j] = (obd[5 + j] - qn) / 1.0f; o[17 + j] = obd[17 + j] * ivstd[j % 3];
     }
-    o[29] = obd[29] / 0.7f; o[30] = obd[30] / 0.7f; o[31] = (obd[31] - 1.0f) / 0.7f;
-    o[32] = obd[32] / 3.0f; o[33] = obd[33] / 3.0f; o[34] = obd[34] / 3.0f;
+    o[29] = obd[29] * (1.0f / 0.7f); o[30] = obd[30] * (1.0f / 0.7f); o[31] = (obd[31] - 1.0f) * (1.0f / 0.7f);
+    o[32] = obd[32] * (1.0f / 3.0f); o[33] = obd[33] * (1.0f / 3.0f); o[34] = obd[34] * (1.0f / 3.0f);
 }
 
 // ------------------------------------------------------------------ probes: M (row-major 18x18), M^-1 (ENV:1375-1391), h (ENV:1396-1402)

@@ -612,6 +612,14 @@ __device__ __forceinline__ bool integrate_substep(const EnvParams& P, const LegM
     Dyn d; dynamics(P, lm, bm, b, bx, by, bz, k, qd, d, nullptr, nullptr, false, leg);
     PHASE_SYNC(1);
 
+#ifdef EXP_PAD   /* experiment: EXP_PAD extra (cheap, 4 independent chains) instructions in the hot loop, to read the slope of time against code size */
+    {
+        float p0 = qd.x, p1 = qd.y, p2 = qd.z, p3 = tau.x;
+#pragma unroll
+        for (int i = 0; i < EXP_PAD / 4; ++i) { p0 = fmaf(p0, 1.0001f, 0.5f); p1 = fmaf(p1, 0.9999f, 0.25f); p2 = fmaf(p2, 1.0002f, 0.125f); p3 = fmaf(p3, 0.9998f, 0.0625f); }
+        if (p0 + p1 + p2 + p3 == 123.456f) b.p.x += 1.0f;     /* never true; keeps the chains alive */
+    }
+#endif
     // ---- free acceleration in the factorised form:  t = Dinv r_l,  w = L^-1 (r_b - sum B t)
     f3 rl = mk(tau.x - P.joint_damping * qd.x - d.hl.x, tau.y - P.joint_damping * qd.y - d.hl.y, tau.z - P.joint_damping * qd.z - d.hl.z);
     f3 t = mul(d.Dinv, rl);

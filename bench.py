@@ -28,6 +28,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")              # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line) unless the caller asks for more
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")      # CPU arm: OpenMP workers must not spin while numpy's BLAS threads run the LSTM act
 
 import numpy as np

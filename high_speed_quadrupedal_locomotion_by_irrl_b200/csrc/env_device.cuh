@@ -123,6 +123,45 @@ __device__ __forceinline__ p2 sub2(p2 a, p2 b) { return __fadd2_rn(a, make_float
 __device__ __forceinline__ float hsum(p2 a) { return a.x + a.y; }
 __device__ __forceinline__ float half_of(p2 a, int odd) { return odd ? a.y : a.x; }
 
+// two 3-vectors / two symmetric 3x3 side by side (links 2 and 3 of a leg: same formulas, different data): .x half = first, .y half = second
+struct f3p { p2 x, y, z; };
+struct S3p { p2 xx, xy, xz, yy, yz, zz; };
+__device__ __forceinline__ f3p mkp(f3 a, f3 b) { f3p r; r.x = mk2(a.x, b.x); r.y = mk2(a.y, b.y); r.z = mk2(a.z, b.z); return r; }
+__device__ __forceinline__ f3 lo(const f3p& v) { return mk(v.x.x, v.y.x, v.z.x); }
+__device__ __forceinline__ f3 hi(const f3p& v) { return mk(v.x.y, v.y.y, v.z.y); }
+__device__ __forceinline__ S3 lo(const S3p& s) { return S3{s.xx.x, s.xy.x, s.xz.x, s.yy.x, s.yz.x, s.zz.x}; }
+__device__ __forceinline__ S3 hi(const S3p& s) { return S3{s.xx.y, s.xy.y, s.xz.y, s.yy.y, s.yz.y, s.zz.y}; }
+__device__ __forceinline__ p2 neg2(p2 a) { return mk2(-a.x, -a.y); }
+__device__ __forceinline__ f3p operator+(const f3p& a, const f3p& b) { f3p r; r.x = add2(a.x, b.x); r.y = add2(a.y, b.y); r.z = add2(a.z, b.z); return r; }
+// same operation order per half as cross(): t = a.z b.y ; x = a.y b.z - t ; ...
+__device__ __forceinline__ f3p crossp(const f3p& a, const f3p& b) {
+    f3p r;
+    r.x = fma2(a.y, b.z, neg2(mul2(a.z, b.y))); r.y = fma2(a.z, b.x, neg2(mul2(a.x, b.z))); r.z = fma2(a.x, b.y, neg2(mul2(a.y, b.x)));
+    return r;
+}
+__device__ __forceinline__ f3p mulp(const S3p& s, const f3p& v) {      // same order per half as mul(S3, f3)
+    f3p r;
+    r.x = fma2(s.xx, v.x, fma2(s.xy, v.y, mul2(s.xz, v.z)));
+    r.y = fma2(s.xy, v.x, fma2(s.yy, v.y, mul2(s.yz, v.z)));
+    r.z = fma2(s.xz, v.x, fma2(s.yz, v.y, mul2(s.zz, v.z)));
+    return r;
+}
+// s = k e e^T (first term of a sum: the scalar code's fmaf(.., 0) is the rounded product) and s += k e e^T, same order as add_outer
+__device__ __forceinline__ void set_outerp(S3p& s, p2 k, const f3p& e) {
+    const p2 kx = mul2(k, e.x), ky = mul2(k, e.y), kz = mul2(k, e.z);
+    s.xx = mul2(kx, e.x); s.xy = mul2(kx, e.y); s.xz = mul2(kx, e.z); s.yy = mul2(ky, e.y); s.yz = mul2(ky, e.z); s.zz = mul2(kz, e.z);
+}
+__device__ __forceinline__ void add_outerp(S3p& s, p2 k, const f3p& e) {
+    const p2 kx = mul2(k, e.x), ky = mul2(k, e.y), kz = mul2(k, e.z);
+    s.xx = fma2(kx, e.x, s.xx); s.xy = fma2(kx, e.y, s.xy); s.xz = fma2(kx, e.z, s.xz);
+    s.yy = fma2(ky, e.y, s.yy); s.yz = fma2(ky, e.z, s.yz); s.zz = fma2(kz, e.z, s.zz);
+}
+__device__ __forceinline__ void add_outerps(S3p& s, p2 k, f3 e) {      // the same axis for both halves (e1y)
+    const p2 kx = mul2s(k, e.x), ky = mul2s(k, e.y), kz = mul2s(k, e.z);
+    s.xx = fma2s(kx, e.x, s.xx); s.xy = fma2s(kx, e.y, s.xy); s.xz = fma2s(kx, e.z, s.xz);
+    s.yy = fma2s(ky, e.y, s.yy); s.yz = fma2s(ky, e.z, s.yz); s.zz = fma2s(kz, e.z, s.zz);
+}
+
 // ------------------------------------------------------------------ quad (4-lane group) collectives
 __device__ __forceinline__ float qsum(float v) {
     v += __shfl_xor_sync(FULLMASK, v, 1); v += __shfl_xor_sync(FULLMASK, v, 2); return v;
@@ -208,12 +247,13 @@ __device__ __forceinline__ void leg_fk(const EnvParams& P, const LegModel& lm, f
     k.r2 = axpy(lm.com2.x, k.e2x, axpy(lm.com2.y, k.e1y, lm.com2.z * k.e2z));
     k.r3 = axpy(lm.com3.x, k.e3x, axpy(lm.com3.y, k.e1y, lm.com3.z * k.e3z));
 }
-// world-frame link inertia tensors about the link COM
-__device__ __forceinline__ void leg_inertias(const EnvParams& P, const LegModel& lm, f3 bx, const LegKin& k, S3& I1, S3& I2, S3& I3) {
+// world-frame link inertia tensors about the link COM; links 2 and 3 side by side (I23: .x halves = thigh, .y halves = shank)
+__device__ __forceinline__ void leg_inertias(const EnvParams& P, const LegModel& lm, f3 bx, const LegKin& k, S3& I1, S3p& I23) {
     I1 = S3{0, 0, 0, 0, 0, 0}; add_outer(I1, P.I1[0], bx); add_outer(I1, P.I1[1], k.e1y); add_outer(I1, P.I1[2], k.e1z);
-    I2 = S3{0, 0, 0, 0, 0, 0}; add_outer(I2, P.I2[0], k.e2x); add_outer(I2, P.I2[1], k.e1y); add_outer(I2, P.I2[2], k.e2z);
+    set_outerp(I23, mk2(P.I2[0], P.I3[0]), mkp(k.e2x, k.e3x)); add_outerps(I23, mk2(P.I2[1], P.I3[1]), k.e1y); add_outerp(I23, mk2(P.I2[2], P.I3[2]), mkp(k.e2z, k.e3z));
+    S3 I2 = lo(I23);
     add_sym_outer(I2, -P.I2[3] * lm.sy, k.e1y, k.e2z);            // iyz = -0.000228 * sy  (URDF:92,210)
-    I3 = S3{0, 0, 0, 0, 0, 0}; add_outer(I3, P.I3[0], k.e3x); add_outer(I3, P.I3[1], k.e1y); add_outer(I3, P.I3[2], k.e3z);
+    I23.xx.x = I2.xx; I23.xy.x = I2.xy; I23.xz.x = I2.xz; I23.yy.x = I2.yy; I23.yz.x = I2.yz; I23.zz.x = I2.zz;
 }
 
 // Factorised dynamics of one robot, distributed over the quad.
@@ -239,28 +279,33 @@ __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) 
 __device__ __forceinline__ void dynamics(const EnvParams& P, const LegModel& lm, const BaseModel& bm, const Base& b,
                                          f3 bx, f3 by, f3 bz, const LegKin& k, f3 qd, Dyn& d,
                                          float* Aout = nullptr, S3* Dout = nullptr, bool reduce_hb = true, int leg = 0) {
-    S3 I1, I2, I3; leg_inertias(P, lm, bx, k, I1, I2, I3);
+    S3 I1; S3p I23; leg_inertias(P, lm, bx, k, I1, I23);
+    const S3 I2 = lo(I23), I3 = hi(I23);
     const f3 w0 = b.w;
     // ---- velocities
     f3 w1 = axpy(qd.x, k.a1, w0), w2 = axpy(qd.y, k.a2, w1), w3 = axpy(qd.z, k.a2, w2);
-    // ---- bias accelerations (joint accelerations and trunk acceleration zero)
+    // ---- bias accelerations (joint accelerations and trunk acceleration zero); w2 x a2 == w1 x a2 (hip and knee axes are parallel)
     f3 al1 = qd.x * cross(w0, k.a1);
-    f3 al2 = axpy(qd.y, cross(w1, k.a2), al1);
-    f3 al3 = axpy(qd.z, cross(w2, k.a2), al2);
+    const f3 w1xa2 = cross(w1, k.a2);
+    f3 al2 = axpy(qd.y, w1xa2, al1);
+    f3 al3 = axpy(qd.z, w1xa2, al2);
     f3 d12 = k.j2 - k.j1, d23 = k.j3 - k.j2;
     f3 aj1 = cross(w0, cross(w0, k.j1));
     f3 aj2 = aj1 + cross(al1, d12) + cross(w1, cross(w1, d12));
     f3 aj3 = aj2 + cross(al2, d23) + cross(w2, cross(w2, d23));
     f3 g = mk(0.f, 0.f, P.gravity);
     f3 F1 = lm.m1 * (aj1 + cross(al1, k.r1) + cross(w1, cross(w1, k.r1)) + g);
-    f3 F2 = lm.m2 * (aj2 + cross(al2, k.r2) + cross(w2, cross(w2, k.r2)) + g);
-    f3 F3 = lm.m3 * (aj3 + cross(al3, k.r3) + cross(w3, cross(w3, k.r3)) + g);
     f3 N1 = mul(I1, al1) + cross(w1, mul(I1, w1));
-    f3 N2 = mul(I2, al2) + cross(w2, mul(I2, w2));
-    f3 N3 = mul(I3, al3) + cross(w3, mul(I3, w3));
+    // links 2 and 3 side by side (packed): the same formulas as for link 1, two links per instruction
+    const f3p W23 = mkp(w2, w3), AL23 = mkp(al2, al3), R23 = mkp(k.r2, k.r3);
+    f3p F23 = (mkp(aj2, aj3) + crossp(AL23, R23)) + crossp(W23, crossp(W23, R23));
+    { const p2 m23 = mk2(lm.m2, lm.m3); F23.z = add2(F23.z, mk2(P.gravity, P.gravity)); F23.x = mul2(F23.x, m23); F23.y = mul2(F23.y, m23); F23.z = mul2(F23.z, m23); }
+    const f3p N23 = mulp(I23, AL23) + crossp(W23, mulp(I23, W23));
+    const f3p RXF = crossp(R23, F23);
+    const f3 F2 = lo(F23), F3 = hi(F23), N2 = lo(N23), N3 = hi(N23);
     // ---- backward pass: moments about the joint origins
-    f3 n3 = N3 + cross(k.r3, F3), f3_ = F3;
-    f3 n2 = N2 + cross(k.r2, F2) + n3 + cross(d23, f3_), f2_ = F2 + f3_;
+    f3 n3 = N3 + hi(RXF), f3_ = F3;
+    f3 n2 = N2 + lo(RXF) + n3 + cross(d23, f3_), f2_ = F2 + f3_;
     f3 n1 = N1 + cross(k.r1, F1) + n2 + cross(d12, f2_), f1_ = F1 + f2_;
     d.hl = mk(dot(k.a1, n1), dot(k.a2, n2), dot(k.a2, n3));
     f3 fb = f1_, nb = n1 + cross(k.j1, f1_);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Target of scripts/r2_sanitize.sh (compute-sanitizer memcheck / racecheck / synccheck): every kernel of the hot path on small, awkward
-shapes -- 300 environments (ragged last tile of the tcgen05 act kernel, partial last CTA of the step kernel), forced resets inside the
+shapes -- 300 environments (ragged last tile of the tcgen05 act kernel, partial last CTA of the step kernel), forced resets and trunk-box contacts (loop hand-over) inside the
 step kernel, heightfield terrain, the meteor sphere, the 128-thread barrier variant of the step kernel, the fused host entry with chunks,
 the GAE kernel and the sequence-persistent BPTT kernels."""
 import os, sys
@@ -23,6 +23,8 @@ for name, kw in (("flat + forced resets", dict()), ("stairs", dict(Terrain=True,
     for t in range(5):
         if t == 2:   # tip a third of the robots over: terminations + auto-resets inside the step kernel
             s = c.get_state(); s[::3, 3] = np.cos(0.6); s[::3, 4] = np.sin(0.6); s[::3, 5:7] = 0; c.set_state(s)
+        if t == 3:   # lay another third on the belly: trunk-box contacts, i.e. the hot substep loop hands over to the complete one
+            s = c.get_state(); s[1::3, 2] = 0.06; s[1::3, 7:19] = np.tile([0.0, -1.4, 2.6], 4).astype(np.float32); c.set_state(s)
         act, val, st, nlp = pol.step(ob, st, done)
         ob, rew, done, ex = c.step(np.clip(act, -1, 1)); nd += int(done.sum())
     print(f"{name}: 5 steps ok, {nd} auto-resets, reward mean {rew.mean():.3f}", flush=True)

@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     L.irrl_lstm_seq_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10
     L.irrl_lstm_seq_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
     L.irrl_lstm_seq_ctas.argtypes = [C.c_int]
+    L.irrl_lstm_seq_set_path.argtypes = [C.c_int]
     L.irrl_lstm_pw_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
     L.irrl_lstm_pw_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9
     L.irrl_set_heightfield.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]

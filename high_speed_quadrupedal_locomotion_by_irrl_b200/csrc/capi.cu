@@ -1117,6 +1117,7 @@ int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* d
     launch_lstm_seq_bwd(T, K, n_env, dH, wh, c0, keep, gates, Cs, dz, db_part, reinterpret_cast<cudaStream_t>(cuda_stream)); CUDA_OK(cudaGetLastError()); return 0;
 }
 int irrl_lstm_seq_ctas(int n_env) { return lstm_seq_ctas(n_env); }
+int irrl_lstm_seq_set_path(int path) { return lstm_seq_set_path(path); }
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,
                      float* c_out, float* h_out, float* hm_next, float* cm_next) {
     launch_lstm_pw_fwd(rows, n_env, z, c_prev_masked, keep_next, gates, c_out, h_out, hm_next, cm_next, reinterpret_cast<cudaStream_t>(cuda_stream));

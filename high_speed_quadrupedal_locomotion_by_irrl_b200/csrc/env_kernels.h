@@ -79,6 +79,12 @@ void launch_lstm_seq_fwd(int T, int K, int N, const float* xw, const float* wh, 
 void launch_lstm_seq_bwd(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
                          float* dz, float* db_part, cudaStream_t st);
 int lstm_seq_ctas(int N);   // CTAs per tower of the sequence kernels = rows of db_part
+int lstm_seq_set_path(int path);   // 0 tensor-core kernels (default), 1 FP32-FMA kernels; returns the previous value
+// the FP32-FMA variants (policy_kernels.cu); launch_lstm_seq_fwd / _bwd (lstm_seq_mma.cu) dispatch to the tensor-core kernels unless IRRL_SEQ_PATH=fma
+void launch_lstm_seq_fwd_fma(int T, int K, int N, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep, float* gates, float* Cs,
+                             float* Hs, const float* bias, float* HM, cudaStream_t st);
+void launch_lstm_seq_bwd_fma(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
+                             float* dz, float* db_part, cudaStream_t st);
 void launch_lstm_pw_fwd(int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates, float* c_out,
                         float* h_out, float* hm_next, float* cm_next, cudaStream_t st);
 void launch_lstm_pw_bwd(int rows, int n_env, const float* dh_out, const float* carry_h, const float* carry_c, const float* keep_up,

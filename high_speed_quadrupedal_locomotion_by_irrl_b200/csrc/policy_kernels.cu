@@ -443,13 +443,13 @@ __global__ void __launch_bounds__(SEQ_THR) lstm_seq_bwd_kernel(int T, int K, int
             }
     }
 }
-void launch_lstm_seq_fwd(int T, int K, int N, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep, float* gates, float* Cs,
+void launch_lstm_seq_fwd_fma(int T, int K, int N, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep, float* gates, float* Cs,
                          float* Hs, const float* bias, float* HM, cudaStream_t st) {
     dim3 grid((N + SEQ_TM - 1) / SEQ_TM, K);
     lstm_seq_fwd_kernel<<<grid, SEQ_THR, 0, st>>>(T, K, N, xw, wh, c0, h0, keep, gates, Cs, Hs, bias, HM);
 }
 int lstm_seq_ctas(int N) { return (N + SEQ_TM - 1) / SEQ_TM; }
-void launch_lstm_seq_bwd(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
+void launch_lstm_seq_bwd_fma(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
                          float* dz, float* db_part, cudaStream_t st) {
     dim3 grid((N + SEQ_TM - 1) / SEQ_TM, K);
     constexpr int smem = sizeof(float) * (G4 * H + G4 * SEQ_TM);

@@ -193,6 +193,9 @@ int irrl_lstm_seq_fwd(void* cuda_stream, int T, int K, int n_env, const float* x
 int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates,
                       const float* Cs, float* dz, float* db_part /*[irrl_lstm_seq_ctas(n_env),K,192] out: per-CTA sums of dz (bias gradient), may be NULL*/);
 int irrl_lstm_seq_ctas(int n_env);
+/* which kernels serve irrl_lstm_seq_fwd / _bwd: 0 = tensor-core recurrence (mma.sync tf32 in 3xTF32 form, default), 1 = FP32-FMA recurrence
+ * (the regression reference; also IRRL_SEQ_PATH=fma in the environment).  Returns the previous value; any other argument only queries. */
+int irrl_lstm_seq_set_path(int path);
 /* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,
  * z / gates [rows,192] in gate order i,f,o,g, the rest [rows,48]; keep = 1 - done mask per env (run_bp_v5.py:151-153 lstm(..., masks, ...)) */
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,

@@ -4,7 +4,8 @@ rep = sys.argv[1]
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-hi = starts[0]; end = starts[1] - 1 if len(starts) > 1 else len(rows)
+ki = int(sys.argv[3]) if len(sys.argv) > 3 else 0        # which kernel of the report
+hi = starts[ki]; end = starts[ki + 1] - 1 if len(starts) > ki + 1 else len(rows)
 hdr = rows[hi]; data = [r for r in rows[hi + 1:end] if len(r) == len(hdr) and r[hdr.index("# Samples")].isdigit()]
 ia = hdr.index("Source"); isamp = hdr.index("# Samples"); iex = hdr.index("Instructions Executed"); ith = hdr.index("Thread Instructions Executed")
 tot_s = sum(int(r[isamp]) for r in data); tot_e = sum(int(r[iex]) for r in data); tot_t = sum(int(r[ith]) for r in data)

@@ -1118,6 +1118,23 @@ int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* d
 }
 int irrl_lstm_seq_ctas(int n_env) { return lstm_seq_ctas(n_env); }
 int irrl_lstm_seq_set_path(int path) { return lstm_seq_set_path(path); }
+int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* W, int w_trans, float* Y, int n_out) {
+    NvtxRange nvtx_("irrl_proj_rows");
+    if (!X || !W || !Y || T <= 0 || K <= 0 || n_env <= 0) return fail(-1, "irrl_proj_rows: bad argument");
+    const int rc = launch_proj_rows(X, x_cols, x_has_tower, W, w_trans, Y, n_out, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (rc == -1) return fail(-1, "irrl_proj_rows: unsupported shape (x_cols <= 40 or 48 with n_out 192; x_cols 192 with n_out 48)");
+    if (rc) return fail(rc, "irrl_proj_rows: kernel configuration failed");
+    CUDA_OK(cudaGetLastError()); return 0;
+}
+int irrl_gram_rows_ctas(int T, int K, int n_env) { return gram_rows_ctas(T, n_env, K); }
+int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial) {
+    NvtxRange nvtx_("irrl_gram_rows");
+    if (!X || !D || !partial || T <= 0 || K <= 0 || n_env <= 0) return fail(-1, "irrl_gram_rows: bad argument");
+    const int rc = launch_gram_rows(X, x_cols, x_has_tower, D, partial, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (rc == -1) return fail(-1, "irrl_gram_rows: x_cols must be in 1..48");
+    if (rc) return fail(rc, "irrl_gram_rows: kernel configuration failed");
+    CUDA_OK(cudaGetLastError()); return 0;
+}
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,
                      float* c_out, float* h_out, float* hm_next, float* cm_next) {
     launch_lstm_pw_fwd(rows, n_env, z, c_prev_masked, keep_next, gates, c_out, h_out, hm_next, cm_next, reinterpret_cast<cudaStream_t>(cuda_stream));

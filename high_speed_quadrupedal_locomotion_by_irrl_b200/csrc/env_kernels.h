@@ -85,6 +85,10 @@ void launch_lstm_seq_fwd_fma(int T, int K, int N, const float* xw, const float* 
                              float* Hs, const float* bias, float* HM, cudaStream_t st);
 void launch_lstm_seq_bwd_fma(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
                              float* dz, float* db_part, cudaStream_t st);
+// non-recurrent products of the learner on the tensor cores (learner_gemm.cu)
+int launch_proj_rows(const float* X, int x_cols, int x_has_tower, const float* W, int w_trans, float* Y, int n_out, int T, int K, int N, cudaStream_t st);
+int gram_rows_ctas(int T, int N, int K);
+int launch_gram_rows(const float* X, int x_cols, int x_has_tower, const float* D, float* partial, int T, int K, int N, cudaStream_t st);
 void launch_lstm_pw_fwd(int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates, float* c_out,
                         float* h_out, float* hm_next, float* cm_next, cudaStream_t st);
 void launch_lstm_pw_bwd(int rows, int n_env, const float* dh_out, const float* carry_h, const float* carry_c, const float* keep_up,

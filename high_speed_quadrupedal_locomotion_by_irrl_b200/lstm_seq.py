@@ -1,12 +1,15 @@
 """Manual BPTT through one LSTM layer of BOTH towers over a whole rollout, for the PPO learner (ppo2.py:136-197).
 
-Time loop = [batched h W_h GEMM (cuBLAS) -> fused cell kernel (irrl_lstm_pw_fwd / _bwd)]: two launches per step in each direction.
-The input projections x W_x + b of all T steps and the weight gradient dW_h = sum_t h_{t-1}^T dz_t are single large GEMMs outside
-the loop.  Layout is time-major ([T, tower, env, ...]) -- exactly how the device rollout stores mb_* -- so every step is a contiguous slice.
+LstmLayerSeqPersistent: the whole time loop inside one kernel per direction (irrl_lstm_seq_fwd / _bwd, recurrent products on the
+tensor cores); ProjRows: the input projections x W_x of all T steps, their input gradient and the weight gradients
+dW = sum_t x_t^T dz_t as streaming tensor-core kernels (irrl_proj_rows / irrl_gram_rows) -- IRRL_LEARNER_GEMM=cublas keeps
+torch.matmul for A/B.  LstmLayerSeq: the older step-wise path [batched h W_h GEMM (cuBLAS) -> fused cell kernel], two launches per
+step.  Layout is time-major ([T, tower, env, ...]) -- exactly how the device rollout stores mb_* -- so every step is a contiguous slice.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -15,6 +18,64 @@ from . import _lib
 
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _own_gemm() -> bool:
+    return os.environ.get("IRRL_LEARNER_GEMM", "") != "cublas"
+
+
+def gram_rows(X, D):
+    """sum over (t, n) of X[t,(k),n,:]^T D[t,k,n,:] -> [K, x_cols, 192]; X [T,N,c] (shared by the towers) or [T,K,N,c], c <= 48."""
+    L = _lib.load()
+    T, K, N, _ = D.shape
+    c = X.shape[-1]
+    st = C.c_void_p(torch.cuda.current_stream(D.device).cuda_stream)
+    part = D.new_empty((L.irrl_gram_rows_ctas(T, K, N), K, 48, 192))
+    _lib.check(L.irrl_gram_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(D), _p(part)), "gram_rows")
+    return part.sum(0)[:, :c]
+
+
+class ProjRows(torch.autograd.Function):
+    """Y[T,K,N,192] = X . W_k for all T steps; X [T,N,c] (the observation, shared by both towers) or [T,K,N,48]; W [K,c,192]."""
+
+    @staticmethod
+    def forward(ctx, X, W):
+        L = _lib.load()
+        X = X.contiguous(); W = W.contiguous()
+        K, c, n_out = W.shape
+        T, N = X.shape[0], X.shape[-2]
+        st = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+        Y = X.new_empty((T, K, N, n_out))
+        _lib.check(L.irrl_proj_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(W), 0, _p(Y), n_out), "proj_rows")
+        ctx.save_for_backward(X, W)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        L = _lib.load()
+        X, W = ctx.saved_tensors
+        dY = dY.contiguous()
+        T, K, N, n_out = dY.shape
+        c = X.shape[-1]
+        dW = gram_rows(X, dY) if ctx.needs_input_grad[1] else None
+        dX = None
+        if ctx.needs_input_grad[0]:
+            if X.dim() == 4 and c == 48:
+                st = C.c_void_p(torch.cuda.current_stream(dY.device).cuda_stream)
+                dX = torch.empty_like(X)
+                _lib.check(L.irrl_proj_rows(st, T, K, N, _p(dY), n_out, 1, _p(W), 1, _p(dX), c), "proj_rows^T")
+            else:
+                dX = torch.matmul(dY, W.transpose(1, 2))
+                dX = dX.sum(1) if X.dim() == 3 else dX
+        return dX, dW
+
+
+def proj_rows(X, W):
+    """x W_x for every step and tower: tensor-core streaming kernel on CUDA for the learner's shapes, torch.matmul otherwise."""
+    K, c, n_out = W.shape
+    if X.is_cuda and _own_gemm() and n_out == 192 and (c == 48 or (c <= 40 and X.dim() == 3)):
+        return ProjRows.apply(X, W)
+    return torch.matmul(X.unsqueeze(1) if X.dim() == 3 else X, W)
 
 
 def _with_bias(fn):
@@ -102,7 +163,7 @@ class LstmLayerSeqPersistent(torch.autograd.Function):
         _lib.check(L.irrl_lstm_seq_bwd(st, T, K, N, _p(dH), _p(wh), _p(c0), _p(keep), _p(gates), _p(Cs), _p(DZ), _p(db_part)))
         # dW_h[k] = sum_{t,n} HM[t,k,n,:]^T DZ[t,k,n,:]: T*K batched [48 x N] x [N x 192] products on strided views (no copies, and
         # far more parallel than one skinny GEMM with a 1.5 M-long reduction), then a sum over T
-        dwh = torch.matmul(HM.transpose(-1, -2), DZ).sum(0)
+        dwh = gram_rows(HM, DZ) if _own_gemm() else torch.matmul(HM.transpose(-1, -2), DZ).sum(0)
         return DZ, dwh, db_part.sum(0), None, None, None
 
 

@@ -77,7 +77,7 @@ class LstmActorCritic(torch.nn.Module):
     def forward_time_major(self, obs, keep, state, fused: Optional[bool] = None):
         """obs [T,N,35] (time-major, as the device rollout stores it), keep [T,N] = 1 - mask, state [N,384] at t = 0.
         Returns mean [T,N,12], value [T,N].  On CUDA the recurrence runs through the fused BPTT path (lstm_seq.LstmLayerSeq)."""
-        from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, lstm_layer_reference, _with_bias
+        from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, lstm_layer_reference, _with_bias, proj_rows
         T, N, _ = obs.shape
         H = 48
         fused = obs.is_cuda if fused is None else fused
@@ -87,9 +87,10 @@ class LstmActorCritic(torch.nn.Module):
         c1 = st[:, :, 1, 0].transpose(0, 1).contiguous(); h1 = st[:, :, 1, 1].transpose(0, 1).contiguous()
         wx0 = torch.stack([self.lstm_pi0_wx, self.lstm_v0_wx]); wh0 = torch.stack([self.lstm_pi0_wh, self.lstm_v0_wh]); b0 = torch.stack([self.lstm_pi0_b, self.lstm_v0_b])
         wx1 = torch.stack([self.lstm_pi1_wx, self.lstm_v1_wx]); wh1 = torch.stack([self.lstm_pi1_wh, self.lstm_v1_wh]); b1 = torch.stack([self.lstm_pi1_b, self.lstm_v1_b])
-        xw0 = torch.matmul(obs.unsqueeze(1), wx0)                                    # [T,2,N,192]: all input projections in one GEMM (bias added by the layer)
+        own = fused is True                                                          # the persistent path: projections on the streaming tensor-core kernels too
+        xw0 = proj_rows(obs, wx0) if own else torch.matmul(obs.unsqueeze(1), wx0)    # [T,2,N,192]: all input projections in one pass (bias added by the layer)
         H0, _, _ = layer(xw0, wh0, b0, c0, h0, keep)
-        xw1 = torch.matmul(H0, wx1)
+        xw1 = proj_rows(H0, wx1) if own else torch.matmul(H0, wx1)
         H1, _, _ = layer(xw1, wh1, b1, c1, h1, keep)
         mean = H1[:, 0] @ self.pi_w + self.pi_b
         value = (H1[:, 1] @ self.vf_w + self.vf_b).squeeze(-1)

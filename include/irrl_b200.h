@@ -196,6 +196,15 @@ int irrl_lstm_seq_ctas(int n_env);
 /* which kernels serve irrl_lstm_seq_fwd / _bwd: 0 = tensor-core recurrence (mma.sync tf32 in 3xTF32 form, default), 1 = FP32-FMA recurrence
  * (the regression reference; also IRRL_SEQ_PATH=fma in the environment).  Returns the previous value; any other argument only queries. */
 int irrl_lstm_seq_set_path(int path);
+/* the non-recurrent products of the same BPTT on the tensor cores (3xTF32, fp32-grade), device pointers, time-major rows (t, tower k, env n):
+ *   irrl_proj_rows  Y[T,K,N,n_out] = X . B_k, B_k = W_k [x_cols,n_out] or, with w_trans, W_k^T of W_k [n_out,x_cols]; X is [T,K,N,x_cols] or, with
+ *                   x_has_tower = 0, [T,N,x_cols] shared by the towers.  Shapes served: (x_cols <= 40 or 48, n_out 192) = the input projections
+ *                   x W_x (run_bp_v5.py:151-166), (x_cols 192, n_out 48) = their input gradient dz W_x^T.
+ *   irrl_gram_rows  partial[irrl_gram_rows_ctas(T,K,N), K, 48, 192] = per-CTA sums of X[row,:]^T D[row,:] over the rows (t, n) of tower k, x_cols <= 48
+ *                   (rows of the result past x_cols are zero); the caller sums the partials (fixed order: deterministic) = dW_x / dW_h. */
+int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* W, int w_trans, float* Y, int n_out);
+int irrl_gram_rows_ctas(int T, int K, int n_env);
+int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial);
 /* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,
  * z / gates [rows,192] in gate order i,f,o,g, the rest [rows,48]; keep = 1 - done mask per env (run_bp_v5.py:151-153 lstm(..., masks, ...)) */
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,

@@ -17,6 +17,7 @@ namespace irrl {
 namespace lgemm {
 
 constexpr int THR = 256;
+constexpr int NSTAGE = 3;       // cp.async stages: tiles i+1 and i+2 are in flight while tile i is multiplied; ONE barrier per tile
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -64,7 +65,7 @@ template <int KT, int NT>
 struct ProjSmem {
     static constexpr int PITCH = KT * 8 + 4;                           // (4 g + q) mod 32 distinct: conflict-free A fragments
     float2 Bhi[KT][NT][32]; uint32_t Blo[KT][NT][32];
-    float Xs[2][64][PITCH];
+    float Xs[NSTAGE][64][PITCH];
 };
 template <int KT, int NT>
 __global__ void __launch_bounds__(THR, (KT <= 6) ? 2 : 1) proj_rows_kernel(const __grid_constant__ RowArgs A) {
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(THR, (KT <= 6) ? 2 : 1) proj_rows_kernel(const
         const float h0 = tf32_hi(v0), h1 = tf32_hi(v1);
         s.Bhi[kt][nt][ln] = make_float2(h0, h1); s.Blo[kt][nt][ln] = pack_lo(v0 - h0, v1 - h1);
     }
-    for (int i = t_; i < 2 * 64 * PITCH; i += THR) (&s.Xs[0][0][0])[i] = 0.f;      // pad columns stay zero (the copies never touch them)
+    for (int i = t_; i < NSTAGE * 64 * PITCH; i += THR) (&s.Xs[0][0][0])[i] = 0.f;      // pad columns stay zero (the copies never touch them)
     __syncthreads();
     const int tiles_per_t = (A.N + 63) / 64, tiles = A.T * tiles_per_t;
     const bool vec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
@@ -92,11 +93,13 @@ __global__ void __launch_bounds__(THR, (KT <= 6) ? 2 : 1) proj_rows_kernel(const
         cp_commit();
     };
     int tile = blockIdx.x, stage = 0;
-    if (tile < tiles) issue(tile, 0);
-    for (; tile < tiles; tile += gridDim.x, stage ^= 1) {
-        const int next = tile + gridDim.x;
-        if (next < tiles) { issue(next, stage ^ 1); cp_wait<1>(); } else cp_wait<0>();
-        __syncthreads();
+    if (tile < tiles) issue(tile, 0); else cp_commit();
+    if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, 1); else cp_commit();
+    for (; tile < tiles; tile += gridDim.x, stage = (stage + 1) % NSTAGE) {
+        cp_wait<1>();                                                       // every group but the newest has landed: this tile is in shared memory
+        __syncthreads();                                                    // ... for every thread, and everybody has finished the previous tile
+        const int ahead = tile + 2 * (int)gridDim.x;                        // refill the stage the previous tile was multiplied from
+        if (ahead < tiles) issue(ahead, (stage + 2) % NSTAGE); else cp_commit();
         float acc[NH][4];
 #pragma unroll
         for (int i = 0; i < NH; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -129,7 +132,6 @@ __global__ void __launch_bounds__(THR, (KT <= 6) ? 2 : 1) proj_rows_kernel(const
                 for (int i = 0; i < NH; ++i) *reinterpret_cast<float2*>(yb + (size_t)n * (NT * 8) + 8 * (ch * NH + i) + 2 * q) = make_float2(acc[i][2 * half], acc[i][2 * half + 1]);
             }
         }
-        __syncthreads();                                                    // the stage may be refilled by the next iteration's copies
     }
 }
 
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(THR, (KT <= 6) ? 2 : 1) proj_rows_kernel(const
 template <int MT>
 struct GramSmem {
     static constexpr int XP = MT * 16 + 8, DP = 200;                   // (24 q + g) / (8 q + g) mod 32 distinct: conflict-free fragments
-    float Xs[2][32][XP]; float Ds[2][32][DP];
+    float Xs[NSTAGE][32][XP]; float Ds[NSTAGE][32][DP];
 };
 template <int MT>
 __global__ void __launch_bounds__(THR, 2) gram_rows_kernel(const __grid_constant__ RowArgs A) {
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(THR, 2) gram_rows_kernel(const __grid_constant
     constexpr int XP = S::XP, DP = S::DP;
     const int t_ = threadIdx.x, w = t_ >> 5, lane = t_ & 31, g = lane >> 2, q = lane & 3;
     const int k = blockIdx.y;
-    for (int i = t_; i < 2 * 32 * XP; i += THR) (&s.Xs[0][0][0])[i] = 0.f;          // pad columns (features past x_cols) stay zero
+    for (int i = t_; i < NSTAGE * 32 * XP; i += THR) (&s.Xs[0][0][0])[i] = 0.f;          // pad columns (features past x_cols) stay zero
     __syncthreads();
     const int tiles_per_t = (A.N + 31) / 32, tiles = A.T * tiles_per_t;
     const bool xvec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
@@ -166,11 +168,13 @@ __global__ void __launch_bounds__(THR, 2) gram_rows_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 3; ++i) acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f;
     int tile = blockIdx.x, stage = 0;
-    if (tile < tiles) issue(tile, 0);
-    for (; tile < tiles; tile += gridDim.x, stage ^= 1) {
-        const int next = tile + gridDim.x;
-        if (next < tiles) { issue(next, stage ^ 1); cp_wait<1>(); } else cp_wait<0>();
-        __syncthreads();
+    if (tile < tiles) issue(tile, 0); else cp_commit();
+    if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, 1); else cp_commit();
+    for (; tile < tiles; tile += gridDim.x, stage = (stage + 1) % NSTAGE) {
+        cp_wait<1>();                                                       // every group but the newest has landed: this tile is in shared memory
+        __syncthreads();                                                    // ... for every thread, and everybody has finished the previous tile
+        const int ahead = tile + 2 * (int)gridDim.x;                        // refill the stage the previous tile was multiplied from
+        if (ahead < tiles) issue(ahead, (stage + 2) % NSTAGE); else cp_commit();
         const float (*X)[XP] = s.Xs[stage]; const float (*D)[DP] = s.Ds[stage];
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt) {
@@ -195,7 +199,6 @@ __global__ void __launch_bounds__(THR, 2) gram_rows_kernel(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 3; ++i) mma(acc[m][i], ah[m], bh[i][0], bh[i][1]);
         }
-        __syncthreads();
     }
     float* out = A.Y + ((size_t)blockIdx.x * A.K + k) * (MT * 16) * 192;
 #pragma unroll

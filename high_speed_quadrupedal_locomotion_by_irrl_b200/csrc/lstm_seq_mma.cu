@@ -33,7 +33,15 @@ namespace seqmma {
 constexpr int H = LSTM_H;       // 48
 constexpr int G4 = 4 * H;       // 192
 constexpr int TM = 32;          // environments per CTA (two m16 tiles)
-constexpr int THR = 192;        // 6 warps, warp w <-> hidden units 8w .. 8w+7
+constexpr int THR = 192;        // 6 warps per environment tile, warp w <-> hidden units 8w .. 8w+7
+// Environment tiles per CTA (each tile: 6 warps, its own named barrier and shared-memory block).  Two tiles in one CTA were tried to
+// spread the 12 warps evenly over the 4 schedulers (3,3,3,3 instead of 2 x (2,2,1,1)): measured SLOWER at 8192 envs x 750 steps
+// (forward 7.97 vs 6.75 ms, backward 8.98 vs 7.94 ms), so one tile per CTA, two CTAs per SM, stays the default.
+#ifndef SEQ_GROUPS
+#define SEQ_GROUPS 1
+#endif
+constexpr int GROUPS = SEQ_GROUPS;
+__device__ __forceinline__ void tile_sync(int gi) { asm volatile("bar.sync %0, %1;" ::"r"(1 + gi), "n"(THR) : "memory"); }
 constexpr int HS_PITCH = 52;    // floats per row of the h tile: (52 g + q) mod 32 distinct over a warp
 constexpr int RED_PITCH = 56;   // floats per row of a partial-sum tile: conflict-free float2 stores per half warp
 
@@ -59,15 +67,22 @@ __device__ __forceinline__ uint32_t pack_lo(float lo0, float lo1) { return ((__f
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // xw, gates [T,K,N,192] (gate order i,f,o,g); Cs, Hs, HM [T,K,N,48]; keep [T,N]; c0, h0 [K,N,48]; wh [K,48,192]; bias [K,192] or null
-__global__ void __launch_bounds__(THR, 2) lstm_seq_fwd_mma_kernel(int T, int K, int N, const float* __restrict__ xw, const float* __restrict__ wh,
+struct FwdSmem {
+    uint32_t Blo[6][4][6][32];        // lo parts of the B fragments [warp][gate j][k-tile][lane] = bf16 (b0, b1)
+    float hsh[2][TM][HS_PITCH];       // masked h(t-1), tf32-exact part, row = environment; double buffered over t (one barrier per step)
+    float hsl[2][TM][HS_PITCH];       // its remainder
+    float bsm[G4];
+};
+__global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_kernel(int T, int K, int N, const float* __restrict__ xw, const float* __restrict__ wh,
                                                                    const float* __restrict__ c0, const float* __restrict__ h0, const float* __restrict__ keep,
                                                                    float* __restrict__ gates, float* __restrict__ Cs, float* __restrict__ Hs,
                                                                    const float* __restrict__ bias, float* __restrict__ HM) {
-    __shared__ __align__(16) uint32_t Blo[6][4][6][32];        // lo parts of the B fragments [warp][gate j][k-tile][lane] = bf16 (b0, b1)
-    __shared__ __align__(16) float hsh[2][TM][HS_PITCH];       // masked h(t-1), tf32-exact part, row = environment; double buffered over t (one barrier per step)
-    __shared__ __align__(16) float hsl[2][TM][HS_PITCH];       // its remainder
-    __shared__ __align__(16) float bsm[G4];
-    const int tower = blockIdx.y, e0 = blockIdx.x * TM, t_ = threadIdx.x, w = t_ >> 5, lane = t_ & 31, g = lane >> 2, q = lane & 3;
+    extern __shared__ __align__(16) unsigned char seq_smem_f[];
+    const int gi = threadIdx.x / THR, tile = blockIdx.x * GROUPS + gi;
+    const int tower = blockIdx.y, e0 = tile * TM, t_ = threadIdx.x - gi * THR, w = t_ >> 5, lane = t_ & 31, g = lane >> 2, q = lane & 3;
+    if (e0 >= N) return;                                    // the whole group leaves: its barrier is never used
+    FwdSmem& S = reinterpret_cast<FwdSmem*>(seq_smem_f)[gi];
+    auto& Blo = S.Blo; auto& hsh = S.hsh; auto& hsl = S.hsl; auto& bsm = S.bsm;
     const int u0 = 8 * w + 2 * q;                          // this thread's units u0, u0 + 1
     const float* whk = wh + (size_t)tower * H * G4;
     uint32_t bh[4][6][2];
@@ -105,7 +120,7 @@ __global__ void __launch_bounds__(THR, 2) lstm_seq_fwd_mma_kernel(int T, int K, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) xin[e][j] = *reinterpret_cast<const float2*>(xw + (((size_t)0 * K + tower) * N + envs[e]) * G4 + j * H + u0);
     }
-    __syncthreads();
+    tile_sync(gi);
     for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
         float acc[2][4][4];                                                 // [m-tile][gate][C fragment]: env e = 2 mt + (c >> 1), unit u0 + (c & 1)
@@ -176,20 +191,23 @@ __global__ void __launch_bounds__(THR, 2) lstm_seq_fwd_mma_kernel(int T, int K, 
             put_h(buf ^ 1, e, hn[0] * knc[e], hn[1] * knc[e]);              // the other buffer: nobody reads it before the barrier below
             if (HM && valid[e] && t + 1 < T) *reinterpret_cast<float2*>(HM + (((size_t)(t + 1) * K + tower) * N + envs[e]) * H + u0) = make_float2(hn[0] * knc[e], hn[1] * knc[e]);
         }
-        __syncthreads();                                                    // h(t) complete; everybody has also finished reading h(t-1)
+        tile_sync(gi);                                                    // h(t) complete; everybody has also finished reading h(t-1)
     }
 }
 
 // dH [T,K,N,48], gates / dz [T,K,N,192], Cs [T,K,N,48], keep [T,N], c0 [K,N,48], wh [K,48,192]; db_part [CTAs,K,192] or null
 constexpr int BWD_SMEM = 6 * 4 * 6 * 32 * (8 + 4) + 6 * TM * RED_PITCH * 4;     // B hi (float2) + B lo (2 x bf16) + partial sums = 98 304 B
-__global__ void __launch_bounds__(THR, 2) lstm_seq_bwd_mma_kernel(int T, int K, int N, const float* __restrict__ dH, const float* __restrict__ wh,
+__global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_kernel(int T, int K, int N, const float* __restrict__ dH, const float* __restrict__ wh,
                                                                    const float* __restrict__ c0, const float* __restrict__ keep, const float* __restrict__ gates,
                                                                    const float* __restrict__ Cs, float* __restrict__ dz, float* __restrict__ db_part) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char seq_smem_b[];
+    const int gi = threadIdx.x / THR, tile = blockIdx.x * GROUPS + gi;
+    unsigned char* smem = seq_smem_b + (size_t)gi * BWD_SMEM;
     float2 (*Bhi)[4][6][32] = reinterpret_cast<float2 (*)[4][6][32]>(smem);                                  // [warp][k-tile = gate j][n-tile][lane] = (b0, b1), tf32-exact
     uint32_t (*Blo)[4][6][32] = reinterpret_cast<uint32_t (*)[4][6][32]>(smem + 6 * 4 * 6 * 32 * 8);         // remainders as two bf16 (b0 low half, b1 high half)
     float (*red)[TM][RED_PITCH] = reinterpret_cast<float (*)[TM][RED_PITCH]>(smem + 6 * 4 * 6 * 32 * 12);    // [warp] partial dh[32][48]
-    const int tower = blockIdx.y, e0 = blockIdx.x * TM, t_ = threadIdx.x, w = t_ >> 5, lane = t_ & 31, g = lane >> 2, q = lane & 3;
+    const int tower = blockIdx.y, e0 = tile * TM, t_ = threadIdx.x - gi * THR, w = t_ >> 5, lane = t_ & 31, g = lane >> 2, q = lane & 3;
+    if (e0 >= N) return;
     const int u0 = 8 * w + 2 * q;
     const float* whk = wh + (size_t)tower * H * G4;
     // B = W_h^T restricted to this warp's 32 dz columns: k-tile j = gate j, MMA k index q <-> column j*48 + u0, q+4 <-> column j*48 + u0 + 1; n = 8 nt + g
@@ -242,7 +260,7 @@ __global__ void __launch_bounds__(THR, 2) lstm_seq_bwd_mma_kernel(int T, int K, 
             }
         }
     };
-    __syncthreads();
+    tile_sync(gi);
     for (int t = T - 1; t >= 0; --t) {
         In cur[4];
         load_step(t, cur);
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(THR, 2) lstm_seq_bwd_mma_kernel(int T, int K, 
                     *reinterpret_cast<float2*>(&red[w][16 * mt + g + 8][col]) = make_float2(part[mt][n3][2], part[mt][n3][3]);
                 }
         }
-        __syncthreads();
+        tile_sync(gi);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float2 s = *reinterpret_cast<const float2*>(&red[0][g + 8 * e][u0]);
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(THR, 2) lstm_seq_bwd_mma_kernel(int T, int K, 
             for (int w2 = 1; w2 < 6; ++w2) { const float2 v = *reinterpret_cast<const float2*>(&red[w2][g + 8 * e][u0]); s.x += v.x; s.y += v.y; }
             ch[e][0] = s.x; ch[e][1] = s.y;
         }
-        __syncthreads();
+        tile_sync(gi);
     }
     if (db_part) {   // the 8 environment groups of a unit pair are lanes q, q+4, .., q+28: fixed-order butterfly, one partial per CTA (summed afterwards: deterministic)
 #pragma unroll
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(THR, 2) lstm_seq_bwd_mma_kernel(int T, int K, 
             for (int j = 0; j < 4; ++j) {
                 float v = dbacc[u][j];
                 v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (g == 0) db_part[((size_t)blockIdx.x * K + tower) * G4 + j * H + u0 + u] = v;
+                if (g == 0) db_part[((size_t)tile * K + tower) * G4 + j * H + u0 + u] = v;
             }
     }
 }
@@ -343,21 +361,31 @@ static bool seq_use_fma() { return g_seq_path == 1; }
 void launch_lstm_seq_fwd(int T, int K, int N, const float* xw, const float* wh, const float* c0, const float* h0, const float* keep, float* gates, float* Cs,
                          float* Hs, const float* bias, float* HM, cudaStream_t st) {
     if (seq_use_fma()) { launch_lstm_seq_fwd_fma(T, K, N, xw, wh, c0, h0, keep, gates, Cs, Hs, bias, HM, st); return; }
-    dim3 grid((N + seqmma::TM - 1) / seqmma::TM, K);
-    seqmma::lstm_seq_fwd_mma_kernel<<<grid, seqmma::THR, 0, st>>>(T, K, N, xw, wh, c0, h0, keep, gates, Cs, Hs, bias, HM);
+    const int tiles = (N + seqmma::TM - 1) / seqmma::TM;
+    dim3 grid((tiles + seqmma::GROUPS - 1) / seqmma::GROUPS, K);
+    constexpr int smem = sizeof(seqmma::FwdSmem) * seqmma::GROUPS;
+    {   // the attribute is per device (a process may hold envs / policies on several GPUs through the C ABI)
+        static unsigned long long configured_devices = 0ull; int dev = 0; cudaGetDevice(&dev);
+        if (dev >= 64 || !((configured_devices >> dev) & 1ull)) {
+            cudaFuncSetAttribute(seqmma::lstm_seq_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (dev < 64) configured_devices |= 1ull << dev;
+        }
+    }
+    seqmma::lstm_seq_fwd_mma_kernel<<<grid, seqmma::THR * seqmma::GROUPS, smem, st>>>(T, K, N, xw, wh, c0, h0, keep, gates, Cs, Hs, bias, HM);
 }
 void launch_lstm_seq_bwd(int T, int K, int N, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates, const float* Cs,
                          float* dz, float* db_part, cudaStream_t st) {
     if (seq_use_fma()) { launch_lstm_seq_bwd_fma(T, K, N, dH, wh, c0, keep, gates, Cs, dz, db_part, st); return; }
-    dim3 grid((N + seqmma::TM - 1) / seqmma::TM, K);
+    const int tiles = (N + seqmma::TM - 1) / seqmma::TM;
+    dim3 grid((tiles + seqmma::GROUPS - 1) / seqmma::GROUPS, K);
     {   // the attribute is per device (a process may hold envs / policies on several GPUs through the C ABI)
         static unsigned long long configured_devices = 0ull; int dev = 0; cudaGetDevice(&dev);
         if (dev >= 64 || !((configured_devices >> dev) & 1ull)) {
-            cudaFuncSetAttribute(seqmma::lstm_seq_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seqmma::BWD_SMEM);
+            cudaFuncSetAttribute(seqmma::lstm_seq_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seqmma::BWD_SMEM * seqmma::GROUPS);
             if (dev < 64) configured_devices |= 1ull << dev;
         }
     }
-    seqmma::lstm_seq_bwd_mma_kernel<<<grid, seqmma::THR, seqmma::BWD_SMEM, st>>>(T, K, N, dH, wh, c0, keep, gates, Cs, dz, db_part);
+    seqmma::lstm_seq_bwd_mma_kernel<<<grid, seqmma::THR * seqmma::GROUPS, seqmma::BWD_SMEM * seqmma::GROUPS, st>>>(T, K, N, dH, wh, c0, keep, gates, Cs, dz, db_part);
 }
 
 }  // namespace irrl

@@ -92,6 +92,11 @@ class LstmActorCritic(torch.nn.Module):
         H0, _, _ = layer(xw0, wh0, b0, c0, h0, keep)
         xw1 = proj_rows(H0, wx1) if own else torch.matmul(H0, wx1)
         H1, _, _ = layer(xw1, wh1, b1, c1, h1, keep)
+        if own:   # both heads as ONE batched product on the [T,2,N,48] tensor (vf_w zero-padded to 12 columns): no strided tower slices, no
+            #       zero-filled select_backward copies of 2.4 GB each in the backward pass
+            head_w = torch.stack([self.pi_w, F.pad(self.vf_w, (0, self.pi_w.shape[1] - self.vf_w.shape[1]))])
+            out = torch.matmul(H1, head_w)                                           # [T,2,N,12]
+            return out[:, 0] + self.pi_b, out[:, 1, :, 0] + self.vf_b
         mean = H1[:, 0] @ self.pi_w + self.pi_b
         value = (H1[:, 1] @ self.vf_w + self.vf_b).squeeze(-1)
         return mean, value

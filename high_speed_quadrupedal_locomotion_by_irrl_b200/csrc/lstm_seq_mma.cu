@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_ker
         }
     bsm[t_] = bias ? bias[tower * G4 + t_] : 0.f;
     float c[4][2];
-    int envs[4]; bool valid[4];
+    int envs[4];
     auto put_h = [&](int buf, int e, float a, float b) {   // split at the producer: the MMA phase loads ready-made fragments
         const float ah = tf32_hi(a), bh_ = tf32_hi(b);
         *reinterpret_cast<float2*>(&hsh[buf][g + 8 * e][u0]) = make_float2(ah, bh_);
@@ -105,13 +105,13 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_ker
     };
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        envs[e] = min(e0 + g + 8 * e, N - 1); valid[e] = (e0 + g + 8 * e) < N;
+        envs[e] = min(e0 + g + 8 * e, N - 1);
         const size_t o = ((size_t)tower * N + envs[e]) * H + u0;
         const float k0 = keep[envs[e]];                                     // keep[0][env]
         const float2 cc = *reinterpret_cast<const float2*>(c0 + o), hh = *reinterpret_cast<const float2*>(h0 + o);
         c[e][0] = cc.x * k0; c[e][1] = cc.y * k0;
         put_h(0, e, hh.x * k0, hh.y * k0);
-        if (HM && valid[e]) *reinterpret_cast<float2*>(HM + o) = make_float2(hh.x * k0, hh.y * k0);      // row (t = 0, tower, env)
+        if (HM) *reinterpret_cast<float2*>(HM + o) = make_float2(hh.x * k0, hh.y * k0);                    // row (t = 0, tower, env)
     }
     float2 xin[4][4]; float kn[4];
 #pragma unroll
@@ -169,27 +169,35 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_ker
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) mma(acc[mt][j], ah[mt], bh[j][kt][0], bh[j][kt][1]);
         }
+        // per m-tile: its 4 cells as one block of independent arithmetic, then the stores (all 8 at once costs spills at 168 registers).
+        // Rows past N alias row N-1 (envs[] is clamped): those threads compute bit-identical values from identical inputs, so the stores
+        // need no predicate.
+        const size_t rowbase = ((size_t)t * K + tower) * N;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float gi[2], gf[2], go[2], gg[2], hn[2];
+        for (int mt = 0; mt < 2; ++mt) {
+            float gI[2][2], gF[2][2], gO[2][2], gG[2][2], hN[2][2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int ci = 2 * (e & 1) + u;
-                gi[u] = sig_(acc[e >> 1][0][ci]); gf[u] = sig_(acc[e >> 1][1][ci]); go[u] = sig_(acc[e >> 1][2][ci]); gg[u] = tanh__(acc[e >> 1][3][ci]);
-                c[e][u] = gf[u] * c[e][u] + gi[u] * gg[u];
-                hn[u] = go[u] * tanh__(c[e][u]);
-            }
-            if (valid[e]) {
-                const size_t row = ((size_t)t * K + tower) * N + envs[e];
+            for (int eh = 0; eh < 2; ++eh)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = 2 * mt + eh, ci = 2 * eh + u;
+                    gI[eh][u] = sig_(acc[mt][0][ci]); gF[eh][u] = sig_(acc[mt][1][ci]); gO[eh][u] = sig_(acc[mt][2][ci]); gG[eh][u] = tanh__(acc[mt][3][ci]);
+                    c[e][u] = gF[eh][u] * c[e][u] + gI[eh][u] * gG[eh][u];
+                    hN[eh][u] = gO[eh][u] * tanh__(c[e][u]);
+                }
+#pragma unroll
+            for (int eh = 0; eh < 2; ++eh) {
+                const int e = 2 * mt + eh;
+                const size_t row = rowbase + envs[e];
                 float* gr = gates + row * G4 + u0;
-                *reinterpret_cast<float2*>(gr) = make_float2(gi[0], gi[1]); *reinterpret_cast<float2*>(gr + H) = make_float2(gf[0], gf[1]);
-                *reinterpret_cast<float2*>(gr + 2 * H) = make_float2(go[0], go[1]); *reinterpret_cast<float2*>(gr + 3 * H) = make_float2(gg[0], gg[1]);
+                *reinterpret_cast<float2*>(gr) = make_float2(gI[eh][0], gI[eh][1]); *reinterpret_cast<float2*>(gr + H) = make_float2(gF[eh][0], gF[eh][1]);
+                *reinterpret_cast<float2*>(gr + 2 * H) = make_float2(gO[eh][0], gO[eh][1]); *reinterpret_cast<float2*>(gr + 3 * H) = make_float2(gG[eh][0], gG[eh][1]);
                 *reinterpret_cast<float2*>(Cs + row * H + u0) = make_float2(c[e][0], c[e][1]);
-                *reinterpret_cast<float2*>(Hs + row * H + u0) = make_float2(hn[0], hn[1]);
+                *reinterpret_cast<float2*>(Hs + row * H + u0) = make_float2(hN[eh][0], hN[eh][1]);
+                c[e][0] *= knc[e]; c[e][1] *= knc[e];                       // SB lstm(): c *= 1-m ; h *= 1-m before the next cell
+                put_h(buf ^ 1, e, hN[eh][0] * knc[e], hN[eh][1] * knc[e]);  // the other buffer: nobody reads it before the barrier below
+                if (HM && t + 1 < T) *reinterpret_cast<float2*>(HM + (rowbase + (size_t)K * N + envs[e]) * H + u0) = make_float2(hN[eh][0] * knc[e], hN[eh][1] * knc[e]);
             }
-            c[e][0] *= knc[e]; c[e][1] *= knc[e];                           // SB lstm(): c *= 1-m ; h *= 1-m before the next cell
-            put_h(buf ^ 1, e, hn[0] * knc[e], hn[1] * knc[e]);              // the other buffer: nobody reads it before the barrier below
-            if (HM && valid[e] && t + 1 < T) *reinterpret_cast<float2*>(HM + (((size_t)(t + 1) * K + tower) * N + envs[e]) * H + u0) = make_float2(hn[0] * knc[e], hn[1] * knc[e]);
         }
         tile_sync(gi);                                                    // h(t) complete; everybody has also finished reading h(t-1)
     }
@@ -261,9 +269,15 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
         }
     };
     tile_sync(gi);
+#ifdef SEQ_BWD_LATE_LOADS
+    In cur[4];
+    load_step(T - 1, cur);
+#endif
     for (int t = T - 1; t >= 0; --t) {
+#ifndef SEQ_BWD_LATE_LOADS
         In cur[4];
         load_step(t, cur);
+#endif
         float dzv[4][2][4];                                                 // [env e][unit u][gate]
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -279,10 +293,11 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
                 dzv[e][u][2] = dhv[u] * tc * ov[u] * (1.f - ov[u]); dzv[e][u][3] = dc * iv[u] * (1.f - gv[u] * gv[u]);
                 cc[e][u] = dc * fv[u];
             }
-            if (valid[e]) {
+            {   // rows past N alias row N-1 with bit-identical values (envs[] is clamped): no predicate on the stores, a 0 / 1 weight on the bias sums
                 float* dr = dz + row * G4 + u0;
+                const float vw = valid[e] ? 1.f : 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { *reinterpret_cast<float2*>(dr + j * H) = make_float2(dzv[e][0][j], dzv[e][1][j]); dbacc[0][j] += dzv[e][0][j]; dbacc[1][j] += dzv[e][1][j]; }
+                for (int j = 0; j < 4; ++j) { *reinterpret_cast<float2*>(dr + j * H) = make_float2(dzv[e][0][j], dzv[e][1][j]); dbacc[0][j] = fmaf(vw, dzv[e][0][j], dbacc[0][j]); dbacc[1][j] = fmaf(vw, dzv[e][1][j], dbacc[1][j]); }
             }
             ccur[e] = cur[e].cp; kuc[e] = kt;                               // c(t-1) and keep(t) are what step t-1 calls c and keep(t+1)
         }
@@ -329,6 +344,9 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
                 }
         }
         tile_sync(gi);
+#ifdef SEQ_BWD_LATE_LOADS                                                   // variant: register loads behind the reduction (spills 192 B at 168 registers)
+        if (t > 0) load_step(t - 1, cur);
+#endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float2 s = *reinterpret_cast<const float2*>(&red[0][g + 8 * e][u0]);

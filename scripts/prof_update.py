@@ -15,4 +15,4 @@ mb_states, _ = model._rollout()
 model._update(mb_states, 1e-4, 0.2); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     model._update(mb_states, 1e-4, 0.2); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))

@@ -4,7 +4,7 @@ cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
 TAG=${1:-r02c}
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mma_kernel -s 6 -c 2 -o gpurun_out/${TAG}_lstm_seq_mma -f \
   python scripts/r2c_seq_ab.py 8192 96 > gpurun_out/${TAG}_ncu_seq.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rows_kernel -s 42 -c 5 -o gpurun_out/${TAG}_learner_gemm -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rows_kernel -s 30 -c 17 -o gpurun_out/${TAG}_learner_gemm -f \
   python scripts/r2c_gemm_ab.py 8192 96 > gpurun_out/${TAG}_ncu_gemm.log 2>&1
 for r in lstm_seq_mma learner_gemm; do
   ncu -i gpurun_out/${TAG}_$r.ncu-rep --page details > gpurun_out/${TAG}_${r}_details.txt 2>&1

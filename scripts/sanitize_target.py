@@ -2,7 +2,7 @@
 """Target of scripts/r2_sanitize.sh (compute-sanitizer memcheck / racecheck / synccheck): every kernel of the hot path on small, awkward
 shapes -- 300 environments (ragged last tile of the tcgen05 act kernel, partial last CTA of the step kernel), forced resets and trunk-box contacts (loop hand-over) inside the
 step kernel, heightfield terrain, the meteor sphere, the 128-thread barrier variant of the step kernel, the fused host entry with chunks,
-the GAE kernel and the sequence-persistent BPTT kernels."""
+the GAE kernel and the learner kernels (tensor-core sequence-persistent BPTT, streaming projections / weight gradients) on ragged tiles."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
@@ -39,7 +39,7 @@ print("fused host entry ok (1 and 2 chunks)", flush=True)
 from high_speed_quadrupedal_locomotion_by_irrl_b200._flexible_robot import FlexibleGymEnv
 from high_speed_quadrupedal_locomotion_by_irrl_b200.vec_env import RaisimGymVecEnv
 from high_speed_quadrupedal_locomotion_by_irrl_b200.ppo2 import PPO2
-env = RaisimGymVecEnv(FlexibleGymEnv("", dump_yaml(trot_cfg(num_envs=64, StochasticDynamics=True, ObsNoise=2.0))))
+env = RaisimGymVecEnv(FlexibleGymEnv("", dump_yaml(trot_cfg(num_envs=77, StochasticDynamics=True, ObsNoise=2.0))))      # 77: ragged last tiles of the learner kernels (32- / 64-row tiles)
 model = PPO2(env, policy_params=W, n_steps=12, noptepochs=1, learning_rate=1e-4, verbose=0)
-h = model.learn(total_timesteps=64 * 12)
+h = model.learn(total_timesteps=77 * 12)
 print("ppo iteration ok: loss", h[-1].get("policy_loss"), flush=True)

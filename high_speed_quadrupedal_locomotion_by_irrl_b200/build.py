@@ -9,8 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libirrl_b200.so")
-SOURCES = ["env_kernels.cu", "policy_kernels.cu", "policy_tc_kernels.cu", "lstm_seq_mma.cu", "learner_gemm.cu", "capi.cu"]
-HEADERS = ["env_device.cuh", "env_kernels.h", "irrl_params.h", os.path.join("..", "..", "include", "irrl_b200.h")]
+SOURCES = ["env_kernels.cu", "policy_kernels.cu", "policy_tc_kernels.cu", "lstm_seq_mma.cu", "learner_gemm.cu", "learner_tc.cu", "capi.cu"]
+HEADERS = ["env_device.cuh", "env_kernels.h", "irrl_params.h", "tc_common.cuh", os.path.join("..", "..", "include", "irrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
 if os.environ.get("IRRL_FASTDIV"):

@@ -1121,11 +1121,14 @@ int irrl_lstm_seq_set_path(int path) { return lstm_seq_set_path(path); }
 int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* W, int w_trans, float* Y, int n_out) {
     NvtxRange nvtx_("irrl_proj_rows");
     if (!X || !W || !Y || T <= 0 || K <= 0 || n_env <= 0) return fail(-1, "irrl_proj_rows: bad argument");
-    const int rc = launch_proj_rows(X, x_cols, x_has_tower, W, w_trans, Y, n_out, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
+    int rc = -1;
+    if (!w_trans && n_out == 192) rc = launch_proj_rows_tc(X, x_cols, x_has_tower, W, Y, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));      // tcgen05 where the shape fits a TMEM tile
+    if (rc == -1) rc = launch_proj_rows(X, x_cols, x_has_tower, W, w_trans, Y, n_out, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (rc == -1) return fail(-1, "irrl_proj_rows: unsupported shape (x_cols <= 40 or 48 with n_out 192; x_cols 192 with n_out 48)");
     if (rc) return fail(rc, "irrl_proj_rows: kernel configuration failed");
     CUDA_OK(cudaGetLastError()); return 0;
 }
+int irrl_proj_rows_set_path(int path) { return proj_rows_set_path(path); }
 int irrl_gram_rows_ctas(int T, int K, int n_env) { return gram_rows_ctas(T, n_env, K); }
 int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial) {
     NvtxRange nvtx_("irrl_gram_rows");

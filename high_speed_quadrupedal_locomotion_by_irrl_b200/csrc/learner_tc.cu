@@ -1,0 +1,201 @@
+// tcgen05 version of the learner's input projections  Y[t,k,n,0:192] = X[t,(k),n,:] . W_k  (ppo2.py:136-197 over run_bp_v5.py:151-166:
+// x W_x of all T steps, both towers), the streaming product with the M = rows / N = 192 / K = 35 | 48 shape that fits a 128-lane TMEM
+// accumulator exactly.  Same 3xTF32 arithmetic and the same operand layouts as the act kernel (policy_tc_kernels.cu, tc_common.cuh):
+// UMMA canonical K-major no-swizzle tiles [k-step][hi|lo][16-byte k-chunk (2)][row][4 floats], tcgen05.mma.kind::tf32 M128 N192 K8
+// (98 cycles each, 4x the rate of the warp-level MMAs of learner_gemm.cu), fp32 accumulators in tensor memory.
+//
+// One persistent CTA per SM (256 threads) walks 128-row tiles of one tower:
+//   * raw rows arrive through a double-buffered cp.async stage (coalesced 16-byte chunks; 4-byte chunks for the 35-column observation
+//     whose rows are not 16-byte aligned),
+//   * every thread converts (row, 4 k) items into the hi / lo operand tile (row-per-lane writes: conflict-free),
+//   * one elected lane issues KS x 3 MMAs into TMEM buffer i % 2 and commits to an mbarrier,
+//   * while they run, all threads drain the PREVIOUS tile's accumulator: tcgen05.ld (lane = row, 16 columns) -> padded staging tile
+//     -> coalesced float4 stores (a row-per-lane store straight from registers would cost 32 L1 tag look-ups per instruction).
+// W is packed once per CTA (hi / lo split, K-major rows = output columns).  Rows past N in the last tile of a time step are never stored.
+#include <algorithm>
+#include <cstdlib>
+#include "env_device.cuh"
+#include "env_kernels.h"
+#include "tc_common.cuh"
+
+namespace irrl {
+namespace ltc {
+using namespace tc;
+
+constexpr int THR = 256;
+constexpr int TM = 128, NG = 192;
+constexpr int A_HALF = 2 * TM * 16, A_KSTEP = 2 * A_HALF;       // 4096 / 8192 bytes
+constexpr int B_HALF = 2 * NG * 16, B_KSTEP = 2 * B_HALF;       // 6144 / 12288 bytes
+constexpr int STAGE_PITCH = 100;                                // floats per row of the output staging tile (96 columns + 4): 16-byte groups 25 r mod 8 distinct
+constexpr int TMEM_COLS = 512;                                  // 2 x 192 accumulator columns -> next power of two
+
+__device__ __forceinline__ void cp16(void* s, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(s)), "l"(g)); }
+__device__ __forceinline__ void cp4(void* s, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(s)), "l"(g)); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct ProjTcArgs {
+    const float* X; int x_cols; long long x_t_stride, x_k_stride;      // row (t,k,n) of X starts at X + (t*x_t_stride + k*x_k_stride + n) * x_cols
+    const float* W; long long w_k_stride;                              // W_k [x_cols][192]
+    float* Y;                                                          // [T,K,N,192]
+    int T, K, N;
+};
+
+template <int KS> struct Lay {                                         // KS k-steps of 8 (x_cols padded)
+    static constexpr int RAW_PITCH = KS * 8 + 4;                       // floats; 16-byte groups (KS*2+1) r mod 8 distinct for row-per-lane float4 reads
+    static constexpr int OFF_B = 0;
+    static constexpr int OFF_A = OFF_B + KS * B_KSTEP;
+    static constexpr int OFF_RAW = OFF_A + KS * A_KSTEP;
+    static constexpr int OFF_STAGE = OFF_RAW + 2 * TM * RAW_PITCH * 4;
+    static constexpr int OFF_BAR = OFF_STAGE + TM * STAGE_PITCH * 4;
+    static constexpr int BYTES = OFF_BAR + 2 * 8 + 16;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_constant__ ProjTcArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    using L = Lay<KS>;
+    constexpr int RP = L::RAW_PITCH;
+    static_assert(L::BYTES <= 232448, "shared memory");
+    const int t_ = threadIdx.x, warp = t_ >> 5, lane = t_ & 31, k = blockIdx.y;
+    unsigned char* sB = smem + L::OFF_B;
+    unsigned char* sA = smem + L::OFF_A;
+    float* raw = reinterpret_cast<float*>(smem + L::OFF_RAW);
+    float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGE);
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_done + 2);
+
+    if (t_ == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
+    // W_k -> B operand: row n of the tile = output column n, K-major, hi / lo split, zero rows past x_cols
+    const float* Wk = A.W + (size_t)k * A.w_k_stride;
+    for (int i = t_; i < NG * KS * 8; i += THR) {
+        const int n = i % NG, kk = i / NG;
+        const float v = kk < A.x_cols ? Wk[(size_t)kk * NG + n] : 0.f;
+        const float hi = tf32_hi(v);
+        *reinterpret_cast<float*>(sB + op_off(kk, n, NG)) = hi;
+        *reinterpret_cast<float*>(sB + op_off(kk, n, NG) + B_HALF) = v - hi;
+    }
+    for (int i = t_; i < 2 * TM * RP; i += THR) raw[i] = 0.f;          // pad columns stay zero (the copies never touch them)
+    fence_proxy_async();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    const int tiles_per_t = (A.N + TM - 1) / TM, tiles = A.T * tiles_per_t;
+    const bool vec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
+    auto issue = [&](int tile, int buf) {
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM;
+        const float* src = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * A.x_cols;
+        float* dst = raw + buf * TM * RP;
+        if (vec) {
+            const int cpr = A.x_cols >> 2;
+            for (int i = t_; i < TM * cpr; i += THR) { const int r = i / cpr, c = i - r * cpr; if (n0 + r < A.N) cp16(dst + r * RP + 4 * c, src + (size_t)r * A.x_cols + 4 * c); }
+        } else {
+            for (int i = t_; i < TM * A.x_cols; i += THR) { const int r = i / A.x_cols, c = i - r * A.x_cols; if (n0 + r < A.N) cp4(dst + r * RP + c, src + (size_t)r * A.x_cols + c); }
+        }
+        cp_commit();
+    };
+    // accumulator of a finished tile: TMEM -> registers -> padded staging tile -> coalesced stores, 96 columns at a time
+    auto drain = [&](int tile, int buf) {
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = min(TM, A.N - n0);
+        float* yb = A.Y + (((size_t)t * A.K + k) * A.N + n0) * NG;
+        const int wq = warp & 3, sub = warp >> 2, row = 32 * wq + lane;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                uint32_t v[16];
+                tmem_ld16(tmem + ((uint32_t)(32 * wq) << 16) + buf * NG + 96 * h + 48 * sub + 16 * i, v);
+                tmem_ld_wait();
+                float4* d = reinterpret_cast<float4*>(stage + row * STAGE_PITCH + 48 * sub + 16 * i);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            __syncthreads();
+            for (int i = t_; i < TM * 24; i += THR) {
+                const int r = i / 24, c4 = i - r * 24;
+                if (r < rows) *reinterpret_cast<float4*>(yb + (size_t)r * NG + 96 * h + 4 * c4) = *reinterpret_cast<const float4*>(stage + r * STAGE_PITCH + 4 * c4);
+            }
+            __syncthreads();
+        }
+    };
+
+    int tile = blockIdx.x, it = 0, prev_tile = -1;
+    if (tile < tiles) issue(tile, 0); else cp_commit();
+    if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, 1); else cp_commit();
+    for (; tile < tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        cp_wait<1>();                                                   // every copy group but the newest has landed: the raw rows of this tile
+        __syncthreads();
+        if (it >= 1) { mbar_wait(&mma_done[b ^ 1], ((it - 1) >> 1) & 1); tc_fence_after(); }     // previous tile multiplied: the operand tile is free, its accumulator full
+        const float* rw = raw + b * TM * RP;
+        for (int i = t_; i < TM * KS * 2; i += THR) {                   // item = (row, 4 k): row-per-lane reads and writes
+            const int r = i & (TM - 1), q = i >> 7;
+            const float4 x = *reinterpret_cast<const float4*>(rw + r * RP + 4 * q);
+            const float v[4] = {x.x, x.y, x.z, x.w};
+            store_hilo(sA, op_off(4 * q, r, TM), A_HALF, v);
+        }
+        fence_proxy_async();
+        tc_fence_before(); __syncthreads(); tc_fence_after();
+        {   // the raw buffer of this tile is free again: rows of the tile after next
+            const int ahead = tile + 2 * (int)gridDim.x;
+            if (ahead < tiles) issue(ahead, b); else cp_commit();
+        }
+        if (warp == 0) {
+            if (elect_one()) {
+                const uint32_t idesc = make_idesc(TM, NG), d = tmem + b * NG;
+#pragma unroll 1
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t ab = smem_u32(sA) + ks * A_KSTEP, bb = smem_u32(sB) + ks * B_KSTEP;
+                    const uint64_t ah = make_desc(ab, TM * 16, 128), al = make_desc(ab + A_HALF, TM * 16, 128);
+                    const uint64_t bh = make_desc(bb, NG * 16, 128), bl = make_desc(bb + B_HALF, NG * 16, 128);
+                    mma_tf32(d, al, bh, idesc, ks > 0);
+                    mma_tf32(d, ah, bl, idesc, 1);
+                    mma_tf32(d, ah, bh, idesc, 1);
+                }
+                umma_commit(&mma_done[b]);
+            }
+            __syncwarp();
+        }
+        if (it >= 1) drain(prev_tile, b ^ 1);                           // overlaps the MMAs just issued
+        prev_tile = tile;
+    }
+    if (it >= 1) {
+        const int b = (it - 1) & 1;
+        mbar_wait(&mma_done[b], ((it - 1) >> 1) & 1); tc_fence_after();
+        drain(prev_tile, b);
+    }
+    cp_wait<0>();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, TMEM_COLS); }
+}
+
+}  // namespace ltc
+
+static int sm_count_tc() { static int n = 0; if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; } return n; }
+
+// 0 (default) = tcgen05 kernel of this file for the forward projections, 1 = warp-level MMA kernels of learner_gemm.cu (A/B, regression reference)
+static int g_proj_path = [] { const char* e = getenv("IRRL_PROJ_PATH"); return (e && e[0] == 'm') ? 1 : 0; }();
+int proj_rows_set_path(int path) { const int prev = g_proj_path; if (path == 0 || path == 1) g_proj_path = path; return prev; }
+
+// Y[T,K,N,192] = X . W_k on tcgen05; x_cols <= 40 (shared observation or per-tower) or 48.  Returns -1 for other shapes.
+int launch_proj_rows_tc(const float* X, int x_cols, int x_has_tower, const float* W, float* Y, int T, int K, int N, cudaStream_t st) {
+    using namespace ltc;
+    if (g_proj_path == 1) return -1;
+    ProjTcArgs a{}; a.X = X; a.x_cols = x_cols; a.x_t_stride = x_has_tower ? (long long)K * N : N; a.x_k_stride = x_has_tower ? N : 0;
+    a.W = W; a.w_k_stride = (long long)x_cols * NG; a.Y = Y; a.T = T; a.K = K; a.N = N;
+    const int tiles = T * ((N + TM - 1) / TM);
+    if (tiles <= 0) return 0;
+    const dim3 grid(std::min(tiles, std::max(1, sm_count_tc() / K)), K);
+    if (x_cols <= 40 && x_cols > 32) {
+        if (cudaFuncSetAttribute(proj_rows_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<5>::BYTES) != cudaSuccess) return -2;
+        proj_rows_tc_kernel<5><<<grid, THR, Lay<5>::BYTES, st>>>(a);
+    } else if (x_cols == 48) {
+        if (cudaFuncSetAttribute(proj_rows_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<6>::BYTES) != cudaSuccess) return -2;
+        proj_rows_tc_kernel<6><<<grid, THR, Lay<6>::BYTES, st>>>(a);
+    } else return -1;
+    return 0;
+}
+
+}  // namespace irrl

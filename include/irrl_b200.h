@@ -203,6 +203,8 @@ int irrl_lstm_seq_set_path(int path);
  *   irrl_gram_rows  partial[irrl_gram_rows_ctas(T,K,N), K, 48, 192] = per-CTA sums of X[row,:]^T D[row,:] over the rows (t, n) of tower k, x_cols <= 48
  *                   (rows of the result past x_cols are zero); the caller sums the partials (fixed order: deterministic) = dW_x / dW_h. */
 int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* W, int w_trans, float* Y, int n_out);
+/* forward projections (n_out 192, no transpose): 0 = tcgen05 kernel (TMEM accumulators, default), 1 = warp-level MMA kernel; returns the previous value */
+int irrl_proj_rows_set_path(int path);
 int irrl_gram_rows_ctas(int T, int K, int n_env);
 int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial);
 /* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,

@@ -61,4 +61,8 @@ if __name__ == "__main__":
     ]
     for name, own, ref, g_ in rows:
         a, b = timed(own), timed(ref)
-        print(f"{name} N={N} T={T}: tensor-core {a:6.2f} ms ({g_ / a * 1e3:5.0f} GB/s algorithmic)   torch.matmul fp32 {b:6.2f} ms")
+        extra = ""
+        if name.startswith("proj") and "192->48" not in name:          # the forward projections default to the tcgen05 kernel: time the warp-level MMA kernel too
+            L.irrl_proj_rows_set_path(1); c = timed(own); L.irrl_proj_rows_set_path(0)
+            extra = f"   warp-level MMA kernel {c:6.2f} ms"
+        print(f"{name} N={N} T={T}: tensor-core {a:6.2f} ms ({g_ / a * 1e3:5.0f} GB/s algorithmic)   torch.matmul fp32 {b:6.2f} ms{extra}")

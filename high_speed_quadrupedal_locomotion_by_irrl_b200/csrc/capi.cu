@@ -1129,6 +1129,15 @@ int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, i
     CUDA_OK(cudaGetLastError()); return 0;
 }
 int irrl_proj_rows_set_path(int path) { return proj_rows_set_path(path); }
+int irrl_gram2_rows_ctas(int T, int K, int n_env) { return gram2_rows_tc_ctas(T, n_env, K); }
+int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial) {
+    NvtxRange nvtx_("irrl_gram2_rows");
+    if (!X || !HM || !D || !partial || T <= 0 || K <= 0 || n_env <= 0) return fail(-1, "irrl_gram2_rows: bad argument");
+    const int rc = launch_gram2_rows_tc(X, x_cols, x_has_tower, HM, D, partial, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (rc == -1) return fail(-1, "irrl_gram2_rows: x_cols must be in 1..48");
+    if (rc) return fail(rc, "irrl_gram2_rows: kernel configuration failed");
+    CUDA_OK(cudaGetLastError()); return 0;
+}
 int irrl_gram_rows_ctas(int T, int K, int n_env) { return gram_rows_ctas(T, n_env, K); }
 int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial) {
     NvtxRange nvtx_("irrl_gram_rows");

@@ -171,6 +171,131 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, TMEM_COLS); }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------- gram2_rows (tcgen05)
+// Both weight gradients of one LSTM layer in ONE pass over dz:  G[0:48] = sum_rows x^T dz (dW_x),  G[48:96] = sum_rows hm^T dz (dW_h),
+// rows = (t, n) of tower k (~6 M).  MMA view: D[128 x 192] += A[128 x 8] . B[8 x 192] with M = feature (96 used), N = gate column, K = ROWS,
+// so both operands must be K-major over rows: the transform transposes while it splits -- an item is (feature or column, 4 consecutive
+// rows): four strided scalar reads (lanes along the feature: conflict-free), hi / lo split, one float4 store each into the operand tile.
+// The fp32 accumulator stays in tensor memory over all tiles of the CTA; one partial [128 x 192] per CTA is written at the end (summed
+// afterwards in a fixed order: deterministic).  Raw rows stream through a double-buffered cp.async stage, 32 rows (4 k-steps) per tile.
+struct GramTcArgs {
+    const float* X; int x_cols; long long x_t_stride, x_k_stride;      // [T,(K),N,x_cols], x_cols <= 48
+    const float* HM;                                                   // [T,K,N,48]
+    const float* D;                                                    // [T,K,N,192]
+    float* P;                                                          // partial sums [gridDim.x][K][128][192]
+    int T, K, N;
+};
+constexpr int GR = 32;                                                 // rows per tile
+constexpr int G_OFF_A = 0, G_OFF_B = G_OFF_A + 4 * A_KSTEP, G_OFF_RAW = G_OFF_B + 4 * B_KSTEP;
+constexpr int G_RAW_STAGE = GR * (48 + 48 + NG) * 4;                   // [32][48] x | [32][48] hm | [32][192] dz
+constexpr int G_OFF_BAR = G_OFF_RAW + 2 * G_RAW_STAGE;
+constexpr int G_BYTES = G_OFF_BAR + 8 + 16;
+
+__global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_constant__ GramTcArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int t_ = threadIdx.x, warp = t_ >> 5, lane = t_ & 31, k = blockIdx.y;
+    unsigned char* sA = smem + G_OFF_A;
+    unsigned char* sB = smem + G_OFF_B;
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_done + 1);
+    if (t_ == 0) { mbar_init(mma_done, 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+    for (int i = t_; i < (G_OFF_BAR - G_OFF_A) / 4; i += THR) reinterpret_cast<float*>(smem)[i] = 0.f;     // operand rows 96..127, feature columns past x_cols: zero for good
+    fence_proxy_async();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    const int tiles_per_t = (A.N + GR - 1) / GR, tiles = A.T * tiles_per_t;
+    const bool xvec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
+    auto rows_in = [&](float* dst, int pitch, const float* src, int cols, int n0, bool vec) {
+        if (vec) {
+            const int cpr = cols >> 2;
+            for (int i = t_; i < GR * cpr; i += THR) {
+                const int r = i / cpr, c = i - r * cpr;
+                if (n0 + r < A.N) cp16(dst + r * pitch + 4 * c, src + (size_t)r * cols + 4 * c);
+                else *reinterpret_cast<float4*>(dst + r * pitch + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int i = t_; i < GR * cols; i += THR) {
+                const int r = i / cols, c = i - r * cols;
+                if (n0 + r < A.N) cp4(dst + r * pitch + c, src + (size_t)r * cols + c); else dst[r * pitch + c] = 0.f;
+            }
+        }
+    };
+    auto issue = [&](int tile, int buf) {
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * GR;
+        float* rx = reinterpret_cast<float*>(smem + G_OFF_RAW + buf * G_RAW_STAGE);
+        rows_in(rx, 48, A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * A.x_cols, A.x_cols, n0, xvec);
+        rows_in(rx + GR * 48, 48, A.HM + (((size_t)t * A.K + k) * A.N + n0) * 48, 48, n0, true);
+        rows_in(rx + GR * 96, NG, A.D + (((size_t)t * A.K + k) * A.N + n0) * NG, NG, n0, true);
+        cp_commit();
+    };
+    int tile = blockIdx.x, it = 0;
+    if (tile < tiles) issue(tile, 0); else cp_commit();
+    if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, 1); else cp_commit();
+    for (; tile < tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        cp_wait<1>();
+        __syncthreads();
+        if (it >= 1) { mbar_wait(mma_done, (it - 1) & 1); tc_fence_after(); }          // the MMAs of the previous tile have read the operand tiles
+        const float* rx = reinterpret_cast<const float*>(smem + G_OFF_RAW + b * G_RAW_STAGE);
+        const float* rd = rx + GR * 96;
+        for (int i = t_; i < 96 * 8; i += THR) {                        // A: (feature m, rows 4c .. 4c+3); features 0..47 = x, 48..95 = hm
+            const int m = i % 96, c = i / 96;
+            const float* col = rx + (m < 48 ? m : GR * 48 + (m - 48));
+            const float v[4] = {col[(4 * c) * 48], col[(4 * c + 1) * 48], col[(4 * c + 2) * 48], col[(4 * c + 3) * 48]};
+            store_hilo(sA, op_off(4 * c, m, TM), A_HALF, v);
+        }
+        for (int i = t_; i < NG * 8; i += THR) {                        // B: (gate column n, rows 4c .. 4c+3)
+            const int n = i % NG, c = i / NG;
+            const float v[4] = {rd[(4 * c) * NG + n], rd[(4 * c + 1) * NG + n], rd[(4 * c + 2) * NG + n], rd[(4 * c + 3) * NG + n]};
+            store_hilo(sB, op_off(4 * c, n, NG), B_HALF, v);
+        }
+        fence_proxy_async();
+        tc_fence_before(); __syncthreads(); tc_fence_after();
+        {
+            const int ahead = tile + 2 * (int)gridDim.x;
+            if (ahead < tiles) issue(ahead, b); else cp_commit();
+        }
+        if (warp == 0) {
+            if (elect_one()) {
+                const uint32_t idesc = make_idesc(TM, NG);
+#pragma unroll 1
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ab = smem_u32(sA) + ks * A_KSTEP, bb = smem_u32(sB) + ks * B_KSTEP;
+                    const uint64_t ah = make_desc(ab, TM * 16, 128), al = make_desc(ab + A_HALF, TM * 16, 128);
+                    const uint64_t bh = make_desc(bb, NG * 16, 128), bl = make_desc(bb + B_HALF, NG * 16, 128);
+                    mma_tf32(tmem, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32(tmem, ah, bl, idesc, 1);
+                    mma_tf32(tmem, ah, bh, idesc, 1);
+                }
+                umma_commit(mma_done);
+            }
+            __syncwarp();
+        }
+    }
+    cp_wait<0>();
+    if (it >= 1) { mbar_wait(mma_done, (it - 1) & 1); tc_fence_after(); }
+    if (warp < 4) {                                                     // lane = feature row m: 96 of them are real
+        const int m = 32 * warp + lane;
+        float* out = A.P + (((size_t)blockIdx.x * A.K + k) * TM + m) * NG;
+#pragma unroll 1
+        for (int i = 0; i < NG / 16; ++i) {
+            uint32_t v[16];
+            tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + 16 * i, v);
+            tmem_ld_wait();
+            if (it >= 1 && m < 96) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(out + 16 * i)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
+}
+
 }  // namespace ltc
 
 static int sm_count_tc() { static int n = 0; if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; } return n; }
@@ -198,4 +323,18 @@ int launch_proj_rows_tc(const float* X, int x_cols, int x_has_tower, const float
     return 0;
 }
 
+}  // namespace irrl
+
+namespace irrl {
+int gram2_rows_tc_ctas(int T, int N, int K) { const int tiles = T * ((N + ltc::GR - 1) / ltc::GR); return std::max(1, std::min(tiles, sm_count_tc() / std::max(K, 1))); }
+// partial[gram2_rows_tc_ctas][K][128][192]: rows 0..x_cols-1 = sum x^T dz, rows 48..95 = sum hm^T dz (rows 96..127 are not written)
+int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial, int T, int K, int N, cudaStream_t st) {
+    using namespace ltc;
+    if (x_cols <= 0 || x_cols > 48) return -1;
+    GramTcArgs a{}; a.X = X; a.x_cols = x_cols; a.x_t_stride = x_has_tower ? (long long)K * N : N; a.x_k_stride = x_has_tower ? N : 0;
+    a.HM = HM; a.D = D; a.P = partial; a.T = T; a.K = K; a.N = N;
+    if (cudaFuncSetAttribute(gram2_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_BYTES) != cudaSuccess) return -2;
+    gram2_rows_tc_kernel<<<dim3(gram2_rows_tc_ctas(T, N, K), K), THR, G_BYTES, st>>>(a);
+    return 0;
+}
 }  // namespace irrl

@@ -35,6 +35,64 @@ def gram_rows(X, D):
     return part.sum(0)[:, :c]
 
 
+def gram2_rows(X, HM, D):
+    """dW_x = sum x^T dz and dW_h = sum hm^T dz of one layer in one pass over dz (tcgen05): ([K,c,192], [K,48,192])."""
+    L = _lib.load()
+    T, K, N, _ = D.shape
+    c = X.shape[-1]
+    st = C.c_void_p(torch.cuda.current_stream(D.device).cuda_stream)
+    part = D.new_empty((L.irrl_gram2_rows_ctas(T, K, N), K, 128, 192))
+    _lib.check(L.irrl_gram2_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(HM), _p(D), _p(part)), "gram2_rows")
+    G = part[:, :, :96].sum(0)
+    return G[:, :c], G[:, 48:96]
+
+
+class LstmLayerFused(torch.autograd.Function):
+    """One LSTM layer of both towers over the whole rollout, projection included: H = lstm(X W_x + b, W_h).  Forward = irrl_proj_rows
+    (tcgen05) + irrl_lstm_seq_fwd; backward = irrl_lstm_seq_bwd, then BOTH weight gradients from one pass over dz (irrl_gram2_rows, tcgen05)
+    and, for a layer fed by another layer, dX = dz W_x^T (irrl_proj_rows).  The projection xw is not kept for the backward pass."""
+
+    @staticmethod
+    def forward(ctx, X, wx, wh, b, c0, h0, keep):
+        L = _lib.load()
+        X = X.contiguous(); wx = wx.contiguous(); wh = wh.contiguous(); b = b.contiguous(); c0 = c0.contiguous(); h0 = h0.contiguous(); keep = keep.contiguous()
+        K, c, _ = wx.shape
+        T, N = X.shape[0], X.shape[-2]
+        st = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+        xw = X.new_empty((T, K, N, 192))
+        _lib.check(L.irrl_proj_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(wx), 0, _p(xw), 192), "proj_rows")
+        gates = torch.empty_like(xw); Cs = X.new_empty((T, K, N, 48)); Hs = X.new_empty((T, K, N, 48)); HM = X.new_empty((T, K, N, 48))
+        _lib.check(L.irrl_lstm_seq_fwd(st, T, K, N, _p(xw), _p(wh), _p(c0), _p(h0), _p(keep), _p(gates), _p(Cs), _p(Hs), _p(b), _p(HM)), "lstm_seq_fwd")
+        ctx.save_for_backward(X, wx, wh, keep, gates, Cs, HM, c0)
+        return Hs
+
+    @staticmethod
+    def backward(ctx, dH):
+        L = _lib.load()
+        X, wx, wh, keep, gates, Cs, HM, c0 = ctx.saved_tensors
+        T, K, N, _ = gates.shape
+        c = X.shape[-1]
+        st = C.c_void_p(torch.cuda.current_stream(gates.device).cuda_stream)
+        dH = dH.contiguous()
+        DZ = torch.empty_like(gates)
+        db_part = gates.new_empty((L.irrl_lstm_seq_ctas(N), K, 192))
+        _lib.check(L.irrl_lstm_seq_bwd(st, T, K, N, _p(dH), _p(wh), _p(c0), _p(keep), _p(gates), _p(Cs), _p(DZ), _p(db_part)), "lstm_seq_bwd")
+        dwx, dwh = gram2_rows(X, HM, DZ)
+        dX = None
+        if ctx.needs_input_grad[0]:
+            if X.dim() == 4 and c == 48:
+                dX = torch.empty_like(X)
+                _lib.check(L.irrl_proj_rows(st, T, K, N, _p(DZ), 192, 1, _p(wx), 1, _p(dX), c), "proj_rows^T")
+            else:
+                dX = torch.matmul(DZ, wx.transpose(1, 2)); dX = dX.sum(1) if X.dim() == 3 else dX
+        return dX, dwx, dwh, db_part.sum(0), None, None, None
+
+
+def fused_layer_ok(X, wx) -> bool:
+    K, c, n_out = wx.shape
+    return X.is_cuda and _own_gemm() and os.environ.get("IRRL_LEARNER_FUSED", "1") != "0" and n_out == 192 and (c == 48 or (32 < c <= 40 and X.dim() == 3))
+
+
 class ProjRows(torch.autograd.Function):
     """Y[T,K,N,192] = X . W_k for all T steps; X [T,N,c] (the observation, shared by both towers) or [T,K,N,48]; W [K,c,192]."""
 

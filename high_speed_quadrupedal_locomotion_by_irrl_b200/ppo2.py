@@ -77,7 +77,7 @@ class LstmActorCritic(torch.nn.Module):
     def forward_time_major(self, obs, keep, state, fused: Optional[bool] = None):
         """obs [T,N,35] (time-major, as the device rollout stores it), keep [T,N] = 1 - mask, state [N,384] at t = 0.
         Returns mean [T,N,12], value [T,N].  On CUDA the recurrence runs through the fused BPTT path (lstm_seq.LstmLayerSeq)."""
-        from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, lstm_layer_reference, _with_bias, proj_rows
+        from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, LstmLayerFused, fused_layer_ok, lstm_layer_reference, _with_bias, proj_rows
         T, N, _ = obs.shape
         H = 48
         fused = obs.is_cuda if fused is None else fused
@@ -88,10 +88,14 @@ class LstmActorCritic(torch.nn.Module):
         wx0 = torch.stack([self.lstm_pi0_wx, self.lstm_v0_wx]); wh0 = torch.stack([self.lstm_pi0_wh, self.lstm_v0_wh]); b0 = torch.stack([self.lstm_pi0_b, self.lstm_v0_b])
         wx1 = torch.stack([self.lstm_pi1_wx, self.lstm_v1_wx]); wh1 = torch.stack([self.lstm_pi1_wh, self.lstm_v1_wh]); b1 = torch.stack([self.lstm_pi1_b, self.lstm_v1_b])
         own = fused is True                                                          # the persistent path: projections on the streaming tensor-core kernels too
-        xw0 = proj_rows(obs, wx0) if own else torch.matmul(obs.unsqueeze(1), wx0)    # [T,2,N,192]: all input projections in one pass (bias added by the layer)
-        H0, _, _ = layer(xw0, wh0, b0, c0, h0, keep)
-        xw1 = proj_rows(H0, wx1) if own else torch.matmul(H0, wx1)
-        H1, _, _ = layer(xw1, wh1, b1, c1, h1, keep)
+        if own and fused_layer_ok(obs, wx0) and wx1.shape[1] == 48:                  # whole layers as one autograd node each (lstm_seq.LstmLayerFused)
+            H0 = LstmLayerFused.apply(obs, wx0, wh0, b0, c0, h0, keep)
+            H1 = LstmLayerFused.apply(H0, wx1, wh1, b1, c1, h1, keep)
+        else:
+            xw0 = proj_rows(obs, wx0) if own else torch.matmul(obs.unsqueeze(1), wx0)    # [T,2,N,192]: all input projections in one pass (bias added by the layer)
+            H0, _, _ = layer(xw0, wh0, b0, c0, h0, keep)
+            xw1 = proj_rows(H0, wx1) if own else torch.matmul(H0, wx1)
+            H1, _, _ = layer(xw1, wh1, b1, c1, h1, keep)
         if own:   # both heads as ONE batched product on the [T,2,N,48] tensor (vf_w zero-padded to 12 columns): no strided tower slices, no
             #       zero-filled select_backward copies of 2.4 GB each in the backward pass
             head_w = torch.stack([self.pi_w, F.pad(self.vf_w, (0, self.pi_w.shape[1] - self.vf_w.shape[1]))])

@@ -206,6 +206,11 @@ int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, i
 /* forward projections (n_out 192, no transpose): 0 = tcgen05 kernel (TMEM accumulators, default), 1 = warp-level MMA kernel; returns the previous value */
 int irrl_proj_rows_set_path(int path);
 int irrl_gram_rows_ctas(int T, int K, int n_env);
+/* both weight gradients of one LSTM layer in one pass over dz, on tcgen05 (accumulator in tensor memory over all rows of a CTA):
+ * partial[irrl_gram2_rows_ctas(T,K,N), K, 128, 192], rows 0..x_cols-1 = per-CTA sums of X^T D (dW_x), rows 48..95 = sums of HM^T D (dW_h);
+ * rows 96..127 are padding and NOT written.  X as in irrl_gram_rows (x_cols <= 48), HM [T,K,N,48], D [T,K,N,192]. */
+int irrl_gram2_rows_ctas(int T, int K, int n_env);
+int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial);
 int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial);
 /* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,
  * z / gates [rows,192] in gate order i,f,o,g, the rest [rows,48]; keep = 1 - done mask per env (run_bp_v5.py:151-153 lstm(..., masks, ...)) */

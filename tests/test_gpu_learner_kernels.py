@@ -125,3 +125,43 @@ def test_learner_gradients_do_not_depend_on_the_kernel_family():
         if gb is None:
             assert ga is None; continue
         assert float((ga - gb).abs().max()) <= 2e-4 * (float(gb.abs().max()) + 1e-12), n
+
+
+@pytest.mark.parametrize("T,K,N,cx", [(7, 2, 37, 35), (5, 2, 77, 48), (3, 2, 64, 48), (4, 1, 200, 35), (2, 2, 1, 48), (9, 2, 33, 35)])
+def test_tcgen05_weight_gradients_match_float64(T, K, N, cx):
+    """irrl_gram2_rows: dW_x and dW_h of a layer from one pass over dz, accumulators in tensor memory over all tiles of a CTA; ragged
+    32-row tiles, the shared 35-column observation and a per-tower 48-column input"""
+    torch, _lib, L, dev = _setup()
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import gram2_rows
+    g = torch.Generator(device=dev); g.manual_seed(N + cx)
+    r = lambda *s: torch.randn(*s, device=dev, generator=g)
+    X = r(T, N, cx) if cx == 35 else r(T, K, N, cx)
+    HM, D = r(T, K, N, 48), r(T, K, N, 192)
+    dwx, dwh = gram2_rows(X, HM, D)
+    Xk = (X.double().unsqueeze(1).expand(T, K, N, -1) if X.dim() == 3 else X.double())
+    rx = torch.matmul(Xk.transpose(-1, -2), D.double()).sum(0); rh = torch.matmul(HM.double().transpose(-1, -2), D.double()).sum(0)
+    assert dwx.shape == rx.shape and dwh.shape == rh.shape
+    assert float((dwx.double() - rx).abs().max()) <= 3e-6 * float(rx.abs().max())
+    assert float((dwh.double() - rh).abs().max()) <= 3e-6 * float(rh.abs().max())
+
+
+def test_forward_projection_kernels_agree():
+    """the tcgen05 projection kernel (default) and the warp-level MMA kernel compute the same 3xTF32 products"""
+    torch, _lib, L, dev = _setup()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    T, K, N = 6, 2, 300
+    for X, W, c, tw in ((torch.randn(T, N, 35, device=dev, generator=g), torch.randn(K, 35, 192, device=dev, generator=g), 35, 0),
+                        (torch.randn(T, K, N, 48, device=dev, generator=g), torch.randn(K, 48, 192, device=dev, generator=g), 48, 1)):
+        out = []
+        for path in (0, 1):
+            prev = L.irrl_proj_rows_set_path(path)
+            try:
+                Y = torch.full((T, K, N, 192), float("nan"), device=dev)
+                _lib.check(L.irrl_proj_rows(None, T, K, N, p(X), c, tw, p(W), 0, p(Y), 192)); torch.cuda.synchronize()
+            finally:
+                L.irrl_proj_rows_set_path(prev)
+            out.append(Y)
+        ref = torch.matmul(X.double().unsqueeze(1) if tw == 0 else X.double(), W.double())
+        for Y in out:
+            assert float((Y.double() - ref).abs().max()) <= 3e-6 * float(ref.abs().max())

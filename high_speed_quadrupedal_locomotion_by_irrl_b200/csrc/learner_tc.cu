@@ -4,7 +4,7 @@
 // UMMA canonical K-major no-swizzle tiles [k-step][hi|lo][16-byte k-chunk (2)][row][4 floats], tcgen05.mma.kind::tf32 M128 N192 K8
 // (98 cycles each, 4x the rate of the warp-level MMAs of learner_gemm.cu), fp32 accumulators in tensor memory.
 //
-// One persistent CTA per SM (256 threads) walks 128-row tiles of one tower:
+// One persistent CTA per SM (512 threads) walks 128-row tiles of one tower:
 //   * raw rows arrive through a double-buffered cp.async stage (coalesced 16-byte chunks; 4-byte chunks for the 35-column observation
 //     whose rows are not 16-byte aligned),
 //   * every thread converts (row, 4 k) items into the hi / lo operand tile (row-per-lane writes: conflict-free),
@@ -22,7 +22,7 @@ namespace irrl {
 namespace ltc {
 using namespace tc;
 
-constexpr int THR = 256;
+constexpr int THR = 512;                                        // 16 warps: the per-tile transform / staging work is issue- and latency-bound, not MMA-bound
 constexpr int TM = 128, NG = 192;
 constexpr int A_HALF = 2 * TM * 16, A_KSTEP = 2 * A_HALF;       // 4096 / 8192 bytes
 constexpr int B_HALF = 2 * NG * 16, B_KSTEP = 2 * B_HALF;       // 6144 / 12288 bytes
@@ -51,6 +51,13 @@ template <int KS> struct Lay {                                         // KS k-s
     static constexpr int BYTES = OFF_BAR + 2 * 8 + 16;
 };
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+
+// Everything a thread does per tile is the same list of (source, destination) pairs: the index arithmetic (divisions by the row length,
+// operand-tile offsets) is done once before the tile loop and kept in registers.
 template <int KS>
 __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_constant__ ProjTcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -83,15 +90,36 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
 
     const int tiles_per_t = (A.N + TM - 1) / TM, tiles = A.T * tiles_per_t;
     const bool vec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
+    // ---- per-thread work lists
+    constexpr int NCP = (TM * KS * 8 + THR - 1) / THR;                  // copy chunks (upper bound: 4-byte chunks of a KS*8-column row)
+    uint32_t cp_src[NCP], cp_dst[NCP]; int cp_row[NCP];
+    {
+        const int per_row = vec ? (A.x_cols >> 2) : A.x_cols, w = vec ? 4 : 1;
+#pragma unroll
+        for (int j = 0; j < NCP; ++j) {
+            const int i = t_ + j * THR, r = i / per_row, c = i - r * per_row;
+            cp_row[j] = r < TM ? r : (1 << 20); cp_src[j] = r * A.x_cols + w * c; cp_dst[j] = r * RP + w * c;
+        }
+    }
+    constexpr int NIT = (TM * KS * 2 + THR - 1) / THR;                  // transform items (row, 4 k)
+    uint32_t it_src[NIT], it_dst[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) { const int i = t_ + j * THR, r = i & (TM - 1), q = i >> 7; it_src[j] = r * RP + 4 * q; it_dst[j] = (q < KS * 2) ? op_off(4 * q, r, TM) : 0xFFFFFFFFu; }
+    constexpr int NCO = TM * 24 / THR;                                   // copy-out float4s per 96-column round
+    uint32_t co_src[NCO], co_dst[NCO]; int co_row[NCO];
+#pragma unroll
+    for (int j = 0; j < NCO; ++j) { const int i = t_ + j * THR, r = i / 24, c4 = i - r * 24; co_row[j] = r; co_src[j] = r * STAGE_PITCH + 4 * c4; co_dst[j] = r * NG + 4 * c4; }
+
     auto issue = [&](int tile, int buf) {
-        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM;
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = A.N - n0;
         const float* src = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * A.x_cols;
         float* dst = raw + buf * TM * RP;
         if (vec) {
-            const int cpr = A.x_cols >> 2;
-            for (int i = t_; i < TM * cpr; i += THR) { const int r = i / cpr, c = i - r * cpr; if (n0 + r < A.N) cp16(dst + r * RP + 4 * c, src + (size_t)r * A.x_cols + 4 * c); }
+#pragma unroll
+            for (int j = 0; j < NCP; ++j) if (cp_row[j] < rows) cp16(dst + cp_dst[j], src + cp_src[j]);
         } else {
-            for (int i = t_; i < TM * A.x_cols; i += THR) { const int r = i / A.x_cols, c = i - r * A.x_cols; if (n0 + r < A.N) cp4(dst + r * RP + c, src + (size_t)r * A.x_cols + c); }
+#pragma unroll
+            for (int j = 0; j < NCP; ++j) if (cp_row[j] < rows) cp4(dst + cp_dst[j], src + cp_src[j]);
         }
         cp_commit();
     };
@@ -99,23 +127,23 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
     auto drain = [&](int tile, int buf) {
         const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = min(TM, A.N - n0);
         float* yb = A.Y + (((size_t)t * A.K + k) * A.N + n0) * NG;
-        const int wq = warp & 3, sub = warp >> 2, row = 32 * wq + lane;
+        const int wq = warp & 3, sub = warp >> 2, row = 32 * wq + lane;            // 16 warps: TMEM lane quarter x 24-column block
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+            uint32_t v[3][8];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tmem_ld8(tmem + ((uint32_t)(32 * wq) << 16) + buf * NG + 96 * h + 24 * sub + 8 * i, v[i]);
+            tmem_ld_wait();
+            float4* d = reinterpret_cast<float4*>(stage + row * STAGE_PITCH + 24 * sub);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                uint32_t v[16];
-                tmem_ld16(tmem + ((uint32_t)(32 * wq) << 16) + buf * NG + 96 * h + 48 * sub + 16 * i, v);
-                tmem_ld_wait();
-                float4* d = reinterpret_cast<float4*>(stage + row * STAGE_PITCH + 48 * sub + 16 * i);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                d[2 * i] = make_float4(__uint_as_float(v[i][0]), __uint_as_float(v[i][1]), __uint_as_float(v[i][2]), __uint_as_float(v[i][3]));
+                d[2 * i + 1] = make_float4(__uint_as_float(v[i][4]), __uint_as_float(v[i][5]), __uint_as_float(v[i][6]), __uint_as_float(v[i][7]));
             }
             __syncthreads();
-            for (int i = t_; i < TM * 24; i += THR) {
-                const int r = i / 24, c4 = i - r * 24;
-                if (r < rows) *reinterpret_cast<float4*>(yb + (size_t)r * NG + 96 * h + 4 * c4) = *reinterpret_cast<const float4*>(stage + r * STAGE_PITCH + 4 * c4);
-            }
+#pragma unroll
+            for (int j = 0; j < NCO; ++j)
+                if (co_row[j] < rows) *reinterpret_cast<float4*>(yb + co_dst[j] + 96 * h) = *reinterpret_cast<const float4*>(stage + co_src[j]);
             __syncthreads();
         }
     };
@@ -129,11 +157,13 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
         __syncthreads();
         if (it >= 1) { mbar_wait(&mma_done[b ^ 1], ((it - 1) >> 1) & 1); tc_fence_after(); }     // previous tile multiplied: the operand tile is free, its accumulator full
         const float* rw = raw + b * TM * RP;
-        for (int i = t_; i < TM * KS * 2; i += THR) {                   // item = (row, 4 k): row-per-lane reads and writes
-            const int r = i & (TM - 1), q = i >> 7;
-            const float4 x = *reinterpret_cast<const float4*>(rw + r * RP + 4 * q);
-            const float v[4] = {x.x, x.y, x.z, x.w};
-            store_hilo(sA, op_off(4 * q, r, TM), A_HALF, v);
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {                                 // item = (row, 4 k): row-per-lane reads and writes
+            if (it_dst[j] != 0xFFFFFFFFu) {
+                const float4 x = *reinterpret_cast<const float4*>(rw + it_src[j]);
+                const float v[4] = {x.x, x.y, x.z, x.w};
+                store_hilo(sA, it_dst[j], A_HALF, v);
+            }
         }
         fence_proxy_async();
         tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -208,27 +238,50 @@ __global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_cons
 
     const int tiles_per_t = (A.N + GR - 1) / GR, tiles = A.T * tiles_per_t;
     const bool xvec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
-    auto rows_in = [&](float* dst, int pitch, const float* src, int cols, int n0, bool vec) {
-        if (vec) {
-            const int cpr = cols >> 2;
-            for (int i = t_; i < GR * cpr; i += THR) {
-                const int r = i / cpr, c = i - r * cpr;
-                if (n0 + r < A.N) cp16(dst + r * pitch + 4 * c, src + (size_t)r * cols + 4 * c);
-                else *reinterpret_cast<float4*>(dst + r * pitch + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        } else {
-            for (int i = t_; i < GR * cols; i += THR) {
-                const int r = i / cols, c = i - r * cols;
-                if (n0 + r < A.N) cp4(dst + r * pitch + c, src + (size_t)r * cols + c); else dst[r * pitch + c] = 0.f;
+    // ---- per-thread work lists (the same for every tile): copy chunks of dz (3), hm (<= 1), x (<= 3); transform items of A (<= 2) and B (3)
+    uint32_t d_off[3]; int d_row[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / 48, c = i - r * 48; d_row[j] = r; d_off[j] = r * NG + 4 * c; }
+    const int h_row = t_ < GR * 12 ? t_ / 12 : (1 << 20); const uint32_t h_off = (t_ / 12) * 48 + 4 * (t_ % 12);
+    uint32_t x_off[3]; int x_row[3];
+    {
+        const int per_row = xvec ? (A.x_cols >> 2) : A.x_cols, w = xvec ? 4 : 1;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / per_row, c = i - r * per_row; x_row[j] = r < GR ? r : (1 << 20); x_off[j] = r * 48 + w * c; }
+    }
+    const int x_cols = A.x_cols;
+    uint32_t a_src[2], a_dst[2], b_src[3], b_dst[3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = t_ + j * THR, m = i % 96, c = i / 96;
+        a_src[j] = (m < 48 ? m : GR * 48 + (m - 48)) + 4 * c * 48; a_dst[j] = i < 96 * 8 ? op_off(4 * c, m, TM) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, n = i % NG, c = i / NG; b_src[j] = GR * 96 + 4 * c * NG + n; b_dst[j] = op_off(4 * c, n, NG); }
+
+    auto issue = [&](int tile, int buf) {
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * GR, rows = A.N - n0;
+        float* rx = reinterpret_cast<float*>(smem + G_OFF_RAW + buf * G_RAW_STAGE);
+        const float* xs = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * x_cols;
+        const float* hs = A.HM + (((size_t)t * A.K + k) * A.N + n0) * 48;
+        const float* ds = A.D + (((size_t)t * A.K + k) * A.N + n0) * NG;
+        // rows past N are zero-filled: they must not contribute to the sums
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (d_row[j] < rows) cp16(rx + GR * 96 + d_off[j], ds + d_off[j]);
+            else *reinterpret_cast<float4*>(rx + GR * 96 + d_off[j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (h_row < GR) {
+            if (h_row < rows) cp16(rx + GR * 48 + h_off, hs + h_off); else *reinterpret_cast<float4*>(rx + GR * 48 + h_off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (x_row[j] < GR) {
+                const uint32_t so = xvec ? x_off[j] : (uint32_t)(x_row[j] * x_cols) + (x_off[j] - x_row[j] * 48);      // source rows are x_cols long, staged rows 48
+                if (xvec) { if (x_row[j] < rows) cp16(rx + x_off[j], xs + so); else *reinterpret_cast<float4*>(rx + x_off[j]) = make_float4(0.f, 0.f, 0.f, 0.f); }
+                else { if (x_row[j] < rows) cp4(rx + x_off[j], xs + so); else rx[x_off[j]] = 0.f; }
             }
         }
-    };
-    auto issue = [&](int tile, int buf) {
-        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * GR;
-        float* rx = reinterpret_cast<float*>(smem + G_OFF_RAW + buf * G_RAW_STAGE);
-        rows_in(rx, 48, A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * A.x_cols, A.x_cols, n0, xvec);
-        rows_in(rx + GR * 48, 48, A.HM + (((size_t)t * A.K + k) * A.N + n0) * 48, 48, n0, true);
-        rows_in(rx + GR * 96, NG, A.D + (((size_t)t * A.K + k) * A.N + n0) * NG, NG, n0, true);
         cp_commit();
     };
     int tile = blockIdx.x, it = 0;
@@ -240,17 +293,19 @@ __global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_cons
         __syncthreads();
         if (it >= 1) { mbar_wait(mma_done, (it - 1) & 1); tc_fence_after(); }          // the MMAs of the previous tile have read the operand tiles
         const float* rx = reinterpret_cast<const float*>(smem + G_OFF_RAW + b * G_RAW_STAGE);
-        const float* rd = rx + GR * 96;
-        for (int i = t_; i < 96 * 8; i += THR) {                        // A: (feature m, rows 4c .. 4c+3); features 0..47 = x, 48..95 = hm
-            const int m = i % 96, c = i / 96;
-            const float* col = rx + (m < 48 ? m : GR * 48 + (m - 48));
-            const float v[4] = {col[(4 * c) * 48], col[(4 * c + 1) * 48], col[(4 * c + 2) * 48], col[(4 * c + 3) * 48]};
-            store_hilo(sA, op_off(4 * c, m, TM), A_HALF, v);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                                   // A: (feature m, rows 4c .. 4c+3); features 0..47 = x, 48..95 = hm
+            if (a_dst[j] != 0xFFFFFFFFu) {
+                const float* col = rx + a_src[j];
+                const float v[4] = {col[0], col[48], col[96], col[144]};
+                store_hilo(sA, a_dst[j], A_HALF, v);
+            }
         }
-        for (int i = t_; i < NG * 8; i += THR) {                        // B: (gate column n, rows 4c .. 4c+3)
-            const int n = i % NG, c = i / NG;
-            const float v[4] = {rd[(4 * c) * NG + n], rd[(4 * c + 1) * NG + n], rd[(4 * c + 2) * NG + n], rd[(4 * c + 3) * NG + n]};
-            store_hilo(sB, op_off(4 * c, n, NG), B_HALF, v);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                                   // B: (gate column n, rows 4c .. 4c+3)
+            const float* col = rx + b_src[j];
+            const float v[4] = {col[0], col[NG], col[2 * NG], col[3 * NG]};
+            store_hilo(sB, b_dst[j], B_HALF, v);
         }
         fence_proxy_async();
         tc_fence_before(); __syncthreads(); tc_fence_after();

@@ -1122,6 +1122,7 @@ int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, i
     NvtxRange nvtx_("irrl_proj_rows");
     if (!X || !W || !Y || T <= 0 || K <= 0 || n_env <= 0) return fail(-1, "irrl_proj_rows: bad argument");
     int rc = -1;
+    if (w_trans && n_out == 48 && x_cols == 192 && x_has_tower) rc = launch_projT_rows_tc(X, W, Y, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (!w_trans && n_out == 192) rc = launch_proj_rows_tc(X, x_cols, x_has_tower, W, Y, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));      // tcgen05 where the shape fits a TMEM tile
     if (rc == -1) rc = launch_proj_rows(X, x_cols, x_has_tower, W, w_trans, Y, n_out, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (rc == -1) return fail(-1, "irrl_proj_rows: unsupported shape (x_cols <= 40 or 48 with n_out 192; x_cols 192 with n_out 48)");

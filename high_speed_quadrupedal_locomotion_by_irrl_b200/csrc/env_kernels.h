@@ -91,6 +91,7 @@ int gram_rows_ctas(int T, int N, int K);
 // tcgen05 forward projections (learner_tc.cu): returns -1 when the shape / path selection asks for the warp-level kernel instead
 int launch_proj_rows_tc(const float* X, int x_cols, int x_has_tower, const float* W, float* Y, int T, int K, int N, cudaStream_t st);
 int proj_rows_set_path(int path);
+int launch_projT_rows_tc(const float* D, const float* W, float* Y, int T, int K, int N, cudaStream_t st);
 int gram2_rows_tc_ctas(int T, int N, int K);
 int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial, int T, int K, int N, cudaStream_t st);
 // proj_rows_set_path: 0 tcgen05 (default), 1 warp-level MMAs; returns the previous value

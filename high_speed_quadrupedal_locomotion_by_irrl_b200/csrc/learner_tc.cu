@@ -202,6 +202,139 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------- projT_rows (tcgen05)
+// Input gradient of a projection:  dX[t,k,n,0:48] = dz[t,k,n,0:192] . W_k^T  (W_k [48][192], so its rows are already K-major B rows).
+// K = 192 does not fit one operand tile next to the rest, so a 128-row tile is multiplied as 4 column chunks of 48 (6 k-steps each)
+// accumulating into the same 48 TMEM columns: the pipeline of proj_rows_tc_kernel runs over (tile, chunk) pairs, the accumulator is
+// drained after every 4th pair.
+constexpr int NT48 = 48;
+constexpr int BT_HALF = 2 * NT48 * 16, BT_KSTEP = 2 * BT_HALF;         // 1536 / 3072 bytes
+struct LayT {
+    static constexpr int RAW_PITCH = 52;
+    static constexpr int OFF_B = 0;                                    // 24 k-steps of W^T: 73,728 B
+    static constexpr int OFF_A = OFF_B + 24 * BT_KSTEP;
+    static constexpr int OFF_RAW = OFF_A + 6 * A_KSTEP;
+    static constexpr int OFF_STAGE = OFF_RAW + 2 * TM * RAW_PITCH * 4;
+    static constexpr int OFF_BAR = OFF_STAGE + TM * RAW_PITCH * 4;     // staging tile [128][52]
+    static constexpr int BYTES = OFF_BAR + 2 * 8 + 16;
+};
+struct ProjTTcArgs { const float* D; const float* W; long long w_k_stride; float* Y; int T, K, N; };
+
+__global__ void __launch_bounds__(THR, 1) projT_rows_tc_kernel(const __grid_constant__ ProjTTcArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    using L = LayT;
+    constexpr int RP = L::RAW_PITCH;
+    const int t_ = threadIdx.x, warp = t_ >> 5, lane = t_ & 31, k = blockIdx.y;
+    unsigned char* sB = smem + L::OFF_B;
+    unsigned char* sA = smem + L::OFF_A;
+    float* raw = reinterpret_cast<float*>(smem + L::OFF_RAW);
+    float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGE);
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_done + 2);
+    if (t_ == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(tmem_ptr, 128); tmem_relinquish(); }
+    const float* Wk = A.W + (size_t)k * A.w_k_stride;                  // [48][192]
+    for (int i = t_; i < NT48 * NG; i += THR) {                        // element (n, kk): chunk kk / 48, local k = kk % 48
+        const int kk = i % NG, n = i / NG;
+        const float v = Wk[(size_t)n * NG + kk];
+        const float hi = tf32_hi(v);
+        unsigned char* dst = sB + (kk / 48) * 6 * BT_KSTEP + op_off(kk % 48, n, NT48);
+        *reinterpret_cast<float*>(dst) = hi; *reinterpret_cast<float*>(dst + BT_HALF) = v - hi;
+    }
+    fence_proxy_async();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    const int tiles_per_t = (A.N + TM - 1) / TM, tiles = A.T * tiles_per_t;
+    // virtual tile v = 4 * (index of this CTA's tile) + chunk
+    uint32_t cp_src[3], cp_dst[3]; int cp_row[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / 12, c = i - r * 12; cp_row[j] = r; cp_src[j] = r * NG + 4 * c; cp_dst[j] = r * RP + 4 * c; }
+    uint32_t it_src[3], it_dst[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i & (TM - 1), q = i >> 7; it_src[j] = r * RP + 4 * q; it_dst[j] = op_off(4 * q, r, TM); }
+    uint32_t co_src[3], co_dst[3]; int co_row[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / 12, c4 = i - r * 12; co_row[j] = r; co_src[j] = r * RP + 4 * c4; co_dst[j] = r * NT48 + 4 * c4; }
+    const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, vt_total = 4 * my_tiles;
+    auto issue = [&](int vt, int buf) {
+        const int tile = blockIdx.x + (vt >> 2) * gridDim.x, ch = vt & 3;
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = A.N - n0;
+        const float* src = A.D + (((size_t)t * A.K + k) * A.N + n0) * NG + 48 * ch;
+        float* dst = raw + buf * TM * RP;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (cp_row[j] < rows) cp16(dst + cp_dst[j], src + cp_src[j]);
+        cp_commit();
+    };
+    auto drain = [&](int tile, int buf) {
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = min(TM, A.N - n0);
+        float* yb = A.Y + (((size_t)t * A.K + k) * A.N + n0) * NT48;
+        const int wq = warp & 3, sub = warp >> 2, row = 32 * wq + lane;
+        if (sub < 2) {                                                  // 8 warps cover 128 lanes x 48 columns
+            uint32_t v[3][8];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tmem_ld8(tmem + ((uint32_t)(32 * wq) << 16) + buf * NT48 + 24 * sub + 8 * i, v[i]);
+            tmem_ld_wait();
+            float4* d = reinterpret_cast<float4*>(stage + row * RP + 24 * sub);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                d[2 * i] = make_float4(__uint_as_float(v[i][0]), __uint_as_float(v[i][1]), __uint_as_float(v[i][2]), __uint_as_float(v[i][3]));
+                d[2 * i + 1] = make_float4(__uint_as_float(v[i][4]), __uint_as_float(v[i][5]), __uint_as_float(v[i][6]), __uint_as_float(v[i][7]));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (co_row[j] < rows) *reinterpret_cast<float4*>(yb + co_dst[j]) = *reinterpret_cast<const float4*>(stage + co_src[j]);
+        __syncthreads();
+    };
+    if (vt_total > 0) issue(0, 0); else cp_commit();
+    if (vt_total > 1) issue(1, 1); else cp_commit();
+    for (int vt = 0; vt < vt_total; ++vt) {
+        const int b = vt & 1, ch = vt & 3, tb = (vt >> 2) & 1;          // raw buffer, column chunk, TMEM buffer of this tile
+        cp_wait<1>();
+        __syncthreads();
+        if (vt >= 1) { mbar_wait(&mma_done[0], (vt - 1) & 1); tc_fence_after(); }      // one commit per virtual tile on mma_done[0]: operand tile free
+        const float* rw = raw + b * TM * RP;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(rw + it_src[j]);
+            const float v[4] = {x.x, x.y, x.z, x.w};
+            store_hilo(sA, it_dst[j], A_HALF, v);
+        }
+        fence_proxy_async();
+        tc_fence_before(); __syncthreads(); tc_fence_after();
+        if (vt + 2 < vt_total) issue(vt + 2, b); else cp_commit();
+        if (warp == 0) {
+            if (elect_one()) {
+                const uint32_t idesc = make_idesc(TM, NT48), d = tmem + tb * NT48;
+#pragma unroll 1
+                for (int ks = 0; ks < 6; ++ks) {
+                    const uint32_t ab = smem_u32(sA) + ks * A_KSTEP, bb = smem_u32(sB) + (ch * 6 + ks) * BT_KSTEP;
+                    const uint64_t ah = make_desc(ab, TM * 16, 128), al = make_desc(ab + A_HALF, TM * 16, 128);
+                    const uint64_t bh = make_desc(bb, NT48 * 16, 128), bl = make_desc(bb + BT_HALF, NT48 * 16, 128);
+                    mma_tf32(d, al, bh, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32(d, ah, bl, idesc, 1);
+                    mma_tf32(d, ah, bh, idesc, 1);
+                }
+                umma_commit(&mma_done[0]);
+            }
+            __syncwarp();
+        }
+        // the accumulator of the previous tile is complete once that tile's 4th chunk has been multiplied, i.e. at the wait above of vt = 4i:
+        // drain it behind the MMAs just issued
+        if (ch == 0 && vt >= 4) drain(blockIdx.x + ((vt >> 2) - 1) * gridDim.x, tb ^ 1);
+    }
+    if (vt_total > 0) {
+        mbar_wait(&mma_done[0], (vt_total - 1) & 1); tc_fence_after();
+        drain(blockIdx.x + (my_tiles - 1) * gridDim.x, (my_tiles - 1) & 1);
+    }
+    cp_wait<0>();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 128); }
+}
+
 // ---------------------------------------------------------------------------------------------------------------- gram2_rows (tcgen05)
 // Both weight gradients of one LSTM layer in ONE pass over dz:  G[0:48] = sum_rows x^T dz (dW_x),  G[48:96] = sum_rows hm^T dz (dW_h),
 // rows = (t, n) of tower k (~6 M).  MMA view: D[128 x 192] += A[128 x 8] . B[8 x 192] with M = feature (96 used), N = gate column, K = ROWS,
@@ -381,6 +514,17 @@ int launch_proj_rows_tc(const float* X, int x_cols, int x_has_tower, const float
 }  // namespace irrl
 
 namespace irrl {
+// dX[T,K,N,48] = D[T,K,N,192] . W_k^T (W [K,48,192]) on tcgen05; -1 when the warp-level path is selected
+int launch_projT_rows_tc(const float* D, const float* W, float* Y, int T, int K, int N, cudaStream_t st) {
+    using namespace ltc;
+    if (g_proj_path == 1 || (reinterpret_cast<uintptr_t>(D) & 15)) return -1;
+    ProjTTcArgs a{}; a.D = D; a.W = W; a.w_k_stride = 48 * 192; a.Y = Y; a.T = T; a.K = K; a.N = N;
+    const int tiles = T * ((N + TM - 1) / TM);
+    if (tiles <= 0) return 0;
+    if (cudaFuncSetAttribute(projT_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LayT::BYTES) != cudaSuccess) return -2;
+    projT_rows_tc_kernel<<<dim3(std::min(tiles, std::max(1, sm_count_tc() / K)), K), THR, LayT::BYTES, st>>>(a);
+    return 0;
+}
 int gram2_rows_tc_ctas(int T, int N, int K) { const int tiles = T * ((N + ltc::GR - 1) / ltc::GR); return std::max(1, std::min(tiles, sm_count_tc() / std::max(K, 1))); }
 // partial[gram2_rows_tc_ctas][K][128][192]: rows 0..x_cols-1 = sum x^T dz, rows 48..95 = sum hm^T dz (rows 96..127 are not written)
 int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial, int T, int K, int N, cudaStream_t st) {

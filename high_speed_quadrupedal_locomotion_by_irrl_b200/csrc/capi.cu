@@ -1024,7 +1024,7 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
     if (host && !E->d_fused_act) { void* q = nullptr; CUDA_OK(cudaMalloc(&q, N * 26 * sizeof(float))); E->allocs.push_back(q); E->d_fused_act = (float*)q; }
     // measured (scripts/r2_e2e.py): the kernels are latency-bound below ~8k environments (a half-size launch takes as long as a full
     // one) and every extra stream hop costs ~5 us, so the batch is cut only from 12k environments on (2 chunks)
-    int K = chunks > 0 ? chunks : (N >= 12288 ? 2 : 1);
+    int K = chunks > 0 ? chunks : (N >= 24576 ? 4 : (N >= 12288 ? 2 : 1));        // measured (scripts/r2_e2e.py): 16384 envs 262 / 280 us with 2 / 4 chunks, 32768 envs 461 / 397 us
     if (!host || E->P.flag_crucial) K = 1;
     K = std::min(K, 8);
     size_t per = ((N + K - 1) / K + 127) / 128 * 128;      // chunk boundaries on multiples of 128 environments (the tile of the tensor-core act kernel)

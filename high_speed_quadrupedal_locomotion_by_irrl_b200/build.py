@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libirrl_b200.so")
-SOURCES = ["env_kernels.cu", "policy_kernels.cu", "policy_tc_kernels.cu", "lstm_seq_mma.cu", "learner_gemm.cu", "learner_tc.cu", "capi.cu"]
+SOURCES = ["env_kernels.cu", "policy_kernels.cu", "policy_tc_kernels.cu", "lstm_seq_mma.cu", "learner_gemm.cu", "learner_tc.cu", "ppo_head_loss.cu", "capi.cu"]
 HEADERS = ["env_device.cuh", "env_kernels.h", "irrl_params.h", "tc_common.cuh", os.path.join("..", "..", "include", "irrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]

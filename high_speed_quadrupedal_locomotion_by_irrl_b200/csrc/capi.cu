@@ -1130,6 +1130,17 @@ int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, i
     CUDA_OK(cudaGetLastError()); return 0;
 }
 int irrl_proj_rows_set_path(int path) { return proj_rows_set_path(path); }
+int irrl_ppo_head_loss_ctas(int T, int n_env) { return ppo_head_loss_ctas((long long)T * n_env); }
+int irrl_ppo_head_loss(void* cuda_stream, int T, int n_env, const float* H1, const float* pi_w, const float* pi_b, const float* vf_w, const float* vf_b, const float* logstd,
+                       const float* actions, const float* adv, const float* returns, const float* old_values, const float* old_neglogp,
+                       float cliprange, float vf_coef, float inv_count, float* dH, float* G, float* partial) {
+    NvtxRange nvtx_("irrl_ppo_head_loss");
+    if (!H1 || !pi_w || !pi_b || !vf_w || !vf_b || !logstd || !actions || !adv || !returns || !old_values || !old_neglogp || !dH || !G || !partial || T <= 0 || n_env <= 0)
+        return fail(-1, "irrl_ppo_head_loss: bad argument");
+    launch_ppo_head_loss(H1, pi_w, pi_b, vf_w, vf_b, logstd, actions, adv, returns, old_values, old_neglogp, dH, G, partial, cliprange, vf_coef, inv_count, T, n_env,
+                         reinterpret_cast<cudaStream_t>(cuda_stream));
+    CUDA_OK(cudaGetLastError()); return 0;
+}
 int irrl_gram2_rows_ctas(int T, int K, int n_env) { return gram2_rows_tc_ctas(T, n_env, K); }
 int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial) {
     NvtxRange nvtx_("irrl_gram2_rows");

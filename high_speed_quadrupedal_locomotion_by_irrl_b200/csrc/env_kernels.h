@@ -96,6 +96,13 @@ int gram2_rows_tc_ctas(int T, int N, int K);
 int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial, int T, int K, int N, cudaStream_t st);
 // proj_rows_set_path: 0 tcgen05 (default), 1 warp-level MMAs; returns the previous value
 int launch_gram_rows(const float* X, int x_cols, int x_has_tower, const float* D, float* partial, int T, int K, int N, cudaStream_t st);
+// heads + PPO loss + gradients in one pass (ppo_head_loss.cu); partial [ppo_head_loss_ctas][HL_PART] = per-CTA sums of
+// (pg, vf, 0.5 (neglogp - old)^2, clipped count, d loss / d logstd[12])
+constexpr int HL_PART = 16;
+int ppo_head_loss_ctas(long long rows);
+void launch_ppo_head_loss(const float* H1, const float* pi_w, const float* pi_b, const float* vf_w, const float* vf_b, const float* logstd, const float* actions,
+                          const float* adv, const float* ret, const float* old_v, const float* old_nlp, float* dH, float* G, float* partial,
+                          float cliprange, float vf_coef, float inv_count, int T, int N, cudaStream_t st);
 void launch_lstm_pw_fwd(int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates, float* c_out,
                         float* h_out, float* hm_next, float* cm_next, cudaStream_t st);
 void launch_lstm_pw_bwd(int rows, int n_env, const float* dh_out, const float* carry_h, const float* carry_c, const float* keep_up,

@@ -88,6 +88,40 @@ class LstmLayerFused(torch.autograd.Function):
         return dX, dwx, dwh, db_part.sum(0), None, None, None
 
 
+class HeadLossFused(torch.autograd.Function):
+    """Heads + PPO2 loss (ppo2.py:152-175) and their gradients in one kernel (irrl_ppo_head_loss): returns
+    (mean(pg) + vf_coef * 0.5 * mean(vf), [pg_loss, vf_loss, approxkl, clipfrac]); the entropy term stays outside."""
+
+    @staticmethod
+    def forward(ctx, H1, pi_w, pi_b, vf_w, vf_b, logstd, actions, advs, returns, old_values, old_neglogp, cliprange, vf_coef):
+        L = _lib.load()
+        T, K, N, _ = H1.shape
+        H1 = H1.contiguous()
+        c = lambda x: x.detach().contiguous()
+        st = C.c_void_p(torch.cuda.current_stream(H1.device).cuda_stream)
+        dH = torch.empty_like(H1); G = H1.new_empty((T, N, 16))
+        part = H1.new_empty((L.irrl_ppo_head_loss_ctas(T, N), 16))
+        inv = 1.0 / float(T * N)
+        a = [c(pi_w), c(pi_b), c(vf_w), c(vf_b), c(logstd), c(actions), c(advs), c(returns), c(old_values), c(old_neglogp)]
+        _lib.check(L.irrl_ppo_head_loss(st, T, N, _p(H1), *[_p(x) for x in a], float(cliprange), float(vf_coef), inv, _p(dH), _p(G), _p(part)), "ppo_head_loss")
+        s = part.sum(0)
+        pg, vf = s[0] * inv, 0.5 * s[1] * inv
+        stats = torch.stack([pg, vf, s[2] * inv, s[3] * inv])
+        ctx.save_for_backward(H1, G, dH, s[4:16].clone())
+        ctx.mark_non_differentiable(stats)
+        return pg + float(vf_coef) * vf, stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        H1, G, dH, dls = ctx.saved_tensors
+        gm = G[..., :12]
+        d_pi_w = torch.matmul(H1[:, 0].transpose(-1, -2), gm).sum(0)               # T batched [48 x N] x [N x 12] products on strided views
+        d_vf_w = torch.matmul(H1[:, 1].transpose(-1, -2), G[..., 12:13]).sum(0)
+        d_pi_b = gm.sum((0, 1)); d_vf_b = G[..., 12].sum().reshape(1)
+        g = g_loss
+        return (dH * g, d_pi_w * g, d_pi_b * g, d_vf_w * g, d_vf_b * g, dls.reshape(1, 12) * g, None, None, None, None, None, None, None)
+
+
 def fused_layer_ok(X, wx) -> bool:
     K, c, n_out = wx.shape
     return X.is_cuda and _own_gemm() and os.environ.get("IRRL_LEARNER_FUSED", "1") != "0" and n_out == 192 and (c == 48 or (32 < c <= 40 and X.dim() == 3))

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 from typing import Dict, List, Optional, Sequence
 
@@ -74,9 +75,10 @@ class LstmActorCritic(torch.nn.Module):
         new_state = torch.cat([cs[0], hs[0], cs[1], hs[1], cs[2], hs[2], cs[3], hs[3]], 1)
         return mean, value, new_state
 
-    def forward_time_major(self, obs, keep, state, fused: Optional[bool] = None):
+    def features_time_major(self, obs, keep, state, fused: Optional[bool] = None):
         """obs [T,N,35] (time-major, as the device rollout stores it), keep [T,N] = 1 - mask, state [N,384] at t = 0.
-        Returns mean [T,N,12], value [T,N].  On CUDA the recurrence runs through the fused BPTT path (lstm_seq.LstmLayerSeq)."""
+        Returns the top-layer activations of both towers H1 [T,2,N,48] and whether the tensor-core learner kernels served them.
+        On CUDA the recurrence runs through the fused BPTT path (lstm_seq.LstmLayerFused / LstmLayerSeqPersistent)."""
         from .lstm_seq import LstmLayerSeq, LstmLayerSeqPersistent, LstmLayerFused, fused_layer_ok, lstm_layer_reference, _with_bias, proj_rows
         T, N, _ = obs.shape
         H = 48
@@ -96,6 +98,11 @@ class LstmActorCritic(torch.nn.Module):
             H0, _, _ = layer(xw0, wh0, b0, c0, h0, keep)
             xw1 = proj_rows(H0, wx1) if own else torch.matmul(H0, wx1)
             H1, _, _ = layer(xw1, wh1, b1, c1, h1, keep)
+        return H1, own
+
+    def forward_time_major(self, obs, keep, state, fused: Optional[bool] = None):
+        """Returns mean [T,N,12], value [T,N] (features_time_major + the two heads)."""
+        H1, own = self.features_time_major(obs, keep, state, fused)
         if own:   # both heads as ONE batched product on the [T,2,N,48] tensor (vf_w zero-padded to 12 columns): no strided tower slices, no
             #       zero-filled select_backward copies of 2.4 GB each in the backward pass
             head_w = torch.stack([self.pi_w, F.pad(self.vf_w, (0, self.pi_w.shape[1] - self.vf_w.shape[1]))])
@@ -116,6 +123,15 @@ class LstmActorCritic(torch.nn.Module):
 def ppo_loss(model: LstmActorCritic, obs, masks, state, actions, advs, returns, old_values, old_neglogp, cliprange, ent_coef, vf_coef, time_major=False):
     """ppo2.py:152-175.  Env-major [N,T,...] tensors (swap_and_flatten order) or, with time_major=True, [T,N,...] ones
     (the device rollout's native layout, served by the fused BPTT path); advs already normalised."""
+    if time_major and obs.is_cuda and os.environ.get("IRRL_LEARNER_HEADS", "") != "torch" and os.environ.get("IRRL_LEARNER_GEMM", "") != "cublas":
+        # heads + loss + their gradients as ONE kernel over the top-layer activations (lstm_seq.HeadLossFused)
+        from .lstm_seq import HeadLossFused
+        H1, own = model.features_time_major(obs, 1.0 - masks, state)
+        if own:
+            main, st = HeadLossFused.apply(H1, model.pi_w, model.pi_b, model.vf_w, model.vf_b, model.pi_logstd, actions, advs, returns, old_values, old_neglogp,
+                                           float(cliprange), float(vf_coef))
+            entropy = model.entropy()
+            return main - entropy * ent_coef, dict(policy_loss=st[0], value_loss=st[1], policy_entropy=entropy.detach(), approxkl=st[2], clipfrac=st[3])
     if time_major:
         mean, vpred = model.forward_time_major(obs, 1.0 - masks, state)
     else:

@@ -212,6 +212,16 @@ int irrl_gram_rows_ctas(int T, int K, int n_env);
 int irrl_gram2_rows_ctas(int T, int K, int n_env);
 int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial);
 int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial);
+/* heads + PPO2 loss + their gradients in one pass over the top-layer activations H1 [T,2,N,48] (ppo2.py:152-175 over run_bp_v5.py:167-176):
+ * per sample the Gaussian mean (pi head), the value (V head), neglogp, the clipped surrogate and the clipped value loss, and the gradients of
+ *   loss = mean(pg) + vf_coef * 0.5 * mean(vf)    (scaled by inv_count = 1 / samples)
+ * w.r.t. the head outputs -> G [T,N,16] = (d/d mean[12], d/d v, 0, 0, 0) and, through the heads, dH [T,2,N,48].  partial
+ * [irrl_ppo_head_loss_ctas(T,N), 16] = per-CTA sums of (pg, vf, 0.5 (neglogp - old)^2, clipped count, d loss / d logstd[12]); the caller sums them
+ * (fixed order: deterministic).  adv is the normalised advantage; logstd [12]; device pointers. */
+int irrl_ppo_head_loss_ctas(int T, int n_env);
+int irrl_ppo_head_loss(void* cuda_stream, int T, int n_env, const float* H1, const float* pi_w, const float* pi_b, const float* vf_w, const float* vf_b, const float* logstd,
+                       const float* actions, const float* adv, const float* returns, const float* old_values, const float* old_neglogp,
+                       float cliprange, float vf_coef, float inv_count, float* dH, float* G, float* partial);
 /* fused element-wise halves of one LSTM training step (forward / backward through the cell), device pointers only; rows = towers * envs,
  * z / gates [rows,192] in gate order i,f,o,g, the rest [rows,48]; keep = 1 - done mask per env (run_bp_v5.py:151-153 lstm(..., masks, ...)) */
 int irrl_lstm_pw_fwd(void* cuda_stream, int rows, int n_env, const float* z, const float* c_prev_masked, const float* keep_next, float* gates,

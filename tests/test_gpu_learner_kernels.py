@@ -99,8 +99,9 @@ def test_streaming_products_reject_unsupported_shapes():
 
 
 def test_learner_gradients_do_not_depend_on_the_kernel_family():
-    """one PPO loss / gradient evaluation at a rollout-like size: tensor-core kernels (default) against the FMA recurrence with
-    torch.matmul projections (IRRL_LEARNER_GEMM=cublas, path 1) -- all 17 used parameter gradients within 2e-4 of their scale"""
+    """one PPO loss / gradient evaluation at a rollout-like size: tensor-core kernels + the fused heads / loss kernel (default) against the
+    FMA recurrence with torch.matmul projections and the autograd loss (IRRL_LEARNER_GEMM=cublas, path 1) -- loss, statistics and all 17
+    used parameter gradients (ent_coef != 0 so that the logstd gradient has both its parts)"""
     import os
     torch, _lib, L, dev = _setup()
     from high_speed_quadrupedal_locomotion_by_irrl_b200.ppo2 import LstmActorCritic, ppo_loss
@@ -116,11 +117,13 @@ def test_learner_gradients_do_not_depend_on_the_kernel_family():
         prev = L.irrl_lstm_seq_set_path(path); os.environ["IRRL_LEARNER_GEMM"] = gemm
         try:
             m = LstmActorCritic(W).to(dev)
-            loss, _ = ppo_loss(m, obs, masks, st, act, adv, ret, oldv, oldn, 0.2, 0.0, 0.5, time_major=True)
-            res.append((float(loss), torch.autograd.grad(loss, m.param_list(), allow_unused=True)))
+            loss, stats = ppo_loss(m, obs, masks, st, act, adv, ret, oldv, oldn, 0.2, 0.01, 0.5, time_major=True)
+            res.append((float(loss.detach()), torch.autograd.grad(loss, m.param_list(), allow_unused=True), {k: float(v) for k, v in stats.items()}))
         finally:
             L.irrl_lstm_seq_set_path(prev); os.environ.pop("IRRL_LEARNER_GEMM", None)
     assert abs(res[0][0] - res[1][0]) <= 1e-5 * max(1.0, abs(res[1][0]))
+    for k in ("policy_loss", "value_loss", "policy_entropy", "approxkl", "clipfrac"):          # the fused heads + loss kernel reports the same statistics
+        assert abs(res[0][2][k] - res[1][2][k]) <= 1e-5 * max(1.0, abs(res[1][2][k])), (k, res[0][2][k], res[1][2][k])
     for n, ga, gb in zip(PARAM_NAMES, res[0][1], res[1][1]):
         if gb is None:
             assert ga is None; continue

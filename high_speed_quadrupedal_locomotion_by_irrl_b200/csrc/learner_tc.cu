@@ -349,122 +349,117 @@ struct GramTcArgs {
     float* P;                                                          // partial sums [gridDim.x][K][128][192]
     int T, K, N;
 };
-constexpr int GR = 32;                                                 // rows per tile
-constexpr int G_OFF_A = 0, G_OFF_B = G_OFF_A + 4 * A_KSTEP, G_OFF_RAW = G_OFF_B + 4 * B_KSTEP;
-constexpr int G_RAW_STAGE = GR * (48 + 48 + NG) * 4;                   // [32][48] x | [32][48] hm | [32][192] dz
-constexpr int G_OFF_BAR = G_OFF_RAW + 2 * G_RAW_STAGE;
-constexpr int G_BYTES = G_OFF_BAR + 8 + 16;
+constexpr int GR = 24, GKS = GR / 8;                                   // rows per tile = 3 k-steps: small enough for TWO operand-tile slots and THREE raw stages
+constexpr int G_SLOT = GKS * (A_KSTEP + B_KSTEP);                      // operand tiles of one slot: A (128 x 24) then B (192 x 24), hi / lo each
+constexpr int G_OFF_OP = 0, G_OFF_RAW = G_OFF_OP + 2 * G_SLOT;
+constexpr int G_RAW_STAGE = GR * (48 + 48 + NG) * 4;                   // [24][48] x | [24][48] hm | [24][192] dz
+constexpr int G_NRAW = 3;
+constexpr int G_OFF_BAR = G_OFF_RAW + G_NRAW * G_RAW_STAGE;
+constexpr int G_BYTES = G_OFF_BAR + (2 + G_NRAW) * 8 + 16;
+static_assert(G_BYTES <= 232448, "shared memory");
 
+// Pipeline: the transform of tile i+1 (into the other operand slot) runs while the MMAs of tile i execute; a slot is reused when the
+// MMAs of tile i-2 have committed; raw rows are three tiles ahead.
 __global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_constant__ GramTcArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int t_ = threadIdx.x, warp = t_ >> 5, lane = t_ & 31, k = blockIdx.y;
-    unsigned char* sA = smem + G_OFF_A;
-    unsigned char* sB = smem + G_OFF_B;
-    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_done + 1);
-    if (t_ == 0) { mbar_init(mma_done, 1); fence_mbar_init(); }
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);            // [2]: one per operand slot
+    uint64_t* raw_full = mma_done + 2;                                             // [G_NRAW]: bulk copies of a raw stage have landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(raw_full + G_NRAW);
+    if (t_ == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); for (int i = 0; i < G_NRAW; ++i) mbar_init(&raw_full[i], 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
-    for (int i = t_; i < (G_OFF_BAR - G_OFF_A) / 4; i += THR) reinterpret_cast<float*>(smem)[i] = 0.f;     // operand rows 96..127, feature columns past x_cols: zero for good
+    for (int i = t_; i < (G_OFF_BAR - G_OFF_OP) / 4; i += THR) reinterpret_cast<float*>(smem)[i] = 0.f;     // operand rows 96..127, feature columns past x_cols: zero for good
     fence_proxy_async();
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
 
     const int tiles_per_t = (A.N + GR - 1) / GR, tiles = A.T * tiles_per_t;
-    const bool xvec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
-    // ---- per-thread work lists (the same for every tile): copy chunks of dz (3), hm (<= 1), x (<= 3); transform items of A (<= 2) and B (3)
-    uint32_t d_off[3]; int d_row[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / 48, c = i - r * 48; d_row[j] = r; d_off[j] = r * NG + 4 * c; }
-    const int h_row = t_ < GR * 12 ? t_ / 12 : (1 << 20); const uint32_t h_off = (t_ / 12) * 48 + 4 * (t_ % 12);
-    uint32_t x_off[3]; int x_row[3];
-    {
-        const int per_row = xvec ? (A.x_cols >> 2) : A.x_cols, w = xvec ? 4 : 1;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / per_row, c = i - r * per_row; x_row[j] = r < GR ? r : (1 << 20); x_off[j] = r * 48 + w * c; }
-    }
     const int x_cols = A.x_cols;
-    uint32_t a_src[2], a_dst[2], b_src[3], b_dst[3];
+    uint32_t a_src[2], a_dst[2], b_src[3], b_dst[3]; int a_pitch[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int i = t_ + j * THR, m = i % 96, c = i / 96;
-        a_src[j] = (m < 48 ? m : GR * 48 + (m - 48)) + 4 * c * 48; a_dst[j] = i < 96 * 8 ? op_off(4 * c, m, TM) : 0xFFFFFFFFu;
+        a_pitch[j] = m < 48 ? x_cols : 48;
+        a_src[j] = m < 48 ? m + 4 * c * x_cols : GR * 48 + (m - 48) + 4 * c * 48;
+        a_dst[j] = (i < 96 * (GR / 4) && (m >= 48 || m < x_cols)) ? op_off(4 * c, m, TM) : 0xFFFFFFFFu;      // features past x_cols: their operand rows stay zero
     }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, n = i % NG, c = i / NG; b_src[j] = GR * 96 + 4 * c * NG + n; b_dst[j] = op_off(4 * c, n, NG); }
+    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, n = i % NG, c = i / NG; b_src[j] = GR * 96 + 4 * c * NG + n; b_dst[j] = i < NG * (GR / 4) ? GKS * A_KSTEP + op_off(4 * c, n, NG) : 0xFFFFFFFFu; }
 
+    // Raw rows come through the bulk-copy engine (three contiguous blocks per tile, completion on an mbarrier), NOT through per-thread cp.async:
+    // fence.proxy.async, which every thread needs after writing the operand tile, waits for the thread's own outstanding asynchronous copies,
+    // i.e. for a full HBM round trip per tile (measured: ~3 k cycles per tile whatever its size).
     auto issue = [&](int tile, int buf) {
-        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * GR, rows = A.N - n0;
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * GR, rows = min(GR, A.N - n0);
         float* rx = reinterpret_cast<float*>(smem + G_OFF_RAW + buf * G_RAW_STAGE);
-        const float* xs = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * x_cols;
-        const float* hs = A.HM + (((size_t)t * A.K + k) * A.N + n0) * 48;
-        const float* ds = A.D + (((size_t)t * A.K + k) * A.N + n0) * NG;
-        // rows past N are zero-filled: they must not contribute to the sums
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            if (d_row[j] < rows) cp16(rx + GR * 96 + d_off[j], ds + d_off[j]);
-            else *reinterpret_cast<float4*>(rx + GR * 96 + d_off[j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rows < GR) {                                                // ragged last tile of a time step: the rows past N must be zero
+            for (int i = t_; i < (GR - rows) * 48; i += THR) { rx[rows * 48 + i] = 0.f; rx[GR * 48 + rows * 48 + i] = 0.f; }
+            for (int i = t_; i < (GR - rows) * NG; i += THR) rx[GR * 96 + rows * NG + i] = 0.f;
         }
-        if (h_row < GR) {
-            if (h_row < rows) cp16(rx + GR * 48 + h_off, hs + h_off); else *reinterpret_cast<float4*>(rx + GR * 48 + h_off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t_ == 32) {
+            const float* xs = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * x_cols;
+            const float* hs = A.HM + (((size_t)t * A.K + k) * A.N + n0) * 48;
+            const float* ds = A.D + (((size_t)t * A.K + k) * A.N + n0) * NG;
+            const uint32_t bx = rows * x_cols * 4, bh = rows * 48 * 4, bd = rows * NG * 4;
+            mbar_expect_tx(&raw_full[buf], bx + bh + bd);
+            bulk_g2s(smem_u32(rx), xs, bx, &raw_full[buf]);
+            bulk_g2s(smem_u32(rx + GR * 48), hs, bh, &raw_full[buf]);
+            bulk_g2s(smem_u32(rx + GR * 96), ds, bd, &raw_full[buf]);
         }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            if (x_row[j] < GR) {
-                const uint32_t so = xvec ? x_off[j] : (uint32_t)(x_row[j] * x_cols) + (x_off[j] - x_row[j] * 48);      // source rows are x_cols long, staged rows 48
-                if (xvec) { if (x_row[j] < rows) cp16(rx + x_off[j], xs + so); else *reinterpret_cast<float4*>(rx + x_off[j]) = make_float4(0.f, 0.f, 0.f, 0.f); }
-                else { if (x_row[j] < rows) cp4(rx + x_off[j], xs + so); else rx[x_off[j]] = 0.f; }
-            }
-        }
-        cp_commit();
     };
     int tile = blockIdx.x, it = 0;
-    if (tile < tiles) issue(tile, 0); else cp_commit();
-    if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, 1); else cp_commit();
+#pragma unroll
+    for (int j = 0; j < G_NRAW; ++j) if (tile + j * (int)gridDim.x < tiles) issue(tile + j * gridDim.x, j);
     for (; tile < tiles; tile += gridDim.x, ++it) {
-        const int b = it & 1;
-        cp_wait<1>();
-        __syncthreads();
-        if (it >= 1) { mbar_wait(mma_done, (it - 1) & 1); tc_fence_after(); }          // the MMAs of the previous tile have read the operand tiles
-        const float* rx = reinterpret_cast<const float*>(smem + G_OFF_RAW + b * G_RAW_STAGE);
+        const int s = it & 1, rb = it % G_NRAW;
+        mbar_wait(&raw_full[rb], (it / G_NRAW) & 1);                    // the raw rows of this tile have landed
+        if (it >= 2) { mbar_wait(&mma_done[s], ((it - 2) >> 1) & 1); tc_fence_after(); }     // the MMAs of tile it-2 have read this operand slot
+        unsigned char* sA = smem + G_OFF_OP + s * G_SLOT;
+        const float* rx = reinterpret_cast<const float*>(smem + G_OFF_RAW + rb * G_RAW_STAGE);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {                                   // A: (feature m, rows 4c .. 4c+3); features 0..47 = x, 48..95 = hm
             if (a_dst[j] != 0xFFFFFFFFu) {
                 const float* col = rx + a_src[j];
-                const float v[4] = {col[0], col[48], col[96], col[144]};
+                const int ap = a_pitch[j];
+                const float v[4] = {col[0], col[ap], col[2 * ap], col[3 * ap]};
                 store_hilo(sA, a_dst[j], A_HALF, v);
             }
         }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {                                   // B: (gate column n, rows 4c .. 4c+3)
-            const float* col = rx + b_src[j];
-            const float v[4] = {col[0], col[NG], col[2 * NG], col[3 * NG]};
-            store_hilo(sB, b_dst[j], B_HALF, v);
+            if (b_dst[j] != 0xFFFFFFFFu) {
+                const float* col = rx + b_src[j];
+                const float v[4] = {col[0], col[NG], col[2 * NG], col[3 * NG]};
+                store_hilo(sA, b_dst[j], B_HALF, v);
+            }
         }
         fence_proxy_async();
         tc_fence_before(); __syncthreads(); tc_fence_after();
         {
-            const int ahead = tile + 2 * (int)gridDim.x;
-            if (ahead < tiles) issue(ahead, b); else cp_commit();
+            const int ahead = tile + G_NRAW * (int)gridDim.x;
+            if (ahead < tiles) issue(ahead, rb);
         }
         if (warp == 0) {
             if (elect_one()) {
                 const uint32_t idesc = make_idesc(TM, NG);
 #pragma unroll 1
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t ab = smem_u32(sA) + ks * A_KSTEP, bb = smem_u32(sB) + ks * B_KSTEP;
+                for (int ks = 0; ks < GKS; ++ks) {
+                    const uint32_t ab = smem_u32(sA) + ks * A_KSTEP, bb = smem_u32(sA) + GKS * A_KSTEP + ks * B_KSTEP;
                     const uint64_t ah = make_desc(ab, TM * 16, 128), al = make_desc(ab + A_HALF, TM * 16, 128);
                     const uint64_t bh = make_desc(bb, NG * 16, 128), bl = make_desc(bb + B_HALF, NG * 16, 128);
                     mma_tf32(tmem, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
                     mma_tf32(tmem, ah, bl, idesc, 1);
                     mma_tf32(tmem, ah, bh, idesc, 1);
                 }
-                umma_commit(mma_done);
+                umma_commit(&mma_done[s]);
             }
             __syncwarp();
         }
     }
-    cp_wait<0>();
-    if (it >= 1) { mbar_wait(mma_done, (it - 1) & 1); tc_fence_after(); }
+    // all MMAs complete when the last commit of each slot has arrived (commits are in issue order)
+    if (it >= 2) { const int j = it - 2; mbar_wait(&mma_done[j & 1], (j >> 1) & 1); }
+    if (it >= 1) { const int j = it - 1; mbar_wait(&mma_done[j & 1], (j >> 1) & 1); }
+    tc_fence_after();
     if (warp < 4) {                                                     // lane = feature row m: 96 of them are real
         const int m = 32 * warp + lane;
         float* out = A.P + (((size_t)blockIdx.x * A.K + k) * TM + m) * NG;
@@ -530,6 +525,8 @@ int gram2_rows_tc_ctas(int T, int N, int K) { const int tiles = T * ((N + ltc::G
 int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial, int T, int K, int N, cudaStream_t st) {
     using namespace ltc;
     if (x_cols <= 0 || x_cols > 48) return -1;
+    // the bulk-copy engine wants 16-byte aligned blocks of a multiple of 16 bytes: true for every tile when N is a multiple of 4
+    if ((N & 3) || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(HM) | reinterpret_cast<uintptr_t>(D)) & 15)) return -3;
     GramTcArgs a{}; a.X = X; a.x_cols = x_cols; a.x_t_stride = x_has_tower ? (long long)K * N : N; a.x_k_stride = x_has_tower ? N : 0;
     a.HM = HM; a.D = D; a.P = partial; a.T = T; a.K = K; a.N = N;
     if (cudaFuncSetAttribute(gram2_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_BYTES) != cudaSuccess) return -2;

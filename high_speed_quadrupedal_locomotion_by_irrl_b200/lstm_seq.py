@@ -41,6 +41,8 @@ def gram2_rows(X, HM, D):
     T, K, N, _ = D.shape
     c = X.shape[-1]
     st = C.c_void_p(torch.cuda.current_stream(D.device).cuda_stream)
+    if N % 4 or (X.data_ptr() | HM.data_ptr() | D.data_ptr()) % 16:        # the tcgen05 kernel streams whole 16-byte aligned blocks: odd batches go through the warp-level kernel
+        return gram_rows(X, D), gram_rows(HM, D)
     part = D.new_empty((L.irrl_gram2_rows_ctas(T, K, N), K, 128, 192))
     _lib.check(L.irrl_gram2_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(HM), _p(D), _p(part)), "gram2_rows")
     G = part[:, :, :96].sum(0)

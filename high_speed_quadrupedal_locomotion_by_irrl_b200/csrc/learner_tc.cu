@@ -48,7 +48,7 @@ template <int KS> struct Lay {                                         // KS k-s
     static constexpr int OFF_RAW = OFF_A + KS * A_KSTEP;
     static constexpr int OFF_STAGE = OFF_RAW + 2 * TM * RAW_PITCH * 4;
     static constexpr int OFF_BAR = OFF_STAGE + TM * STAGE_PITCH * 4;
-    static constexpr int BYTES = OFF_BAR + 2 * 8 + 16;
+    static constexpr int BYTES = OFF_BAR + 4 * 8 + 16;
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -70,9 +70,11 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
     float* raw = reinterpret_cast<float*>(smem + L::OFF_RAW);
     float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGE);
     uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_done + 2);
+    uint64_t* raw_full = mma_done + 2;                                 // raw rows of a stage have landed (bulk-copy engine)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(raw_full + 2);
+    constexpr bool VEC4 = (KS == 6);                                   // 48-column rows are read as float4s (rotated chunk order: conflict-free at the natural pitch), 35-column rows as scalars
 
-    if (t_ == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); fence_mbar_init(); }
+    if (t_ == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); mbar_init(&raw_full[0], 1); mbar_init(&raw_full[1], 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
     // W_k -> B operand: row n of the tile = output column n, K-major, hi / lo split, zero rows past x_cols
     const float* Wk = A.W + (size_t)k * A.w_k_stride;
@@ -83,45 +85,40 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
         *reinterpret_cast<float*>(sB + op_off(kk, n, NG)) = hi;
         *reinterpret_cast<float*>(sB + op_off(kk, n, NG) + B_HALF) = v - hi;
     }
-    for (int i = t_; i < 2 * TM * RP; i += THR) raw[i] = 0.f;          // pad columns stay zero (the copies never touch them)
+    for (int i = t_; i < 2 * TM * RP; i += THR) raw[i] = 0.f;
     fence_proxy_async();
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
 
     const int tiles_per_t = (A.N + TM - 1) / TM, tiles = A.T * tiles_per_t;
-    const bool vec = (A.x_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.X) & 15) == 0);
+    const int x_cols = A.x_cols;
     // ---- per-thread work lists
-    constexpr int NCP = (TM * KS * 8 + THR - 1) / THR;                  // copy chunks (upper bound: 4-byte chunks of a KS*8-column row)
-    uint32_t cp_src[NCP], cp_dst[NCP]; int cp_row[NCP];
-    {
-        const int per_row = vec ? (A.x_cols >> 2) : A.x_cols, w = vec ? 4 : 1;
-#pragma unroll
-        for (int j = 0; j < NCP; ++j) {
-            const int i = t_ + j * THR, r = i / per_row, c = i - r * per_row;
-            cp_row[j] = r < TM ? r : (1 << 20); cp_src[j] = r * A.x_cols + w * c; cp_dst[j] = r * RP + w * c;
-        }
-    }
     constexpr int NIT = (TM * KS * 2 + THR - 1) / THR;                  // transform items (row, 4 k)
-    uint32_t it_src[NIT], it_dst[NIT];
+    uint32_t it_src[NIT], it_dst[NIT]; int it_nv[NIT];
 #pragma unroll
-    for (int j = 0; j < NIT; ++j) { const int i = t_ + j * THR, r = i & (TM - 1), q = i >> 7; it_src[j] = r * RP + 4 * q; it_dst[j] = (q < KS * 2) ? op_off(4 * q, r, TM) : 0xFFFFFFFFu; }
+    for (int j = 0; j < NIT; ++j) {
+        // the raw tile is one contiguous block (rows x_cols apart).  Scalar reads (35 columns): 3 r mod 32 distinct over a warp.  float4 reads
+        // (48 columns = 12 chunks): lane r takes chunk (jj + r / 2) mod 12, so that 8 consecutive rows hit 8 different 16-byte bank groups.
+        const int i = t_ + j * THR, r = i & (TM - 1), jj = i >> 7, q = VEC4 ? (jj + (r >> 1)) % (KS * 2) : jj;
+        it_src[j] = r * x_cols + 4 * q;
+        it_nv[j] = min(4, max(0, x_cols - 4 * q));
+        it_dst[j] = (jj < KS * 2) ? op_off(4 * q, r, TM) : 0xFFFFFFFFu;
+    }
     constexpr int NCO = TM * 24 / THR;                                   // copy-out float4s per 96-column round
     uint32_t co_src[NCO], co_dst[NCO]; int co_row[NCO];
 #pragma unroll
     for (int j = 0; j < NCO; ++j) { const int i = t_ + j * THR, r = i / 24, c4 = i - r * 24; co_row[j] = r; co_src[j] = r * STAGE_PITCH + 4 * c4; co_dst[j] = r * NG + 4 * c4; }
 
+    // Raw rows come through the bulk-copy engine, not per-thread cp.async: fence.proxy.async (needed after the operand-tile writes) waits for
+    // the issuing thread's outstanding asynchronous copies, which exposed one HBM round trip per tile.
     auto issue = [&](int tile, int buf) {
-        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = A.N - n0;
-        const float* src = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * A.x_cols;
+        const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = min(TM, A.N - n0);
+        const float* src = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * x_cols;
         float* dst = raw + buf * TM * RP;
-        if (vec) {
-#pragma unroll
-            for (int j = 0; j < NCP; ++j) if (cp_row[j] < rows) cp16(dst + cp_dst[j], src + cp_src[j]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < NCP; ++j) if (cp_row[j] < rows) cp4(dst + cp_dst[j], src + cp_src[j]);
+        if (t_ == 32) {                                                 // ONE copy per tile: per-row 192-byte copies were measured slower (3.1 vs 2.8 ms with cp.async)
+            mbar_expect_tx(&raw_full[buf], rows * x_cols * 4);
+            bulk_g2s(smem_u32(dst), src, rows * x_cols * 4, &raw_full[buf]);
         }
-        cp_commit();
     };
     // accumulator of a finished tile: TMEM -> registers -> padded staging tile -> coalesced stores, 96 columns at a time
     auto drain = [&](int tile, int buf) {
@@ -149,19 +146,22 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
     };
 
     int tile = blockIdx.x, it = 0, prev_tile = -1;
-    if (tile < tiles) issue(tile, 0); else cp_commit();
-    if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, 1); else cp_commit();
+    if (tile < tiles) issue(tile, 0);
+    if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x, 1);
     for (; tile < tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
-        cp_wait<1>();                                                   // every copy group but the newest has landed: the raw rows of this tile
-        __syncthreads();
+        mbar_wait(&raw_full[b], (it >> 1) & 1);                         // the raw rows of this tile have landed
         if (it >= 1) { mbar_wait(&mma_done[b ^ 1], ((it - 1) >> 1) & 1); tc_fence_after(); }     // previous tile multiplied: the operand tile is free, its accumulator full
         const float* rw = raw + b * TM * RP;
 #pragma unroll
         for (int j = 0; j < NIT; ++j) {                                 // item = (row, 4 k): row-per-lane reads and writes
             if (it_dst[j] != 0xFFFFFFFFu) {
-                const float4 x = *reinterpret_cast<const float4*>(rw + it_src[j]);
-                const float v[4] = {x.x, x.y, x.z, x.w};
+                float v[4];
+                if (VEC4) { const float4 x = *reinterpret_cast<const float4*>(rw + it_src[j]); v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = e < it_nv[j] ? rw[it_src[j] + e] : 0.f;      // columns past x_cols are zero
+                }
                 store_hilo(sA, it_dst[j], A_HALF, v);
             }
         }
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
         tc_fence_before(); __syncthreads(); tc_fence_after();
         {   // the raw buffer of this tile is free again: rows of the tile after next
             const int ahead = tile + 2 * (int)gridDim.x;
-            if (ahead < tiles) issue(ahead, b); else cp_commit();
+            if (ahead < tiles) issue(ahead, b);
         }
         if (warp == 0) {
             if (elect_one()) {
@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(THR, 1) proj_rows_tc_kernel(const __grid_const
         mbar_wait(&mma_done[b], ((it - 1) >> 1) & 1); tc_fence_after();
         drain(prev_tile, b);
     }
-    cp_wait<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, TMEM_COLS); }
@@ -216,7 +215,7 @@ struct LayT {
     static constexpr int OFF_RAW = OFF_A + 6 * A_KSTEP;
     static constexpr int OFF_STAGE = OFF_RAW + 2 * TM * RAW_PITCH * 4;
     static constexpr int OFF_BAR = OFF_STAGE + TM * RAW_PITCH * 4;     // staging tile [128][52]
-    static constexpr int BYTES = OFF_BAR + 2 * 8 + 16;
+    static constexpr int BYTES = OFF_BAR + 4 * 8 + 16;
 };
 struct ProjTTcArgs { const float* D; const float* W; long long w_k_stride; float* Y; int T, K, N; };
 
@@ -230,8 +229,9 @@ __global__ void __launch_bounds__(THR, 1) projT_rows_tc_kernel(const __grid_cons
     float* raw = reinterpret_cast<float*>(smem + L::OFF_RAW);
     float* stage = reinterpret_cast<float*>(smem + L::OFF_STAGE);
     uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_done + 2);
-    if (t_ == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); fence_mbar_init(); }
+    uint64_t* raw_full = mma_done + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(raw_full + 2);
+    if (t_ == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); mbar_init(&raw_full[0], TM); mbar_init(&raw_full[1], TM); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(tmem_ptr, 128); tmem_relinquish(); }
     const float* Wk = A.W + (size_t)k * A.w_k_stride;                  // [48][192]
     for (int i = t_; i < NT48 * NG; i += THR) {                        // element (n, kk): chunk kk / 48, local k = kk % 48
@@ -247,12 +247,12 @@ __global__ void __launch_bounds__(THR, 1) projT_rows_tc_kernel(const __grid_cons
 
     const int tiles_per_t = (A.N + TM - 1) / TM, tiles = A.T * tiles_per_t;
     // virtual tile v = 4 * (index of this CTA's tile) + chunk
-    uint32_t cp_src[3], cp_dst[3]; int cp_row[3];
+    uint32_t cp_src[6], cp_dst[6]; int cp_row[6];                        // copy chunks of the loader threads (256 threads x 6 = 128 rows x 12 chunks)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / 12, c = i - r * 12; cp_row[j] = r; cp_src[j] = r * NG + 4 * c; cp_dst[j] = r * RP + 4 * c; }
-    uint32_t it_src[3], it_dst[3];
+    for (int j = 0; j < 6; ++j) { const int i = (t_ & 255) + j * 256, r = i / 12, c = i - r * 12; cp_row[j] = r; cp_src[j] = r * NG + 4 * c; cp_dst[j] = r * RP + 4 * c; }
+    uint32_t it_src[6], it_dst[6];                                       // transform items of the lower 256 threads
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i & (TM - 1), q = i >> 7; it_src[j] = r * RP + 4 * q; it_dst[j] = op_off(4 * q, r, TM); }
+    for (int j = 0; j < 6; ++j) { const int i = (t_ & 255) + j * 256, r = i & (TM - 1), q = i >> 7; it_src[j] = r * RP + 4 * q; it_dst[j] = op_off(4 * q, r, TM); }
     uint32_t co_src[3], co_dst[3]; int co_row[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) { const int i = t_ + j * THR, r = i / 12, c4 = i - r * 12; co_row[j] = r; co_src[j] = r * RP + 4 * c4; co_dst[j] = r * NT48 + 4 * c4; }
@@ -262,9 +262,14 @@ __global__ void __launch_bounds__(THR, 1) projT_rows_tc_kernel(const __grid_cons
         const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = A.N - n0;
         const float* src = A.D + (((size_t)t * A.K + k) * A.N + n0) * NG + 48 * ch;
         float* dst = raw + buf * TM * RP;
+        // Column chunks of a [rows x 192] block are not contiguous, and per-row bulk copies are slow (6.0 vs 4.2 ms): cp.async it is, but issued by
+        // the upper 8 warps only.  The lower 8 warps write the operand tile and execute fence.proxy.async, which waits for the issuing thread's own
+        // outstanding asynchronous copies -- they have none.
+        if (t_ >= 256) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) if (cp_row[j] < rows) cp16(dst + cp_dst[j], src + cp_src[j]);
-        cp_commit();
+            for (int j = 0; j < 6; ++j) if (cp_row[j] < rows) cp16(dst + cp_dst[j], src + cp_src[j]);
+            cp_commit();
+        }
     };
     auto drain = [&](int tile, int buf) {
         const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * TM, rows = min(TM, A.N - n0);
@@ -288,23 +293,25 @@ __global__ void __launch_bounds__(THR, 1) projT_rows_tc_kernel(const __grid_cons
             if (co_row[j] < rows) *reinterpret_cast<float4*>(yb + co_dst[j]) = *reinterpret_cast<const float4*>(stage + co_src[j]);
         __syncthreads();
     };
-    if (vt_total > 0) issue(0, 0); else cp_commit();
-    if (vt_total > 1) issue(1, 1); else cp_commit();
+    if (vt_total > 0) issue(0, 0); else if (t_ >= 256) cp_commit();
+    if (vt_total > 1) issue(1, 1); else if (t_ >= 256) cp_commit();
     for (int vt = 0; vt < vt_total; ++vt) {
         const int b = vt & 1, ch = vt & 3, tb = (vt >> 2) & 1;          // raw buffer, column chunk, TMEM buffer of this tile
-        cp_wait<1>();
+        if (t_ >= 256) cp_wait<1>();                                    // loaders: every copy group but the newest has landed
         __syncthreads();
         if (vt >= 1) { mbar_wait(&mma_done[0], (vt - 1) & 1); tc_fence_after(); }      // one commit per virtual tile on mma_done[0]: operand tile free
         const float* rw = raw + b * TM * RP;
+        if (t_ < 256) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(rw + it_src[j]);
-            const float v[4] = {x.x, x.y, x.z, x.w};
-            store_hilo(sA, it_dst[j], A_HALF, v);
+            for (int j = 0; j < 6; ++j) {
+                const float4 x = *reinterpret_cast<const float4*>(rw + it_src[j]);
+                const float v[4] = {x.x, x.y, x.z, x.w};
+                store_hilo(sA, it_dst[j], A_HALF, v);
+            }
+            fence_proxy_async();
         }
-        fence_proxy_async();
         tc_fence_before(); __syncthreads(); tc_fence_after();
-        if (vt + 2 < vt_total) issue(vt + 2, b); else cp_commit();
+        if (vt + 2 < vt_total) issue(vt + 2, b); else if (t_ >= 256) cp_commit();
         if (warp == 0) {
             if (elect_one()) {
                 const uint32_t idesc = make_idesc(TM, NT48), d = tmem + tb * NT48;
@@ -496,7 +503,9 @@ int launch_proj_rows_tc(const float* X, int x_cols, int x_has_tower, const float
     const int tiles = T * ((N + TM - 1) / TM);
     if (tiles <= 0) return 0;
     const dim3 grid(std::min(tiles, std::max(1, sm_count_tc() / K)), K);
+    if (reinterpret_cast<uintptr_t>(X) & 15) return -1;                 // bulk copies want 16-byte aligned sources
     if (x_cols <= 40 && x_cols > 32) {
+        if ((x_cols & 3) && (N & 3)) return -1;                          // whole-block copies: every tile must start on and span a multiple of 16 bytes
         if (cudaFuncSetAttribute(proj_rows_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<5>::BYTES) != cudaSuccess) return -2;
         proj_rows_tc_kernel<5><<<grid, THR, Lay<5>::BYTES, st>>>(a);
     } else if (x_cols == 48) {

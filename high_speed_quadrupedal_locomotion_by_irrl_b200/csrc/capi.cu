@@ -1130,6 +1130,11 @@ int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, i
     CUDA_OK(cudaGetLastError()); return 0;
 }
 int irrl_proj_rows_set_path(int path) { return proj_rows_set_path(path); }
+int irrl_scale_unless_one(void* cuda_stream, float* x, long long n, const float* scale) {
+    if (!x || !scale || n < 0 || (n & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) return fail(-1, "irrl_scale_unless_one: bad argument (n % 4 == 0, 16-byte aligned)");
+    if (n) launch_scale_unless_one(x, n, scale, reinterpret_cast<cudaStream_t>(cuda_stream));
+    CUDA_OK(cudaGetLastError()); return 0;
+}
 int irrl_ppo_head_loss_ctas(int T, int n_env) { return ppo_head_loss_ctas((long long)T * n_env); }
 int irrl_ppo_head_loss(void* cuda_stream, int T, int n_env, const float* H1, const float* pi_w, const float* pi_b, const float* vf_w, const float* vf_b, const float* logstd,
                        const float* actions, const float* adv, const float* returns, const float* old_values, const float* old_neglogp,

@@ -100,6 +100,7 @@ int launch_gram_rows(const float* X, int x_cols, int x_has_tower, const float* D
 // (pg, vf, 0.5 (neglogp - old)^2, clipped count, d loss / d logstd[12])
 constexpr int HL_PART = 16;
 int ppo_head_loss_ctas(long long rows);
+void launch_scale_unless_one(float* x, long long n, const float* scale, cudaStream_t st);   // n a multiple of 4, x 16-byte aligned
 void launch_ppo_head_loss(const float* H1, const float* pi_w, const float* pi_b, const float* vf_w, const float* vf_b, const float* logstd, const float* actions,
                           const float* adv, const float* ret, const float* old_v, const float* old_nlp, float* dH, float* G, float* partial,
                           float cliprange, float vf_coef, float inv_count, int T, int N, cudaStream_t st);

@@ -138,6 +138,16 @@ __global__ void __launch_bounds__(HL_THR) ppo_head_loss_kernel(const __grid_cons
     }
 }
 
+// x *= *scale unless *scale == 1 (the upstream gradient of a terminal loss): the common case costs one launch and no memory traffic
+__global__ void scale_unless_one_kernel(float4* __restrict__ x, long long n4, const float* __restrict__ scale) {
+    const float s = *scale;
+    if (s == 1.0f) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) { float4 v = x[i]; v.x *= s; v.y *= s; v.z *= s; v.w *= s; x[i] = v; }
+}
+void launch_scale_unless_one(float* x, long long n, const float* scale, cudaStream_t st) {
+    scale_unless_one_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<float4*>(x), n / 4, scale);
+}
+
 int ppo_head_loss_ctas(long long rows) {
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long need = (rows + HL_THR - 1) / HL_THR;

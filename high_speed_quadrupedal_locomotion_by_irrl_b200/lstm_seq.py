@@ -121,7 +121,11 @@ class HeadLossFused(torch.autograd.Function):
         d_vf_w = torch.matmul(H1[:, 1].transpose(-1, -2), G[..., 12:13]).sum(0)
         d_pi_b = gm.sum((0, 1)); d_vf_b = G[..., 12].sum().reshape(1)
         g = g_loss
-        return (dH * g, d_pi_w * g, d_pi_b * g, d_vf_w * g, d_vf_b * g, dls.reshape(1, 12) * g, None, None, None, None, None, None, None)
+        # the 2.4 GB activation gradient is scaled in place, and only if the upstream gradient is not 1 (it is 1 for a terminal loss)
+        L = _lib.load()
+        gs = g.detach().reshape(1).float().contiguous()
+        _lib.check(L.irrl_scale_unless_one(C.c_void_p(torch.cuda.current_stream(dH.device).cuda_stream), _p(dH), dH.numel(), _p(gs)), "scale")
+        return (dH, d_pi_w * g, d_pi_b * g, d_vf_w * g, d_vf_b * g, dls.reshape(1, 12) * g, None, None, None, None, None, None, None)
 
 
 def fused_layer_ok(X, wx) -> bool:

@@ -220,6 +220,8 @@ int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, i
  * [irrl_ppo_head_loss_ctas(T,N), 16] = per-CTA sums of (pg, vf, 0.5 (neglogp - old)^2, clipped count, d loss / d logstd[12]); the caller sums them
  * (fixed order: deterministic).  adv is the normalised advantage; logstd [12]; device pointers. */
 int irrl_ppo_head_loss_ctas(int T, int n_env);
+/* x[0:n] *= *scale on the device unless *scale == 1 (the upstream gradient of a terminal loss: no memory traffic then); n % 4 == 0, x 16-byte aligned */
+int irrl_scale_unless_one(void* cuda_stream, float* x, long long n, const float* scale);
 int irrl_ppo_head_loss(void* cuda_stream, int T, int n_env, const float* H1, const float* pi_w, const float* pi_b, const float* vf_w, const float* vf_b, const float* logstd,
                        const float* actions, const float* adv, const float* returns, const float* old_values, const float* old_neglogp,
                        float cliprange, float vf_coef, float inv_count, float* dH, float* G, float* partial);

@@ -168,3 +168,21 @@ def test_forward_projection_kernels_agree():
         ref = torch.matmul(X.double().unsqueeze(1) if tw == 0 else X.double(), W.double())
         for Y in out:
             assert float((Y.double() - ref).abs().max()) <= 3e-6 * float(ref.abs().max())
+
+
+def test_fused_head_loss_scales_with_the_upstream_gradient():
+    """the activation gradient of the fused heads + loss kernel is scaled on the device only when the upstream gradient is not 1"""
+    torch, _lib, L, dev = _setup()
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import HeadLossFused
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    r = lambda *s, sc=1.0: torch.randn(*s, device=dev, generator=g) * sc
+    T, N = 5, 52
+    args = (r(48, 12, sc=0.1), r(12, sc=0.1), r(48, 1, sc=0.1), r(1), r(1, 12, sc=0.2), r(T, N, 12), r(T, N), r(T, N), r(T, N), r(T, N) - 15.0)
+    out = []
+    for scale in (1.0, 2.5):
+        H1 = r(T, 2, N, 48).requires_grad_(True) if not out else out[0][2].detach().clone().requires_grad_(True)
+        pw = args[0].clone().requires_grad_(True)
+        loss, _ = HeadLossFused.apply(H1, pw, *args[1:], 0.2, 0.5)
+        gh, gw = torch.autograd.grad(loss * scale, (H1, pw))
+        out.append((gh, gw, H1))
+    assert torch.allclose(out[1][0], 2.5 * out[0][0], rtol=1e-6, atol=0) and torch.allclose(out[1][1], 2.5 * out[0][1], rtol=1e-5, atol=1e-12)

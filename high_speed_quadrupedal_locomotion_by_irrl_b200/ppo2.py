@@ -305,9 +305,9 @@ class PPO2:
         stats: List[Dict[str, torch.Tensor]] = []
         full = self.nminibatches == 1
         for epoch in range(self.noptepochs):
-            perm = torch.randperm(N, generator=gen).to(self.dev)                          # ppo2.py:388 shuffle env indices
+            perm = None if full else torch.randperm(N, generator=gen).to(self.dev)        # ppo2.py:388 shuffle env indices (irrelevant with one minibatch)
             for start in range(0, N, envs_per_batch):
-                idx = perm[start:start + envs_per_batch]
+                idx = None if full else perm[start:start + envs_per_batch]
                 sel = (lambda x: x) if full else (lambda x: x.index_select(1, idx))        # with one minibatch the order is irrelevant
                 advs = sel(returns) - sel(values)                                         # ppo2.py:262
                 mean, std = global_mean_std(advs)

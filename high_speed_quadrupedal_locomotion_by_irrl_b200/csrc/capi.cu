@@ -88,6 +88,7 @@ struct irrl_env_impl {
     std::vector<void*> allocs;
     // irrl_act_step: device copies of the act outputs [action | clipped | value | neglogp], chunk streams and their join events
     float* d_fused_act = nullptr; cudaStream_t chunk_stream[8] = {}; cudaEvent_t chunk_done[8] = {}; cudaEvent_t fork_ev = nullptr; int n_chunk_streams = 0;
+    cudaStream_t side_stream[8] = {}; cudaEvent_t act_done[8] = {}, side_done[8] = {};      // act results go home behind the step kernel of their chunk
     // optional per-kernel timing of irrl_rollout (CUDA events on the env's stream)
     bool profiling = false; std::vector<cudaEvent_t> prof_events; size_t prof_cursor = 0; double prof_act_ms = 0, prof_step_ms = 0; long prof_count = 0;
 };
@@ -372,7 +373,7 @@ void irrl_destroy(irrl_env* env) {
     if (E->stream) cudaStreamSynchronize(E->stream);
     for (void* p : E->allocs) cudaFree(p);
     if (E->h_pin) cudaFreeHost(E->h_pin);
-    for (int i = 0; i < E->n_chunk_streams; ++i) { cudaStreamDestroy(E->chunk_stream[i]); cudaEventDestroy(E->chunk_done[i]); }
+    for (int i = 0; i < E->n_chunk_streams; ++i) { cudaStreamDestroy(E->chunk_stream[i]); cudaEventDestroy(E->chunk_done[i]); cudaStreamDestroy(E->side_stream[i]); cudaEventDestroy(E->act_done[i]); cudaEventDestroy(E->side_done[i]); }
     if (E->fork_ev) cudaEventDestroy(E->fork_ev);
     if (E->own_stream && E->stream) cudaStreamDestroy(E->stream);
     delete E;
@@ -1030,7 +1031,10 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
     size_t per = ((N + K - 1) / K + 127) / 128 * 128;      // chunk boundaries on multiples of 128 environments (the tile of the tensor-core act kernel)
     while (E->n_chunk_streams < K) {
         CUDA_OK(cudaStreamCreateWithFlags(&E->chunk_stream[E->n_chunk_streams], cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&E->chunk_done[E->n_chunk_streams], cudaEventDisableTiming)); E->n_chunk_streams++;
+        CUDA_OK(cudaEventCreateWithFlags(&E->chunk_done[E->n_chunk_streams], cudaEventDisableTiming));
+        CUDA_OK(cudaStreamCreateWithFlags(&E->side_stream[E->n_chunk_streams], cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&E->act_done[E->n_chunk_streams], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&E->side_done[E->n_chunk_streams], cudaEventDisableTiming)); E->n_chunk_streams++;
     }
     if (!E->fork_ev) CUDA_OK(cudaEventCreateWithFlags(&E->fork_ev, cudaEventDisableTiming));
     float *d_act = host ? E->d_fused_act : io->action, *d_clip = host ? E->d_fused_act + N * 12 : (io->clipped ? io->clipped : E->d_action),
@@ -1043,6 +1047,10 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
     const bool act_block = host && io->clipped && io->clipped == io->action + N * 12 && io->value == io->clipped + N * 12 && io->neglogp == io->value + N;
     if (E->P.flag_crucial) { StepArgs m = make_args(E, nullptr, nullptr, nullptr, nullptr, nullptr); launch_env_meteor(m, 0, E->stream); }
     if (K > 1) CUDA_OK(cudaEventRecord(E->fork_ev, E->stream));
+    // with chunks, the act results (action, clipped, value, neglogp: 104 of the 273 bytes per env that go home) are copied on a side stream as soon
+    // as the act kernel of their chunk has finished, i.e. behind its step kernel, instead of after it (IRRL_ACT_SIDE=0 switches that off)
+    static const bool side_on = [] { const char* e = getenv("IRRL_ACT_SIDE"); return !e || atoi(e) != 0; }();
+    const bool side = side_on && host && K > 1;
     int used = 0;
     for (size_t lo = 0; lo < N; lo += per, ++used) {
         const size_t hi = std::min(N, lo + per), n = hi - lo;
@@ -1062,6 +1070,15 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
         a.obs = d_obs_in + lo * 35; a.done = d_done_in ? d_done_in + lo : nullptr; a.state = io->state + lo * 384;
         a.action = d_act + lo * 12; a.clipped = d_clip + lo * 12; a.value = d_val + lo; a.neglogp = d_nlp + lo;
         launch_lstm_act(a, st);
+        if (side) {
+            CUDA_OK(cudaEventRecord(E->act_done[used], st)); CUDA_OK(cudaStreamWaitEvent(E->side_stream[used], E->act_done[used], 0));
+            void* dst[4]; void* src[4]; size_t by[4]; int c = 0;
+            auto add = [&](void* h, void* d, size_t b) { if (h) { dst[c] = h; src[c] = d; by[c] = b; ++c; } };
+            add(io->action + lo * 12, d_act + lo * 12, n * 48); if (io->clipped) add(io->clipped + lo * 12, d_clip + lo * 12, n * 48);
+            add(io->value + lo, d_val + lo, n * 4); add(io->neglogp + lo, d_nlp + lo, n * 4);
+            if (int rc = batch_copy(dst, src, by, c, cudaMemcpyDeviceToHost, E->side_stream[used])) return rc;
+            CUDA_OK(cudaEventRecord(E->side_done[used], E->side_stream[used]));
+        }
         StepArgs s = make_args(E, d_clip, d_ob, d_rew, d_done, d_ext ? d_ext : E->d_extra);
         s.r_begin = (int)lo; s.r_end = (int)hi;
         launch_env_step(s, st);
@@ -1072,14 +1089,17 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
             } else {
                 void* dst[8]; void* src[8]; size_t by[8]; int c = 0;
                 auto add = [&](void* h, void* d, size_t b) { if (h) { dst[c] = h; src[c] = d; by[c] = b; ++c; } };
-                add(io->action + lo * 12, d_act + lo * 12, n * 48); if (io->clipped) add(io->clipped + lo * 12, d_clip + lo * 12, n * 48);
-                add(io->value + lo, d_val + lo, n * 4); add(io->neglogp + lo, d_nlp + lo, n * 4);
+                if (!side) {
+                    add(io->action + lo * 12, d_act + lo * 12, n * 48); if (io->clipped) add(io->clipped + lo * 12, d_clip + lo * 12, n * 48);
+                    add(io->value + lo, d_val + lo, n * 4); add(io->neglogp + lo, d_nlp + lo, n * 4);
+                }
                 add(io->next_obs + lo * 35, d_ob + lo * 35, n * 140); add(io->reward + lo, d_rew + lo, n * 4);
                 if (io->extra) add(io->extra + lo * 6, E->d_extra + lo * 6, n * 24); add(io->next_done + lo, d_done + lo, n);
                 if (int rc = batch_copy(dst, src, by, c, cudaMemcpyDeviceToHost, st)) return rc;
             }
         }
         if (K > 1) { CUDA_OK(cudaEventRecord(E->chunk_done[used], st)); CUDA_OK(cudaStreamWaitEvent(E->stream, E->chunk_done[used], 0)); }
+        if (side) CUDA_OK(cudaStreamWaitEvent(E->stream, E->side_done[used], 0));
     }
     CUDA_OK(cudaGetLastError());
     E->tick++;

@@ -1029,7 +1029,7 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
     if (!host || E->P.flag_crucial) K = 1;
     K = std::min(K, 8);
     size_t per = ((N + K - 1) / K + 127) / 128 * 128;      // chunk boundaries on multiples of 128 environments (the tile of the tensor-core act kernel)
-    while (E->n_chunk_streams < K) {
+    while (E->n_chunk_streams < std::max(K, 1)) {
         CUDA_OK(cudaStreamCreateWithFlags(&E->chunk_stream[E->n_chunk_streams], cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&E->chunk_done[E->n_chunk_streams], cudaEventDisableTiming));
         CUDA_OK(cudaStreamCreateWithFlags(&E->side_stream[E->n_chunk_streams], cudaStreamNonBlocking));
@@ -1047,10 +1047,11 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
     const bool act_block = host && io->clipped && io->clipped == io->action + N * 12 && io->value == io->clipped + N * 12 && io->neglogp == io->value + N;
     if (E->P.flag_crucial) { StepArgs m = make_args(E, nullptr, nullptr, nullptr, nullptr, nullptr); launch_env_meteor(m, 0, E->stream); }
     if (K > 1) CUDA_OK(cudaEventRecord(E->fork_ev, E->stream));
-    // with chunks, the act results (action, clipped, value, neglogp: 104 of the 273 bytes per env that go home) are copied on a side stream as soon
-    // as the act kernel of their chunk has finished, i.e. behind its step kernel, instead of after it (IRRL_ACT_SIDE=0 switches that off)
-    static const bool side_on = [] { const char* e = getenv("IRRL_ACT_SIDE"); return !e || atoi(e) != 0; }();
-    const bool side = side_on && host && K > 1;
+    // the act results (action, clipped, value, neglogp: 104 of the 273 bytes per env that go home) are copied on a side stream as soon as the act
+    // kernel of their chunk has finished, i.e. behind its step kernel, instead of after it (measured: 4096 envs 137.6 -> 128.4 us per step,
+    // 8192: 184 -> 167, 16384: 270 -> 257; IRRL_ACT_SIDE=0 switches that off)
+    static const int side_mode = [] { const char* e = getenv("IRRL_ACT_SIDE"); return e ? atoi(e) : 2; }();      // 0 off, 1 only with chunks, 2 always (default)
+    const bool side = side_mode != 0 && host && (K > 1 || side_mode == 2);
     int used = 0;
     for (size_t lo = 0; lo < N; lo += per, ++used) {
         const size_t hi = std::min(N, lo + per), n = hi - lo;
@@ -1076,7 +1077,8 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
             auto add = [&](void* h, void* d, size_t b) { if (h) { dst[c] = h; src[c] = d; by[c] = b; ++c; } };
             add(io->action + lo * 12, d_act + lo * 12, n * 48); if (io->clipped) add(io->clipped + lo * 12, d_clip + lo * 12, n * 48);
             add(io->value + lo, d_val + lo, n * 4); add(io->neglogp + lo, d_nlp + lo, n * 4);
-            if (int rc = batch_copy(dst, src, by, c, cudaMemcpyDeviceToHost, E->side_stream[used])) return rc;
+            if (K == 1 && env_block && act_block) { CUDA_OK(cudaMemcpyAsync(io->action, E->d_fused_act, N * 26 * sizeof(float), cudaMemcpyDeviceToHost, E->side_stream[used])); }
+            else if (int rc = batch_copy(dst, src, by, c, cudaMemcpyDeviceToHost, E->side_stream[used])) return rc;
             CUDA_OK(cudaEventRecord(E->side_done[used], E->side_stream[used]));
         }
         StepArgs s = make_args(E, d_clip, d_ob, d_rew, d_done, d_ext ? d_ext : E->d_extra);
@@ -1084,7 +1086,7 @@ int irrl_act_step(irrl_env* env, irrl_policy* pol, const irrl_act_step_io* io, i
         launch_env_step(s, st);
         if (host) {
             if (K == 1 && env_block && act_block) {
-                CUDA_OK(cudaMemcpyAsync(io->action, E->d_fused_act, N * 26 * sizeof(float), cudaMemcpyDeviceToHost, st));
+                if (!side) CUDA_OK(cudaMemcpyAsync(io->action, E->d_fused_act, N * 26 * sizeof(float), cudaMemcpyDeviceToHost, st));
                 CUDA_OK(cudaMemcpyAsync(io->next_obs, E->d_ob, N * 168 + N, cudaMemcpyDeviceToHost, st));
             } else {
                 void* dst[8]; void* src[8]; size_t by[8]; int c = 0;

@@ -10,7 +10,8 @@
 // inputs, fp32 accumulation; HMMA.1688.F32.TF32 in SASS) in the 3xTF32 form of the act kernel (policy_tc_kernels.cu):
 // both operands split x = hi + lo, hi the nearest tf32 number, three products lo.hi + hi.lo + hi.hi, error ~2^-22 -- fp32
 // results on tf32 hardware.  144 MMAs per warp and step instead of 1536 FFMAs per thread; measured rate of this MMA on
-// B200: one per 8 cycles and scheduler (scripts/microbench/mma_tf32_rate.cu), i.e. 1728 SM cycles per CTA step.
+// B200: one per 8 cycles and scheduler (scripts/microbench/mma_tf32_rate.cu), i.e. 1728 SM cycles per CTA step.  The FORWARD product
+// goes one step further: a 2-term fp16 split on the f16 m16n8k16 MMA (same issue rate, twice the k: 72 MMAs), see SEQ_FWD_F16 below.
 // tcgen05 is the wrong tool for THIS product: the tile per step is 32 x 48 x 192 on a serial dependency (step t+1 needs the
 // activations of step t), the weights fit in registers / one shared-memory copy, and the per-step hand-offs of a TMEM
 // pipeline (~1.5 k cycles in the act kernel) would cost as much as the product itself.
@@ -24,6 +25,7 @@
 //             warp's units" (with the k order (2q, 2q+1) <-> (q, q+4), applied to B as well), so dz never goes through shared
 //             memory; every warp produces a partial dh[32 x 48] that is summed over the 6 warps through shared memory.
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "env_device.cuh"
 #include "env_kernels.h"
 
@@ -67,10 +69,30 @@ __device__ __forceinline__ uint32_t pack_lo(float lo0, float lo1) { return ((__f
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // xw, gates [T,K,N,192] (gate order i,f,o,g); Cs, Hs, HM [T,K,N,48]; keep [T,N]; c0, h0 [K,N,48]; wh [K,48,192]; bias [K,192] or null
+#ifndef SEQ_FWD_TF32
+#define SEQ_FWD_F16 1          // default; -DSEQ_FWD_TF32 restores the 3xTF32 forward product (6.64 ms against 5.47 ms per launch, error 5.3e-7 against 3.5e-7)
+#endif
+// ---- SEQ_FWD_F16: the forward product as a 2-term fp16 split (x = x1 + x2, both fp16; x1 x1' + x1 x2' + x2 x1', 2^-22-grade) on the f16
+// m16n8k16 MMA, which issues at the same 8 cycles as the tf32 m16n8k8 (scripts/microbench): 72 instead of 144 MMAs per warp and step.
+// Only the forward operands (|h| < 1, |W_h| = O(1)) sit safely inside the fp16 range; the remainders of small values land in fp16 subnormals
+// (absolute floor 6e-8), which is what bounds the error.
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (a, b) -> half2 of the leading parts and half2 of the remainders
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& x1, uint32_t& x2) {
+    const __half2 h1 = __floats2half2_rn(a, b);
+    const float2 f1 = __half22float2(h1);
+    const __half2 h2 = __floats2half2_rn(a - f1.x, b - f1.y);
+    x1 = *reinterpret_cast<const uint32_t*>(&h1); x2 = *reinterpret_cast<const uint32_t*>(&h2);
+}
+constexpr int HS16_PITCH = 28;   // 32-bit words (half2) per row of the fp16 h tile: (28 g + q) mod 32 distinct over a warp
+
 struct FwdSmem {
     uint32_t Blo[6][4][6][32];        // lo parts of the B fragments [warp][gate j][k-tile][lane] = bf16 (b0, b1)
     float hsh[2][TM][HS_PITCH];       // masked h(t-1), tf32-exact part, row = environment; double buffered over t (one barrier per step)
-    float hsl[2][TM][HS_PITCH];       // its remainder
+    float hsl[2][TM][HS_PITCH];       // its remainder   (SEQ_FWD_F16: the same storage viewed as half2 tiles [2][TM][HS16_PITCH])
     float bsm[G4];
 };
 __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_kernel(int T, int K, int N, const float* __restrict__ xw, const float* __restrict__ wh,
@@ -85,6 +107,21 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_ker
     auto& Blo = S.Blo; auto& hsh = S.hsh; auto& hsl = S.hsl; auto& bsm = S.bsm;
     const int u0 = 8 * w + 2 * q;                          // this thread's units u0, u0 + 1
     const float* whk = wh + (size_t)tower * H * G4;
+#ifdef SEQ_FWD_F16
+    uint32_t b1f[4][3][2], b2f[4][3][2];                   // [gate j][k-tile of 16][b0: k = 2q, 2q+1 | b1: k = 2q+8, 2q+9], leading parts and remainders
+    uint32_t (*h1s)[TM][HS16_PITCH] = reinterpret_cast<uint32_t (*)[TM][HS16_PITCH]>(&hsh[0][0][0]);
+    uint32_t (*h2s)[TM][HS16_PITCH] = reinterpret_cast<uint32_t (*)[TM][HS16_PITCH]>(&hsl[0][0][0]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int k0 = 16 * kt + 2 * q + 8 * hh, col = j * H + 8 * w + g;
+                split_h2(whk[(size_t)k0 * G4 + col], whk[(size_t)(k0 + 1) * G4 + col], b1f[j][kt][hh], b2f[j][kt][hh]);
+            }
+    (void)Blo;
+#else
     uint32_t bh[4][6][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -95,13 +132,19 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_ker
             bh[j][kt][0] = __float_as_uint(h0_); bh[j][kt][1] = __float_as_uint(h1_);
             Blo[w][j][kt][lane] = pack_lo(v0 - h0_, v1 - h1_);
         }
+#endif
     bsm[t_] = bias ? bias[tower * G4 + t_] : 0.f;
     float c[4][2];
     int envs[4];
     auto put_h = [&](int buf, int e, float a, float b) {   // split at the producer: the MMA phase loads ready-made fragments
+#ifdef SEQ_FWD_F16
+        uint32_t x1, x2; split_h2(a, b, x1, x2);
+        h1s[buf][g + 8 * e][u0 >> 1] = x1; h2s[buf][g + 8 * e][u0 >> 1] = x2;
+#else
         const float ah = tf32_hi(a), bh_ = tf32_hi(b);
         *reinterpret_cast<float2*>(&hsh[buf][g + 8 * e][u0]) = make_float2(ah, bh_);
         *reinterpret_cast<float2*>(&hsl[buf][g + 8 * e][u0]) = make_float2(a - ah, b - bh_);
+#endif
     };
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -142,6 +185,31 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_ker
                 for (int j = 0; j < 4; ++j) xin[e][j] = *reinterpret_cast<const float2*>(xw + (((size_t)(t + 1) * K + tower) * N + envs[e]) * G4 + j * H + u0);
             }
         }
+#ifdef SEQ_FWD_F16
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            uint32_t a1[2][4], a2[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {                            // (g, 2q..) (g+8, 2q..) (g, 2q+8..) (g+8, 2q+8..), two consecutive k per word
+                a1[mt][0] = h1s[buf][16 * mt + g][8 * kt + q];     a1[mt][1] = h1s[buf][16 * mt + g + 8][8 * kt + q];
+                a1[mt][2] = h1s[buf][16 * mt + g][8 * kt + q + 4]; a1[mt][3] = h1s[buf][16 * mt + g + 8][8 * kt + q + 4];
+                a2[mt][0] = h2s[buf][16 * mt + g][8 * kt + q];     a2[mt][1] = h2s[buf][16 * mt + g + 8][8 * kt + q];
+                a2[mt][2] = h2s[buf][16 * mt + g][8 * kt + q + 4]; a2[mt][3] = h2s[buf][16 * mt + g + 8][8 * kt + q + 4];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_f16(acc[mt][j], a2[mt], b1f[j][kt][0], b1f[j][kt][1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_f16(acc[mt][j], a1[mt], b2f[j][kt][0], b2f[j][kt][1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_f16(acc[mt][j], a1[mt], b1f[j][kt][0], b1f[j][kt][1]);
+        }
+#else
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {
             uint32_t ah[2][4], al[2][4];
@@ -169,6 +237,7 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_fwd_mma_ker
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) mma(acc[mt][j], ah[mt], bh[j][kt][0], bh[j][kt][1]);
         }
+#endif
         // per m-tile: its 4 cells as one block of independent arithmetic, then the stores (all 8 at once costs spills at 168 registers).
         // Rows past N alias row N-1 (envs[] is clamped): those threads compute bit-identical values from identical inputs, so the stores
         // need no predicate.

@@ -57,9 +57,12 @@ __device__ __forceinline__ void split4(const float (&v)[4], uint32_t (&hi)[4], u
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const float h = tf32_hi(v[i]); hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(v[i] - h); }
 }
-#ifndef SEQ_LIBM_ACT     // ex2.approx / rcp.approx forms (relative error ~1e-6, the forms of the act kernels); measured 9.5 -> 7.6 ms per forward launch
-__device__ __forceinline__ float sig_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh__(float x) { const float e = __expf(-2.0f * fabsf(x)); return copysignf(__fdividef(1.0f - e, 1.0f + e), x); }
+#ifndef SEQ_LIBM_ACT     // MUFU forms written out (relative error ~1e-6): sigmoid = rcp(1 + 2^(-x log2 e)), tanh = 1 - 2 rcp(1 + 2^(2 x log2 e)), 4 / 5 instructions each
+// (the __expf / __fdividef spellings of the same forms cost about twice the instructions: range fix-ups; libdevice expf / tanhf: 9.5 vs 7.6 ms)
+__device__ __forceinline__ float ex2_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sig_(float x) { return rcp_(1.0f + ex2_(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh__(float x) { return fmaf(-2.0f, rcp_(1.0f + ex2_(2.8853900817779268f * x)), 1.0f); }
 #else
 __device__ __forceinline__ float sig_(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float tanh__(float x) { return tanhf(x); }

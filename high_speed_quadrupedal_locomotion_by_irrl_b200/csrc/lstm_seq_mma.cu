@@ -284,6 +284,10 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
     extern __shared__ __align__(16) unsigned char seq_smem_b[];
     const int gi = threadIdx.x / THR, tile = blockIdx.x * GROUPS + gi;
     unsigned char* smem = seq_smem_b + (size_t)gi * BWD_SMEM;
+#ifdef SEQ_BWD_F16
+    uint2 (*B1s)[2][6][32] = reinterpret_cast<uint2 (*)[2][6][32]>(smem);                                    // [warp][k-tile = gate pair][n-tile][lane] = (b0, b1) half2 leading parts
+    uint2 (*B2s)[2][6][32] = reinterpret_cast<uint2 (*)[2][6][32]>(smem + 6 * 2 * 6 * 32 * 8);                // their remainders
+#endif
     float2 (*Bhi)[4][6][32] = reinterpret_cast<float2 (*)[4][6][32]>(smem);                                  // [warp][k-tile = gate j][n-tile][lane] = (b0, b1), tf32-exact
     uint32_t (*Blo)[4][6][32] = reinterpret_cast<uint32_t (*)[4][6][32]>(smem + 6 * 4 * 6 * 32 * 8);         // remainders as two bf16 (b0 low half, b1 high half)
     float (*red)[TM][RED_PITCH] = reinterpret_cast<float (*)[TM][RED_PITCH]>(smem + 6 * 4 * 6 * 32 * 12);    // [warp] partial dh[32][48]
@@ -292,6 +296,19 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
     const int u0 = 8 * w + 2 * q;
     const float* whk = wh + (size_t)tower * H * G4;
     // B = W_h^T restricted to this warp's 32 dz columns: k-tile j = gate j, MMA k index q <-> column j*48 + u0, q+4 <-> column j*48 + u0 + 1; n = 8 nt + g
+#ifdef SEQ_BWD_F16
+    // f16 m16n8k16: a k-tile is a gate PAIR (2 kp, 2 kp + 1): MMA k = 2q, 2q+1 <-> gate 2 kp, units u0, u0+1; k = 2q+8, 2q+9 <-> gate 2 kp + 1
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp)
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+            const float2 v0 = *reinterpret_cast<const float2*>(whk + (size_t)(8 * nt + g) * G4 + (2 * kp) * H + u0);
+            const float2 v1 = *reinterpret_cast<const float2*>(whk + (size_t)(8 * nt + g) * G4 + (2 * kp + 1) * H + u0);
+            uint2 x1, x2; split_h2(v0.x, v0.y, x1.x, x2.x); split_h2(v1.x, v1.y, x1.y, x2.y);
+            B1s[w][kp][nt][lane] = x1; B2s[w][kp][nt][lane] = x2;
+        }
+    (void)Bhi; (void)Blo;
+#else
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -302,6 +319,7 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
             const uint32_t lx = (__float_as_uint(v.x - hx) + 0x8000u) >> 16, ly = (__float_as_uint(v.y - hy) + 0x8000u) & 0xFFFF0000u;
             Blo[w][j][nt][lane] = lx | ly;
         }
+#endif
     int envs[4]; bool valid[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { envs[e] = min(e0 + g + 8 * e, N - 1); valid[e] = (e0 + g + 8 * e) < N; }
@@ -375,6 +393,70 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
             ccur[e] = cur[e].cp; kuc[e] = kt;                               // c(t-1) and keep(t) are what step t-1 calls c and keep(t+1)
         }
         if (t > 0) prefetch_step(t - 1);
+#ifdef SEQ_BWD_F16
+        // 2-term fp16 split on the f16 m16n8k16 MMA (72 instead of 144 MMAs).  Gradients have no fixed range, so the warp scales its 32 x 32 dz block
+        // by a power of two that puts the largest magnitude at 2^13..2^14 (exact), and un-scales its partial sums (exact): elements far below the
+        // block maximum keep an ABSOLUTE accuracy of ~2^-39 of that maximum, the rest 2^-22 relative.
+        float sf, isf;
+        {
+            float m = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m = fmaxf(m, fabsf(dzv[e][u][j]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;             // floor(log2 m); m = 0 or denormal -> -127
+            const int sh = max(-100, min(100, 13 - ex));
+            sf = __uint_as_float((uint32_t)(sh + 127) << 23); isf = __uint_as_float((uint32_t)(127 - sh) << 23);
+        }
+        uint32_t a1[2][2][4], a2[2][2][4];                                  // [gate pair][m-tile][fragment]: (g, gate 2kp) (g+8, gate 2kp) (g, gate 2kp+1) (g+8, gate 2kp+1), units (u0, u0+1) per word
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                split_h2(dzv[2 * mt][0][2 * kp] * sf, dzv[2 * mt][1][2 * kp] * sf, a1[kp][mt][0], a2[kp][mt][0]);
+                split_h2(dzv[2 * mt + 1][0][2 * kp] * sf, dzv[2 * mt + 1][1][2 * kp] * sf, a1[kp][mt][1], a2[kp][mt][1]);
+                split_h2(dzv[2 * mt][0][2 * kp + 1] * sf, dzv[2 * mt][1][2 * kp + 1] * sf, a1[kp][mt][2], a2[kp][mt][2]);
+                split_h2(dzv[2 * mt + 1][0][2 * kp + 1] * sf, dzv[2 * mt + 1][1][2 * kp + 1] * sf, a1[kp][mt][3], a2[kp][mt][3]);
+            }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            float part[2][3][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int n3 = 0; n3 < 3; ++n3) part[mt][n3][0] = part[mt][n3][1] = part[mt][n3][2] = part[mt][n3][3] = 0.f;
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+                uint2 b1[3], b2[3];
+#pragma unroll
+                for (int n3 = 0; n3 < 3; ++n3) { b1[n3] = B1s[w][kp][3 * p + n3][lane]; b2[n3] = B2s[w][kp][3 * p + n3][lane]; }
+#pragma unroll
+                for (int n3 = 0; n3 < 3; ++n3)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) mma_f16(part[mt][n3], a2[kp][mt], b1[n3].x, b1[n3].y);
+#pragma unroll
+                for (int n3 = 0; n3 < 3; ++n3)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) mma_f16(part[mt][n3], a1[kp][mt], b2[n3].x, b2[n3].y);
+#pragma unroll
+                for (int n3 = 0; n3 < 3; ++n3)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) mma_f16(part[mt][n3], a1[kp][mt], b1[n3].x, b1[n3].y);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int n3 = 0; n3 < 3; ++n3) {
+                    const int col = 8 * (3 * p + n3) + 2 * q;
+                    *reinterpret_cast<float2*>(&red[w][16 * mt + g][col]) = make_float2(part[mt][n3][0] * isf, part[mt][n3][1] * isf);
+                    *reinterpret_cast<float2*>(&red[w][16 * mt + g + 8][col]) = make_float2(part[mt][n3][2] * isf, part[mt][n3][3] * isf);
+                }
+        }
+#else
         // partial dh of this warp: A fragment of (m-tile mt, k-tile j) = dz values this thread already holds
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
@@ -416,6 +498,7 @@ __global__ void __launch_bounds__(THR * GROUPS, 2 / GROUPS) lstm_seq_bwd_mma_ker
                     *reinterpret_cast<float2*>(&red[w][16 * mt + g + 8][col]) = make_float2(part[mt][n3][2], part[mt][n3][3]);
                 }
         }
+#endif
         tile_sync(gi);
 #ifdef SEQ_BWD_LATE_LOADS                                                   // variant: register loads behind the reduction (spills 192 B at 168 registers)
         if (t > 0) load_step(t - 1, cur);

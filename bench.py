@@ -513,7 +513,7 @@ def ppo_iteration(args, rank, local, world, dist, dev):
     return {"metric": "PPO iteration wall-time", "unit": "s", "value": it, "rollout_s": ro, "update_s": up, "envs_per_gpu": n, "total_envs": n * world, "n_steps": T,
             "noptepochs": E, "nminibatches": 1, "samples_per_iteration": n * world * T, "env_steps_per_s_incl_learning": n * world * T / it,
             "gradient_allreduce": ar, "workload": "bp5 relaxation, PPO2 (clipped surrogate, BPTT over 750 steps), weights bp5_155",
-            "learner_kernels": "sequence-persistent BPTT + streaming projection / weight-gradient kernels, tensor-core MMAs (tf32 inputs in 3xTF32 form = fp32-grade results)", "timing": "host wall clock around rollout + update with a device synchronise, max over ranks"}
+            "learner_kernels": "sequence-persistent BPTT recurrence on warp-level tensor-core MMAs (fp16 2-term / tf32 3-term splits = fp32-grade results), streaming projections and weight gradients on tcgen05 + TMEM (3xTF32), heads + PPO loss + gradients in one kernel", "timing": "host wall clock around rollout + update with a device synchronise, max over ranks"}
 
 
 def main():

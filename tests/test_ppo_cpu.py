@@ -143,3 +143,23 @@ def test_time_major_forward_equals_env_major_forward_cpu():
     mean_a, val_a, _ = m.forward_sequence(torch.tensor(obs), torch.tensor(masks), torch.tensor(st))
     mean_b, val_b = m.forward_time_major(torch.tensor(obs).transpose(0, 1).contiguous(), 1.0 - torch.tensor(masks).t().contiguous(), torch.tensor(st), fused=False)
     assert torch.allclose(mean_a.transpose(0, 1), mean_b, atol=1e-5) and torch.allclose(val_a.t(), val_b, atol=1e-5)
+
+
+def test_learner_kernel_wrappers_fall_back_off_the_gpu():
+    """lstm_seq's tensor-core wrappers are CUDA-only: on CPU tensors the learner takes the plain torch path (no CUDA library is touched),
+    and the time-major forward agrees with the env-major reference forward"""
+    import torch
+    from high_speed_quadrupedal_locomotion_by_irrl_b200 import lstm_seq
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.ppo2 import LstmActorCritic
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(4, 5, 35, generator=g); W = torch.randn(2, 35, 192, generator=g)
+    assert not lstm_seq.fused_layer_ok(X, W)
+    assert torch.equal(lstm_seq.proj_rows(X, W), torch.matmul(X.unsqueeze(1), W))
+    m = LstmActorCritic()
+    T, N = 6, 5
+    obs = torch.randn(T, N, 35, generator=g); masks = (torch.rand(T, N, generator=g) < 0.2).float(); st = torch.randn(N, 384, generator=g) * 0.3
+    mean_t, val_t = m.forward_time_major(obs, 1.0 - masks, st)
+    mean_e, val_e, _ = m.forward_sequence(obs.transpose(0, 1), masks.transpose(0, 1), st)
+    assert torch.allclose(mean_t, mean_e.transpose(0, 1), atol=1e-5) and torch.allclose(val_t, val_e.transpose(0, 1), atol=1e-5)
+    H1, own = m.features_time_major(obs, 1.0 - masks, st)
+    assert own is False and H1.shape == (T, 2, N, 48)

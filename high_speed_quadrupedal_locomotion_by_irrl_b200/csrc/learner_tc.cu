@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_cons
     int tile = blockIdx.x, it = 0;
 #pragma unroll
     for (int j = 0; j < G_NRAW; ++j) if (tile + j * (int)gridDim.x < tiles) issue(tile + j * gridDim.x, j);
+    __syncthreads();                                                    // the zero rows a ragged first tile got from other threads (later refills sit behind the per-tile barriers)
     for (; tile < tiles; tile += gridDim.x, ++it) {
         const int s = it & 1, rb = it % G_NRAW;
         mbar_wait(&raw_full[rb], (it / G_NRAW) & 1);                    // the raw rows of this tile have landed

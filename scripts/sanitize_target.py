@@ -43,3 +43,11 @@ env = RaisimGymVecEnv(FlexibleGymEnv("", dump_yaml(trot_cfg(num_envs=76, Stochas
 model = PPO2(env, policy_params=W, n_steps=12, noptepochs=1, learning_rate=1e-4, verbose=0)
 h = model.learn(total_timesteps=76 * 12)
 print("ppo iteration ok: loss", h[-1].get("policy_loss"), flush=True)
+# the persistent tcgen05 learner kernels with several tiles per CTA (stage / slot / TMEM-buffer reuse), ragged last tiles
+from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import ProjRows, gram2_rows
+g = torch.Generator(device="cuda:0"); g.manual_seed(5)
+T, K, N = 48, 2, 520
+obs_ = torch.randn(T, N, 35, device="cuda:0", generator=g); H0_ = torch.randn(T, K, N, 48, device="cuda:0", generator=g, requires_grad=True)
+D_ = torch.randn(T, K, N, 192, device="cuda:0", generator=g); w0_ = torch.randn(K, 35, 192, device="cuda:0", generator=g); w1_ = torch.randn(K, 48, 192, device="cuda:0", generator=g, requires_grad=True)
+ProjRows.apply(obs_, w0_); (ProjRows.apply(H0_, w1_) * D_).sum().backward(); gram2_rows(obs_, H0_.detach(), D_); gram2_rows(H0_.detach(), H0_.detach(), D_)
+torch.cuda.synchronize(); print("persistent tcgen05 learner kernels ok (multi-tile CTAs)", flush=True)

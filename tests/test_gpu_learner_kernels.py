@@ -186,3 +186,30 @@ def test_fused_head_loss_scales_with_the_upstream_gradient():
         gh, gw = torch.autograd.grad(loss * scale, (H1, pw))
         out.append((gh, gw, H1))
     assert torch.allclose(out[1][0], 2.5 * out[0][0], rtol=1e-6, atol=0) and torch.allclose(out[1][1], 2.5 * out[0][1], rtol=1e-5, atol=1e-12)
+
+
+def test_streaming_kernels_with_many_tiles_per_cta():
+    """the persistent tcgen05 kernels in their steady state: several tiles per CTA (stage / slot / TMEM-buffer reuse, barrier parities wrapping),
+    ragged last tiles, against float64"""
+    torch, _lib, L, dev = _setup()
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import ProjRows, gram2_rows
+    g = torch.Generator(device=dev); g.manual_seed(21)
+    r = lambda *s: torch.randn(*s, device=dev, generator=g)
+    T, K, N = 160, 2, 520                    # 800 projection tiles and 3520 weight-gradient tiles per tower on 74 CTAs
+    obs, H0, D = r(T, N, 35), r(T, K, N, 48), r(T, K, N, 192)
+    wx0, wx1 = r(K, 35, 192) * 0.3, r(K, 48, 192) * 0.3
+    for X, W in ((obs, wx0), (H0, wx1)):
+        Xr = X.clone().requires_grad_(X.dim() == 4); Wr = W.clone().requires_grad_(True)
+        Y = ProjRows.apply(Xr, Wr); (Y * D).sum().backward()
+        Xk = X.double().unsqueeze(1).expand(T, K, N, -1) if X.dim() == 3 else X.double()
+        Yd = torch.matmul(Xk, W.double())
+        assert float((Y.detach().double() - Yd).abs().max()) <= 3e-6 * float(Yd.abs().max())
+        if X.dim() == 4:
+            dX = torch.matmul(D.double(), W.double().transpose(1, 2))
+            assert float((Xr.grad.double() - dX).abs().max()) <= 3e-6 * float(dX.abs().max())
+        dwx, dwh = gram2_rows(X, H0, D)
+        rx = torch.matmul(Xk.transpose(-1, -2), D.double()).sum(0); rh = torch.matmul(H0.double().transpose(-1, -2), D.double()).sum(0)
+        # 83 200-row reductions of O(1) random products accumulated in fp32 (tensor memory, then 74 partials): the bar is the rounding noise of an
+        # fp32 accumulator that wanders to ~1e3 (measured 8e-6 of the scale; torch.matmul in fp32 sits at the same level)
+        assert float((dwx.double() - rx).abs().max()) <= 2e-5 * float(rx.abs().max())
+        assert float((dwh.double() - rh).abs().max()) <= 2e-5 * float(rh.abs().max())

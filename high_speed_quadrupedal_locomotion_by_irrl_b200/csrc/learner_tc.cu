@@ -5,12 +5,16 @@
 // (98 cycles each, 4x the rate of the warp-level MMAs of learner_gemm.cu), fp32 accumulators in tensor memory.
 //
 // One persistent CTA per SM (512 threads) walks 128-row tiles of one tower:
-//   * raw rows arrive through a double-buffered cp.async stage (coalesced 16-byte chunks; 4-byte chunks for the 35-column observation
-//     whose rows are not 16-byte aligned),
-//   * every thread converts (row, 4 k) items into the hi / lo operand tile (row-per-lane writes: conflict-free),
+//   * raw rows arrive through the bulk-copy engine: ONE cp.async.bulk per tile (its rows are contiguous), completing on an mbarrier, two
+//     tiles ahead.  Per-thread cp.async was measured slower: fence.proxy.async -- which every thread needs after writing the operand tile
+//     -- waits for the thread's own outstanding asynchronous copies, i.e. one HBM round trip per tile.  (35-column rows need n_env % 4 == 0
+//     for 16-byte alignment; otherwise the warp-level kernel of learner_gemm.cu serves the call.)
+//   * every thread converts its fixed list of (row, 4 k) items into the hi / lo operand tile (row-per-lane writes: conflict-free; 48-column
+//     rows are read as float4s in a rotated chunk order, conflict-free at the natural pitch of the copied block),
 //   * one elected lane issues KS x 3 MMAs into TMEM buffer i % 2 and commits to an mbarrier,
-//   * while they run, all threads drain the PREVIOUS tile's accumulator: tcgen05.ld (lane = row, 16 columns) -> padded staging tile
-//     -> coalesced float4 stores (a row-per-lane store straight from registers would cost 32 L1 tag look-ups per instruction).
+//   * while they run, all threads drain the PREVIOUS tile's accumulator: tcgen05.ld (lane = row)
+//     (24 columns per warp) -> padded staging tile -> coalesced float4 stores (a row-per-lane store straight from registers would cost 32 L1
+//     tag look-ups per instruction).
 // W is packed once per CTA (hi / lo split, K-major rows = output columns).  Rows past N in the last tile of a time step are never stored.
 #include <algorithm>
 #include <cstdlib>

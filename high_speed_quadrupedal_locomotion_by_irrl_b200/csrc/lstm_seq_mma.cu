@@ -19,8 +19,9 @@
 // Fragment ownership (g = lane / 4, q = lane % 4, warp w): the thread owns environments {g, g+8, g+16, g+24} of the tile and
 // hidden units {8w+2q, 8w+2q+1} with all four gates -- exactly the C fragments of MMA n-tiles "gate j of units 8w..8w+7"
 // -- so the cell update / its derivative run in registers as before.
-//   forward:  B fragments (W_h, hi part) live in registers for the whole sequence, lo parts in shared memory in fragment
-//             order; A fragments (hm) come from a [32][52] shared tile (conflict-free for the fragment pattern).
+//   forward:  B fragments (W_h: fp16 leading parts and remainders, 48 registers) live in registers for the whole sequence; A fragments
+//             (hm) come from a double-buffered half2 tile that the producers of h write already split (conflict-free fragment
+//             reads, one barrier per step).  (-DSEQ_FWD_TF32: tf32 hi parts in registers, bf16 remainders in shared memory, [32][52] tiles.)
 //   backward: split-K over warps.  The dz values a thread just computed ARE the A fragments of the k-tile "gate j of this
 //             warp's units" (with the k order (2q, 2q+1) <-> (q, q+4), applied to B as well), so dz never goes through shared
 //             memory; every warp produces a partial dh[32 x 48] that is summed over the 6 warps through shared memory.

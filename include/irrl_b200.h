@@ -193,7 +193,8 @@ int irrl_lstm_seq_fwd(void* cuda_stream, int T, int K, int n_env, const float* x
 int irrl_lstm_seq_bwd(void* cuda_stream, int T, int K, int n_env, const float* dH, const float* wh, const float* c0, const float* keep, const float* gates,
                       const float* Cs, float* dz, float* db_part /*[irrl_lstm_seq_ctas(n_env),K,192] out: per-CTA sums of dz (bias gradient), may be NULL*/);
 int irrl_lstm_seq_ctas(int n_env);
-/* which kernels serve irrl_lstm_seq_fwd / _bwd: 0 = tensor-core recurrence (mma.sync tf32 in 3xTF32 form, default), 1 = FP32-FMA recurrence
+/* which kernels serve irrl_lstm_seq_fwd / _bwd: 0 = tensor-core recurrence (default; forward product as a 2-term fp16 split on the f16 MMA -- it assumes
+ * |W_h| < 6.5e4, the fp16 range, and |h| < 1 which the cell guarantees -- backward product as tf32 in 3xTF32 form), 1 = FP32-FMA recurrence
  * (the regression reference; also IRRL_SEQ_PATH=fma in the environment).  Returns the previous value; any other argument only queries. */
 int irrl_lstm_seq_set_path(int path);
 /* the non-recurrent products of the same BPTT on the tensor cores (3xTF32, fp32-grade), device pointers, time-major rows (t, tower k, env n):

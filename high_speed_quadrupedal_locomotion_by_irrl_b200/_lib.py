@@ -82,7 +82,7 @@ def load() -> C.CDLL:
     L.irrl_scale_unless_one.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     L.irrl_ppo_head_loss.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 11 + [C.c_float, C.c_float, C.c_float] + [C.c_void_p] * 3
     L.irrl_gram2_rows_ctas.argtypes = [C.c_int, C.c_int, C.c_int]
-    L.irrl_gram2_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.irrl_gram2_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.irrl_gram_rows_ctas.argtypes = [C.c_int, C.c_int, C.c_int]
     L.irrl_gram_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.irrl_lstm_pw_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8

@@ -1169,10 +1169,11 @@ int irrl_ppo_head_loss(void* cuda_stream, int T, int n_env, const float* H1, con
     CUDA_OK(cudaGetLastError()); return 0;
 }
 int irrl_gram2_rows_ctas(int T, int K, int n_env) { return gram2_rows_tc_ctas(T, n_env, K); }
-int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial) {
+int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* Hs, const float* h0, const float* keep, const float* D,
+                    float* partial) {
     NvtxRange nvtx_("irrl_gram2_rows");
-    if (!X || !HM || !D || !partial || T <= 0 || K <= 0 || n_env <= 0) return fail(-1, "irrl_gram2_rows: bad argument");
-    const int rc = launch_gram2_rows_tc(X, x_cols, x_has_tower, HM, D, partial, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (!X || !Hs || !h0 || !keep || !D || !partial || T <= 0 || K <= 0 || n_env <= 0) return fail(-1, "irrl_gram2_rows: bad argument");
+    const int rc = launch_gram2_rows_tc(X, x_cols, x_has_tower, Hs, h0, keep, D, partial, T, K, n_env, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (rc == -1) return fail(-1, "irrl_gram2_rows: x_cols must be in 1..48");
     if (rc == -3) return fail(-3, "irrl_gram2_rows: needs n_env % 4 == 0 and 16-byte aligned tensors (use irrl_gram_rows)");
     if (rc) return fail(rc, "irrl_gram2_rows: kernel configuration failed");

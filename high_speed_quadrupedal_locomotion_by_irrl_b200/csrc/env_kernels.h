@@ -93,7 +93,8 @@ int launch_proj_rows_tc(const float* X, int x_cols, int x_has_tower, const float
 int proj_rows_set_path(int path);
 int launch_projT_rows_tc(const float* D, const float* W, float* Y, int T, int K, int N, cudaStream_t st);
 int gram2_rows_tc_ctas(int T, int N, int K);
-int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial, int T, int K, int N, cudaStream_t st);
+int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* Hs, const float* h0, const float* keep, const float* D, float* partial, int T, int K, int N,
+                         cudaStream_t st);
 // proj_rows_set_path: 0 tcgen05 (default), 1 warp-level MMAs; returns the previous value
 int launch_gram_rows(const float* X, int x_cols, int x_has_tower, const float* D, float* partial, int T, int K, int N, cudaStream_t st);
 // heads + PPO loss + gradients in one pass (ppo_head_loss.cu); partial [ppo_head_loss_ctas][HL_PART] = per-CTA sums of

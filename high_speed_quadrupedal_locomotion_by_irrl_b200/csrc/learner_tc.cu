@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(THR, 1) projT_rows_tc_kernel(const __grid_cons
 
 // ---------------------------------------------------------------------------------------------------------------- gram2_rows (tcgen05)
 // Both weight gradients of one LSTM layer in ONE pass over dz:  G[0:48] = sum_rows x^T dz (dW_x),  G[48:96] = sum_rows hm^T dz (dW_h),
+// hm(t) = h(t-1) * keep(t) formed here from the layer's OUTPUT sequence (the forward kernel does not store a masked copy),
 // rows = (t, n) of tower k (~6 M).  MMA view: D[128 x 192] += A[128 x 8] . B[8 x 192] with M = feature (96 used), N = gate column, K = ROWS,
 // so both operands must be K-major over rows: the transform transposes while it splits -- an item is (feature or column, 4 consecutive
 // rows): four strided scalar reads (lanes along the feature: conflict-free), hi / lo split, one float4 store each into the operand tile.
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(THR, 1) projT_rows_tc_kernel(const __grid_cons
 // afterwards in a fixed order: deterministic).  Raw rows stream through a double-buffered cp.async stage, 32 rows (4 k-steps) per tile.
 struct GramTcArgs {
     const float* X; int x_cols; long long x_t_stride, x_k_stride;      // [T,(K),N,x_cols], x_cols <= 48
-    const float* HM;                                                   // [T,K,N,48]
+    const float* Hs; const float* h0; const float* keep;               // masked input state of step t = Hs[t-1] * keep[t] (h0 * keep[0] at t = 0): Hs [T,K,N,48], h0 [K,N,48], keep [T,N]
     const float* D;                                                    // [T,K,N,192]
     float* P;                                                          // partial sums [gridDim.x][K][128][192]
     int T, K, N;
@@ -363,7 +364,7 @@ struct GramTcArgs {
 constexpr int GR = 24, GKS = GR / 8;                                   // rows per tile = 3 k-steps: small enough for TWO operand-tile slots and THREE raw stages
 constexpr int G_SLOT = GKS * (A_KSTEP + B_KSTEP);                      // operand tiles of one slot: A (128 x 24) then B (192 x 24), hi / lo each
 constexpr int G_OFF_OP = 0, G_OFF_RAW = G_OFF_OP + 2 * G_SLOT;
-constexpr int G_RAW_STAGE = GR * (48 + 48 + NG) * 4;                   // [24][48] x | [24][48] hm | [24][192] dz
+constexpr int G_RAW_STAGE = GR * (48 + 48 + NG + 4) * 4;               // [24][48] x | [24][48] h(t-1) | [24][192] dz | [24] keep(t) (+ pad to 16 bytes per 4 rows)
 constexpr int G_NRAW = 3;
 constexpr int G_OFF_BAR = G_OFF_RAW + G_NRAW * G_RAW_STAGE;
 constexpr int G_BYTES = G_OFF_BAR + (2 + G_NRAW) * 8 + 16;
@@ -386,11 +387,11 @@ __global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_cons
 
     const int tiles_per_t = (A.N + GR - 1) / GR, tiles = A.T * tiles_per_t;
     const int x_cols = A.x_cols;
-    uint32_t a_src[2], a_dst[2], b_src[3], b_dst[3]; int a_pitch[2];
+    uint32_t a_src[2], a_dst[2], b_src[3], b_dst[3]; int a_pitch[2], a_keep[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int i = t_ + j * THR, m = i % 96, c = i / 96;
-        a_pitch[j] = m < 48 ? x_cols : 48;
+        a_pitch[j] = m < 48 ? x_cols : 48; a_keep[j] = m < 48 ? -1 : 4 * c;
         a_src[j] = m < 48 ? m + 4 * c * x_cols : GR * 48 + (m - 48) + 4 * c * 48;
         a_dst[j] = (i < 96 * (GR / 4) && (m >= 48 || m < x_cols)) ? op_off(4 * c, m, TM) : 0xFFFFFFFFu;      // features past x_cols: their operand rows stay zero
     }
@@ -404,18 +405,21 @@ __global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_cons
         const int t = tile / tiles_per_t, n0 = (tile - t * tiles_per_t) * GR, rows = min(GR, A.N - n0);
         float* rx = reinterpret_cast<float*>(smem + G_OFF_RAW + buf * G_RAW_STAGE);
         if (rows < GR) {                                                // ragged last tile of a time step: the rows past N must be zero
-            for (int i = t_; i < (GR - rows) * 48; i += THR) { rx[rows * 48 + i] = 0.f; rx[GR * 48 + rows * 48 + i] = 0.f; }
+            for (int i = t_; i < (GR - rows) * x_cols; i += THR) rx[rows * x_cols + i] = 0.f;
+            for (int i = t_; i < (GR - rows) * 48; i += THR) rx[GR * 48 + rows * 48 + i] = 0.f;
             for (int i = t_; i < (GR - rows) * NG; i += THR) rx[GR * 96 + rows * NG + i] = 0.f;
         }
         if (t_ == 32) {
             const float* xs = A.X + ((size_t)t * A.x_t_stride + (size_t)k * A.x_k_stride + n0) * x_cols;
-            const float* hs = A.HM + (((size_t)t * A.K + k) * A.N + n0) * 48;
+            const float* hs = t > 0 ? A.Hs + (((size_t)(t - 1) * A.K + k) * A.N + n0) * 48 : A.h0 + ((size_t)k * A.N + n0) * 48;
+            const float* ks = A.keep + (size_t)t * A.N + n0;
             const float* ds = A.D + (((size_t)t * A.K + k) * A.N + n0) * NG;
             const uint32_t bx = rows * x_cols * 4, bh = rows * 48 * 4, bd = rows * NG * 4;
-            mbar_expect_tx(&raw_full[buf], bx + bh + bd);
+            mbar_expect_tx(&raw_full[buf], bx + bh + bd + rows * 4);
             bulk_g2s(smem_u32(rx), xs, bx, &raw_full[buf]);
             bulk_g2s(smem_u32(rx + GR * 48), hs, bh, &raw_full[buf]);
             bulk_g2s(smem_u32(rx + GR * 96), ds, bd, &raw_full[buf]);
+            bulk_g2s(smem_u32(rx + GR * 288), ks, rows * 4, &raw_full[buf]);
         }
     };
     int tile = blockIdx.x, it = 0;
@@ -433,7 +437,11 @@ __global__ void __launch_bounds__(THR, 1) gram2_rows_tc_kernel(const __grid_cons
             if (a_dst[j] != 0xFFFFFFFFu) {
                 const float* col = rx + a_src[j];
                 const int ap = a_pitch[j];
-                const float v[4] = {col[0], col[ap], col[2 * ap], col[3 * ap]};
+                float v[4] = {col[0], col[ap], col[2 * ap], col[3 * ap]};
+                if (a_keep[j] >= 0) {                                   // h(t-1) rows: SB lstm() masks the state fed into step t (h *= 1 - m)
+                    const float4 kp = *reinterpret_cast<const float4*>(rx + GR * 288 + a_keep[j]);
+                    v[0] *= kp.x; v[1] *= kp.y; v[2] *= kp.z; v[3] *= kp.w;
+                }
                 store_hilo(sA, a_dst[j], A_HALF, v);
             }
         }
@@ -536,13 +544,14 @@ int launch_projT_rows_tc(const float* D, const float* W, float* Y, int T, int K,
 }
 int gram2_rows_tc_ctas(int T, int N, int K) { const int tiles = T * ((N + ltc::GR - 1) / ltc::GR); return std::max(1, std::min(tiles, sm_count_tc() / std::max(K, 1))); }
 // partial[gram2_rows_tc_ctas][K][128][192]: rows 0..x_cols-1 = sum x^T dz, rows 48..95 = sum hm^T dz (rows 96..127 are not written)
-int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial, int T, int K, int N, cudaStream_t st) {
+int launch_gram2_rows_tc(const float* X, int x_cols, int x_has_tower, const float* Hs, const float* h0, const float* keep, const float* D, float* partial, int T, int K, int N,
+                         cudaStream_t st) {
     using namespace ltc;
     if (x_cols <= 0 || x_cols > 48) return -1;
     // the bulk-copy engine wants 16-byte aligned blocks of a multiple of 16 bytes: true for every tile when N is a multiple of 4
-    if ((N & 3) || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(HM) | reinterpret_cast<uintptr_t>(D)) & 15)) return -3;
+    if ((N & 3) || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Hs) | reinterpret_cast<uintptr_t>(h0) | reinterpret_cast<uintptr_t>(keep) | reinterpret_cast<uintptr_t>(D)) & 15)) return -3;
     GramTcArgs a{}; a.X = X; a.x_cols = x_cols; a.x_t_stride = x_has_tower ? (long long)K * N : N; a.x_k_stride = x_has_tower ? N : 0;
-    a.HM = HM; a.D = D; a.P = partial; a.T = T; a.K = K; a.N = N;
+    a.Hs = Hs; a.h0 = h0; a.keep = keep; a.D = D; a.P = partial; a.T = T; a.K = K; a.N = N;
     if (cudaFuncSetAttribute(gram2_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_BYTES) != cudaSuccess) return -2;
     gram2_rows_tc_kernel<<<dim3(gram2_rows_tc_ctas(T, N, K), K), THR, G_BYTES, st>>>(a);
     return 0;

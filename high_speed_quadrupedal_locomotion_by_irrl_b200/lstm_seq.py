@@ -35,16 +35,26 @@ def gram_rows(X, D):
     return part.sum(0)[:, :c]
 
 
-def gram2_rows(X, HM, D):
-    """dW_x = sum x^T dz and dW_h = sum hm^T dz of one layer in one pass over dz (tcgen05): ([K,c,192], [K,48,192])."""
+def masked_input_state(Hs, h0, keep):
+    """HM[t] = h(t-1) * keep[t], the state SB's lstm() feeds into step t (h0 * keep[0] at t = 0): [T,K,N,48]"""
+    T, K, N, _ = Hs.shape
+    prev = torch.cat([h0.unsqueeze(0), Hs[:-1]], 0)
+    return prev * keep.view(T, 1, N, 1)
+
+
+def gram2_rows(X, Hs, h0, keep, D):
+    """dW_x = sum x^T dz and dW_h = sum hm^T dz of one layer in one pass over dz (tcgen05), hm(t) = Hs(t-1) * keep(t) formed on the fly from
+    the layer's output sequence: ([K,c,192], [K,48,192])."""
     L = _lib.load()
     T, K, N, _ = D.shape
     c = X.shape[-1]
     st = C.c_void_p(torch.cuda.current_stream(D.device).cuda_stream)
-    if N % 4 or (X.data_ptr() | HM.data_ptr() | D.data_ptr()) % 16:        # the tcgen05 kernel streams whole 16-byte aligned blocks: odd batches go through the warp-level kernel
-        return gram_rows(X, D), gram_rows(HM, D)
+    Hs = Hs.contiguous(); h0 = h0.contiguous(); keep = keep.contiguous()
+    if N % 4 or (X.data_ptr() | Hs.data_ptr() | h0.data_ptr() | keep.data_ptr() | D.data_ptr()) % 16:
+        # the tcgen05 kernel streams whole 16-byte aligned blocks: odd batches go through the warp-level kernel
+        return gram_rows(X, D), gram_rows(masked_input_state(Hs, h0, keep), D)
     part = D.new_empty((L.irrl_gram2_rows_ctas(T, K, N), K, 128, 192))
-    _lib.check(L.irrl_gram2_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(HM), _p(D), _p(part)), "gram2_rows")
+    _lib.check(L.irrl_gram2_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(Hs), _p(h0), _p(keep), _p(D), _p(part)), "gram2_rows")
     G = part[:, :, :96].sum(0)
     return G[:, :c], G[:, 48:96]
 
@@ -63,15 +73,16 @@ class LstmLayerFused(torch.autograd.Function):
         st = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
         xw = X.new_empty((T, K, N, 192))
         _lib.check(L.irrl_proj_rows(st, T, K, N, _p(X), c, 1 if X.dim() == 4 else 0, _p(wx), 0, _p(xw), 192), "proj_rows")
-        gates = torch.empty_like(xw); Cs = X.new_empty((T, K, N, 48)); Hs = X.new_empty((T, K, N, 48)); HM = X.new_empty((T, K, N, 48))
-        _lib.check(L.irrl_lstm_seq_fwd(st, T, K, N, _p(xw), _p(wh), _p(c0), _p(h0), _p(keep), _p(gates), _p(Cs), _p(Hs), _p(b), _p(HM)), "lstm_seq_fwd")
-        ctx.save_for_backward(X, wx, wh, keep, gates, Cs, HM, c0)
+        gates = torch.empty_like(xw); Cs = X.new_empty((T, K, N, 48)); Hs = X.new_empty((T, K, N, 48))
+        # no masked copy of the hidden state: the weight-gradient kernel forms hm(t) = Hs(t-1) * keep(t) itself
+        _lib.check(L.irrl_lstm_seq_fwd(st, T, K, N, _p(xw), _p(wh), _p(c0), _p(h0), _p(keep), _p(gates), _p(Cs), _p(Hs), _p(b), None), "lstm_seq_fwd")
+        ctx.save_for_backward(X, wx, wh, keep, gates, Cs, Hs, c0, h0)
         return Hs
 
     @staticmethod
     def backward(ctx, dH):
         L = _lib.load()
-        X, wx, wh, keep, gates, Cs, HM, c0 = ctx.saved_tensors
+        X, wx, wh, keep, gates, Cs, Hs, c0, h0 = ctx.saved_tensors
         T, K, N, _ = gates.shape
         c = X.shape[-1]
         st = C.c_void_p(torch.cuda.current_stream(gates.device).cuda_stream)
@@ -79,7 +90,7 @@ class LstmLayerFused(torch.autograd.Function):
         DZ = torch.empty_like(gates)
         db_part = gates.new_empty((L.irrl_lstm_seq_ctas(N), K, 192))
         _lib.check(L.irrl_lstm_seq_bwd(st, T, K, N, _p(dH), _p(wh), _p(c0), _p(keep), _p(gates), _p(Cs), _p(DZ), _p(db_part)), "lstm_seq_bwd")
-        dwx, dwh = gram2_rows(X, HM, DZ)
+        dwx, dwh = gram2_rows(X, Hs, h0, keep, DZ)
         dX = None
         if ctx.needs_input_grad[0]:
             if X.dim() == 4 and c == 48:

@@ -208,11 +208,14 @@ int irrl_proj_rows(void* cuda_stream, int T, int K, int n_env, const float* X, i
 int irrl_proj_rows_set_path(int path);
 int irrl_gram_rows_ctas(int T, int K, int n_env);
 /* both weight gradients of one LSTM layer in one pass over dz, on tcgen05 (accumulator in tensor memory over all rows of a CTA):
- * partial[irrl_gram2_rows_ctas(T,K,N), K, 128, 192], rows 0..x_cols-1 = per-CTA sums of X^T D (dW_x), rows 48..95 = sums of HM^T D (dW_h);
- * rows 96..127 are padding and NOT written.  X as in irrl_gram_rows (x_cols <= 48), HM [T,K,N,48], D [T,K,N,192].  The rows stream through the
- * bulk-copy engine: n_env % 4 == 0 and 16-byte aligned tensors are required (-3 otherwise: use irrl_gram_rows). */
+ * partial[irrl_gram2_rows_ctas(T,K,N), K, 128, 192], rows 0..x_cols-1 = per-CTA sums of X^T D (dW_x), rows 48..95 = sums of HM^T D (dW_h) where
+ * HM(t) = Hs(t-1) * keep(t) (h0 * keep(0) at t = 0) is the masked state fed into step t, formed on the fly from the layer's output sequence
+ * Hs [T,K,N,48], its initial state h0 [K,N,48] and keep [T,N]; rows 96..127 are padding and NOT written.  X as in irrl_gram_rows (x_cols <= 48),
+ * D [T,K,N,192].  The rows stream through the bulk-copy engine: n_env % 4 == 0 and 16-byte aligned tensors are required (-3 otherwise: use
+ * irrl_gram_rows). */
 int irrl_gram2_rows_ctas(int T, int K, int n_env);
-int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* HM, const float* D, float* partial);
+int irrl_gram2_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* Hs, const float* h0, const float* keep, const float* D,
+                    float* partial);
 int irrl_gram_rows(void* cuda_stream, int T, int K, int n_env, const float* X, int x_cols, int x_has_tower, const float* D, float* partial);
 /* heads + PPO2 loss + their gradients in one pass over the top-layer activations H1 [T,2,N,48] (ppo2.py:152-175 over run_bp_v5.py:167-176):
  * per sample the Gaussian mean (pi head), the value (V head), neglogp, the clipped surrogate and the clipped value loss, and the gradients of

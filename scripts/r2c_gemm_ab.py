@@ -67,6 +67,7 @@ if __name__ == "__main__":
             extra = f"   warp-level MMA kernel {c:6.2f} ms"
         print(f"{name} N={N} T={T}: tensor-core {a:6.2f} ms ({g_ / a * 1e3:5.0f} GB/s algorithmic)   torch.matmul fp32 {b:6.2f} ms{extra}")
     from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import gram2_rows
+    h0_ = torch.randn(K, N, 48, device=dev); keep_ = (torch.rand(T, N, device=dev) > 0.05).float()
     for name, X in (("gram2 [h | hm]^T dz  ", H0), ("gram2 [obs | hm]^T dz", obs)):
-        a = timed(lambda: gram2_rows(X, H0, D))
+        a = timed(lambda: gram2_rows(X, H0, h0_, keep_, D))
         print(f"{name} N={N} T={T}: tcgen05 {a:6.2f} ms ({gb(X, H0, D) / a * 1e3:5.0f} GB/s algorithmic)   (two warp-level gram_rows launches above)")

@@ -49,5 +49,6 @@ g = torch.Generator(device="cuda:0"); g.manual_seed(5)
 T, K, N = 48, 2, 520
 obs_ = torch.randn(T, N, 35, device="cuda:0", generator=g); H0_ = torch.randn(T, K, N, 48, device="cuda:0", generator=g, requires_grad=True)
 D_ = torch.randn(T, K, N, 192, device="cuda:0", generator=g); w0_ = torch.randn(K, 35, 192, device="cuda:0", generator=g); w1_ = torch.randn(K, 48, 192, device="cuda:0", generator=g, requires_grad=True)
-ProjRows.apply(obs_, w0_); (ProjRows.apply(H0_, w1_) * D_).sum().backward(); gram2_rows(obs_, H0_.detach(), D_); gram2_rows(H0_.detach(), H0_.detach(), D_)
+ProjRows.apply(obs_, w0_); (ProjRows.apply(H0_, w1_) * D_).sum().backward(); h0_ = torch.randn(K, N, 48, device="cuda:0", generator=g); keep_ = (torch.rand(T, N, device="cuda:0", generator=g) > 0.1).float()
+gram2_rows(obs_, H0_.detach(), h0_, keep_, D_); gram2_rows(H0_.detach(), H0_.detach(), h0_, keep_, D_)
 torch.cuda.synchronize(); print("persistent tcgen05 learner kernels ok (multi-tile CTAs)", flush=True)

@@ -138,9 +138,12 @@ def test_tcgen05_weight_gradients_match_float64(T, K, N, cx):
     from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import gram2_rows
     g = torch.Generator(device=dev); g.manual_seed(N + cx)
     r = lambda *s: torch.randn(*s, device=dev, generator=g)
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import masked_input_state
     X = r(T, N, cx) if cx == 35 else r(T, K, N, cx)
-    HM, D = r(T, K, N, 48), r(T, K, N, 192)
-    dwx, dwh = gram2_rows(X, HM, D)
+    Hs, h0, D = r(T, K, N, 48), r(K, N, 48), r(T, K, N, 192)
+    keep = (torch.rand(T, N, device=dev, generator=g) > 0.2).float()
+    HM = masked_input_state(Hs, h0, keep)               # hm(t) = Hs(t-1) * keep(t): the kernel forms it on the fly
+    dwx, dwh = gram2_rows(X, Hs, h0, keep, D)
     Xk = (X.double().unsqueeze(1).expand(T, K, N, -1) if X.dim() == 3 else X.double())
     rx = torch.matmul(Xk.transpose(-1, -2), D.double()).sum(0); rh = torch.matmul(HM.double().transpose(-1, -2), D.double()).sum(0)
     assert dwx.shape == rx.shape and dwh.shape == rh.shape
@@ -192,7 +195,7 @@ def test_streaming_kernels_with_many_tiles_per_cta():
     """the persistent tcgen05 kernels in their steady state: several tiles per CTA (stage / slot / TMEM-buffer reuse, barrier parities wrapping),
     ragged last tiles, against float64"""
     torch, _lib, L, dev = _setup()
-    from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import ProjRows, gram2_rows
+    from high_speed_quadrupedal_locomotion_by_irrl_b200.lstm_seq import ProjRows, gram2_rows, masked_input_state
     g = torch.Generator(device=dev); g.manual_seed(21)
     r = lambda *s: torch.randn(*s, device=dev, generator=g)
     T, K, N = 160, 2, 520                    # 800 projection tiles and 3520 weight-gradient tiles per tower on 74 CTAs
@@ -207,8 +210,10 @@ def test_streaming_kernels_with_many_tiles_per_cta():
         if X.dim() == 4:
             dX = torch.matmul(D.double(), W.double().transpose(1, 2))
             assert float((Xr.grad.double() - dX).abs().max()) <= 3e-6 * float(dX.abs().max())
-        dwx, dwh = gram2_rows(X, H0, D)
-        rx = torch.matmul(Xk.transpose(-1, -2), D.double()).sum(0); rh = torch.matmul(H0.double().transpose(-1, -2), D.double()).sum(0)
+        h0s = r(K, N, 48); keep = (torch.rand(T, N, device=dev, generator=g) > 0.2).float()
+        dwx, dwh = gram2_rows(X, H0, h0s, keep, D)
+        HMd = masked_input_state(H0, h0s, keep).double()
+        rx = torch.matmul(Xk.transpose(-1, -2), D.double()).sum(0); rh = torch.matmul(HMd.transpose(-1, -2), D.double()).sum(0)
         # 83 200-row reductions of O(1) random products accumulated in fp32 (tensor memory, then 74 partials): the bar is the rounding noise of an
         # fp32 accumulator that wanders to ~1e3 (measured 8e-6 of the scale; torch.matmul in fp32 sits at the same level)
         assert float((dwx.double() - rx).abs().max()) <= 2e-5 * float(rx.abs().max())

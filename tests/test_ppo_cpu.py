@@ -163,3 +163,41 @@ def test_learner_kernel_wrappers_fall_back_off_the_gpu():
     assert torch.allclose(mean_t, mean_e.transpose(0, 1), atol=1e-5) and torch.allclose(val_t, val_e.transpose(0, 1), atol=1e-5)
     H1, own = m.features_time_major(obs, 1.0 - masks, st)
     assert own is False and H1.shape == (T, 2, N, 48)
+
+
+def test_closed_form_head_loss_gradients_match_autograd():
+    """the per-sample gradient formulas the fused heads + loss kernel evaluates (csrc/ppo_head_loss.cu: d loss / d mean, d loss / d v, d loss / d logstd
+    with the sub-gradient conventions of torch.maximum / torch.clamp), restated in torch and checked against autograd of ppo_loss's arithmetic"""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(7)
+    B, eps, vf_coef = 4000, 0.2, 0.5
+    mean = torch.randn(B, 12, generator=g, dtype=torch.float64).requires_grad_(True)
+    v = torch.randn(B, generator=g, dtype=torch.float64).requires_grad_(True)
+    logstd = (torch.randn(1, 12, generator=g, dtype=torch.float64) * 0.3).requires_grad_(True)
+    act = mean.detach() + torch.randn(B, 12, generator=g, dtype=torch.float64) * 0.5
+    adv = torch.randn(B, generator=g, dtype=torch.float64); ret = torch.randn(B, generator=g, dtype=torch.float64)
+    oldv = v.detach() + torch.randn(B, generator=g, dtype=torch.float64) * 0.3
+    with torch.no_grad():
+        nlp0 = 0.5 * (((act - mean) / logstd.exp()) ** 2).sum(-1) + 0.5 * math.log(2 * math.pi) * 12 + logstd.sum()
+    oldn = nlp0 + torch.randn(B, generator=g, dtype=torch.float64) * 0.3          # ratios on both sides of the clip range
+    # autograd (the arithmetic of ppo2.ppo_loss)
+    nlp = 0.5 * (((act - mean) / logstd.exp()) ** 2).sum(-1) + 0.5 * math.log(2 * math.pi) * 12 + logstd.sum()
+    ratio = torch.exp(oldn - nlp)
+    pg = torch.maximum(-adv * ratio, -adv * torch.clamp(ratio, 1 - eps, 1 + eps)).mean()
+    vclip = oldv + torch.clamp(v - oldv, -eps, eps)
+    vf = 0.5 * torch.maximum((v - ret) ** 2, (vclip - ret) ** 2).mean()
+    gm, gv, gl = torch.autograd.grad(pg + vf_coef * vf, (mean, v, logstd))
+    # closed form, as in the kernel
+    with torch.no_grad():
+        istd = torch.exp(-logstd); z = (act - mean) * istd
+        r = ratio.detach(); rc = r.clamp(1 - eps, 1 + eps); pg1, pg2 = -adv * r, -adv * rc
+        inside = ((r >= 1 - eps) & (r <= 1 + eps)).double()
+        sel = torch.where(pg1 > pg2, torch.ones_like(r), torch.where(pg2 > pg1, inside, 0.5 + 0.5 * inside))
+        g_nlp = adv * r * sel / B
+        dv = v - oldv; e1 = v - ret; e2 = oldv + dv.clamp(-eps, eps) - ret; l1, l2 = e1 * e1, e2 * e2
+        inside_v = ((dv >= -eps) & (dv <= eps)).double()
+        dvf = torch.where(l1 > l2, 2 * e1, torch.where(l2 > l1, 2 * e2 * inside_v, e1 + e2 * inside_v))
+        cm = -g_nlp.unsqueeze(1) * z * istd; cv = vf_coef * 0.5 * dvf / B; cl = (g_nlp.unsqueeze(1) * (1 - z * z)).sum(0, keepdim=True)
+    assert (0.05 < float((sel == 0).double().mean()) < 0.95) and (0.05 < float((l2 > l1).double().mean()) < 0.95)      # both branches of both clips are exercised
+    assert torch.allclose(cm, gm, rtol=1e-10, atol=1e-14) and torch.allclose(cv, gv, rtol=1e-10, atol=1e-14) and torch.allclose(cl, gl, rtol=1e-9, atol=1e-13)

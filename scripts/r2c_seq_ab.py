@@ -62,7 +62,8 @@ if __name__ == "__main__":
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         for rep in range(2):
             ev[0].record()
-            _lib.check(L.irrl_lstm_seq_fwd(st(), T, K, N, p(d["xw"]), p(d["wh"]), p(d["c0"]), p(d["h0"]), p(d["keep"]), p(gates), p(Cs), p(Hs), p(d["b"]), p(HM)))
+            _lib.check(L.irrl_lstm_seq_fwd(st(), T, K, N, p(d["xw"]), p(d["wh"]), p(d["c0"]), p(d["h0"]), p(d["keep"]), p(gates), p(Cs), p(Hs), p(d["b"]),
+                                           None if os.environ.get("NOHM") else p(HM)))       # NOHM=1: as the learner calls it (no masked copy of h)
             ev[1].record()
             _lib.check(L.irrl_lstm_seq_bwd(st(), T, K, N, p(d["dH"]), p(d["wh"]), p(d["c0"]), p(d["keep"]), p(gates), p(Cs), p(dz), p(db)))
             ev[2].record(); torch.cuda.synchronize()
